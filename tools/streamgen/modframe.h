@@ -1,0 +1,230 @@
+// JPEG XL test-stream writer -- TEST INFRASTRUCTURE.
+// Modular (lossless, "fjxl-shaped") frame writer: 8-bit RGB(A), reversible colour transform,
+// global MA tree, per-group modular sub-bitstreams, prefix codes + LZ77 run-lengths or ANS
+// (SURVEY.md §8d C4, App. E.2/E.3/E.6).
+#pragma once
+#include "modular.h"
+#include "synth.h"
+#include "vardct.h"
+
+namespace jxlgen {
+
+struct ModularParams {
+    int width = 256, height = 256;
+    uint64_t seed = 0;
+    int group_shift = 8;     // 7..10
+    int rct_type = 6;        // 0..41 (type % 7 = transform, type / 7 = permutation); -1 = no RCT
+    int tree_preset = 1;     // 0 single gradient leaf; 1 fjxl-like (gradient, contexts by |residual-ish| props); 2 WP tree
+    bool use_ans = false;    // fjxl uses prefix codes
+    bool lz77 = true;
+    bool alpha = false;      // add an 8-bit alpha extra channel
+    bool container = false;
+    int smooth = 1;          // 0 = raw synthetic photo, 1 = posterise a little so that runs exist
+    int max_clusters = 8;
+};
+
+class ModularFrameEncoder {
+public:
+    ModularParams P;
+    GenStats stats;
+    explicit ModularFrameEncoder(const ModularParams &p) : P(p) {}
+
+    std::vector<uint8_t> encode(const ImageRGB8 &im) {
+        JG_CHECK(im.w == P.width && im.h == P.height);
+        int W = P.width, H = P.height, nch = P.alpha ? 4 : 3;
+        // full-frame planes after the forward transform
+        std::vector<std::vector<int32_t>> plane((size_t) nch, std::vector<int32_t>((size_t) W * (size_t) H));
+        Rng rng(P.seed * 31 + 5);
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+            size_t o = (size_t) y * (size_t) W + (size_t) x;
+            int v[3];
+            for (int c = 0; c < 3; ++c) {
+                int s = im.px[o * 3 + (size_t) c];
+                if (P.smooth) s = (s >> 2) << 2;
+                v[c] = s;
+            }
+            forward_rct(v);
+            for (int c = 0; c < 3; ++c) plane[(size_t) c][o] = v[c];
+            if (P.alpha) plane[3][o] = ((x / 37 + y / 53) % 5 == 0) ? 128 + ((x + y) & 63) : 255;
+        }
+        int gsize = 1 << P.group_shift;
+        int gcols = (W + gsize - 1) / gsize, grows = (H + gsize - 1) / gsize;
+        int num_groups = gcols * grows;
+        int lfcols = (W + gsize * 8 - 1) / (gsize * 8), lfrows = (H + gsize * 8 - 1) / (gsize * 8);
+        int num_lfg = lfcols * lfrows;
+        bool single = num_groups == 1;
+
+        MATree tree = make_tree();
+        stats.tree_nodes = (int32_t) tree.nodes.size();
+        ModularTokenizer mt(tree);
+        std::vector<TokStream> ts((size_t) num_groups);
+        std::vector<int> gwidth((size_t) num_groups);
+        for (int g = 0; g < num_groups; ++g) {
+            int gx = (g % gcols) * gsize, gy = (g / gcols) * gsize;
+            int gw = std::min(W, gx + gsize) - gx, gh = std::min(H, gy + gsize) - gy;
+            gwidth[(size_t) g] = gw;
+            std::vector<Channel> ch((size_t) nch);
+            for (int c = 0; c < nch; ++c) {
+                ch[(size_t) c].w = gw; ch[(size_t) c].h = gh;
+                ch[(size_t) c].px.resize((size_t) gw * (size_t) gh);
+                for (int y = 0; y < gh; ++y) for (int x = 0; x < gw; ++x) {
+                    ch[(size_t) c].px[(size_t) y * (size_t) gw + (size_t) x] = plane[(size_t) c][(size_t) (gy + y) * (size_t) W + (size_t) (gx + x)];
+                }
+            }
+            int64_t sidx = single ? 0 : 1 + 3 * (int64_t) num_lfg + 17 + g;
+            mt.run(ch, sidx, ts[(size_t) g]);
+            stats.lf_symbols += (int64_t) ts[(size_t) g].size();
+        }
+        EntropyOpts eo;
+        eo.use_prefix = !P.use_ans;
+        eo.log_alpha_size = 8;
+        eo.cfg = {4, 1, 0};
+        eo.max_clusters = P.max_clusters;
+        eo.lz77 = P.lz77;
+        if (eo.lz77) for (int g = 0; g < num_groups; ++g) lz77_rle(ts[(size_t) g], eo.min_length, gwidth[(size_t) g], 4);
+        CodeSpec spec;
+        {
+            std::vector<const TokStream *> all;
+            for (auto &s : ts) all.push_back(&s);
+            spec.build(tree.num_leaves, eo, all);
+        }
+        stats.coef_clusters = spec.nclusters;
+
+        // ---- LfGlobal
+        BitWriter lfglobal;
+        lfglobal.bit(1); // LF dequant defaults (parsed even for modular frames)
+        lfglobal.bit(1); // global tree present
+        EntropyOpts to;
+        to.use_prefix = !P.use_ans;
+        to.log_alpha_size = 8;
+        to.cfg = {4, 1, 0};
+        to.max_clusters = 6;
+        write_tree(lfglobal, tree, to);
+        spec.write(lfglobal);
+        ModularHeaderOpts gh;
+        if (P.rct_type >= 0) gh.rcts.push_back({0, P.rct_type});
+        write_modular_header_prefix(lfglobal, gh);
+        if (single) {
+            spec.encode(lfglobal, ts[0]);
+        } else {
+            TokStream empty;
+            spec.encode(lfglobal, empty); // an ANS stream still carries its final state
+        }
+
+        BitWriter out;
+        out.put(0xff, 8); out.put(0x0a, 8);
+        VarDCTEncoder::write_size_header(out, W, H);
+        // ImageMetadata
+        out.bit(0);        // !all_default
+        out.bit(0);        // extra_fields
+        out.bit(0);        // integer samples
+        out.u32(8, 8, 0, 10, 0, 12, 0, 1, 6);
+        out.bit(1);        // modular_16bit_buffers
+        out.u32(P.alpha ? 1 : 0, 0, 0, 1, 0, 2, 4, 1, 12);
+        if (P.alpha) out.bit(1); // d_alpha
+        out.bit(0);        // xyb_encoded
+        out.bit(1);        // ColourEncoding all_default
+        out.u64(0);        // extensions
+        out.bit(1);        // default_m
+        out.pad();
+        // FrameHeader
+        out.bit(0);
+        out.put(0, 2);     // regular
+        out.bit(1);        // modular
+        out.u64(0);        // flags
+        out.bit(0);        // do_ycbcr
+        out.put(0, 2);     // log_upsampling
+        if (P.alpha) out.put(0, 2); // ec upsampling
+        out.put((uint64_t) (P.group_shift - 7), 2);
+        out.u32(1, 1, 0, 2, 0, 3, 0, 4, 3); // passes
+        out.bit(0);        // have_crop
+        out.u32(0, 0, 0, 1, 0, 2, 0, 3, 2); // blend mode (colour)
+        if (P.alpha) out.u32(0, 0, 0, 1, 0, 2, 0, 3, 2); // blend mode (alpha)
+        out.bit(1);        // is_last
+        out.u32(0, 0, 0, 0, 4, 16, 5, 48, 10); // name
+        out.bit(0);        // restoration all_default = 0 (SURVEY B-1)
+        out.bit(0);        // gab off
+        out.put(0, 2);     // epf_iters 0
+        out.u64(0);        // restoration extensions
+        out.u64(0);        // frame extensions
+        // TOC
+        if (single) {
+            lfglobal.pad();
+            out.bit(0); out.pad();
+            out.u32((uint32_t) lfglobal.bytes.size(), 0, 10, 1024, 14, 17408, 22, 4211712, 30);
+            out.pad();
+            out.append_bytes(lfglobal.bytes);
+            stats.sections = 1;
+        } else {
+            std::vector<BitWriter> secs((size_t) (2 + num_lfg + num_groups));
+            secs[0] = lfglobal;
+            for (int g = 0; g < num_groups; ++g) {
+                BitWriter &bw = secs[(size_t) (2 + num_lfg + g)];
+                ModularHeaderOpts mh;
+                write_modular_header_prefix(bw, mh);
+                spec.encode(bw, ts[(size_t) g]);
+            }
+            out.bit(0); out.pad();
+            for (auto &s : secs) { s.pad(); out.u32((uint32_t) s.bytes.size(), 0, 10, 1024, 14, 17408, 22, 4211712, 30); }
+            out.pad();
+            for (auto &s : secs) out.append_bytes(s.bytes);
+            stats.sections = (int64_t) secs.size();
+        }
+        std::vector<uint8_t> code = out.bytes;
+        if (P.container) code = VarDCTEncoder::wrap_container(code, false);
+        stats.bytes = (int64_t) code.size();
+        return code;
+    }
+
+private:
+    static int fl_avg(int a, int b) { return (a + b) >> 1; }
+
+    void forward_rct(int v[3]) const {
+        if (P.rct_type < 0) return;
+        static const uint8_t PERM[6][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0}};
+        // the decoder computes c' from c and then stores c'[i] into channel PERM[type/7][i];
+        // so the transformed triple we need is defined by: inverse(t)[i] == v[PERM[i]]
+        int perm = P.rct_type / 7, op = P.rct_type % 7;
+        int a = v[PERM[perm][0]], b = v[PERM[perm][1]], c = v[PERM[perm][2]]; // desired outputs of the inverse
+        int t0, t1, t2;
+        switch (op) {
+        case 0: t0 = a; t1 = b; t2 = c; break;
+        case 1: t0 = a; t1 = b; t2 = c - a; break;
+        case 2: t0 = a; t1 = b; t2 = c; /* out2 = c1 + c0 overwrites c2 */ t2 = 0; v[PERM[perm][2]] = a + b; break;
+        case 3: t0 = a; t1 = b - a; t2 = c - a; break;
+        case 4: t0 = a; t2 = c; t1 = b - fl_avg(a, c); break;
+        case 5: t0 = a; t2 = c - a; t1 = b - a - (t2 >> 1); break;
+        case 6: { // YCgCo: a = R-like, b = G-like, c = B-like
+            int co = a - c;
+            int tmp = c + (co >> 1);
+            int cg = b - tmp;
+            int yy = tmp + (cg >> 1);
+            t0 = yy; t1 = co; t2 = cg;
+            break;
+        }
+        default: throw GenError("bad rct");
+        }
+        v[0] = t0; v[1] = t1; v[2] = t2;
+    }
+
+    MATree make_tree() const {
+        typedef MATree M;
+        MATree t;
+        if (P.tree_preset == 0) { t.flatten(M::Leaf(5)); return t; }
+        if (P.tree_preset == 1) {
+            // contexts by channel and by local gradient magnitude; gradient predictor everywhere
+            auto sub = [&]() {
+                return M::Branch(10, 8, M::Leaf(5), M::Branch(10, -9, M::Branch(10, 1, M::Leaf(5), M::Branch(10, -2, M::Leaf(5), M::Leaf(5))), M::Leaf(5)));
+            };
+            t.flatten(M::Branch(0, 0, M::Branch(0, 2, M::Leaf(1), sub()), sub()));
+            return t;
+        }
+        auto subw = [&]() {
+            return M::Branch(15, 12, M::Leaf(6), M::Branch(15, -13, M::Branch(15, 2, M::Leaf(6), M::Branch(15, -3, M::Leaf(6), M::Leaf(6))), M::Leaf(6)));
+        };
+        t.flatten(M::Branch(0, 0, M::Branch(16, 0, subw(), M::Leaf(5)), subw()));
+        return t;
+    }
+};
+
+} // namespace jxlgen
