@@ -1,0 +1,291 @@
+// j40-b200: kernel bodies. Each *_body function is what one CUDA thread block executes for one work
+// item; the __global__ wrappers live in j40b_cuda.cu. The CPU kernel-logic tests (tests/hostemu) call
+// the same bodies with nth = 1. Serial bitstream work is done by thread 0, everything else by all
+// threads, separated by `sync` (block barrier on the device).
+#pragma once
+#include "j40b_vardct.h"
+
+namespace j40b {
+
+// one work item per thread block; all pointers are device pointers
+struct LfWork {
+    const DFrame *f;
+    const uint8_t *arena;   // per-image table arena
+    const uint8_t *cs;      // linearised codestream
+    DLfGroup *g;
+    uint32_t *err;          // this section's error word
+    float *llf_scratch;     // [2048] for LF patches larger than 8x8 cells, or null
+};
+
+struct HfWork {
+    const DFrame *f;
+    const uint8_t *arena;
+    const uint8_t *cs;
+    DLfGroup *g;
+    DGroup *grp;
+    DToken *tokens;         // image token array
+    const uint32_t *lf_err; // error word of the LF group this group depends on
+    uint32_t *err;
+};
+
+struct BackWork {
+    const DFrame *f;
+    const uint8_t *arena;
+    const DLfGroup *g;
+    const DGroup *grp;
+    const DToken *tokens;
+    const uint32_t *lf_err, *hf_err;
+    uint8_t *rgba;
+    int32_t rgba_stride;
+    float *big_scratch;     // [4 * 65536] for varblocks larger than 64x64, or null
+};
+
+struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, or the global channels
+    const DFrame *f;
+    const uint8_t *arena;
+    const uint8_t *cs;
+    uint32_t sec_off, sec_size;
+    uint64_t sec_start_bit;
+    int32_t sidx;
+    int32_t header_parsed;  // 1: `m` was filled by the host (global image), 0: parse the header here
+    ModImage m;             // channel views into the frame planes
+    int32_t *wp_scratch;    // [2 * width * 5] or null
+    int32_t *lz_window;     // or null
+    uint32_t lz_mask;
+    uint32_t *err;
+};
+
+struct RenderWork { // modular frames: inverse global transforms + interleave to RGBA8
+    const DFrame *f;
+    int16_t *plane[MOD_MAX_CH]; // full-frame planes, stride = width
+    const uint32_t *any_err;    // non-zero: skip
+    uint8_t *rgba;
+    int32_t rgba_stride;
+};
+
+struct LfShared { // block-shared scratch for lf_group_body
+    uint32_t err;
+    int32_t extra_prec;
+    ModImage m;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class Sync>
+J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nth, Sync sync) {
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    const int n8 = g.width8 * g.height8;
+    for (int i = tid; i < n8; i += nth) g.blocks[i] = 0;
+    // thread-0 state that lives across the barriers
+    BitReader br;
+    ErrSlot es;
+    CodeCtx cc;
+    CodeState cs;
+    es.err = 0;
+    if (tid == 0) {
+        sh.err = 0;
+        br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
+        cc.init(w.arena, f.global_spec_off);
+        sh.extra_prec = (int32_t) br.u(2);
+        ModImage &m = sh.m;
+        m.num_channels = 3;
+        for (int c = 0; c < 3; ++c) {
+            m.ch[c].px = g.lfq + (size_t) c * n8;
+            m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
+            m.ch[c].hshift = m.ch[c].vshift = 0;
+        }
+        modular_header(br, es, f.have_global_tree != 0, m);
+        if (!es.err) {
+            cs.init(g.lz_window, (1u << 18) - 1);
+            const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+            for (int c = 0; c < 3 && !es.err; ++c) {
+                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, m, c, 1 + g.idx);
+            }
+            if (!es.err) finish_code(br, es, cc, cs);
+        }
+        sh.err = es.err;
+    }
+    sync();
+    if (sh.err) { if (tid == 0) *w.err = sh.err; return; }
+    for (int t = sh.m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = sh.m;
+        one.nb_transforms = 1;
+        one.tr[0] = sh.m.tr[t];
+        inverse_transforms(one, tid, nth);
+        sync();
+    }
+    lf_dequant(f, g, sh.extra_prec, tid, nth);
+    sync();
+    if (!f.skip_adapt_lf_smooth) { lf_smooth(f, g, tid, nth); sync(); }
+    if (tid == 0) {
+        int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
+        g.nb_varblocks = nvb;
+        if (!es.err) {
+            ModImage &m = sh.m;
+            m.num_channels = 4;
+            m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
+            m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
+            m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
+            m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
+            for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
+            modular_header(br, es, f.have_global_tree != 0, m);
+            if (!es.err) {
+                cs.init(g.lz_window, (1u << 18) - 1);
+                const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+                for (int c = 0; c < 4 && !es.err; ++c) {
+                    modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, m, c, 1 + 2 * f.num_lf_groups + g.idx);
+                }
+                if (!es.err) finish_code(br, es, cc, cs);
+            }
+        }
+        sh.err = es.err;
+    }
+    sync();
+    if (sh.err) { if (tid == 0) *w.err = sh.err; return; }
+    for (int t = sh.m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = sh.m;
+        one.nb_transforms = 1;
+        one.tr[0] = sh.m.tr[t];
+        inverse_transforms(one, tid, nth);
+        sync();
+    }
+    if (tid == 0) {
+        place_varblocks(f, g, es, br);
+        if (!es.err) {
+            if (g.sec_start_bit == 0) { uint32_t e = br.finish(); if (e) es.set_raw(e); }
+            else if (br.overrun()) es.set_raw(E_SHRT);
+            g.end_bit = br.bits_consumed();
+        }
+        sh.err = es.err;
+    }
+    sync();
+    if (sh.err) { if (tid == 0) *w.err = sh.err; return; }
+    // LLF coefficients: one thread per varblock for patches up to 8x8 cells, the rest by thread 0
+    for (int v = tid; v < g.nb_varblocks; v += nth) {
+        const DVarblock &vb = g.varblocks[v];
+        DctSelectInfo d = dct_select_info(vb.dctsel);
+        if (d.log_rows + d.log_columns - 6 <= 6) {
+            float scratch[64];
+            llf_from_lf(g, vb, scratch, 0, 1, NoSync());
+        }
+    }
+    if (tid == 0 && w.llf_scratch) {
+        for (int v = 0; v < g.nb_varblocks; ++v) {
+            const DVarblock &vb = g.varblocks[v];
+            DctSelectInfo d = dct_select_info(vb.dctsel);
+            if (d.log_rows + d.log_columns - 6 > 6) llf_from_lf(g, vb, w.llf_scratch, 0, 1, NoSync());
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread 0 only; `nonzeros` = 3 * 1024 bytes of scratch
+J40B_HD inline void hf_group_body(const HfWork &w, int8_t *nonzeros) {
+    if (*w.lf_err) return;
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    DGroup &grp = *w.grp;
+    BitReader br;
+    ErrSlot es;
+    es.err = 0;
+    uint64_t start_bit = grp.sec_start_bit == ~0ull ? g.end_bit : grp.sec_start_bit;
+    br.init(w.cs + grp.sec_off, grp.sec_size, start_bit);
+    CodeCtx cc;
+    cc.init(w.arena, f.coeff_spec_off);
+    CodeState cs;
+    cs.init(grp.lz_window, (1u << 18) - 1);
+    int32_t preset = (int32_t) br.u(ceil_lg32((uint32_t) f.num_hf_presets));
+    int32_t ctxoff = 495 * f.nb_block_ctx * preset;
+    if (preset >= f.num_hf_presets) {
+        // contexts beyond the code spec: the reference reads out of bounds here; treat as corrupt
+        es.set(br, E_COEF);
+    } else {
+        hf_coeffs_tokens(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros);
+    }
+    if (!es.err) { uint32_t e = br.finish(); if (e) es.set_raw(e); }
+    if (es.err) *w.err = es.err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all threads; smem: 4 * 4096 floats (varblocks up to 64x64), bigger ones go through w.big_scratch
+template <class Sync>
+J40B_HD inline void back_body(const BackWork &w, float *smem, int tid, int nth, Sync sync) {
+    if (*w.lf_err || *w.hf_err) return;
+    const DFrame &f = *w.f;
+    const DLfGroup &g = *w.g;
+    const DGroup &grp = *w.grp;
+    const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
+    for (int y8 = 0; y8 < gh8; ++y8) for (int x8 = 0; x8 < gw8; ++x8) {
+        int32_t voff = g.blocks[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
+        if ((voff >> 20) < 2) continue;
+        voff &= 0xfffff;
+        const DVarblock &vb = g.varblocks[voff];
+        DctSelectInfo d = dct_select_info(vb.dctsel);
+        int size = 1 << (d.log_rows + d.log_columns);
+        float *buf = size <= 4096 ? smem : w.big_scratch;
+        if (!buf) continue; // cannot happen: the host provides big_scratch when such varblocks may occur
+        int bs = size <= 4096 ? 4096 : 65536;
+        varblock_to_pixels(f, w.arena, g, vb, voff, w.tokens, buf, buf + bs, buf + 2 * bs, buf + 3 * bs,
+                           w.rgba, w.rgba_stride, tid, nth, sync);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ModShared { uint32_t err; ModImage m; };
+
+template <class Sync>
+J40B_HD inline void modular_body(ModWork &w, ModShared &sh, int tid, int nth, Sync sync) {
+    const DFrame &f = *w.f;
+    if (tid == 0) {
+        BitReader br;
+        ErrSlot es;
+        es.err = 0;
+        br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
+        CodeCtx cc;
+        cc.init(w.arena, f.global_spec_off);
+        CodeState cs;
+        sh.m = w.m;
+        if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, sh.m);
+        if (!es.err) {
+            cs.init(w.lz_window, w.lz_mask);
+            const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+            for (int c = 0; c < sh.m.num_channels && !es.err; ++c) {
+                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, sh.m, c, w.sidx);
+            }
+            if (!es.err) finish_code(br, es, cc, cs);
+        }
+        if (!es.err) { uint32_t e = br.finish(); if (e) es.set_raw(e); }
+        sh.err = es.err;
+        if (es.err) *w.err = es.err;
+    }
+    sync();
+    if (sh.err || w.header_parsed) return; // global transforms are applied by the render step
+    for (int t = sh.m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = sh.m;
+        one.nb_transforms = 1;
+        one.tr[0] = sh.m.tr[t];
+        inverse_transforms(one, tid, nth);
+        sync();
+    }
+}
+
+// one thread per pixel: global inverse RCTs (j40.h:8209) + j40__render_to_u8x4_rgba (j40.h:7910-7957)
+J40B_HD inline void render_px(const RenderWork &w, int x, int y) {
+    const DFrame &f = *w.f;
+    int16_t v[MOD_MAX_CH];
+    const size_t o = (size_t) y * (size_t) f.width + (size_t) x;
+    for (int c = 0; c < f.num_channels; ++c) v[c] = w.plane[c][o];
+    for (int t = f.nb_global_transforms - 1; t >= 0; --t) {
+        int b = f.global_tr[t].begin_c;
+        inverse_rct_px(f.global_tr[t].type, v[b], v[b + 1], v[b + 2]);
+    }
+    const int32_t maxpixel = (1 << f.bpp) - 1, half = 1 << (f.bpp - 1);
+    uint8_t *out = w.rgba + (size_t) y * (size_t) w.rgba_stride + (size_t) x * 4;
+    for (int i = 0; i < 4; ++i) {
+        int32_t p = i < 3 ? v[i] : (f.alpha_channel >= 0 ? v[f.alpha_channel] : maxpixel);
+        p = imin(imax(0, p), maxpixel);
+        out[i] = (uint8_t) ((p * 255 + half) / maxpixel);
+    }
+}
+
+} // namespace j40b

@@ -1,0 +1,89 @@
+// j40-b200: host-side front end. Parses everything that is serial and tiny (container, image and frame
+// headers, TOC, LfGlobal, HfGlobal: SURVEY.md §2 "OUT OF SCOPE (host parse)" rows) and turns it into a
+// FramePlan: device-ready tables plus the byte spans of the sections the kernels decode.
+#pragma once
+#include "j40b_vardct.h"
+#include <string>
+#include <vector>
+
+namespace j40b {
+
+struct Arena {
+    std::vector<uint8_t> bytes;
+    Arena() { bytes.resize(16, 0); } // offset 0 is reserved as "none"
+    uint32_t alloc(size_t n, size_t align = 8) {
+        size_t off = (bytes.size() + align - 1) / align * align;
+        bytes.resize(off + n, 0);
+        return (uint32_t) off;
+    }
+    template <class T> T *at(uint32_t off) { return (T *) (bytes.data() + off); }
+};
+
+struct SectionRef {
+    uint64_t off = 0;     // byte offset in the linearised codestream
+    uint32_t size = 0;    // bytes available to this section
+    uint64_t start_bit = 0;
+    int32_t rank = 0;     // position in the reference's decoding order (for first-error selection)
+};
+
+struct ImageInfo {
+    int32_t width = 0, height = 0, bpp = 8, exp_bits = 0;
+    int modular_16bit_buffers = 1, num_extra_channels = 0, xyb_encoded = 1, want_icc = 0;
+    int cspace_grey = 0;
+    struct EC { int type, bpp, exp_bits, dim_shift, alpha_associated; } ec[4];
+    float intensity_target = 255.0f;
+    float opsin_inv_mat[3][3], opsin_bias[3], quant_bias[3], quant_bias_num;
+    int anim = 0, anim_have_timecodes = 0;
+};
+
+struct FrameInfo {
+    int is_last = 1, type = 0, is_modular = 0;
+    int has_noise = 0, has_patches = 0, has_splines = 0, use_lf_frame = 0, skip_adapt_lf_smooth = 0;
+    int do_ycbcr = 0, jpeg_upsampling = 0, group_size_shift = 8, x_qm_scale = 3, b_qm_scale = 2, num_passes = 1;
+    int32_t width = 0, height = 0;
+    int32_t grows = 0, gcolumns = 0, ggrows = 0, ggcolumns = 0;
+    int64_t num_groups = 0, num_lf_groups = 0;
+};
+
+struct FramePlan {
+    uint32_t err = 0;
+    // linearised codestream (points into the caller's buffer for bare codestreams)
+    const uint8_t *cs = nullptr;
+    size_t cs_size = 0;
+    std::vector<uint8_t> cs_owned;
+
+    ImageInfo im;
+    FrameInfo fh;
+    DFrame df;          // table offsets refer to `arena`; pointer-typed members are filled by the executor
+    Arena arena;        // per-image tables (code specs, tree, block context map, custom dq / orders)
+    bool single_section = false;
+    std::vector<SectionRef> lfg_sec, pg_sec; // per LF group / per group (one pass)
+    uint64_t end_codeoff = 0;
+    // custom (non-library) tables: 0 = use the process-wide default tables
+    uint32_t custom_dq_off[17] = {0};
+    uint32_t custom_order_off[13][3] = {{0}};
+    // modular frames: global image
+    ModImage gmod;               // channel geometry (px pointers are assigned by the executor)
+    SectionRef gmod_sec;         // where the globally-coded channels start (inside LfGlobal)
+    int num_gm_channels = 0;
+    bool gmod_has_stream = false; // an entropy-coded stream (possibly empty) follows the global header
+    int rank_lf_global = 0;
+};
+
+// process-wide immutable tables (library dequantisation matrices, natural orders, sRGB thresholds)
+struct GlobalTables {
+    std::vector<float> dq[17];        // [n][3]
+    std::vector<int32_t> order[13];
+    float srgb_thr[255];
+    static const GlobalTables &get();
+};
+
+// Parses `data` up to and including HfGlobal. Returns 0 or a four-character error code.
+uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan);
+
+// helpers shared with tests
+std::vector<float> compute_dq_matrix_default(int idx);
+std::vector<int32_t> compute_natural_order(int log_rows, int log_columns);
+void compute_srgb_thresholds(int bpp, float *thr255);
+
+} // namespace j40b

@@ -1,0 +1,360 @@
+// j40-b200: batch pipeline. Lays a batch of parsed frames out in device memory (one allocation, one
+// H2D copy), builds the per-thread-block work items and issues the kernels:
+//   VarDCT frame:  lf_group (1 block / LF group) -> hf_group (1 warp / group, serial entropy decode)
+//                  -> back (1 block / group: dequant, CfL, IDCT, XYB->sRGB, RGBA8 store)
+//   modular frame: modular (1 warp / group) -> render (1 thread / pixel)
+// Templated over a backend: CudaBackend (j40b_cuda.cu) is the product; tests/hostemu provides a CPU
+// backend that runs the very same kernel bodies single-threaded for the `-m "not gpu"` logic tests.
+#pragma once
+#include "j40b_exec.h"
+#include "j40b_host.h"
+#include <memory>
+#include <string.h>
+#include <algorithm>
+
+namespace j40b {
+
+struct ImageResult {
+    uint32_t err = 0;
+    int32_t width = 0, height = 0, stride = 0;
+    size_t rgba_off = 0; // offset of the RGBA8 plane inside the batch's device block
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <class BE>
+class Batch {
+public:
+    explicit Batch(BE &be_) : be(be_) {}
+    ~Batch() { release(); }
+
+    BE &be;
+    std::vector<std::unique_ptr<FramePlan>> plans;
+    std::vector<ImageResult> results;
+    bool full_token_cap = false;
+
+    // ---- step 1: host parse (no device work)
+    void add(const uint8_t *data, size_t size) {
+        std::unique_ptr<FramePlan> p(new FramePlan);
+        parse_frame(data, size, *p);
+        plans.push_back(std::move(p));
+    }
+
+    // ---- step 2: lay out + upload
+    void upload() {
+        release();
+        const GlobalTables &gt = GlobalTables::get();
+        size_t n = plans.size();
+        results.assign(n, ImageResult());
+        img.assign(n, Img());
+        // global tables block (shared by all images)
+        size_t up = 0;                      // upload blob cursor
+        auto up_alloc = [&](size_t bytes) { size_t o = align_up(up, 256); up = o + bytes; return o; };
+        size_t gt_dq[17], gt_order[13], gt_thr;
+        for (int i = 0; i < 17; ++i) gt_dq[i] = up_alloc(gt.dq[i].size() * 4);
+        for (int i = 0; i < 13; ++i) gt_order[i] = up_alloc(gt.order[i].size() * 4);
+        gt_thr = up_alloc(255 * 4);
+        size_t work = 0;                    // device-only area cursor (follows the upload blob)
+        auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
+        size_t n_lf = 0, n_hf = 0, n_mod = 0;
+        for (size_t k = 0; k < n; ++k) {
+            FramePlan &p = *plans[k];
+            Img &im = img[k];
+            results[k].err = p.err;
+            if (p.err) continue;
+            const DFrame &d = p.df;
+            results[k].width = d.width; results[k].height = d.height;
+            results[k].stride = (int32_t) align_up((size_t) d.width * 4 + 1, 32);
+            im.frame_off = up_alloc(sizeof(DFrame));
+            im.arena_off = up_alloc(p.arena.bytes.size());
+            im.cs_off = up_alloc(p.cs_size + 16);
+            im.rgba_off = wk_alloc((size_t) results[k].stride * (size_t) d.height);
+            results[k].rgba_off = im.rgba_off; // relative to the work area for now
+            if (!d.is_modular) {
+                im.nlf = p.lfg_sec.size(); im.ng = p.pg_sec.size();
+                im.lfg_off = up_alloc(sizeof(DLfGroup) * im.nlf);
+                im.grp_off = up_alloc(sizeof(DGroup) * im.ng);
+                im.err_off = wk_alloc(4 * (im.nlf + im.ng + 1));
+                im.lf.resize(im.nlf);
+                bool wp = d.global_tree_uses_wp != 0;
+                bool lz_mod = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
+                bool lz_coef = ((const DCodeSpec *) (p.arena.bytes.data() + d.coeff_spec_off))->lz77_enabled;
+                for (size_t i = 0; i < im.nlf; ++i) {
+                    LfBuf &b = im.lf[i];
+                    int ggx = (int) (i % (size_t) d.ggcolumns), ggy = (int) (i / (size_t) d.ggcolumns);
+                    b.left = ggx * 2048; b.top = ggy * 2048;
+                    b.w = std::min(2048, d.width - b.left); b.h = std::min(2048, d.height - b.top);
+                    b.w8 = ceil_div(b.w, 8); b.h8 = ceil_div(b.h, 8); b.w64 = ceil_div(b.w, 64); b.h64 = ceil_div(b.h, 64);
+                    size_t n8 = (size_t) b.w8 * b.h8, n64 = (size_t) b.w64 * b.h64;
+                    size_t cap = (size_t) 1 << ceil_lg32((uint32_t) n8);
+                    b.lfq = wk_alloc(2 * 3 * n8);
+                    b.lfdeq = wk_alloc(4 * 3 * n8);
+                    b.lf = d.skip_adapt_lf_smooth ? b.lfdeq : wk_alloc(4 * 3 * n8);
+                    b.lfidx = wk_alloc(n8);
+                    b.xfromy = wk_alloc(2 * n64); b.bfromy = wk_alloc(2 * n64);
+                    b.blockinfo = wk_alloc(2 * 2 * cap);
+                    b.sharp = wk_alloc(2 * n8);
+                    b.blocks = wk_alloc(4 * n8);
+                    b.varblocks = wk_alloc(sizeof(DVarblock) * n8);
+                    b.llf = wk_alloc(4 * 3 * n8);
+                    b.wp = wp ? wk_alloc(4 * 2 * 5 * std::max<size_t>(cap, (size_t) b.w8)) : (size_t) -1;
+                    b.lz = lz_mod ? wk_alloc(4u << 18) : (size_t) -1;
+                    b.vb_tok = wk_alloc(4 * 2 * 3 * n8);
+                    b.llf_scratch = wk_alloc(4 * 2048);
+                }
+                im.grp.resize(im.ng);
+                size_t tok_total = 0;
+                for (size_t g = 0; g < im.ng; ++g) {
+                    GrpBuf &gb = im.grp[g];
+                    int grow = (int) (g / (size_t) d.gcolumns), gcol = (int) (g % (size_t) d.gcolumns);
+                    gb.gw = std::min(d.width, (gcol + 1) * 256) - gcol * 256;
+                    gb.gh = std::min(d.height, (grow + 1) * 256) - grow * 256;
+                    size_t full = (size_t) 3 * 64 * ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8);
+                    size_t cap = full_token_cap ? full : std::min(full, (size_t) p.pg_sec[g].size * 3 + 256);
+                    gb.tok_first = tok_total; gb.tok_cap = cap;
+                    tok_total += cap;
+                    gb.lz = lz_coef ? wk_alloc(4u << 18) : (size_t) -1;
+                }
+                im.tok_off = wk_alloc(sizeof(DToken) * std::max<size_t>(tok_total, 1));
+                n_lf += im.nlf; n_hf += im.ng;
+            } else {
+                im.err_off = wk_alloc(4 * (p.pg_sec.size() + 2));
+                int nch = d.num_channels;
+                for (int c = 0; c < nch; ++c) im.plane[c] = wk_alloc(2 * (size_t) d.width * d.height);
+                im.nmod = p.pg_sec.size() + (p.num_gm_channels > 0 ? 1 : 0);
+                bool wp = d.global_tree_uses_wp != 0;
+                bool lz = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
+                int gsize = 1 << d.group_size_shift;
+                im.mod.resize(im.nmod);
+                for (size_t g = 0; g < im.nmod; ++g) {
+                    ModBuf &mb = im.mod[g];
+                    bool global = p.num_gm_channels > 0;
+                    int gw = global ? d.width : std::min(d.width, ((int) (g % (size_t) d.gcolumns) + 1) * gsize) - (int) (g % (size_t) d.gcolumns) * gsize;
+                    int gh = global ? d.height : std::min(d.height, ((int) (g / (size_t) d.gcolumns) + 1) * gsize) - (int) (g / (size_t) d.gcolumns) * gsize;
+                    mb.gw = gw; mb.gh = gh;
+                    mb.wp = wp ? wk_alloc(4 * 2 * 5 * (size_t) gw) : (size_t) -1;
+                    size_t syms = (size_t) nch * gw * gh;
+                    uint32_t capl = 1;
+                    while (capl < syms && capl < (1u << 20)) capl <<= 1;
+                    mb.lz_mask = capl - 1;
+                    mb.lz = lz ? wk_alloc(4 * (size_t) capl) : (size_t) -1;
+                }
+                im.mod_off = up_alloc(sizeof(ModWork) * std::max<size_t>(im.nmod, 1));
+                im.render_off = up_alloc(sizeof(RenderWork));
+                n_mod += im.nmod;
+            }
+        }
+        lfw_off = up_alloc(sizeof(LfWork) * std::max<size_t>(n_lf, 1));
+        hfw_off = up_alloc(sizeof(HfWork) * std::max<size_t>(n_hf, 1));
+        bkw_off = up_alloc(sizeof(BackWork) * std::max<size_t>(n_hf, 1));
+        num_lf = n_lf; num_hf = n_hf;
+        upload_bytes = align_up(up, 256);
+        work_bytes = align_up(work, 256);
+        dev = (uint8_t *) be.dev_alloc(upload_bytes + work_bytes);
+        staging = (uint8_t *) be.host_alloc(upload_bytes);
+        memset(staging, 0, upload_bytes);
+        uint8_t *dwork = dev + upload_bytes;
+        // ---- fill the staging blob with device addresses
+        for (int i = 0; i < 17; ++i) memcpy(staging + gt_dq[i], gt.dq[i].data(), gt.dq[i].size() * 4);
+        for (int i = 0; i < 13; ++i) memcpy(staging + gt_order[i], gt.order[i].data(), gt.order[i].size() * 4);
+        memcpy(staging + gt_thr, gt.srgb_thr, 255 * 4);
+        LfWork *lfw = (LfWork *) (staging + lfw_off);
+        HfWork *hfw = (HfWork *) (staging + hfw_off);
+        BackWork *bkw = (BackWork *) (staging + bkw_off);
+        size_t ilf = 0, ihf = 0;
+        for (size_t k = 0; k < n; ++k) {
+            FramePlan &p = *plans[k];
+            Img &im = img[k];
+            if (p.err) continue;
+            results[k].rgba_off = upload_bytes + im.rgba_off;
+            DFrame d = p.df;
+            // tables: per-image custom ones live in the arena, library defaults in the shared block
+            for (int i = 0; i < 17; ++i) {
+                d.dq[i] = (const float *) (p.custom_dq_off[i] ? dev + im.arena_off + p.custom_dq_off[i] : dev + gt_dq[i]);
+            }
+            for (int i = 0; i < 13; ++i) for (int c = 0; c < 3; ++c) {
+                d.order[i][c] = (const int32_t *) (p.custom_order_off[i][c] ? dev + im.arena_off + p.custom_order_off[i][c] : dev + gt_order[i]);
+            }
+            d.srgb_thr = (const float *) (dev + gt_thr);
+            memcpy(staging + im.frame_off, &d, sizeof(d));
+            memcpy(staging + im.arena_off, p.arena.bytes.data(), p.arena.bytes.size());
+            memcpy(staging + im.cs_off, p.cs, p.cs_size);
+            const DFrame *dframe = (const DFrame *) (dev + im.frame_off);
+            const uint8_t *darena = dev + im.arena_off, *dcs = dev + im.cs_off;
+            uint32_t *derr = (uint32_t *) (dwork + im.err_off);
+            if (!d.is_modular) {
+                DLfGroup *lg = (DLfGroup *) (staging + im.lfg_off);
+                DGroup *gr = (DGroup *) (staging + im.grp_off);
+                DToken *dtok = (DToken *) (dwork + im.tok_off);
+                for (size_t i = 0; i < im.nlf; ++i) {
+                    const LfBuf &b = im.lf[i];
+                    DLfGroup &g = lg[i];
+                    g.idx = (int32_t) i; g.left = b.left; g.top = b.top; g.width = b.w; g.height = b.h;
+                    g.width8 = b.w8; g.height8 = b.h8; g.width64 = b.w64; g.height64 = b.h64;
+                    g.sec_off = (uint32_t) p.lfg_sec[i].off; g.sec_size = p.lfg_sec[i].size; g.sec_start_bit = p.lfg_sec[i].start_bit;
+                    g.lfq = (int16_t *) (dwork + b.lfq); g.lfdeq = (float *) (dwork + b.lfdeq); g.lf = (float *) (dwork + b.lf);
+                    g.lfidx = dwork + b.lfidx; g.xfromy = (int16_t *) (dwork + b.xfromy); g.bfromy = (int16_t *) (dwork + b.bfromy);
+                    g.blockinfo = (int16_t *) (dwork + b.blockinfo); g.sharpness = (int16_t *) (dwork + b.sharp);
+                    g.blocks = (int32_t *) (dwork + b.blocks); g.varblocks = (DVarblock *) (dwork + b.varblocks);
+                    g.llf = (float *) (dwork + b.llf);
+                    g.wp_scratch = b.wp == (size_t) -1 ? nullptr : (int32_t *) (dwork + b.wp);
+                    g.lz_window = b.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + b.lz);
+                    g.vb_tok = (uint32_t *) (dwork + b.vb_tok);
+                    g.nb_varblocks = 0; g.end_bit = 0;
+                    LfWork &w = lfw[ilf++];
+                    w.f = dframe; w.arena = darena; w.cs = dcs;
+                    w.g = (DLfGroup *) (dev + im.lfg_off) + i;
+                    w.err = derr + i;
+                    w.llf_scratch = (float *) (dwork + b.llf_scratch);
+                }
+                for (size_t gi = 0; gi < im.ng; ++gi) {
+                    const GrpBuf &gb = im.grp[gi];
+                    DGroup &g = gr[gi];
+                    int grow = (int) (gi / (size_t) d.gcolumns), gcol = (int) (gi % (size_t) d.gcolumns);
+                    g.idx = (int32_t) gi;
+                    g.lfg = (grow / 8) * d.ggcolumns + gcol / 8;
+                    g.gx8 = (gcol % 8) * 32; g.gy8 = (grow % 8) * 32;
+                    g.gw = gb.gw; g.gh = gb.gh;
+                    g.sec_off = (uint32_t) p.pg_sec[gi].off; g.sec_size = p.pg_sec[gi].size; g.sec_start_bit = p.pg_sec[gi].start_bit;
+                    g.tok_first = (uint32_t) gb.tok_first; g.tok_cap = (uint32_t) gb.tok_cap;
+                    g.lz_window = gb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + gb.lz);
+                    g.tok_used = 0;
+                    HfWork &w = hfw[ihf];
+                    w.f = dframe; w.arena = darena; w.cs = dcs;
+                    w.g = (DLfGroup *) (dev + im.lfg_off) + g.lfg;
+                    w.grp = (DGroup *) (dev + im.grp_off) + gi;
+                    w.tokens = dtok;
+                    w.lf_err = derr + g.lfg;
+                    w.err = derr + im.nlf + gi;
+                    BackWork &bw = bkw[ihf++];
+                    bw.f = dframe; bw.arena = darena; bw.g = w.g; bw.grp = w.grp; bw.tokens = dtok;
+                    bw.lf_err = w.lf_err; bw.hf_err = w.err;
+                    bw.rgba = dwork + im.rgba_off; bw.rgba_stride = results[k].stride;
+                    bw.big_scratch = nullptr;
+                }
+            } else {
+                ModWork *mw = (ModWork *) (staging + im.mod_off);
+                RenderWork *rw = (RenderWork *) (staging + im.render_off);
+                memset(rw, 0, sizeof(*rw));
+                rw->f = dframe;
+                for (int c = 0; c < d.num_channels; ++c) rw->plane[c] = (int16_t *) (dwork + im.plane[c]);
+                rw->any_err = derr + im.nmod; // summary word written by nobody: per-section words are checked on the host
+                rw->rgba = dwork + im.rgba_off; rw->rgba_stride = results[k].stride;
+                int gsize = 1 << d.group_size_shift;
+                for (size_t g = 0; g < im.nmod; ++g) {
+                    ModWork &w = mw[g];
+                    const ModBuf &mb = im.mod[g];
+                    memset(&w, 0, sizeof(w));
+                    w.f = dframe; w.arena = darena; w.cs = dcs;
+                    bool global = p.num_gm_channels > 0;
+                    const SectionRef &s = global ? p.gmod_sec : p.pg_sec[g];
+                    w.sec_off = (uint32_t) s.off; w.sec_size = s.size; w.sec_start_bit = s.start_bit;
+                    w.sidx = global ? 0 : (int32_t) (1 + 3 * d.num_lf_groups + 17 + (int64_t) g);
+                    w.header_parsed = global ? 1 : 0;
+                    int gx = global ? 0 : (int) (g % (size_t) d.gcolumns) * gsize, gy = global ? 0 : (int) (g / (size_t) d.gcolumns) * gsize;
+                    if (global) w.m = p.gmod;
+                    w.m.num_channels = d.num_channels;
+                    for (int c = 0; c < d.num_channels; ++c) {
+                        w.m.ch[c].px = (int16_t *) (dwork + im.plane[c]) + (size_t) gy * d.width + gx;
+                        w.m.ch[c].stride = d.width; w.m.ch[c].w = mb.gw; w.m.ch[c].h = mb.gh;
+                        w.m.ch[c].hshift = w.m.ch[c].vshift = 0;
+                    }
+                    w.wp_scratch = mb.wp == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.wp);
+                    w.lz_window = mb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.lz);
+                    w.lz_mask = mb.lz_mask;
+                    w.err = derr + g;
+                }
+            }
+        }
+        be.h2d(dev, staging, upload_bytes);
+    }
+
+    // ---- step 3: kernels (can be repeated: all state they depend on is re-initialised here)
+    void execute() {
+        uint8_t *dwork = dev + upload_bytes;
+        for (size_t k = 0; k < plans.size(); ++k) {
+            FramePlan &p = *plans[k];
+            Img &im = img[k];
+            if (p.err) continue;
+            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.ng + 1;
+            be.dev_memset(dwork + im.err_off, 0, 4 * nerr);
+            if (!p.df.is_modular) for (const LfBuf &b : im.lf) be.dev_memset(dwork + b.vb_tok, 0, 4 * 2 * 3 * (size_t) b.w8 * b.h8);
+        }
+        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf);
+        if (num_hf) be.launch_hf((const HfWork *) (dev + hfw_off), (int) num_hf);
+        if (num_hf) be.launch_back((const BackWork *) (dev + bkw_off), (int) num_hf);
+        for (size_t k = 0; k < plans.size(); ++k) {
+            FramePlan &p = *plans[k];
+            Img &im = img[k];
+            if (p.err || !p.df.is_modular) continue;
+            if (im.nmod) be.launch_mod((ModWork *) (dev + im.mod_off), (int) im.nmod);
+            be.launch_render((const RenderWork *) (dev + im.render_off), p.df.width, p.df.height);
+        }
+    }
+
+    // ---- step 4: errors (synchronises)
+    void collect_errors() {
+        be.sync();
+        uint8_t *dwork = dev + upload_bytes;
+        for (size_t k = 0; k < plans.size(); ++k) {
+            FramePlan &p = *plans[k];
+            Img &im = img[k];
+            if (p.err) continue;
+            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.ng + 1;
+            std::vector<uint32_t> e(nerr);
+            be.d2h(e.data(), dwork + im.err_off, 4 * nerr);
+            uint32_t best = 0;
+            int64_t best_rank = INT64_MAX;
+            if (!p.df.is_modular) {
+                for (size_t i = 0; i < im.nlf; ++i) if (e[i] && p.lfg_sec[i].rank < best_rank) { best = e[i]; best_rank = p.lfg_sec[i].rank; }
+                for (size_t g = 0; g < im.ng; ++g) if (e[im.nlf + g] && p.pg_sec[g].rank < best_rank) { best = e[im.nlf + g]; best_rank = p.pg_sec[g].rank; }
+            } else {
+                bool global = p.num_gm_channels > 0;
+                for (size_t g = 0; g < im.nmod; ++g) {
+                    int64_t rank = global ? -2 : p.pg_sec[g].rank;
+                    if (e[g] && rank < best_rank) { best = e[g]; best_rank = rank; }
+                }
+            }
+            if (!best) {
+                // nothing may follow the frame (j40.h:8213), and the frame may not be cut short
+                if (p.cs_size > p.end_codeoff) best = E_EXCS;
+                else if (p.cs_size < p.end_codeoff) best = E_SHRT;
+            }
+            results[k].err = best;
+        }
+    }
+
+    void download_pixels(size_t k, uint8_t *dst) {
+        const ImageResult &r = results[k];
+        be.d2h(dst, dev + r.rgba_off, (size_t) r.stride * (size_t) r.height);
+    }
+    uint8_t *device_pixels(size_t k) { return dev + results[k].rgba_off; }
+
+    void release() {
+        if (dev) be.dev_free(dev);
+        if (staging) be.host_free(staging);
+        dev = staging = nullptr;
+    }
+
+    size_t device_bytes() const { return upload_bytes + work_bytes; }
+    size_t h2d_bytes() const { return upload_bytes; }
+
+private:
+    struct LfBuf { int left, top, w, h, w8, h8, w64, h64; size_t lfq, lfdeq, lf, lfidx, xfromy, bfromy, blockinfo, sharp, blocks, varblocks, llf, wp, lz, vb_tok, llf_scratch; };
+    struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz; };
+    struct ModBuf { int gw, gh; size_t wp, lz; uint32_t lz_mask; };
+    struct Img {
+        size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;
+        size_t rgba_off = 0, err_off = 0, tok_off = 0, plane[MOD_MAX_CH] = {0};
+        size_t nlf = 0, ng = 0, nmod = 0;
+        std::vector<LfBuf> lf;
+        std::vector<GrpBuf> grp;
+        std::vector<ModBuf> mod;
+    };
+    std::vector<Img> img;
+    uint8_t *dev = nullptr, *staging = nullptr;
+    size_t upload_bytes = 0, work_bytes = 0;
+    size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, num_lf = 0, num_hf = 0;
+};
+
+} // namespace j40b

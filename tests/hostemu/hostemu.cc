@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE ONLY: CPU emulation of the CUDA kernels' *logic* for the `-m "not gpu"` test suite.
+// The container that runs the CPU tests has no GPU; this backend executes the very same kernel bodies
+// (j40_b200/csrc/j40b_exec.h) one work item after another with a single "thread", so that parser,
+// context modelling, bit-exact float code paths and the batch pipeline can be checked against the oracle
+// before the real kernels run on a B200. It is NOT part of the product: libj40b200.so has no CPU path and
+// the j40_b200 package never loads this library.
+#include "../../j40_b200/csrc/j40b_pipeline.h"
+#include <stdlib.h>
+#include <string.h>
+
+using namespace j40b;
+
+struct HostEmuBackend {
+    void *dev_alloc(size_t n) { return calloc(n ? n : 1, 1); }
+    void dev_free(void *p) { free(p); }
+    void *host_alloc(size_t n) { return malloc(n ? n : 1); }
+    void host_free(void *p) { free(p); }
+    void h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+    void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+    void dev_memset(void *d, int v, size_t n) { memset(d, v, n); }
+    void sync() {}
+    void launch_lf(const LfWork *w, int n) {
+        for (int i = 0; i < n; ++i) { LfShared sh; lf_group_body(w[i], sh, 0, 1, NoSync()); }
+    }
+    void launch_hf(const HfWork *w, int n) {
+        std::vector<int8_t> nz(3 * 1024);
+        for (int i = 0; i < n; ++i) hf_group_body(w[i], nz.data());
+    }
+    void launch_back(const BackWork *w, int n) {
+        std::vector<float> smem(4 * 4096), big(4 * 65536);
+        for (int i = 0; i < n; ++i) {
+            BackWork bw = w[i];
+            bw.big_scratch = big.data();
+            back_body(bw, smem.data(), 0, 1, NoSync());
+        }
+    }
+    void launch_mod(ModWork *w, int n) {
+        for (int i = 0; i < n; ++i) { ModShared sh; modular_body(w[i], sh, 0, 1, NoSync()); }
+    }
+    void launch_render(const RenderWork *w, int width, int height) {
+        for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) render_px(*w, x, y);
+    }
+};
+
+extern "C" {
+
+// decodes one image; returns the error code (0 = ok). *out is malloc'ed (stride*height bytes).
+__attribute__((visibility("default"))) uint32_t hostemu_decode(const uint8_t *data, size_t size, uint8_t **out, int32_t *w, int32_t *h, int32_t *stride) {
+    HostEmuBackend be;
+    *out = nullptr;
+    *w = *h = *stride = 0;
+    uint32_t err = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        Batch<HostEmuBackend> b(be);
+        b.full_token_cap = attempt == 1;
+        b.add(data, size);
+        if (b.plans[0]->err) return b.plans[0]->err;
+        b.upload();
+        b.execute();
+        b.collect_errors();
+        err = b.results[0].err;
+        if (err == E_TOKV && attempt == 0) continue;
+        if (!err) {
+            const ImageResult &r = b.results[0];
+            *out = (uint8_t *) malloc((size_t) r.stride * (size_t) r.height);
+            b.download_pixels(0, *out);
+            *w = r.width; *h = r.height; *stride = r.stride;
+        }
+        break;
+    }
+    return err;
+}
+
+__attribute__((visibility("default"))) void hostemu_free(void *p) { free(p); }
+
+// table helpers exposed for unit tests
+__attribute__((visibility("default"))) int hostemu_dq_matrix(int idx, float *out, int cap) {
+    std::vector<float> m = compute_dq_matrix_default(idx);
+    if ((int) m.size() > cap) return 0;
+    memcpy(out, m.data(), m.size() * 4);
+    return (int) m.size() / 3;
+}
+__attribute__((visibility("default"))) int hostemu_natural_order(int log_rows, int log_columns, int32_t *out) {
+    std::vector<int32_t> o = compute_natural_order(log_rows, log_columns);
+    memcpy(out, o.data(), o.size() * 4);
+    return (int) o.size();
+}
+__attribute__((visibility("default"))) void hostemu_srgb_thresholds(int bpp, float *thr) { compute_srgb_thresholds(bpp, thr); }
+__attribute__((visibility("default"))) int hostemu_srgb_lookup(const float *thr, float v) { return srgb_u8_from_linear(thr, v); }
+__attribute__((visibility("default"))) void hostemu_inverse_transform(int dctsel, float *buf) {
+    DctSelectInfo d = dct_select_info(dctsel);
+    if (is_special_8x8(dctsel)) { inverse_special(dctsel, buf); return; }
+    std::vector<float> scratch((size_t) 1 << (d.log_rows + d.log_columns));
+    inverse_dct2d(buf, scratch.data(), d.log_rows, d.log_columns, 0, 1, NoSync());
+}
+__attribute__((visibility("default"))) void hostemu_forward_llf(float *buf, int log_rows, int log_columns) {
+    std::vector<float> scratch((size_t) 1 << (log_rows + log_columns));
+    forward_dct2d_llf(buf, scratch.data(), log_rows, log_columns, 0, 1, NoSync());
+}
+
+}
