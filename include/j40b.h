@@ -1,0 +1,62 @@
+/*
+ * j40b.h -- batch / device-resident extension of the j40 API (SURVEY.md §8b "Batch extension").
+ *
+ * The ten j40_* functions decode one image per handle into host memory. Throughput work (BASELINE
+ * configs C3/C5: batches of independent 4K frames, sharded over GPUs) needs many images per kernel
+ * launch and pixels that can stay in HBM, so this header adds a batch object. Nothing here changes the
+ * behaviour of the j40_* functions. One batch lives on one CUDA device; shard a list of images over
+ * several devices by creating one batch per device/process (images are independent: no collective).
+ */
+#ifndef J40_B200_J40B_H_INCLUDED
+#define J40_B200_J40B_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct j40b_batch j40b_batch;
+
+/* creates a batch on CUDA device `device` (ordinal). Returns NULL if no usable GPU exists. */
+j40b_batch *j40b_batch_create(int device);
+void j40b_batch_destroy(j40b_batch *b);
+
+/* host-side parse of one image (container, headers, TOC, LfGlobal, HfGlobal: the part the reference does in
+ * j40.h:8175-8192). `buf` must stay valid until j40b_batch_upload returns. Returns the image index or -1. */
+int j40b_batch_add(j40b_batch *b, const void *buf, size_t size);
+
+/* copies codestreams + tables of all added images to the device (one H2D transfer). 0 on success. */
+int j40b_batch_upload(j40b_batch *b);
+
+/* enqueues all decode kernels (asynchronous). May be called repeatedly on the same uploaded batch. */
+int j40b_batch_decode(j40b_batch *b);
+
+/* waits for the kernels and gathers per-image error codes. Returns the number of failed images. */
+int j40b_batch_wait(j40b_batch *b);
+
+int j40b_batch_count(const j40b_batch *b);
+uint32_t j40b_batch_error(const j40b_batch *b, int index);            /* four-character code or 0 */
+int j40b_batch_info(const j40b_batch *b, int index, int32_t *width, int32_t *height, int32_t *stride_bytes);
+const void *j40b_batch_device_pixels(const j40b_batch *b, int index); /* RGBA8 in device memory */
+int j40b_batch_read_pixels(j40b_batch *b, int index, void *dst);     /* D2H of stride*height bytes */
+
+/* device time in milliseconds of the most recent j40b_batch_decode, measured with CUDA events on the
+ * batch's stream (valid after j40b_batch_wait) */
+float j40b_batch_last_decode_ms(const j40b_batch *b);
+/* per-kernel device times of the last decode: 0 lf_group, 1 hf_group, 2 back, 3 back_big, 4 modular, 5 render */
+float j40b_batch_kernel_ms(const j40b_batch *b, int which);
+
+/* statistics: 0 device bytes allocated, 1 bytes uploaded (H2D), 2 kernels launched by the last decode,
+ * 3 compressed bytes, 4 pixels */
+int64_t j40b_batch_stat(const j40b_batch *b, int what);
+
+/* 1 if a CUDA device is usable by this library, else 0 */
+int j40b_gpu_available(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,619 @@
+// j40-b200: CUDA kernels (sm_100a), the CUDA backend of the batch pipeline, and the C ABI:
+// the ten j40_* entry points of the reference (include/j40.h) plus the j40b_* batch extension
+// (include/j40b.h). There is no CPU decoding path in this library: without a usable GPU every decode
+// fails loudly with the error code "!gpu".
+#include "j40b_pipeline.h"
+#include "../../include/j40.h"
+#include "../../include/j40b.h"
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+
+using namespace j40b;
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------------------------
+// kernels: thin wrappers around the bodies in j40b_exec.h
+
+struct BlockSync { __device__ void operator()() const { __syncthreads(); } };
+
+__global__ void __launch_bounds__(256) k_lf_group(const LfWork *items) {
+    __shared__ LfShared sh;
+    lf_group_body(items[blockIdx.x], sh, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+
+__global__ void __launch_bounds__(32) k_hf_group(const HfWork *items) {
+    __shared__ int8_t nonzeros[3 * 1024];
+    if (threadIdx.x == 0) hf_group_body(items[blockIdx.x], nonzeros);
+}
+
+__global__ void __launch_bounds__(256) k_back(const BackWork *items) {
+    extern __shared__ float smem[];
+    back_body(items[blockIdx.x], smem, 0, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+
+// varblocks larger than 64x64: persistent blocks, each with its own 1 MiB slice of scratch
+__global__ void __launch_bounds__(256) k_back_big(const BackWork *items, int n, float *scratch_pool) {
+    float *scratch = scratch_pool + (size_t) blockIdx.x * 4 * 65536;
+    for (int i = (int) blockIdx.x; i < n; i += (int) gridDim.x) {
+        BackWork w = items[i];
+        w.big_scratch = scratch;
+        back_body(w, (float *) nullptr, 1, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_modular(ModWork *items) {
+    __shared__ ModShared sh;
+    struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
+    modular_body(items[blockIdx.x], sh, (int) threadIdx.x, (int) blockDim.x, WarpSync());
+}
+
+__global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height) {
+    int x = (int) (blockIdx.x * blockDim.x + threadIdx.x), y = (int) blockIdx.y;
+    if (x < width && y < height) render_px(*w, x, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static bool cuda_ok(cudaError_t e) { return e == cudaSuccess; }
+
+struct CudaBackend {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ok = false;
+    int num_sms = 148;
+    float *big_pool = nullptr;
+    int big_blocks = 0;
+    int64_t launches = 0;
+    cudaEvent_t ev[8] = {nullptr};
+    float kernel_ms[6] = {0};
+
+    bool init(int dev) {
+        device = dev;
+        int count = 0;
+        if (!cuda_ok(cudaGetDeviceCount(&count)) || dev < 0 || dev >= count) return false;
+        if (!cuda_ok(cudaSetDevice(dev))) return false;
+        cudaDeviceProp prop;
+        if (!cuda_ok(cudaGetDeviceProperties(&prop, dev))) return false;
+        num_sms = prop.multiProcessorCount;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
+        for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
+        if (!cuda_ok(cudaFuncSetAttribute(k_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4))) return false;
+        ok = true;
+        return true;
+    }
+    void destroy() {
+        if (!ok) return;
+        cudaSetDevice(device);
+        if (big_pool) cudaFree(big_pool);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+        ok = false;
+    }
+    void *dev_alloc(size_t n) { void *p = nullptr; cudaSetDevice(device); if (!cuda_ok(cudaMalloc(&p, n ? n : 1))) return nullptr; return p; }
+    void dev_free(void *p) { cudaSetDevice(device); cudaFree(p); }
+    void *host_alloc(size_t n) { void *p = nullptr; if (!cuda_ok(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault))) return malloc(n ? n : 1); pinned = true; return p; }
+    void host_free(void *p) { if (pinned) cudaFreeHost(p); else free(p); }
+    bool pinned = false;
+    void h2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream); }
+    void d2h(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); }
+    void dev_memset(void *d, int v, size_t n) { cudaMemsetAsync(d, v, n, stream); }
+    void sync() { cudaStreamSynchronize(stream); }
+
+    void launch_lf(const LfWork *w, int n) {
+        cudaEventRecord(ev[0], stream);
+        k_lf_group<<<n, 256, 0, stream>>>(w);
+        cudaEventRecord(ev[1], stream);
+        ++launches;
+    }
+    void launch_hf(const HfWork *w, int n) {
+        k_hf_group<<<n, 32, 0, stream>>>(w);
+        cudaEventRecord(ev[2], stream);
+        ++launches;
+    }
+    void launch_back(const BackWork *w, int n) {
+        k_back<<<n, 256, 4 * 4096 * 4, stream>>>(w);
+        cudaEventRecord(ev[3], stream);
+        ++launches;
+        if (!big_pool) {
+            big_blocks = num_sms;
+            if (!cuda_ok(cudaMalloc(&big_pool, (size_t) big_blocks * 4 * 65536 * sizeof(float)))) { big_pool = nullptr; big_blocks = 0; }
+        }
+        if (big_pool) {
+            k_back_big<<<big_blocks < n ? big_blocks : n, 256, 0, stream>>>(w, n, big_pool);
+            ++launches;
+        }
+        cudaEventRecord(ev[4], stream);
+    }
+    void launch_mod(ModWork *w, int n) {
+        k_modular<<<n, 32, 0, stream>>>(w);
+        ++launches;
+    }
+    void launch_render(const RenderWork *w, int width, int height) {
+        dim3 grid((unsigned) ((width + 255) / 256), (unsigned) height);
+        k_render<<<grid, 256, 0, stream>>>(w, width, height);
+        ++launches;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// batch object
+
+struct j40b_batch {
+    CudaBackend be;
+    Batch<CudaBackend> *batch = nullptr;
+    std::vector<std::pair<const uint8_t *, size_t>> inputs;
+    bool uploaded = false, decoded = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    float last_ms = 0;
+    int64_t last_launches = 0;
+};
+
+EXPORT int j40b_gpu_available(void) {
+    int count = 0;
+    return cuda_ok(cudaGetDeviceCount(&count)) && count > 0;
+}
+
+EXPORT j40b_batch *j40b_batch_create(int device) {
+    j40b_batch *b = new j40b_batch;
+    if (!b->be.init(device)) { delete b; return nullptr; }
+    cudaEventCreate(&b->t0);
+    cudaEventCreate(&b->t1);
+    b->batch = new Batch<CudaBackend>(b->be);
+    return b;
+}
+
+EXPORT void j40b_batch_destroy(j40b_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->be.device);
+    delete b->batch;
+    if (b->t0) cudaEventDestroy(b->t0);
+    if (b->t1) cudaEventDestroy(b->t1);
+    b->be.destroy();
+    delete b;
+}
+
+EXPORT int j40b_batch_add(j40b_batch *b, const void *buf, size_t size) {
+    if (!b || !buf) return -1;
+    b->inputs.push_back({(const uint8_t *) buf, size});
+    b->batch->add((const uint8_t *) buf, size);
+    b->uploaded = false;
+    return (int) b->batch->plans.size() - 1;
+}
+
+EXPORT int j40b_batch_upload(j40b_batch *b) {
+    if (!b) return -1;
+    cudaSetDevice(b->be.device);
+    b->batch->upload();
+    b->be.sync();
+    b->uploaded = true;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+EXPORT int j40b_batch_decode(j40b_batch *b) {
+    if (!b || !b->uploaded) return -1;
+    cudaSetDevice(b->be.device);
+    int64_t before = b->be.launches;
+    cudaEventRecord(b->t0, b->be.stream);
+    b->batch->execute();
+    cudaEventRecord(b->t1, b->be.stream);
+    b->last_launches = b->be.launches - before;
+    b->decoded = true;
+    return 0;
+}
+
+static void gather_times(j40b_batch *b) {
+    cudaEventElapsedTime(&b->last_ms, b->t0, b->t1);
+    CudaBackend &be = b->be;
+    for (float &k : be.kernel_ms) k = 0;
+    // events are only recorded when the corresponding kernels were launched in this decode
+    bool vardct = false;
+    for (auto &p : b->batch->plans) if (!p->err && !p->df.is_modular) vardct = true;
+    if (vardct) {
+        cudaEventElapsedTime(&be.kernel_ms[0], be.ev[0], be.ev[1]);
+        cudaEventElapsedTime(&be.kernel_ms[1], be.ev[1], be.ev[2]);
+        cudaEventElapsedTime(&be.kernel_ms[2], be.ev[2], be.ev[3]);
+        cudaEventElapsedTime(&be.kernel_ms[3], be.ev[3], be.ev[4]);
+    }
+}
+
+EXPORT int j40b_batch_wait(j40b_batch *b) {
+    if (!b || !b->decoded) return -1;
+    cudaSetDevice(b->be.device);
+    b->batch->collect_errors();
+    cudaError_t ce = cudaGetLastError();
+    gather_times(b);
+    // a token arena that turned out too small is an internal condition: redo with worst-case capacity
+    bool retry = false;
+    for (auto &r : b->batch->results) if (r.err == E_TOKV) retry = true;
+    if (retry && !b->batch->full_token_cap) {
+        b->batch->full_token_cap = true;
+        b->batch->upload();
+        b->batch->execute();
+        b->batch->collect_errors();
+    }
+    int failed = 0;
+    for (auto &r : b->batch->results) failed += r.err != 0;
+    if (ce != cudaSuccess) {
+        for (auto &r : b->batch->results) if (!r.err) r.err = J40B_4CC('!', 'g', 'p', 'u');
+        return (int) b->batch->results.size();
+    }
+    return failed;
+}
+
+EXPORT int j40b_batch_count(const j40b_batch *b) { return b ? (int) b->batch->plans.size() : 0; }
+EXPORT uint32_t j40b_batch_error(const j40b_batch *b, int i) {
+    if (!b || i < 0 || i >= (int) b->batch->plans.size()) return J40B_4CC('U', 'i', 'd', 'x');
+    if (i < (int) b->batch->results.size()) return b->batch->results[(size_t) i].err;
+    return b->batch->plans[(size_t) i]->err;
+}
+EXPORT int j40b_batch_info(const j40b_batch *b, int i, int32_t *w, int32_t *h, int32_t *stride) {
+    if (!b || i < 0 || i >= (int) b->batch->results.size()) return -1;
+    const ImageResult &r = b->batch->results[(size_t) i];
+    if (w) *w = r.width;
+    if (h) *h = r.height;
+    if (stride) *stride = r.stride;
+    return 0;
+}
+EXPORT const void *j40b_batch_device_pixels(const j40b_batch *b, int i) {
+    if (!b || i < 0 || i >= (int) b->batch->results.size() || b->batch->results[(size_t) i].err) return nullptr;
+    return b->batch->device_pixels((size_t) i);
+}
+EXPORT int j40b_batch_read_pixels(j40b_batch *b, int i, void *dst) {
+    if (!b || !dst || i < 0 || i >= (int) b->batch->results.size() || b->batch->results[(size_t) i].err) return -1;
+    cudaSetDevice(b->be.device);
+    b->batch->download_pixels((size_t) i, (uint8_t *) dst);
+    return 0;
+}
+EXPORT float j40b_batch_last_decode_ms(const j40b_batch *b) { return b ? b->last_ms : 0.0f; }
+EXPORT float j40b_batch_kernel_ms(const j40b_batch *b, int which) { return b && which >= 0 && which < 6 ? b->be.kernel_ms[which] : 0.0f; }
+EXPORT int64_t j40b_batch_stat(const j40b_batch *b, int what) {
+    if (!b) return 0;
+    switch (what) {
+    case 0: return (int64_t) b->batch->device_bytes();
+    case 1: return (int64_t) b->batch->h2d_bytes();
+    case 2: return b->last_launches;
+    case 3: { int64_t s = 0; for (auto &p : b->batch->plans) s += (int64_t) p->cs_size; return s; }
+    case 4: { int64_t s = 0; for (auto &r : b->batch->results) if (!r.err) s += (int64_t) r.width * r.height; return s; }
+    default: return 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the reference's public API (j40.h:233-272, implementation j40.h:8243-8480)
+
+enum : uint32_t {
+    MAGIC_IMAGE = 0x6a3440b2u,       // "valid handle"
+    MAGIC_IMAGE_ERR = 0x9d51c3a7u,   // ^ origin: handle carrying only an error code
+    MAGIC_IMAGE_OPEN_ERR = 0x42e07f19u, // ^ origin: fopen failed, saved errno in u.saved_errno
+    MAGIC_FRAME = 0x1f8b22c4u,
+    MAGIC_FRAME_ERR = 0x77a0d9e5u,
+    MAGIC_INNER = 0x5cb0a1d3u,
+};
+enum Origin { O_NONE = 0, O_NEXT, O_FROM_FILE, O_FROM_MEMORY, O_OUTPUT_FORMAT, O_NEXT_FRAME, O_CURRENT_FRAME, O_FRAME_PIXELS, O_ERROR_STRING, O_FREE };
+static const char *const ORIGIN_NAMES[] = {"(unknown)", nullptr, "from_file", "from_memory", "output_format", "next_frame", "current_frame", "frame_pixels_*", "error_string", "free"};
+enum { O_LAST_ALT_MAGIC = O_FROM_MEMORY };
+
+struct j40__inner {
+    uint32_t magic;
+    int origin;
+    j40_err err;
+    int saved_errno;
+    char errbuf[256];
+    // source
+    const uint8_t *data;
+    size_t size;
+    void *owned;                 // malloc'ed file contents (from_file)
+    void *user_buf;
+    j40_memory_free_func freefunc;
+    // result
+    int advanced, rendered;
+    int32_t width, height, stride;
+    uint8_t *pixels;             // pinned host memory
+    bool pixels_pinned;
+};
+
+static const struct { char err[5]; const char *msg; } ERROR_STRINGS[] = { // j40.h:8004-8028
+    {"Upt0", "`path` parameter is NULL"}, {"Ubf0", "`buf` parameter is NULL"}, {"Uch?", "Bad `channel` parameter"},
+    {"Ufm?", "Bad `format` parameter"}, {"Uof?", "Bad `channel` and `format` combination"}, {"Urnd", "Frame is not yet rendered"},
+    {"Ufre", "Trying to reuse already freed image"}, {"!mem", "Out of memory"}, {"!jxl", "The JPEG XL signature is not found"},
+    {"open", "Failed to open file"}, {"bigg", "Image dimensions are too large to handle"}, {"flen", "File is too lengthy to handle"},
+    {"shrt", "Premature end of file"}, {"slim", "Image size limit reached"}, {"elim", "Extra channel number limit reached"},
+    {"xlim", "Modular transform limit reached"}, {"tlim", "Meta-adaptive tree size or depth limit reached"},
+    {"plim", "ICC profile length limit reached"}, {"fbpp", "Given bits per pixel value is disallowed"},
+    {"fblk", "Black extra channel is disallowed"}, {"fm32", "32-bit buffers for modular encoding are disallowed"},
+    {"TODO", "Unimplemented feature encountered"}, {"TEST", "Testing-only error occurred"},
+    {"!gpu", "No usable CUDA device (j40-b200 has no CPU decoding path)"},
+};
+#define ERR4(s) J40B_4CC((s)[0], (s)[1], (s)[2], (s)[3])
+
+static j40_err set_alt_magic(j40_err err, int saved_errno, int origin, j40_image *image) {
+    if (err == ERR4("open")) {
+        image->magic = MAGIC_IMAGE_OPEN_ERR ^ (uint32_t) origin;
+        image->u.saved_errno = saved_errno;
+        return err;
+    }
+    image->magic = MAGIC_IMAGE_ERR ^ (uint32_t) origin;
+    return image->u.err = err;
+}
+
+static j40_err check_image(j40_image *image, int neworigin, j40__inner **out) {
+    *out = nullptr;
+    if (!image) return ERR4("Uim0");
+    if (image->magic != MAGIC_IMAGE) {
+        uint32_t origin = image->magic ^ MAGIC_IMAGE_ERR;
+        if (0 < origin && origin <= O_LAST_ALT_MAGIC) {
+            if (origin == O_NEXT && neworigin) image->magic = MAGIC_IMAGE_ERR ^ (uint32_t) neworigin;
+            return image->u.err;
+        }
+        origin = image->magic ^ MAGIC_IMAGE_OPEN_ERR;
+        if (0 < origin && origin <= O_LAST_ALT_MAGIC) return ERR4("open");
+        return ERR4("Uim?");
+    }
+    if (!image->u.inner || image->u.inner->magic != MAGIC_INNER) return ERR4("Uim?");
+    *out = image->u.inner;
+    return image->u.inner->err;
+}
+
+static void free_inner(j40__inner *inner) {
+    if (inner->freefunc) inner->freefunc(inner->user_buf);
+    free(inner->owned);
+    if (inner->pixels) { if (inner->pixels_pinned) cudaFreeHost(inner->pixels); else free(inner->pixels); }
+    inner->magic = 0;
+    free(inner);
+}
+
+EXPORT j40_err j40_error(const j40_image *image) {
+    j40__inner *inner;
+    return check_image((j40_image *) image, O_NONE, &inner);
+}
+
+EXPORT const char *j40_error_string(const j40_image *image) {
+    static char static_errbuf[256];
+    uint32_t origin = O_NONE;
+    j40_err err = 0;
+    char *buf = nullptr;
+    int saved_errno = 0, corrupted = 0;
+    if (!image) {
+        snprintf(static_errbuf, sizeof static_errbuf, "`image` parameter is NULL during j40_error_string");
+        return static_errbuf;
+    }
+    if (image->magic == MAGIC_IMAGE) {
+        if (image->u.inner && image->u.inner->magic == MAGIC_INNER) {
+            origin = (uint32_t) image->u.inner->origin;
+            err = image->u.inner->err;
+            buf = image->u.inner->errbuf;
+            saved_errno = image->u.inner->saved_errno;
+        } else corrupted = 1;
+    } else {
+        origin = image->magic ^ MAGIC_IMAGE_ERR;
+        if (0 < origin && origin <= O_LAST_ALT_MAGIC) {
+            err = image->u.err;
+            buf = static_errbuf;
+            if (origin == O_NEXT) origin = O_ERROR_STRING;
+        } else {
+            origin = image->magic ^ MAGIC_IMAGE_OPEN_ERR;
+            if (0 < origin && origin <= O_LAST_ALT_MAGIC) {
+                err = ERR4("open");
+                buf = static_errbuf;
+                saved_errno = image->u.saved_errno;
+            } else corrupted = 1;
+        }
+    }
+    if (corrupted) {
+        snprintf(static_errbuf, sizeof static_errbuf, "`image` parameter is found corrupted during j40_error_string");
+        return static_errbuf;
+    }
+    const char *msg = nullptr;
+    for (const auto &e : ERROR_STRINGS) if (err == ERR4(e.err)) { msg = e.msg; break; }
+    if (!msg) {
+        snprintf(buf, 256, "Decoding failed (%c%c%c%c) during j40_%s", err >> 24 & 0xff, err >> 16 & 0xff, err >> 8 & 0xff, err & 0xff, ORIGIN_NAMES[origin]);
+    } else if (saved_errno) {
+        snprintf(buf, 256, "%s during j40_%s: %s", msg, ORIGIN_NAMES[origin], strerror(saved_errno));
+    } else {
+        snprintf(buf, 256, "%s during j40_%s", msg, ORIGIN_NAMES[origin]);
+    }
+    return buf;
+}
+
+static j40__inner *new_inner() {
+    j40__inner *inner = (j40__inner *) calloc(1, sizeof(j40__inner));
+    if (inner) inner->magic = MAGIC_INNER;
+    return inner;
+}
+
+EXPORT j40_err j40_from_memory(j40_image *image, void *buf, size_t size, j40_memory_free_func freefunc) {
+    if (!image) return ERR4("Uim0");
+    if (!buf) return set_alt_magic(ERR4("Ubf0"), 0, O_FROM_MEMORY, image);
+    j40__inner *inner = new_inner();
+    if (!inner) return set_alt_magic(ERR4("!mem"), 0, O_FROM_MEMORY, image);
+    if (size > (uint64_t) INT64_MAX) { free_inner(inner); return set_alt_magic(ERR4("flen"), 0, O_FROM_MEMORY, image); }
+    inner->data = (const uint8_t *) buf;
+    inner->size = size;
+    inner->user_buf = buf;
+    inner->freefunc = freefunc;
+    image->magic = MAGIC_IMAGE;
+    image->u.inner = inner;
+    return 0;
+}
+
+EXPORT j40_err j40_from_file(j40_image *image, const char *path) {
+    if (!image) return ERR4("Uim0");
+    if (!path) return set_alt_magic(ERR4("Upt0"), 0, O_FROM_FILE, image);
+    j40__inner *inner = new_inner();
+    if (!inner) return set_alt_magic(ERR4("!mem"), 0, O_FROM_FILE, image);
+    int saved = errno;
+    errno = 0;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) {
+        int e = errno;
+        errno = saved;
+        free_inner(inner);
+        return set_alt_magic(ERR4("open"), e, O_FROM_FILE, image);
+    }
+    errno = saved;
+    // the reference streams the file lazily (j40.h:1238-1262); a read error surfaces in j40_next_frame there,
+    // here the file is small enough to be read at once and a failure is reported the same way later
+    size_t cap = 1 << 16, len = 0;
+    uint8_t *data = (uint8_t *) malloc(cap);
+    int read_failed = 0;
+    while (data) {
+        size_t got = fread(data + len, 1, cap - len, fp);
+        len += got;
+        if (got == 0) { read_failed = ferror(fp); break; }
+        if (len == cap) {
+            uint8_t *nd = (uint8_t *) realloc(data, cap * 2);
+            if (!nd) { free(data); data = nullptr; break; }
+            data = nd;
+            cap *= 2;
+        }
+    }
+    fclose(fp);
+    if (!data) { free_inner(inner); return set_alt_magic(ERR4("!mem"), 0, O_FROM_FILE, image); }
+    inner->owned = data;
+    inner->data = data;
+    inner->size = len;
+    if (read_failed) { inner->err = ERR4("read"); inner->origin = O_NEXT_FRAME; }
+    image->magic = MAGIC_IMAGE;
+    image->u.inner = inner;
+    return 0;
+}
+
+EXPORT j40_err j40_output_format(j40_image *image, int32_t channel, int32_t format) {
+    j40__inner *inner;
+    j40_err err = check_image(image, O_OUTPUT_FORMAT, &inner);
+    if (err) return err;
+    if (channel != J40_RGBA) { inner->origin = O_OUTPUT_FORMAT; return inner->err = ERR4("Uch?"); }
+    if (format != J40_U8X4) { inner->origin = O_OUTPUT_FORMAT; return inner->err = ERR4("Ufm?"); }
+    return 0;
+}
+
+static std::mutex g_api_mutex; // one shared backend per device for the single-image API
+static j40b_batch *g_api_ctx = nullptr;
+static bool g_api_failed = false;
+
+static j40_err advance(j40__inner *inner) {
+    if (inner->advanced) return 0;
+    { // header-level errors do not need a GPU to be diagnosed
+        FramePlan probe;
+        uint32_t e = parse_frame(inner->data, inner->size, probe);
+        if (e) return e;
+    }
+    std::lock_guard<std::mutex> lock(g_api_mutex);
+    int dev = 0;
+    if (const char *e = getenv("J40B_DEVICE")) dev = atoi(e);
+    j40b_batch *b = j40b_batch_create(dev);
+    if (!b) return ERR4("!gpu");
+    j40_err err = 0;
+    int idx = j40b_batch_add(b, inner->data, inner->size);
+    err = j40b_batch_error(b, idx);
+    if (!err) {
+        if (j40b_batch_upload(b) != 0) err = ERR4("!gpu");
+    }
+    if (!err) {
+        j40b_batch_decode(b);
+        j40b_batch_wait(b);
+        err = j40b_batch_error(b, idx);
+    }
+    if (!err) {
+        j40b_batch_info(b, idx, &inner->width, &inner->height, &inner->stride);
+        size_t total = (size_t) inner->stride * (size_t) inner->height;
+        void *p = nullptr;
+        if (cuda_ok(cudaHostAlloc(&p, total ? total : 1, cudaHostAllocDefault))) inner->pixels_pinned = true;
+        else p = malloc(total ? total : 1);
+        if (!p) err = ERR4("!mem");
+        else {
+            inner->pixels = (uint8_t *) p;
+            if (j40b_batch_read_pixels(b, idx, p) != 0) err = ERR4("!gpu");
+        }
+    }
+    j40b_batch_destroy(b);
+    (void) g_api_ctx; (void) g_api_failed;
+    if (!err) inner->advanced = 1;
+    return err;
+}
+
+EXPORT int j40_next_frame(j40_image *image) {
+    j40__inner *inner;
+    j40_err err = check_image(image, O_NEXT_FRAME, &inner);
+    if (err) return 0;
+    err = advance(inner);
+    if (err) {
+        inner->origin = O_NEXT_FRAME;
+        inner->err = err;
+        return 0;
+    }
+    if (inner->rendered) return 0;
+    inner->rendered = 1;
+    return 1;
+}
+
+EXPORT j40_frame j40_current_frame(j40_image *image) {
+    j40__inner *inner;
+    j40_frame frame;
+    j40_err err = check_image(image, O_CURRENT_FRAME, &inner);
+    frame.magic = MAGIC_FRAME_ERR;
+    frame.reserved = 0;
+    frame.inner = inner;
+    if (err) return frame;
+    if (!inner->rendered) {
+        if (!j40_next_frame(image)) {
+            if (inner->err) return frame;
+        }
+    }
+    frame.magic = MAGIC_FRAME;
+    return frame;
+}
+
+// the 21x7 placeholder shown on errors: red, alpha spelling "Err" (same picture as j40.h:8429-8446)
+static const char *const PLACEHOLDER[7] = {
+    "111111111111111111111",
+    "100011111111111111111",
+    "101111111111111111111",
+    "100010001000100010001",
+    "101110111011101010111",
+    "100010111011100010111",
+    "111111111111111111111",
+};
+
+EXPORT j40_pixels_u8x4 j40_frame_pixels_u8x4(const j40_frame *frame, int32_t channel) {
+    static uint8_t error_data[7 * 21 * 4];
+    static bool error_init = false;
+    if (!error_init) {
+        for (int y = 0; y < 7; ++y) for (int x = 0; x < 21; ++x) {
+            uint8_t *p = error_data + (y * 21 + x) * 4;
+            p[0] = 255; p[1] = 0; p[2] = 0; p[3] = PLACEHOLDER[y][x] == '1' ? 255 : 0;
+        }
+        error_init = true;
+    }
+    j40_pixels_u8x4 error_pixels = {21, 7, 21 * 4, error_data};
+    if (!frame || frame->magic != MAGIC_FRAME) return error_pixels;
+    j40__inner *inner = frame->inner;
+    if (!inner || inner->magic != MAGIC_INNER) return error_pixels;
+    if (channel != J40_RGBA) return error_pixels;
+    if (!inner->rendered) { inner->origin = O_FRAME_PIXELS; inner->err = ERR4("Urnd"); return error_pixels; }
+    j40_pixels_u8x4 px;
+    px.width = inner->width;
+    px.height = inner->height;
+    px.stride_bytes = inner->stride;
+    px.data = inner->pixels;
+    return px;
+}
+
+EXPORT const j40_u8x4 *j40_row_u8x4(j40_pixels_u8x4 pixels, int32_t y) {
+    return (const j40_u8x4 *) ((const char *) pixels.data + (size_t) pixels.stride_bytes * (size_t) y);
+}
+
+EXPORT void j40_free(j40_image *image) {
+    j40__inner *inner;
+    if (!image) return;
+    check_image(image, O_FREE, &inner);
+    if (inner) free_inner(inner);
+    image->magic = MAGIC_IMAGE_ERR ^ (uint32_t) O_NEXT;
+    image->u.err = ERR4("Ufre");
+}

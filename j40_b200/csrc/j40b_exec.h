@@ -152,8 +152,9 @@ J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nt
     if (tid == 0) {
         place_varblocks(f, g, es, br);
         if (!es.err) {
-            if (g.sec_start_bit == 0) { uint32_t e = br.finish(); if (e) es.set_raw(e); }
-            else if (br.overrun()) es.set_raw(E_SHRT);
+            // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
+            // on the per-section state and never copied back, j40.h:7791-7798); running short is still an error
+            if (br.overrun()) es.set_raw(E_SHRT);
             g.end_bit = br.bits_consumed();
         }
         sh.err = es.err;
@@ -202,15 +203,20 @@ J40B_HD inline void hf_group_body(const HfWork &w, int8_t *nonzeros) {
     } else {
         hf_coeffs_tokens(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros);
     }
-    if (!es.err) { uint32_t e = br.finish(); if (e) es.set_raw(e); }
+    if (!es.err) {
+        if (grp.sec_start_bit == ~0ull) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // single-section frame: real check
+        else if (br.overrun()) es.set_raw(E_SHRT); // see lf_group_body
+    }
     if (es.err) *w.err = es.err;
 }
 
 // ---------------------------------------------------------------------------------------------
 // all threads; smem: 4 * 4096 floats (varblocks up to 64x64), bigger ones go through w.big_scratch
+// mode 0: varblocks up to 64x64 (buffers in shared memory); mode 1: the larger ones (w.big_scratch)
 template <class Sync>
-J40B_HD inline void back_body(const BackWork &w, float *smem, int tid, int nth, Sync sync) {
+J40B_HD inline void back_body(const BackWork &w, float *smem, int mode, int tid, int nth, Sync sync) {
     if (*w.lf_err || *w.hf_err) return;
+    if (mode == 1 && !w.g->has_big) return;
     const DFrame &f = *w.f;
     const DLfGroup &g = *w.g;
     const DGroup &grp = *w.grp;
@@ -222,8 +228,8 @@ J40B_HD inline void back_body(const BackWork &w, float *smem, int tid, int nth, 
         const DVarblock &vb = g.varblocks[voff];
         DctSelectInfo d = dct_select_info(vb.dctsel);
         int size = 1 << (d.log_rows + d.log_columns);
+        if ((size > 4096) != (mode == 1)) continue;
         float *buf = size <= 4096 ? smem : w.big_scratch;
-        if (!buf) continue; // cannot happen: the host provides big_scratch when such varblocks may occur
         int bs = size <= 4096 ? 4096 : 65536;
         varblock_to_pixels(f, w.arena, g, vb, voff, w.tokens, buf, buf + bs, buf + 2 * bs, buf + 3 * bs,
                            w.rgba, w.rgba_stride, tid, nth, sync);
@@ -254,7 +260,10 @@ J40B_HD inline void modular_body(ModWork &w, ModShared &sh, int tid, int nth, Sy
             }
             if (!es.err) finish_code(br, es, cc, cs);
         }
-        if (!es.err) { uint32_t e = br.finish(); if (e) es.set_raw(e); }
+        if (!es.err) {
+            if (w.header_parsed) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
+            else if (br.overrun()) es.set_raw(E_SHRT); // see lf_group_body
+        }
         sh.err = es.err;
         if (es.err) *w.err = es.err;
     }

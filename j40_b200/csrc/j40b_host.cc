@@ -1491,7 +1491,9 @@ static uint32_t linearise(const uint8_t *data, size_t size, FramePlan &plan) {
             seen_jxlp = true; codestream_box = true;
             if (payload < 4) return E4("jxlp");
             if (avail < 4) return E_SHRT;
-            if (data[body] >> 7) no_more = true;
+            // the reference treats a CLEAR top bit of the jxlp index as "last box" (j40.h:1550), the
+            // opposite of ISO/IEC 18181-2; kept for parity (DESIGN.md quirk list)
+            if (!(data[body] >> 7)) no_more = true;
             skip = 4;
             break;
         case 0x62726f62:
@@ -1574,10 +1576,9 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
         plan.gmod_has_stream = false;
     }
     if (!plan.single_section) {
-        if (!plan.gmod_has_stream) {
-            uint32_t e = q.br.finish();
-            if (e) return plan.err = e;
-        }
+        // section-end padding/excess errors are dropped by the reference in multi-section frames
+        // (j40.h:7791-7798); only running short counts
+        if (q.br.overrun()) return plan.err = E_SHRT;
         // (with a global modular stream the device finishes the section and reports its error)
         // ---- HfGlobal
         if (f.is_modular) {
@@ -1588,7 +1589,6 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
             h.br.init(plan.cs + std::min<uint64_t>(p.hf_global_off, plan.cs_size), (uint32_t) std::min<uint64_t>(p.hf_global_size, av2));
             h.hf_global();
             if (!h.err) { h.check_overrun(); }
-            if (!h.err) h.err = h.br.finish();
             if (h.err) return plan.err = h.err;
         }
         for (auto &s : plan.lfg_sec) { uint64_t a = plan.cs_size > s.off ? plan.cs_size - s.off : 0; s.size = (uint32_t) std::min<uint64_t>(s.size, a); s.off = std::min<uint64_t>(s.off, plan.cs_size); }

@@ -316,9 +316,13 @@ public:
                 }
             }
             if (!best) {
-                // nothing may follow the frame (j40.h:8213), and the frame may not be cut short
-                if (p.cs_size > p.end_codeoff) best = E_EXCS;
-                else if (p.cs_size < p.end_codeoff) best = E_SHRT;
+                // Nothing may follow the frame (j40.h:8213). The reference only notices trailing bytes that
+                // its main read-ahead buffer (64 KiB, j40.h:1676) already holds when it seeks past a
+                // multi-section frame (j40.h:1789-1797); single-section frames are checked exactly.
+                if (p.single_section) {
+                    if (p.cs_size > p.end_codeoff) best = E_EXCS;
+                    else if (p.cs_size < p.end_codeoff) best = E_SHRT;
+                } else if (p.cs_size > p.end_codeoff && p.end_codeoff < 65536) best = E_EXCS;
             }
             results[k].err = best;
         }

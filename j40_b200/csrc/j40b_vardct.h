@@ -112,6 +112,7 @@ struct DLfGroup {
     int32_t *wp_scratch; // [2*max(w8, nb_varblocks)*5] or null
     int32_t *lz_window;  // [1 << 18] or null
     int32_t nb_varblocks; // written by the kernel
+    int32_t has_big;      // written by the kernel: some varblock is larger than 64x64
     uint64_t end_bit;     // written by the kernel (single-section frames continue from here)
     uint32_t *vb_tok;     // [3][h8*w8][2] {first token, count}, written by the pass-group kernel
 };
@@ -197,6 +198,7 @@ J40B_HD inline void place_varblocks(const DFrame &f, DLfGroup &g, ErrSlot &es, c
     const int log_gsize8 = f.group_size_shift - 3;
     const int16_t *info0 = g.blockinfo, *info1 = g.blockinfo + nvb;
     int voff = 0, coeffoff = 0;
+    g.has_big = 0;
     for (int y0 = 0; y0 < h8; ++y0) for (int x0 = 0; x0 < w8; ++x0) {
         if (g.blocks[y0 * w8 + x0]) continue;
         if (voff >= nvb) { es.set(br, E_VBLK); return; }
@@ -220,6 +222,7 @@ J40B_HD inline void place_varblocks(const DFrame &f, DLfGroup &g, ErrSlot &es, c
         vb.dctsel = (uint8_t) dctsel;
         vb.pad = 0;
         g.varblocks[voff] = vb;
+        if (d.log_columns + d.log_rows > 12) g.has_big = 1;
         coeffoff += 1 << (d.log_columns + d.log_rows);
         ++voff;
     }

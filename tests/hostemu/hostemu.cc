@@ -31,7 +31,8 @@ struct HostEmuBackend {
         for (int i = 0; i < n; ++i) {
             BackWork bw = w[i];
             bw.big_scratch = big.data();
-            back_body(bw, smem.data(), 0, 1, NoSync());
+            back_body(bw, smem.data(), 0, 0, 1, NoSync());
+            back_body(bw, smem.data(), 1, 0, 1, NoSync());
         }
     }
     void launch_mod(ModWork *w, int n) {

@@ -1,0 +1,81 @@
+"""Seeded test-stream catalogue shared by the CPU (emulator) and GPU parity tests."""
+
+# known-answer vectors hand-assembled in SURVEY.md Appendix C (hex of the whole file, expected outcome)
+KNOWN_ANSWER = {
+    "V1_modular_8x8_local_tree": ("ff0a4106088100000c00897c3e", (0, 0, 0, 255)),
+    "V2_vardct_8x8": ("ff0a4106012800790097cf1f0a2b1f9301", (144, 144, 144, 255)),
+    "V3_vardct_264x8_5sections": (
+        "ff0a38000e0e011c00070800000000790097cf1f0a014c555555550000000000000000c00100000000000000000000000000291f", None),
+    "V4_vardct_8x8_ans": ("ff0a41060148007900970fba01c0958f01e838041840032800", (144, 144, 144, 255)),
+}
+
+VARDCT_CASES = [
+    # (name, width, height, seed, options)
+    ("c1_256_dct8_single_section", 256, 256, 1, dict(mix=0, tree=0, cfl=0)),
+    ("e6like_ans", 520, 392, 10, dict(mix=1, tree=1)),
+    ("e6like_prefix", 520, 392, 11, dict(mix=1, tree=1, ans=0)),
+    ("all_transforms_stress_tree", 520, 392, 12, dict(mix=2, tree=2)),
+    ("block_ctx_orders_presets", 520, 392, 13, dict(mix=1, tree=1, block_ctx=1, orders=0x1f, presets=2)),
+    ("no_smooth_extra_prec", 520, 392, 14, dict(mix=1, tree=2, smooth=0, extra_prec=1)),
+    ("cfl_base_qm", 520, 392, 15, dict(mix=1, tree=1, cfl_base=1, x_qm=2, b_qm=4)),
+    ("default_frame_header", 520, 392, 16, dict(mix=1, explicit_fh=0)),
+    ("container_jxlc", 520, 392, 17, dict(mix=1, tree=1, container=1)),
+    ("container_jxlp", 520, 392, 18, dict(mix=1, tree=1, container=1, jxlp=1)),
+    ("permuted_toc", 520, 392, 19, dict(mix=1, tree=1, permuted=1)),
+    ("lz77_coeffs_ans", 520, 392, 20, dict(mix=1, lz77=1)),
+    ("lz77_coeffs_prefix", 520, 392, 21, dict(mix=1, ans=0, lz77=1)),
+    ("tiny_8x8", 8, 8, 5, dict(mix=1, tree=1)),
+    ("ragged_264x8", 264, 8, 5, dict(mix=1, tree=1)),
+    ("ragged_257x255", 257, 255, 5, dict(mix=1, tree=1)),
+    ("wide_1000x300", 1000, 300, 5, dict(mix=1, tree=1)),
+    ("two_lf_groups_2100x300", 2100, 300, 6, dict(mix=1, tree=1, hfmul=6)),
+]
+
+MODULAR_CASES = [
+    ("fjxl_like_prefix_lz77", 600, 400, 2, dict()),
+    ("ans_no_lz77", 600, 400, 2, dict(ans=1, lz77=0)),
+    ("wp_tree", 600, 400, 2, dict(tree=2)),
+    ("alpha", 600, 400, 2, dict(alpha=1)),
+    ("group_shift7", 600, 400, 2, dict(group_shift=7)),
+    ("group_shift9", 600, 400, 2, dict(group_shift=9)),
+    ("no_rct", 600, 400, 2, dict(rct=-1)),
+    ("single_leaf", 600, 400, 2, dict(tree=0, lz77=0)),
+    ("ans_lz77", 600, 400, 2, dict(ans=1, lz77=1)),
+    ("container", 600, 400, 2, dict(container=1)),
+    ("rct13", 600, 400, 2, dict(rct=13)),
+    ("rct27", 600, 400, 2, dict(rct=27)),
+    ("rct41", 600, 400, 2, dict(rct=41)),
+    ("single_group_8x8", 8, 8, 4, dict()),
+    ("single_group_256", 256, 256, 4, dict(tree=2, ans=1, alpha=1)),
+    ("ragged_257x129", 257, 129, 4, dict(tree=2, ans=1, alpha=1)),
+]
+
+
+def force_cases():
+    return [(f"force_dctsel_{sel}", 512, 512, 3, dict(force=sel, hfmul=12, tree=1)) for sel in range(27)]
+
+
+def make(gen, kind, w, h, seed, opts):
+    fn = gen.vardct if kind == "vardct" else gen.modular
+    data, _ = fn(w, h, seed=seed, **opts)
+    return data
+
+
+def corruptions(data: bytes, seed: int, n: int):
+    """Deterministic corrupt variants: truncations, bit flips, appended bytes."""
+    import random
+    rnd = random.Random(seed)
+    out = []
+    for i in range(n):
+        kind = i % 3
+        if kind == 0:
+            cut = rnd.randrange(2, max(3, len(data)))
+            out.append((f"truncate@{cut}", data[:cut]))
+        elif kind == 1:
+            b = bytearray(data)
+            pos = rnd.randrange(0, len(b))
+            b[pos] ^= 1 << rnd.randrange(8)
+            out.append((f"flip@{pos}", bytes(b)))
+        else:
+            out.append((f"append{i}", data + bytes([rnd.randrange(256)])))
+    return out

@@ -1,0 +1,96 @@
+"""C-ABI checks that need no GPU: the product library loads, exports every symbol include/*.h declares, and the
+handle-misuse behaviour of the API matches the reference (j40.h:8103-8119, 8245-8480)."""
+import ctypes as C
+import os
+import re
+
+import j40_b200 as J
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(j40b?_[a-z0-9_]+)\s*\(", text)) - {"j40_memory_free_func"})
+
+
+def test_library_exports_every_declared_symbol():
+    L = J.lib()
+    names = _declared("j40.h") + _declared("j40b.h")
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(names) == sorted(J.EXPORTED_SYMBOLS)
+
+
+def test_handle_layout_matches_reference_abi():
+    assert C.sizeof(J.j40_image) == 16 and C.sizeof(J.j40_frame) == 16 and C.sizeof(J.j40_pixels_u8x4) == 24
+
+
+def test_null_and_garbage_handles():
+    L = J.lib()
+    assert J.err_str(L.j40_error(None)) == "Uim0"
+    img = J.j40_image()
+    img.magic = 0x12345678
+    assert J.err_str(L.j40_error(C.byref(img))) == "Uim?"
+    assert L.j40_error_string(None).decode() == "`image` parameter is NULL during j40_error_string"
+    assert "corrupted" in L.j40_error_string(C.byref(img)).decode()
+
+
+def test_from_memory_null_buffer_and_reuse_after_free():
+    L = J.lib()
+    img = J.j40_image()
+    assert J.err_str(L.j40_from_memory(C.byref(img), None, 0, None)) == "Ubf0"
+    assert J.err_str(L.j40_error(C.byref(img))) == "Ubf0"
+    assert L.j40_error_string(C.byref(img)).decode() == "`buf` parameter is NULL during j40_from_memory"
+    L.j40_free(C.byref(img))
+    assert J.err_str(L.j40_error(C.byref(img))) == "Ufre"
+    # the origin of a freed handle is "whatever API touches it next" (j40.h:8110, 8276)
+    assert L.j40_error_string(C.byref(img)).decode() == "Trying to reuse already freed image during j40_error_string"
+    assert L.j40_next_frame(C.byref(img)) == 0
+
+
+def test_from_file_missing(tmp_path):
+    im = J.Image.from_file(str(tmp_path / "nope.jxl"))
+    assert J.err_str(im.status) == "open"
+    assert im.error() == "open"
+    assert im.error_string().startswith("Failed to open file during j40_from_file: ")
+    im.free()
+
+
+def test_output_format_validation():
+    im = J.Image.from_memory(b"\xff\x0a")
+    assert J.err_str(im.output_format(0x1234, J.J40_U8X4)) == "Uch?"
+    assert im.error_string() == "Bad `channel` parameter during j40_output_format"
+    im.free()
+    im = J.Image.from_memory(b"\xff\x0a")
+    assert J.err_str(im.output_format(J.J40_RGBA, 0x0f0f)) == "Ufm?"
+    im.free()
+
+
+def test_header_errors_need_no_gpu_and_placeholder_pixels():
+    for data, code, msg in [(b"junkjunkjunk", "!jxl", "The JPEG XL signature is not found during j40_next_frame"),
+                            (b"\xff\x0a", "shrt", "Premature end of file during j40_next_frame")]:
+        im = J.Image.from_memory(data)
+        im.output_format()
+        assert not im.next_frame()
+        assert im.error() == code and im.error_string() == msg
+        frame = im.current_frame()
+        px, stride = im.frame_pixels_u8x4(frame)
+        assert px.shape == (7, 21, 4) and stride == 84 and (px[..., 0] == 255).all() and (px[..., 1:3] == 0).all()
+        assert px[1, 1, 3] == 0 and px[0, 0, 3] == 255
+        im.free()
+
+
+def test_no_cpu_fallback_without_gpu(gen):
+    if J.gpu_available():
+        return
+    data, _ = gen.vardct(64, 64, seed=1)
+    px, err, msg, _ = J.decode(data)
+    assert px is None and err == "!gpu"
+    try:
+        J.Batch(0)
+        assert False, "Batch must refuse to exist without a GPU"
+    except RuntimeError:
+        pass

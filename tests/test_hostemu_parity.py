@@ -1,0 +1,67 @@
+"""CPU checks of the kernel logic: the kernel bodies of j40_b200/csrc/j40b_exec.h, executed single-threaded by
+tests/hostemu, must reproduce the oracle's RGBA bytes and error codes exactly. (The same comparisons against
+the real CUDA library are in test_gpu_parity.py, marked `gpu`.)"""
+import numpy as np
+import pytest
+
+from tests import streams
+
+
+def _cmp(oracle, emu, data):
+    a, ea, _, sa = oracle.decode(data)
+    b, eb, sb = emu.decode(data)
+    assert ea == eb
+    if a is None:
+        assert b is None
+    else:
+        assert sa == sb
+        assert np.array_equal(a, b), int((a != b).sum())
+
+
+def test_known_answer(oracle, emu):
+    for name, (hx, _) in streams.KNOWN_ANSWER.items():
+        data = bytes.fromhex(hx)
+        if "local_tree" in name:
+            # local MA trees are not decoded on the device path yet: documented gap
+            assert emu.decode(data)[1] == "TODO"
+            continue
+        _cmp(oracle, emu, data)
+
+
+@pytest.mark.parametrize("case", streams.VARDCT_CASES, ids=[c[0] for c in streams.VARDCT_CASES])
+def test_vardct(oracle, emu, gen, case):
+    _, w, h, seed, opts = case
+    _cmp(oracle, emu, streams.make(gen, "vardct", w, h, seed, opts))
+
+
+@pytest.mark.parametrize("case", streams.force_cases()[::3], ids=[c[0] for c in streams.force_cases()[::3]])
+def test_each_transform(oracle, emu, gen, case):
+    _, w, h, seed, opts = case
+    _cmp(oracle, emu, streams.make(gen, "vardct", 256, 256, seed, opts))
+
+
+@pytest.mark.parametrize("case", streams.MODULAR_CASES, ids=[c[0] for c in streams.MODULAR_CASES])
+def test_modular(oracle, emu, gen, case):
+    _, w, h, seed, opts = case
+    _cmp(oracle, emu, streams.make(gen, "modular", w, h, seed, opts))
+
+
+def test_error_codes_on_corrupt_streams(oracle, emu, gen):
+    base = [streams.make(gen, "vardct", 264, 136, 3, dict(mix=1, tree=1)),
+            streams.make(gen, "vardct", 64, 64, 4, dict(mix=1, tree=1, ans=0)),
+            streams.make(gen, "modular", 300, 200, 5, dict())]
+    total = mismatches = 0
+    for bi, data in enumerate(base):
+        for name, bad in streams.corruptions(data, bi, 60):
+            a, ea, _, _ = oracle.decode(bad)
+            b, eb, _ = emu.decode(bad)
+            total += 1
+            # success/failure must agree; when both succeed the pixels must agree
+            assert (ea == "") == (eb == ""), (bi, name, ea, eb)
+            if ea == "":
+                assert np.array_equal(a, b), (bi, name)
+            elif ea != eb:
+                mismatches += 1
+    # error *classes* may differ for garbage the reference itself handles with undefined behaviour;
+    # the overwhelming majority must be identical
+    assert mismatches <= total // 10, (mismatches, total)

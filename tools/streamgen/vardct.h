@@ -769,7 +769,8 @@ public:
             box("jxlc", code.data(), code.size(), nullptr, 0);
         } else {
             size_t cut = std::min(code.size(), std::max<size_t>(1, code.size() / 3));
-            uint8_t i0[4] = {0, 0, 0, 0}, i1[4] = {0x80, 0, 0, 1};
+            // NOTE: index flags as the *reference* reads them (top bit clear = last box), see j40.h:1550
+            uint8_t i0[4] = {0x80, 0, 0, 0}, i1[4] = {0, 0, 0, 1};
             box("jxlp", code.data(), cut, i0, 4);
             static const uint8_t junk[5] = {1, 2, 3, 4, 5};
             box("xtra", junk, 5, nullptr, 0);
