@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the JPEG XL group-decode hot path on B200 (BASELINE.json metric: Mpixels/s decoded,
+4K VarDCT batch), with roofline, CPU baseline and end-to-end numbers.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3                    # our CUDA path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, batch-sharded
+  python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # the reference j40.h on the host CPU cores
+
+A "step" is one decode of this rank's batch of synthetic 4K VarDCT frames ("d1/e6-like" streams from
+tools/streamgen; no JPEG XL encoder exists offline). Frames are independent, so ranks share nothing: no
+collective on the data path (weak scaling: the per-GPU batch is fixed).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STREAM_OPTS = dict(mix=1, tree=1, hfmul=10, hfmul_var=4)  # the "d1/e6-like" preset
+
+
+def _gen_one(args):
+    w, h, seed = args
+    from tools import streamgen
+    data, st = streamgen.vardct(w, h, seed=seed, **STREAM_OPTS)
+    return data, st
+
+
+def make_streams(w, h, seeds):
+    from tools import streamgen
+    streamgen._ensure_tables()  # oracle-derived tables, inherited by forked workers
+    procs = max(1, min(len(seeds), (os.cpu_count() or 2) - 1, 32))
+    if procs == 1:
+        return [_gen_one((w, h, s)) for s in seeds]
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(_gen_one, [(w, h, s) for s in seeds])
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _ref_worker(args):
+    data, reps = args
+    from oracle import ref
+    good, secs = ref.time_decode(data, reps)
+    return good, secs
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation (oracle/_ref = unmodified j40.h) on all host cores."""
+    if rank != 0:
+        return
+    w, h = args.width, args.height
+    cores = os.cpu_count() or 1
+    nproc = max(1, min(cores, 64))
+    datas = [d for d, _ in make_streams(w, h, list(range(min(args.distinct, nproc))))]
+    work = [(datas[i % len(datas)], 1) for i in range(nproc)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(nproc) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, work[: max(1, nproc // 4)])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = pool.map(_ref_worker, work)
+            assert all(g == 1 for g, _ in res), "reference failed to decode a bench stream"
+        dt = time.perf_counter() - t0
+    mpix = nproc * args.steps * w * h / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpixels/s decoded (4K VarDCT batch)", "value": mpix, "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w}x{h} VarDCT frames (tools/streamgen d1/e6-like preset), reference j40.h -O3 -ffp-contract=off",
+                   "frames_per_step": nproc, "processes": nproc},
+        "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": nproc, "kind": "reference",
+                         "sample": f"{nproc} frames per step, one process per frame, {args.steps} steps"},
+        "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--frames-per-gpu", type=int, default=64)
+    ap.add_argument("--distinct", type=int, default=8, help="distinct streams per rank (cycled to fill the batch)")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import j40_b200 as J
+    from oracle import ref
+
+    if not J.gpu_available():
+        print(json.dumps({"error": "no CUDA device; j40_b200 has no CPU decoding path"}))
+        sys.exit(1)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w, h = args.width, args.height
+    F = args.frames_per_gpu
+    gen = make_streams(w, h, [rank * args.distinct + i for i in range(args.distinct)])
+    datas = [g[0] for g in gen]
+    stats = [g[1] for g in gen]
+    frames = [datas[i % len(datas)] for i in range(F)]
+    comp_bytes = sum(len(d) for d in frames)
+    pixels = F * w * h
+
+    # ---- parity gate: no number counts unless the GPU output equals the reference's, byte for byte
+    want, e0, _, _ = ref.decode(datas[0])
+    assert e0 == "", "oracle rejected a bench stream"
+
+    # ---- device-resident throughput: inputs + tables already in HBM, kernels only
+    b = J.Batch(local_rank)
+    for d in frames:
+        b.add(d)
+    b.upload()
+    b.decode()
+    failed = b.wait()
+    assert failed == 0, [b.error(i) for i in range(F) if b.error(i)]
+    assert np.array_equal(b.read_pixels(0), want), "GPU output differs from the reference"
+    for _ in range(args.warmup):
+        b.decode()
+        b.wait()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    step_ms, kernel_ms = [], []
+    for _ in range(args.steps):
+        b.decode()
+        b.wait()  # the next step re-initialises state with memsets on the same stream; waiting keeps steps disjoint
+        step_ms.append(b.last_decode_ms())
+        kernel_ms.append(b.kernel_ms())
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    total_ms = sum(step_ms)
+    launches = b.stat(2) * args.steps
+    dev_bytes = b.stat(0)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * pixels * args.steps / (total_ms_max / 1e3) / 1e6
+
+    # ---- end to end through the C ABI with HOST buffers: parse + H2D + kernels + D2H of every frame, per step
+    e2e = None
+    if not args.skip_e2e:
+        host_out = torch.empty((F, h, b.info(0)[2]), dtype=torch.uint8, pin_memory=True)
+        out_np = host_out.numpy()
+
+        def one_e2e():
+            bb = J.Batch(local_rank)
+            for d in frames:
+                bb.add(d)
+            bb.upload()
+            bb.decode()
+            bb.wait()
+            for i in range(F):
+                bb.read_pixels(i, out=out_np[i])
+            h2d = bb.stat(1)
+            bb.close()
+            return h2d
+        one_e2e()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            h2d = one_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert np.array_equal(out_np[0][:, : w * 4].reshape(h, w, 4), want)
+        e2e = {"value": world * pixels * n_e2e / float(te.item()) / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(F * h * b.info(0)[2]), "steps": n_e2e,
+               "includes": "host parse + H2D + kernels + D2H of all frames"}
+    b.close()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the step (HBM): algorithmic bytes = compressed read once + RGBA8 written once
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = comp_bytes + 4 * pixels
+    ms_step = total_ms / args.steps
+    achieved = alg_bytes / (ms_step / 1e3) / 1e9
+    kavg = {k: sum(x[k] for x in kernel_ms) / len(kernel_ms) for k in kernel_ms[0]}
+    dominant = max(kavg, key=kavg.get)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                "algorithmic_bytes_per_step": alg_bytes, "kernel_ms": kavg, "dominant_kernel": dominant,
+                "dominant_kernel_gbs": alg_bytes / (kavg[dominant] / 1e3) / 1e9 if kavg[dominant] > 0 else None}
+
+    # ---- CPU baseline: the reference itself, one thread, bounded sample of the same workload
+    reps = 6
+    good, secs = ref.time_decode(datas[0], reps)
+    cpu = {"value": w * h / statistics.median(secs) / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "reference",
+           "sample": f"{reps} decodes of one {w}x{h} bench frame through j40_from_memory..j40_frame_pixels_u8x4, median",
+           "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": "Mpixels/s decoded (4K VarDCT batch)", "value": value, "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch of {F} independent {w}x{h} VarDCT frames per GPU ({args.distinct} distinct, cycled), "
+                               f"tools/streamgen d1/e6-like preset {STREAM_OPTS}",
+                   "frames_per_gpu": F, "groups_per_gpu": F * ((w + 255) // 256) * ((h + 255) // 256),
+                   "compressed_bytes_per_gpu": comp_bytes, "bits_per_pixel": 8.0 * comp_bytes / pixels,
+                   "hf_symbols_per_pixel": sum(s["hf_symbols"] for s in stats) / (len(stats) * w * h),
+                   "l2": "inputs+outputs per step (%.1f GB) exceed L2" % ((comp_bytes + 4 * pixels) / 1e9),
+                   "parallelism": f"batch-sharded x{world}, no collective"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": sampler.result(), "device_bytes": int(dev_bytes),
+    }
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
