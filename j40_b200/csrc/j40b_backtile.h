@@ -1,0 +1,260 @@
+// j40-b200: tile-parallel back half of the VarDCT path (dequantisation, chroma-from-luma, LLF insertion,
+// inverse transforms, XYB -> sRGB, RGBA8 store) for varblocks up to 64x64 that lie inside one 64x64-pixel
+// tile -- the overwhelmingly common case. One thread block owns one tile: the coefficients of all its
+// varblocks live in shared memory (3 x 4096 floats), every 1-D inverse DCT runs in the registers of one
+// thread, and pixels leave as 256-byte row segments. Larger or tile-straddling varblocks are left to the
+// generic path (varblock_to_pixels in j40b_vardct.h).
+//
+// The arithmetic is the reference's, operation for operation (see j40b_vardct.h for the citations); what
+// changes is who computes what and where the numbers sit:
+//   * j40__inverse_dct2d runs IDCT(columns) -> transpose -> IDCT(rows) over whole arrays; here each 1-D
+//     transform is an independent unit working in place on its own address set, so no transposes and no
+//     barriers inside a pass are needed:
+//       square/tall blocks keep the stored [u][v] layout: pass A transforms along u (stride R), pass B along
+//       v (contiguous), leaving samples as [x][y];
+//       wide blocks keep [v][u]: pass A transforms along u (contiguous), pass B along v (stride C),
+//       leaving samples as [y][x].
+#pragma once
+#include "j40b_vardct.h"
+
+namespace j40b {
+
+// 1-D inverse DCT of N points in place, the recursion of j40__inverse_dct_core (j40.h:5802-5841) unrolled
+template <int N> struct Idct1D {
+    J40B_HD static J40B_INLINE void run(float *v) {
+        float a[N / 2], b[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) a[i] = v[2 * i];
+        b[0] = J40B_FMUL(J40B_SQRT2, v[1]);
+#pragma unroll
+        for (int i = 1; i < N / 2; ++i) b[i] = J40B_FADD(v[2 * i - 1], v[2 * i + 1]);
+        Idct1D<N / 2>::run(a);
+        Idct1D<N / 2>::run(b);
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            float t = J40B_FMUL(b[i], J40B_HALF_SECANT(N / 2 + i));
+            v[i] = J40B_FADD(a[i], t);
+            v[N - 1 - i] = J40B_FSUB(a[i], t);
+        }
+    }
+};
+template <> struct Idct1D<2> {
+    J40B_HD static J40B_INLINE void run(float *v) {
+        float x = v[0], y = v[1];
+        v[0] = J40B_FADD(x, y);
+        v[1] = J40B_FSUB(x, y);
+    }
+};
+template <> struct Idct1D<1> { J40B_HD static J40B_INLINE void run(float *) {} };
+
+template <int N>
+J40B_HD J40B_INLINE void idct_strided(float *p, int stride) {
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = p[i * stride];
+    Idct1D<N>::run(v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i * stride] = v[i];
+}
+
+J40B_HD J40B_INLINE void idct_strided_dispatch(float *p, int stride, int log_n) {
+    switch (log_n) {
+    case 3: idct_strided<8>(p, stride); break;
+    case 4: idct_strided<16>(p, stride); break;
+    case 5: idct_strided<32>(p, stride); break;
+    case 6: idct_strided<64>(p, stride); break;
+    }
+}
+
+struct TileVb {
+    int32_t voff;        // varblock index inside the LF group
+    uint16_t chunk_off;  // offset (floats) of this varblock's coefficients in each channel's 4096-float buffer
+    uint8_t dctsel, log_rows, log_cols;
+    uint8_t cx, cy;      // top-left cell inside the tile
+    uint8_t special;
+    float hfmul_inv, kx_hf, kb_hf;
+    int32_t coeffoff;
+};
+
+struct TileShared {
+    int32_t nvb;
+    TileVb vb[64];
+    uint8_t cover[64];     // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
+    uint8_t chunk_vb[64];  // 64-float chunk -> index into vb[]
+    float thr[255];
+};
+
+// tile (tx, ty) of group w.grp; coef = 3 * 4096 floats of shared memory
+template <class Sync>
+J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coef, TileShared &ts, int tid, int nth, Sync sync) {
+    if (*w.lf_err || *w.hf_err) return;
+    const DFrame &f = *w.f;
+    const DLfGroup &g = *w.g;
+    const DGroup &grp = *w.grp;
+    const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
+    if (tx * 8 >= gw8 || ty * 8 >= gh8) return;
+    const int n8 = g.width8 * g.height8;
+    float *coefx = coef, *coefy = coef + 4096, *coefb = coef + 8192;
+
+    // ---- 0. varblocks of this tile (thread 0), thresholds, zeroed coefficients
+    for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
+    for (int i = tid; i < 3 * 4096; i += nth) coef[i] = 0.0f;
+    if (tid == 0) {
+        int n = 0, off = 0;
+        for (int c = 0; c < 64; ++c) ts.cover[c] = 0xff;
+        for (int cy = 0; cy < 8; ++cy) for (int cx = 0; cx < 8; ++cx) {
+            int x8 = tx * 8 + cx, y8 = ty * 8 + cy;
+            if (x8 >= gw8 || y8 >= gh8) continue;
+            int32_t b = g.blocks[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
+            if ((b >> 20) < 2) continue;
+            int32_t voff = b & 0xfffff;
+            const DVarblock &vb = g.varblocks[voff];
+            if (vb.pad & 1) continue; // generic path
+            DctSelectInfo d = dct_select_info(vb.dctsel);
+            TileVb &t = ts.vb[n];
+            t.voff = voff;
+            t.chunk_off = (uint16_t) off;
+            t.dctsel = vb.dctsel; t.log_rows = (uint8_t) d.log_rows; t.log_cols = (uint8_t) d.log_columns;
+            t.cx = (uint8_t) cx; t.cy = (uint8_t) cy;
+            t.special = is_special_8x8(vb.dctsel) ? 1 : 0;
+            t.hfmul_inv = vb.hfmul_inv;
+            t.coeffoff = vb.coeffoff;
+            t.kx_hf = J40B_FADD(f.base_corr_x, J40B_FMUL(f.inv_colour_factor, (float) g.xfromy[(vb.y8 / 8) * g.width64 + (vb.x8 / 8)]));
+            t.kb_hf = J40B_FADD(f.base_corr_b, J40B_FMUL(f.inv_colour_factor, (float) g.bfromy[(vb.y8 / 8) * g.width64 + (vb.x8 / 8)]));
+            int size = 1 << (d.log_rows + d.log_columns);
+            for (int k = 0; k < size / 64; ++k) ts.chunk_vb[off / 64 + k] = (uint8_t) n;
+            for (int i = 0; i < (1 << (d.log_rows - 3)); ++i) for (int j = 0; j < (1 << (d.log_columns - 3)); ++j) ts.cover[(cy + i) * 8 + cx + j] = (uint8_t) n;
+            off += size;
+            ++n;
+        }
+        ts.nvb = n;
+    }
+    sync();
+    const int nvb = ts.nvb;
+    if (nvb == 0) return;
+
+    // ---- 1. scatter the decoded coefficients (one warp-sized stripe of threads per varblock-channel)
+    {
+        const int lanes = nth < 32 ? nth : 32, groups = nth / lanes;
+        const int lane = tid % lanes, grp_id = tid / lanes;
+        for (int pair = grp_id; pair < nvb * 3; pair += groups) {
+            int v = pair / 3, c = pair - v * 3;
+            const TileVb &t = ts.vb[v];
+            uint32_t first = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 0], cnt = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 1];
+            float *dst = coef + c * 4096 + t.chunk_off;
+            for (uint32_t k = (uint32_t) lane; k < cnt; k += (uint32_t) lanes) {
+                DToken tk = w.tokens[first + k];
+                dst[tk.pos] = J40B_FADD(dst[tk.pos], (float) tk.val);
+            }
+        }
+    }
+    sync();
+
+    // ---- 2. dequantise + chroma from luma (element-wise; j40.h:7078-7094, 7155-7175)
+    {
+        const float gs = J40B_FDIV(65536.0f, (float) f.global_scale);
+        int total = 0;
+        { const TileVb &last = ts.vb[nvb - 1]; total = last.chunk_off + (1 << (last.log_rows + last.log_cols)); }
+        for (int e = tid; e < total; e += nth) {
+            const TileVb &t = ts.vb[ts.chunk_vb[e >> 6]];
+            const int i = e - t.chunk_off;
+            const float *dq = f.dq[dct_select_info(t.dctsel).param_idx] + (size_t) i * 3;
+            float m1 = J40B_FMUL(gs, t.hfmul_inv);
+            float m0 = J40B_FMUL(m1, f.x_qm_mult), m2 = J40B_FMUL(m1, f.b_qm_mult);
+            float vx = coefx[e], vy = coefy[e], vb_ = coefb[e];
+            vx = (-1.0f <= vx && vx <= 1.0f) ? J40B_FMUL(vx, f.quant_bias[0]) : J40B_FSUB(vx, J40B_FDIV(f.quant_bias_num, vx));
+            vy = (-1.0f <= vy && vy <= 1.0f) ? J40B_FMUL(vy, f.quant_bias[1]) : J40B_FSUB(vy, J40B_FDIV(f.quant_bias_num, vy));
+            vb_ = (-1.0f <= vb_ && vb_ <= 1.0f) ? J40B_FMUL(vb_, f.quant_bias[2]) : J40B_FSUB(vb_, J40B_FDIV(f.quant_bias_num, vb_));
+            vx = J40B_FMUL(vx, J40B_FDIV(m0, dq[0]));
+            vy = J40B_FMUL(vy, J40B_FDIV(m1, dq[1]));
+            vb_ = J40B_FMUL(vb_, J40B_FDIV(m2, dq[2]));
+            coefx[e] = J40B_FADD(vx, J40B_FMUL(vy, t.kx_hf));
+            coefy[e] = vy;
+            coefb[e] = J40B_FADD(vb_, J40B_FMUL(vy, t.kb_hf));
+        }
+    }
+    sync();
+    // ---- 3. LLF corner from the LF image (j40.h:7158-7172)
+    for (int slot = tid; slot < nvb * 64; slot += nth) {
+        const TileVb &t = ts.vb[slot >> 6];
+        const int e = slot & 63;
+        const int lmin = t.log_rows < t.log_cols ? t.log_rows : t.log_cols, lmax = t.log_rows < t.log_cols ? t.log_cols : t.log_rows;
+        const int vh8 = 1 << (lmin - 3), vw8 = 1 << (lmax - 3);
+        if (e >= vh8 * vw8) continue;
+        int y = e / vw8, x = e - y * vw8;
+        int p = t.chunk_off + y * vw8 * 8 + x;
+        float l0 = g.llf[(size_t) 0 * n8 + (t.coeffoff >> 6) + e];
+        float l1 = g.llf[(size_t) 1 * n8 + (t.coeffoff >> 6) + e];
+        float l2 = g.llf[(size_t) 2 * n8 + (t.coeffoff >> 6) + e];
+        coefx[p] = J40B_FADD(l0, J40B_FMUL(l1, f.kx_lf));
+        coefy[p] = l1;
+        coefb[p] = J40B_FADD(l2, J40B_FMUL(l1, f.kb_lf));
+    }
+    sync();
+    // ---- 4. pass A: 1-D inverse DCTs along the horizontal frequency u; special 8x8 transforms whole
+    // slot = (channel, tile pixel row, tile cell column); active where the cell starts a varblock's row of cells
+    for (int slot = tid; slot < 3 * 64 * 8; slot += nth) {
+        const int c = slot / 512, r64 = slot & 63, cx = (slot >> 6) & 7;
+        const int cell = (r64 >> 3) * 8 + cx;
+        const uint8_t vi = ts.cover[cell];
+        if (vi == 0xff) continue;
+        const TileVb &t = ts.vb[vi];
+        if (t.cx != cx) continue; // not the leftmost cell of this varblock
+        const int r = r64 - t.cy * 8; // row inside the varblock (vertical frequency index v at this stage)
+        float *blk = coef + c * 4096 + t.chunk_off;
+        if (t.special) {
+            if (r == 0) inverse_special(t.dctsel, blk);
+            continue;
+        }
+        const int R = 1 << t.log_rows, C = 1 << t.log_cols;
+        if (t.log_cols > t.log_rows) idct_strided_dispatch(blk + r * C, 1, t.log_cols);       // [v][u], contiguous
+        else idct_strided_dispatch(blk + r, R, t.log_cols);                                 // [u][v], stride R
+    }
+    sync();
+    // ---- 5. pass B: 1-D inverse DCTs along the vertical frequency v
+    // slot = (channel, tile pixel column, tile cell row); active where the cell starts a varblock's column of cells
+    for (int slot = tid; slot < 3 * 64 * 8; slot += nth) {
+        const int c = slot / 512, x64 = slot & 63, cy = (slot >> 6) & 7;
+        const int cell = cy * 8 + (x64 >> 3);
+        const uint8_t vi = ts.cover[cell];
+        if (vi == 0xff) continue;
+        const TileVb &t = ts.vb[vi];
+        if (t.cy != cy || t.special) continue;
+        const int x = x64 - t.cx * 8;
+        float *blk = coef + c * 4096 + t.chunk_off;
+        const int R = 1 << t.log_rows, C = 1 << t.log_cols;
+        if (t.log_cols > t.log_rows) idct_strided_dispatch(blk + x, C, t.log_rows);          // [v][x] -> [y][x]
+        else idct_strided_dispatch(blk + x * R, 1, t.log_rows);                              // [x][v] -> [x][y]
+    }
+    sync();
+    // ---- 6. XYB -> sRGB -> RGBA8 (j40.h:7208-7237, 7941-7952), one thread per pixel, row-major
+    const int gx0 = g.left + (grp.gx8 + tx * 8) * 8, gy0 = g.top + (grp.gy8 + ty * 8) * 8;
+    for (int pix = tid; pix < 4096; pix += nth) {
+        const int py = pix >> 6, px = pix & 63;
+        const int X = gx0 + px, Y = gy0 + py;
+        if (X >= f.width || Y >= f.height) continue;
+        const uint8_t vi = ts.cover[(py >> 3) * 8 + (px >> 3)];
+        if (vi == 0xff) continue;
+        const TileVb &t = ts.vb[vi];
+        const int ly = py - t.cy * 8, lx = px - t.cx * 8;
+        const int R = 1 << t.log_rows, C = 1 << t.log_cols;
+        // special transforms and wide blocks end as [y][x]; square / tall DCT blocks as [x][y]
+        const int idx = t.chunk_off + ((t.special || t.log_cols > t.log_rows) ? ly * C + lx : lx * R + ly);
+        float sx = coefx[idx], sy = coefy[idx], sb = coefb[idx];
+        float p[3] = {J40B_FADD(sy, sx), J40B_FSUB(sy, sx), sb};
+        float lin[3];
+        for (int c = 0; c < 3; ++c) {
+            float pp = J40B_FSUB(p[c], f.cbrt_opsin_bias[c]);
+            lin[c] = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(pp, pp), pp), f.opsin_bias[c]), f.itscale);
+        }
+        uint32_t out = 0xff000000u;
+        for (int c = 0; c < 3; ++c) {
+            float v = J40B_FADD(J40B_FADD(J40B_FMUL(lin[0], f.opsin_inv_mat[c * 3 + 0]), J40B_FMUL(lin[1], f.opsin_inv_mat[c * 3 + 1])),
+                                J40B_FMUL(lin[2], f.opsin_inv_mat[c * 3 + 2]));
+            out |= (uint32_t) srgb_u8_from_linear(ts.thr, v) << (8 * c);
+        }
+        *(uint32_t *) (w.rgba + (size_t) Y * (size_t) w.rgba_stride + (size_t) X * 4) = out;
+    }
+}
+
+} // namespace j40b

@@ -96,6 +96,7 @@ struct DCodeSpec {
     HybridCfg lz_len_cfg;
     uint32_t cluster_map_off; // uint8_t[num_dist]
     uint32_t clusters_off;    // DCluster[num_clusters]
+    uint32_t blob_lo, blob_hi; // arena byte range holding everything this spec points to (and the spec)
 };
 
 // ANS alias entry: one 64-bit word per bucket (see j40b_entropy.h)

@@ -21,36 +21,52 @@ using namespace j40b;
 
 struct BlockSync { __device__ void operator()() const { __syncthreads(); } };
 
-__global__ void __launch_bounds__(256) k_lf_group(const LfWork *items) {
-    __shared__ LfShared sh;
-    lf_group_body(items[blockIdx.x], sh, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+// dynamic shared memory of the serial-decoder kernels: a copy of the code spec's tables
+enum { SPEC_COPY_BYTES = 40 * 1024 };
+
+__global__ void __launch_bounds__(128) k_lf_group(const LfWork *items) {
+    __shared__ SerialShared sh;
+    extern __shared__ __align__(16) uint8_t spec_copy[];
+    lf_group_body(items[blockIdx.x], sh, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, (int) blockDim.x, BlockSync());
 }
 
-__global__ void __launch_bounds__(32) k_hf_group(const HfWork *items) {
-    __shared__ int8_t nonzeros[3 * 1024];
-    if (threadIdx.x == 0) hf_group_body(items[blockIdx.x], nonzeros);
+// HF coefficient entropy decode, SIMT: one warp per 32 consecutive groups (one group per lane). The work
+// list is ordered image by image, so a warp's lanes nearly always share one image, whose coefficient code
+// spec (cluster map + alias tables / prefix LUTs) is staged in shared memory; lanes of another image (at
+// image boundaries) and specs that do not fit read the tables from global memory instead.
+__global__ void __launch_bounds__(32) k_hf_group(const HfWork *items, int n) {
+    extern __shared__ __align__(16) uint8_t spec_copy[];
+    const int first = (int) blockIdx.x * 32;
+    const HfWork &w0 = items[first];
+    const bool staged = stage_spec_blob(w0.arena, w0.f->coeff_spec_off, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, 32);
+    __syncwarp();
+    const int i = first + (int) threadIdx.x;
+    if (i < n) hf_group_body(items[i], staged ? spec_copy : nullptr, w0.arena);
 }
 
-__global__ void __launch_bounds__(256) k_back(const BackWork *items) {
-    extern __shared__ float smem[];
-    back_body(items[blockIdx.x], smem, 0, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+// one block per 64x64-pixel tile of a group (blockIdx.y = tile index inside the 256x256 group)
+__global__ void __launch_bounds__(256, 2) k_back_tile(const BackWork *items) {
+    extern __shared__ __align__(16) float tile_coef[];
+    __shared__ TileShared ts;
+    back_tile_body(items[blockIdx.x], (int) (blockIdx.y & 3), (int) (blockIdx.y >> 2), tile_coef, ts, (int) threadIdx.x, (int) blockDim.x, BlockSync());
 }
 
-// varblocks larger than 64x64: persistent blocks, each with its own 1 MiB slice of scratch
-__global__ void __launch_bounds__(256) k_back_big(const BackWork *items, int n, float *scratch_pool) {
+// varblocks the tile kernel leaves out: persistent blocks, each with its own 1 MiB slice of scratch
+__global__ void __launch_bounds__(256) k_back_generic(const BackWork *items, int n, float *scratch_pool) {
     float *scratch = scratch_pool + (size_t) blockIdx.x * 4 * 65536;
     for (int i = (int) blockIdx.x; i < n; i += (int) gridDim.x) {
         BackWork w = items[i];
         w.big_scratch = scratch;
-        back_body(w, (float *) nullptr, 1, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+        back_generic_body(w, (int) threadIdx.x, (int) blockDim.x, BlockSync());
         __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(32) k_modular(ModWork *items) {
-    __shared__ ModShared sh;
+    __shared__ SerialShared sh;
+    extern __shared__ __align__(16) uint8_t spec_copy[];
     struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
-    modular_body(items[blockIdx.x], sh, (int) threadIdx.x, (int) blockDim.x, WarpSync());
+    modular_body(items[blockIdx.x], sh, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, (int) blockDim.x, WarpSync());
 }
 
 __global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height) {
@@ -83,7 +99,7 @@ struct CudaBackend {
         num_sms = prop.multiProcessorCount;
         if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
-        if (!cuda_ok(cudaFuncSetAttribute(k_back, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4096 * 4))) return false;
+        if (!cuda_ok(cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4))) return false;
         ok = true;
         return true;
     }
@@ -107,17 +123,17 @@ struct CudaBackend {
 
     void launch_lf(const LfWork *w, int n) {
         cudaEventRecord(ev[0], stream);
-        k_lf_group<<<n, 256, 0, stream>>>(w);
+        k_lf_group<<<n, 128, SPEC_COPY_BYTES, stream>>>(w);
         cudaEventRecord(ev[1], stream);
         ++launches;
     }
     void launch_hf(const HfWork *w, int n) {
-        k_hf_group<<<n, 32, 0, stream>>>(w);
+        k_hf_group<<<(n + 31) / 32, 32, SPEC_COPY_BYTES, stream>>>(w, n);
         cudaEventRecord(ev[2], stream);
         ++launches;
     }
     void launch_back(const BackWork *w, int n) {
-        k_back<<<n, 256, 4 * 4096 * 4, stream>>>(w);
+        k_back_tile<<<dim3((unsigned) n, 16), 256, 3 * 4096 * 4, stream>>>(w);
         cudaEventRecord(ev[3], stream);
         ++launches;
         if (!big_pool) {
@@ -125,13 +141,13 @@ struct CudaBackend {
             if (!cuda_ok(cudaMalloc(&big_pool, (size_t) big_blocks * 4 * 65536 * sizeof(float)))) { big_pool = nullptr; big_blocks = 0; }
         }
         if (big_pool) {
-            k_back_big<<<big_blocks < n ? big_blocks : n, 256, 0, stream>>>(w, n, big_pool);
+            k_back_generic<<<big_blocks < n ? big_blocks : n, 256, 0, stream>>>(w, n, big_pool);
             ++launches;
         }
         cudaEventRecord(ev[4], stream);
     }
     void launch_mod(ModWork *w, int n) {
-        k_modular<<<n, 32, 0, stream>>>(w);
+        k_modular<<<n, 32, SPEC_COPY_BYTES, stream>>>(w);
         ++launches;
     }
     void launch_render(const RenderWork *w, int width, int height) {

@@ -20,10 +20,46 @@ namespace j40b {
 struct BitReader {
     const uint8_t *base; // first byte of the section
     uint32_t size;       // section size in bytes
-    uint32_t pos;        // next (virtual) byte to load; bytes at >= size read as zero
+    uint32_t pos;        // next (virtual) byte to load
     uint64_t buf;
     int32_t nbits;
 
+#if defined(__CUDA_ARCH__)
+    // Device: aligned 32-bit loads. Bytes past the section end are whatever follows in the codestream
+    // buffer (the executor pads it); they are never *accepted*: any consumption past the end is an
+    // overrun, which is the only thing the error model looks at.
+    J40B_HD void init(const uint8_t *b, uint32_t size_bytes, uint64_t start_bit = 0) {
+        base = b;
+        size = size_bytes;
+        const uint8_t *p = b + (start_bit >> 3);
+        uint32_t mis = (uint32_t) ((uintptr_t) p & 3);
+        const uint32_t *wp = (const uint32_t *) (p - mis);
+        buf = (uint64_t) (*wp >> (8 * mis));
+        nbits = 32 - 8 * (int32_t) mis;
+        pos = (uint32_t) (start_bit >> 3) + 4 - mis;
+        int skip = (int) (start_bit & 7);
+        if (skip) { buf >>= skip; nbits -= skip; }
+    }
+    J40B_HD J40B_INLINE void refill() { // precondition: nbits <= 32
+        uint32_t w = *(const uint32_t *) (base + pos);
+        buf |= (uint64_t) w << nbits;
+        nbits += 32;
+        pos += 4;
+    }
+    J40B_HD J40B_INLINE uint32_t u(int n) { // n in [0, 32]
+        if (nbits < 32) refill();
+        uint32_t lo = (uint32_t) buf;
+        uint32_t v = n >= 32 ? lo : (lo & ((1u << n) - 1));
+        buf >>= n;
+        nbits -= n;
+        return v;
+    }
+    J40B_HD J40B_INLINE uint32_t peek(int n) {
+        if (nbits < 32) refill();
+        uint32_t lo = (uint32_t) buf;
+        return n >= 32 ? lo : (lo & ((1u << n) - 1));
+    }
+#else
     J40B_HD void init(const uint8_t *b, uint32_t size_bytes, uint64_t start_bit = 0) {
         base = b;
         size = size_bytes;
@@ -53,6 +89,7 @@ struct BitReader {
         if (nbits < n) refill();
         return (uint32_t) (buf & ((1ull << n) - 1));
     }
+#endif
     J40B_HD J40B_INLINE void skip(int n) { buf >>= n; nbits -= n; }
     J40B_HD J40B_INLINE uint64_t bits_consumed() const { return (uint64_t) pos * 8 - (uint64_t) nbits; }
     J40B_HD J40B_INLINE bool overrun() const { return bits_consumed() > (uint64_t) size * 8; }
@@ -160,6 +197,9 @@ struct CodeCtx { // everything a symbol read needs besides the state
         cluster_map = arena_ + spec->cluster_map_off;
         clusters = (const DCluster *) (arena_ + spec->clusters_off);
     }
+    // `copy` holds the bytes [blob_lo, blob_hi) of the arena (cluster map, clusters, tables, spec): all
+    // table offsets keep working relative to (copy - blob_lo)
+    J40B_HD void init_from_copy(const uint8_t *copy, uint32_t blob_lo, uint32_t spec_off) { init(copy - blob_lo, spec_off); }
 };
 
 J40B_HD J40B_INLINE int32_t cluster_symbol(BitReader &br, const CodeCtx &cc, const DCluster *cl, uint32_t &ans_state) {

@@ -63,29 +63,55 @@ struct RenderWork { // modular frames: inverse global transforms + interleave to
     int32_t rgba_stride;
 };
 
-struct LfShared { // block-shared scratch for lf_group_body
+} // namespace j40b
+#include "j40b_backtile.h" // needs BackWork
+namespace j40b {
+
+enum { PTREE_CAP = 192 };
+
+// block-shared scratch of the serial decoders: pruned tree, WP divisor table, optional copy of the code
+// spec's tables (cluster map, alias / prefix LUTs) so that the symbol loop never leaves the SM
+struct SerialShared {
     uint32_t err;
     int32_t extra_prec;
+    int32_t div24[64];
+    DTreeNode ptree[PTREE_CAP];
     ModImage m;
 };
 
+// cooperative staging of a code spec's blob into `dst` (cap bytes); returns true if it fits
+J40B_HD inline bool stage_spec_blob(const uint8_t *arena, uint32_t spec_off, uint8_t *dst, uint32_t cap, int tid, int nth) {
+    const DCodeSpec *spec = (const DCodeSpec *) (arena + spec_off);
+    uint32_t lo = spec->blob_lo, hi = spec->blob_hi;
+    if (!dst || hi - lo > cap) return false;
+    const uint32_t *src = (const uint32_t *) (arena + lo); // lo is 16-byte aligned, hi 4-byte aligned
+    uint32_t *d32 = (uint32_t *) dst;
+    for (uint32_t i = (uint32_t) tid; i < (hi - lo + 3) / 4; i += (uint32_t) nth) d32[i] = src[i];
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 template <class Sync>
-J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nth, Sync sync) {
+J40B_HD inline void lf_group_body(const LfWork &w, SerialShared &sh, uint8_t *spec_copy, uint32_t spec_copy_cap, int tid, int nth, Sync sync) {
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
     const int n8 = g.width8 * g.height8;
     for (int i = tid; i < n8; i += nth) g.blocks[i] = 0;
+    for (int i = tid; i < 64; i += nth) sh.div24[i] = (int32_t) (0x1000000u / (uint32_t) (i + 1));
+    const bool staged = f.global_spec_off && stage_spec_blob(w.arena, f.global_spec_off, spec_copy, spec_copy_cap, tid, nth);
+    sync();
     // thread-0 state that lives across the barriers
     BitReader br;
     ErrSlot es;
     CodeCtx cc;
     CodeState cs;
     es.err = 0;
+    const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
     if (tid == 0) {
         sh.err = 0;
         br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
-        cc.init(w.arena, f.global_spec_off);
+        if (staged) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (w.arena + f.global_spec_off))->blob_lo, f.global_spec_off);
+        else cc.init(w.arena, f.global_spec_off);
         sh.extra_prec = (int32_t) br.u(2);
         ModImage &m = sh.m;
         m.num_channels = 3;
@@ -97,9 +123,8 @@ J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nt
         modular_header(br, es, f.have_global_tree != 0, m);
         if (!es.err) {
             cs.init(g.lz_window, (1u << 18) - 1);
-            const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
             for (int c = 0; c < 3 && !es.err; ++c) {
-                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, m, c, 1 + g.idx);
+                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, sh.div24, sh.ptree, PTREE_CAP, m, c, 1 + g.idx);
             }
             if (!es.err) finish_code(br, es, cc, cs);
         }
@@ -131,9 +156,9 @@ J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nt
             modular_header(br, es, f.have_global_tree != 0, m);
             if (!es.err) {
                 cs.init(g.lz_window, (1u << 18) - 1);
-                const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
                 for (int c = 0; c < 4 && !es.err; ++c) {
-                    modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, m, c, 1 + 2 * f.num_lf_groups + g.idx);
+                    modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, sh.div24, sh.ptree, PTREE_CAP, m, c,
+                                    1 + 2 * f.num_lf_groups + g.idx);
                 }
                 if (!es.err) finish_code(br, es, cc, cs);
             }
@@ -170,7 +195,7 @@ J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nt
             llf_from_lf(g, vb, scratch, 0, 1, NoSync());
         }
     }
-    if (tid == 0 && w.llf_scratch) {
+    if (tid == 0 && w.llf_scratch && g.has_big) {
         for (int v = 0; v < g.nb_varblocks; ++v) {
             const DVarblock &vb = g.varblocks[v];
             DctSelectInfo d = dct_select_info(vb.dctsel);
@@ -180,19 +205,23 @@ J40B_HD inline void lf_group_body(const LfWork &w, LfShared &sh, int tid, int nt
 }
 
 // ---------------------------------------------------------------------------------------------
-// thread 0 only; `nonzeros` = 3 * 1024 bytes of scratch
-J40B_HD inline void hf_group_body(const HfWork &w, int8_t *nonzeros) {
+// One group per *thread*: the 32 lanes of a warp decode 32 groups side by side (the decoder is a state
+// machine with one symbol read per iteration, so the lanes reconverge at every read). `spec_copy` is an
+// optional shared-memory copy of the coefficient code spec of image `copy_arena` (null = none).
+J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, const uint8_t *copy_arena) {
     if (*w.lf_err) return;
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
     DGroup &grp = *w.grp;
+    int8_t *nonzeros = grp.nonzeros;
     BitReader br;
     ErrSlot es;
     es.err = 0;
     uint64_t start_bit = grp.sec_start_bit == ~0ull ? g.end_bit : grp.sec_start_bit;
     br.init(w.cs + grp.sec_off, grp.sec_size, start_bit);
     CodeCtx cc;
-    cc.init(w.arena, f.coeff_spec_off);
+    if (spec_copy && copy_arena == w.arena) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (w.arena + f.coeff_spec_off))->blob_lo, f.coeff_spec_off);
+    else cc.init(w.arena, f.coeff_spec_off);
     CodeState cs;
     cs.init(grp.lz_window, (1u << 18) - 1);
     int32_t preset = (int32_t) br.u(ceil_lg32((uint32_t) f.num_hf_presets));
@@ -211,12 +240,12 @@ J40B_HD inline void hf_group_body(const HfWork &w, int8_t *nonzeros) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// all threads; smem: 4 * 4096 floats (varblocks up to 64x64), bigger ones go through w.big_scratch
-// mode 0: varblocks up to 64x64 (buffers in shared memory); mode 1: the larger ones (w.big_scratch)
+// generic path: varblocks the tile kernel leaves out (larger than 64x64 or straddling tiles), one at a time
+// with all threads and buffers in w.big_scratch (4 * 65536 floats of global memory)
 template <class Sync>
-J40B_HD inline void back_body(const BackWork &w, float *smem, int mode, int tid, int nth, Sync sync) {
+J40B_HD inline void back_generic_body(const BackWork &w, int tid, int nth, Sync sync) {
     if (*w.lf_err || *w.hf_err) return;
-    if (mode == 1 && !w.g->has_big) return;
+    if (!w.g->has_big) return;
     const DFrame &f = *w.f;
     const DLfGroup &g = *w.g;
     const DGroup &grp = *w.grp;
@@ -226,29 +255,28 @@ J40B_HD inline void back_body(const BackWork &w, float *smem, int mode, int tid,
         if ((voff >> 20) < 2) continue;
         voff &= 0xfffff;
         const DVarblock &vb = g.varblocks[voff];
-        DctSelectInfo d = dct_select_info(vb.dctsel);
-        int size = 1 << (d.log_rows + d.log_columns);
-        if ((size > 4096) != (mode == 1)) continue;
-        float *buf = size <= 4096 ? smem : w.big_scratch;
-        int bs = size <= 4096 ? 4096 : 65536;
-        varblock_to_pixels(f, w.arena, g, vb, voff, w.tokens, buf, buf + bs, buf + 2 * bs, buf + 3 * bs,
+        if (!(vb.pad & 1)) continue;
+        float *buf = w.big_scratch;
+        varblock_to_pixels(f, w.arena, g, vb, voff, w.tokens, buf, buf + 65536, buf + 2 * 65536, buf + 3 * 65536,
                            w.rgba, w.rgba_stride, tid, nth, sync);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-struct ModShared { uint32_t err; ModImage m; };
-
 template <class Sync>
-J40B_HD inline void modular_body(ModWork &w, ModShared &sh, int tid, int nth, Sync sync) {
+J40B_HD inline void modular_body(ModWork &w, SerialShared &sh, uint8_t *spec_copy, uint32_t spec_copy_cap, int tid, int nth, Sync sync) {
     const DFrame &f = *w.f;
+    for (int i = tid; i < 64; i += nth) sh.div24[i] = (int32_t) (0x1000000u / (uint32_t) (i + 1));
+    const bool staged = f.global_spec_off && stage_spec_blob(w.arena, f.global_spec_off, spec_copy, spec_copy_cap, tid, nth);
+    sync();
     if (tid == 0) {
         BitReader br;
         ErrSlot es;
         es.err = 0;
         br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
         CodeCtx cc;
-        cc.init(w.arena, f.global_spec_off);
+        if (staged) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (w.arena + f.global_spec_off))->blob_lo, f.global_spec_off);
+        else cc.init(w.arena, f.global_spec_off);
         CodeState cs;
         sh.m = w.m;
         if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, sh.m);
@@ -256,7 +284,7 @@ J40B_HD inline void modular_body(ModWork &w, ModShared &sh, int tid, int nth, Sy
             cs.init(w.lz_window, w.lz_mask);
             const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
             for (int c = 0; c < sh.m.num_channels && !es.err; ++c) {
-                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, sh.m, c, w.sidx);
+                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, sh.div24, sh.ptree, PTREE_CAP, sh.m, c, w.sidx);
             }
             if (!es.err) finish_code(br, es, cc, cs);
         }

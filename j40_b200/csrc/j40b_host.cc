@@ -470,6 +470,9 @@ struct Parser {
         if (err) return 0;
         std::vector<DCluster> clusters((size_t) spec.num_clusters);
         memset(clusters.data(), 0, clusters.size() * sizeof(DCluster));
+        // everything allocated from here on belongs to this spec alone (nested specs came earlier)
+        uint32_t blob_lo = (uint32_t) ((arena.bytes.size() + 15) / 16 * 16);
+        arena.alloc(0, 16);
         spec.use_prefix_code = (int32_t) u(1);
         if (spec.use_prefix_code) {
             for (auto &c : clusters) c.cfg = hybrid_cfg(15);
@@ -501,11 +504,13 @@ struct Parser {
         }
         if (overrun()) FAILV(E_SHRT, 0);
         spec.num_dist = num_dist;
+        spec.blob_lo = blob_lo;
         spec.cluster_map_off = arena.alloc(map.size(), 8);
         memcpy(arena.at<uint8_t>(spec.cluster_map_off), map.data(), map.size());
         spec.clusters_off = arena.alloc(clusters.size() * sizeof(DCluster), 8);
         memcpy(arena.at<uint8_t>(spec.clusters_off), clusters.data(), clusters.size() * sizeof(DCluster));
-        uint32_t off = arena.alloc(sizeof(DCodeSpec), 8);
+        uint32_t off = arena.alloc(sizeof(DCodeSpec), 16);
+        spec.blob_hi = off + (uint32_t) sizeof(DCodeSpec);
         memcpy(arena.at<uint8_t>(off), &spec, sizeof(spec));
         return off;
     }

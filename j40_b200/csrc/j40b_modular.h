@@ -31,11 +31,15 @@ struct ModImage {
     int32_t dist_mult;
 };
 
-// floor(2^24 / (i + 1)), i in [0, 64)
-J40B_HD J40B_INLINE int32_t div24p1(int32_t i) { return (int32_t) (0x1000000u / (uint32_t) (i + 1)); }
+// floor(2^24 / (i + 1)), i in [0, 64): the divisor table of the weighted predictor (j40.h:3905)
+struct Div24Table {
+    int32_t v[64];
+    constexpr Div24Table() : v() { for (int i = 0; i < 64; ++i) v[i] = (int32_t) (0x1000000u / (uint32_t) (i + 1)); }
+};
+static constexpr Div24Table h_div24_table{};
 
 struct WPState {
-    int32_t *errors; // [2][width][5] or null when the tree does not use the weighted predictor
+    int32_t *errors; // [2][width][5]
     int32_t width;
     int32_t pred[5];
     int32_t trueerrw, trueerrn, trueerrnw, trueerrne;
@@ -46,23 +50,22 @@ J40B_HD J40B_INLINE int32_t mod_gradient(int32_t w, int32_t n, int32_t nw) {
     return imin(imax(lo, w + n - nw), hi);
 }
 
-// j40.h:4011-4072
-J40B_HD J40B_INLINE void wp_before_predict(WPState &s, const WPParams &pr, int32_t x, int32_t y,
+// j40.h:4011-4072. `div24` = the 64-entry divisor table (shared memory on the device).
+J40B_HD J40B_INLINE void wp_before_predict(WPState &s, const WPParams &pr, const int32_t *div24, int32_t x, int32_t y,
                                            int32_t pw, int32_t pn, int32_t pnw, int32_t pne, int32_t pnn) {
-    if (!s.errors) return;
-    const int32_t ZERO[5] = {0, 0, 0, 0, 0};
-    int32_t *err = s.errors + (size_t) ((y & 1) ? s.width : 0) * 5;
-    int32_t *nerr = s.errors + (size_t) ((y & 1) ? 0 : s.width) * 5;
-    const int32_t *errw = x > 0 ? err + (size_t) (x - 1) * 5 : ZERO;
-    const int32_t *errn = y > 0 ? nerr + (size_t) x * 5 : ZERO;
-    const int32_t *errnw = x > 0 && y > 0 ? nerr + (size_t) (x - 1) * 5 : errn;
-    const int32_t *errne = x + 1 < s.width && y > 0 ? nerr + (size_t) (x + 1) * 5 : errn;
-    const int32_t *errww = x > 1 ? err + (size_t) (x - 2) * 5 : ZERO;
-    const int32_t *errw2 = x + 1 < s.width ? ZERO : errw;
-    s.trueerrw = x > 0 ? err[(size_t) (x - 1) * 5 + 4] : 0;
-    s.trueerrn = y > 0 ? nerr[(size_t) x * 5 + 4] : 0;
-    s.trueerrnw = x > 0 && y > 0 ? nerr[(size_t) (x - 1) * 5 + 4] : s.trueerrn;
-    s.trueerrne = x + 1 < s.width && y > 0 ? nerr[(size_t) (x + 1) * 5 + 4] : s.trueerrn;
+    const int32_t *err = s.errors + (size_t) ((y & 1) ? s.width : 0) * 5;
+    const int32_t *nerr = s.errors + (size_t) ((y & 1) ? 0 : s.width) * 5;
+    int32_t ew[5], en[5], enw[5], ene[5], eww[4], ew2[4];
+    for (int i = 0; i < 5; ++i) ew[i] = x > 0 ? err[(size_t) (x - 1) * 5 + i] : 0;
+    for (int i = 0; i < 5; ++i) en[i] = y > 0 ? nerr[(size_t) x * 5 + i] : 0;
+    for (int i = 0; i < 5; ++i) enw[i] = x > 0 && y > 0 ? nerr[(size_t) (x - 1) * 5 + i] : en[i];
+    for (int i = 0; i < 5; ++i) ene[i] = x + 1 < s.width && y > 0 ? nerr[(size_t) (x + 1) * 5 + i] : en[i];
+    for (int i = 0; i < 4; ++i) eww[i] = x > 1 ? err[(size_t) (x - 2) * 5 + i] : 0;
+    for (int i = 0; i < 4; ++i) ew2[i] = x + 1 < s.width ? 0 : ew[i];
+    s.trueerrw = ew[4];
+    s.trueerrn = en[4];
+    s.trueerrnw = enw[4];
+    s.trueerrne = ene[4];
     s.pred[0] = (pw + pne - pn) * 8;
     s.pred[1] = pn * 8 - (((s.trueerrw + s.trueerrn + s.trueerrne) * pr.p1) >> 5);
     s.pred[2] = pw * 8 - (((s.trueerrw + s.trueerrn + s.trueerrnw) * pr.p2) >> 5);
@@ -70,9 +73,9 @@ J40B_HD J40B_INLINE void wp_before_predict(WPState &s, const WPParams &pr, int32
                            (pnn - pn) * 8 * pr.p3[3] + (pnw - pw) * 8 * pr.p3[4]) >> 5);
     int32_t w[4];
     for (int i = 0; i < 4; ++i) {
-        int32_t errsum = errn[i] + errw[i] + errnw[i] + errww[i] + errne[i] + errw2[i];
+        int32_t errsum = en[i] + ew[i] + enw[i] + eww[i] + ene[i] + ew2[i];
         int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
-        w[i] = (int32_t) (4 + (((int64_t) pr.w[i] * div24p1(errsum >> shift)) >> shift));
+        w[i] = (int32_t) (4 + (((int64_t) pr.w[i] * div24[errsum >> shift]) >> shift));
     }
     int32_t logw = floor_lg32((uint32_t) (w[0] + w[1] + w[2] + w[3])) - 4;
     int32_t wsum = 0, sum = 0;
@@ -81,7 +84,7 @@ J40B_HD J40B_INLINE void wp_before_predict(WPState &s, const WPParams &pr, int32
         wsum += w[i];
         sum += s.pred[i] * w[i];
     }
-    s.pred[4] = (int32_t) ((((int64_t) sum + (wsum >> 1) - 1) * div24p1(wsum - 1)) >> 24);
+    s.pred[4] = (int32_t) ((((int64_t) sum + (wsum >> 1) - 1) * div24[wsum - 1]) >> 24);
     if (((s.trueerrn ^ s.trueerrw) | (s.trueerrn ^ s.trueerrnw)) <= 0) {
         int32_t lo = imin(pw, imin(pn, pne)) * 8;
         int32_t hi = imax(pw, imax(pn, pne)) * 8;
@@ -91,28 +94,63 @@ J40B_HD J40B_INLINE void wp_before_predict(WPState &s, const WPParams &pr, int32
 
 // j40.h:4103-4111
 J40B_HD J40B_INLINE void wp_after_predict(WPState &s, int32_t x, int32_t y, int32_t val) {
-    if (!s.errors) return;
     int32_t *err = s.errors + ((size_t) ((y & 1) ? s.width : 0) + (size_t) x) * 5;
     for (int i = 0; i < 4; ++i) err[i] = (iabs(s.pred[i] - val * 8) + 3) >> 3;
     err[4] = s.pred[4] - val * 8;
 }
 
-// Decodes channel `cidx` of `m` (j40.h:4127-4245). `wp_scratch` must hold 2*width*5 int32 when use_wp.
-J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
-                                    const DTreeNode *tree, bool use_wp, int32_t *wp_scratch,
-                                    const ModImage &m, int32_t cidx, int32_t sidx) {
+// Copies the part of `tree` that channel `cidx` of stream `sidx` can reach: branches on the two
+// static properties (0 = channel index, 1 = stream index, j40.h:4181-4182) are resolved now.
+// Returns the number of nodes written (0 if `cap` is too small: use the full tree then) and whether
+// any reachable node needs the weighted predictor (property 15 or predictor 6, j40.h:4142-4154).
+J40B_HD inline int prune_tree(const DTreeNode *tree, int32_t cidx, int32_t sidx, DTreeNode *out, int cap, bool *uses_wp) {
+    // breadth-first copy; out[i].c / .d first hold source indices, patched once the children are placed
+    int n = 0;
+    *uses_wp = false;
+    if (cap < 1) return 0;
+    int32_t src = 0;
+    for (;;) { // resolve static branches at the root
+        const DTreeNode &t = tree[src];
+        if (t.a < 0 && (-1 - t.a) <= 1) { int32_t v = (-1 - t.a) == 0 ? cidx : sidx; src = v > t.b ? t.c : t.d; } else break;
+    }
+    out[n++] = tree[src];
+    for (int i = 0; i < n; ++i) {
+        DTreeNode &o = out[i];
+        if (o.a >= 0) { if (o.b == 6) *uses_wp = true; continue; }
+        if (-1 - o.a == 15) *uses_wp = true;
+        int32_t child[2] = {o.c, o.d};
+        for (int k = 0; k < 2; ++k) {
+            int32_t s2 = child[k];
+            for (;;) {
+                const DTreeNode &t = tree[s2];
+                if (t.a < 0 && (-1 - t.a) <= 1) { int32_t v = (-1 - t.a) == 0 ? cidx : sidx; s2 = v > t.b ? t.c : t.d; } else break;
+            }
+            if (n >= cap) return 0;
+            out[n] = tree[s2];
+            child[k] = n++;
+        }
+        o.c = child[0];
+        o.d = child[1];
+    }
+    return n;
+}
+
+// Decodes channel `cidx` of `m` (j40.h:4127-4245). `wp_scratch` must hold 2*width*5 int32 when the
+// (pruned) tree needs the weighted predictor; `tree` may be the pruned copy or the full tree.
+template <bool USE_WP>
+J40B_HD inline void modular_channel_t(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                      const DTreeNode *tree, int32_t *wp_scratch, const int32_t *div24,
+                                      const ModImage &m, int32_t cidx, int32_t sidx) {
     const ModChannel &c = m.ch[cidx];
     const int32_t width = c.w, height = c.h, stride = c.stride;
-    if (width <= 0 || height <= 0) return;
+    const int32_t dist_mult = m.dist_mult;
+    const WPParams wpp = m.wp;
     WPState wp;
-    wp.errors = 0;
+    wp.errors = wp_scratch;
     wp.width = width;
     for (int i = 0; i < 5; ++i) wp.pred[i] = 0;
     wp.trueerrw = wp.trueerrn = wp.trueerrnw = wp.trueerrne = 0;
-    if (use_wp) {
-        wp.errors = wp_scratch;
-        for (int32_t i = 0; i < width * 2 * 5; ++i) wp_scratch[i] = 0;
-    }
+    if (USE_WP) for (int32_t i = 0; i < width * 2 * 5; ++i) wp_scratch[i] = 0;
     // reference channels for properties >= 16: earlier channels of identical geometry, nearest first
     int32_t refcmap[MOD_MAX_CH], nref = 0;
     for (int32_t i = cidx - 1; i >= 0; --i) {
@@ -122,17 +160,18 @@ J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &c
     }
     for (int32_t y = 0; y < height; ++y) {
         int16_t *row = c.px + (size_t) y * (size_t) stride;
+        int32_t prev = 0, prev2 = 0; // the two samples just decoded in this row (kept out of memory)
         for (int32_t x = 0; x < width; ++x) {
             const int16_t *p = row + x;
-            int32_t pw = x > 0 ? p[-1] : y > 0 ? p[-stride] : 0;
+            int32_t pw = x > 0 ? prev : y > 0 ? p[-stride] : 0;
             int32_t pn = y > 0 ? p[-stride] : pw;
             int32_t pnw = x > 0 && y > 0 ? p[-1 - stride] : pw;
             int32_t pne = x + 1 < width && y > 0 ? p[1 - stride] : pn;
             int32_t pnn = y > 1 ? p[-2 * stride] : pn;
             int32_t pnee = x + 2 < width && y > 0 ? p[2 - stride] : pne;
-            int32_t pww = x > 1 ? p[-2] : pw;
+            int32_t pww = x > 1 ? prev2 : pw;
             int32_t pnww = x > 1 && y > 0 ? p[-2 - stride] : pww;
-            wp_before_predict(wp, m.wp, x, y, pw, pn, pnw, pne, pnn);
+            if (USE_WP) wp_before_predict(wp, wpp, div24, x, y, pw, pn, pnw, pne, pnn);
 
             const DTreeNode *n = tree;
             while (n->a < 0) {
@@ -178,7 +217,7 @@ J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &c
                 n = tree + (val > n->b ? n->c : n->d);
             }
 
-            int32_t val = code(br, es, cc, cs, n->a, m.dist_mult);
+            int32_t val = code(br, es, cc, cs, n->a, dist_mult);
             val = unpack_signed(val) * n->d + n->c;
             int32_t pred;
             switch (n->b) {
@@ -202,9 +241,26 @@ J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &c
             if (es.err) return;
             if (val < -32768 || val > 32767) { es.set(br, E_POVF); return; }
             row[x] = (int16_t) val;
-            wp_after_predict(wp, x, y, val);
+            prev2 = prev;
+            prev = val;
+            if (USE_WP) wp_after_predict(wp, x, y, val);
         }
     }
+}
+
+// `ptree`/`ptree_cap`: scratch for the pruned tree (shared memory on the device); 0 = use the full tree
+J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                    const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch, const int32_t *div24,
+                                    DTreeNode *ptree, int ptree_cap,
+                                    const ModImage &m, int32_t cidx, int32_t sidx) {
+    const ModChannel &c = m.ch[cidx];
+    if (c.w <= 0 || c.h <= 0) return;
+    bool uses_wp = tree_uses_wp;
+    const DTreeNode *t = tree;
+    if (ptree_cap > 0 && prune_tree(tree, cidx, sidx, ptree, ptree_cap, &uses_wp) > 0) t = ptree;
+    else uses_wp = tree_uses_wp;
+    if (uses_wp) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
+    else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
 }
 
 // ModularHeader as far as the device understands it (global tree only; RCT transforms only).

@@ -114,6 +114,7 @@ public:
                     gb.tok_first = tok_total; gb.tok_cap = cap;
                     tok_total += cap;
                     gb.lz = lz_coef ? wk_alloc(4u << 18) : (size_t) -1;
+                    gb.nonzeros = wk_alloc(3 * 1024);
                 }
                 im.tok_off = wk_alloc(sizeof(DToken) * std::max<size_t>(tok_total, 1));
                 n_lf += im.nlf; n_hf += im.ng;
@@ -218,6 +219,7 @@ public:
                     g.sec_off = (uint32_t) p.pg_sec[gi].off; g.sec_size = p.pg_sec[gi].size; g.sec_start_bit = p.pg_sec[gi].start_bit;
                     g.tok_first = (uint32_t) gb.tok_first; g.tok_cap = (uint32_t) gb.tok_cap;
                     g.lz_window = gb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + gb.lz);
+                    g.nonzeros = (int8_t *) (dwork + gb.nonzeros);
                     g.tok_used = 0;
                     HfWork &w = hfw[ihf];
                     w.f = dframe; w.arena = darena; w.cs = dcs;
@@ -345,7 +347,7 @@ public:
 
 private:
     struct LfBuf { int left, top, w, h, w8, h8, w64, h64; size_t lfq, lfdeq, lf, lfidx, xfromy, bfromy, blockinfo, sharp, blocks, varblocks, llf, wp, lz, vb_tok, llf_scratch; };
-    struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz; };
+    struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz, nonzeros; };
     struct ModBuf { int gw, gh; size_t wp, lz; uint32_t lz_mask; };
     struct Img {
         size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;

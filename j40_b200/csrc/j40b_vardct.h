@@ -127,6 +127,7 @@ struct DGroup {
     uint64_t sec_start_bit;
     uint32_t tok_first, tok_cap; // slice of the image's token array
     int32_t *lz_window;          // or null
+    int8_t *nonzeros;            // [3 * 1024] scratch of the coefficient decoder
     uint32_t tok_used;           // written by the kernel
 };
 
@@ -220,9 +221,10 @@ J40B_HD inline void place_varblocks(const DFrame &f, DLfGroup &g, ErrSlot &es, c
         vb.hfmul_inv = J40B_FDIV(1.0f, J40B_FADD((float) m1, 1.0f));
         vb.x8 = (uint16_t) x0; vb.y8 = (uint16_t) y0;
         vb.dctsel = (uint8_t) dctsel;
-        vb.pad = 0;
+        // bit 0: not handled by the tile kernel (larger than 64x64, or straddling a 64x64-pixel tile)
+        vb.pad = (uint16_t) ((d.log_columns + d.log_rows > 12 || (x0 & 7) + vw8 > 8 || (y0 & 7) + vh8 > 8) ? 1 : 0);
         g.varblocks[voff] = vb;
-        if (d.log_columns + d.log_rows > 12) g.has_big = 1;
+        if (vb.pad & 1) g.has_big = 1;
         coeffoff += 1 << (d.log_columns + d.log_rows);
         ++voff;
     }
@@ -546,72 +548,103 @@ J40B_HD inline void llf_from_lf(const DLfGroup &g, const DVarblock &vb, float *s
 // =============================================================================================
 // PassGroup: HF coefficient decoding into per-varblock token lists (serial; j40.h:6888-7004)
 
+// CoeffFreqContext / CoeffNumNonzeroContext of the format, pre-multiplied by 2 (j40.h:6935-6947)
+J40B_HD J40B_INLINE int coeff_freq_ctx2(int k) { // k in [1, 64)
+    return k < 16 ? 2 * (k - 1) : k < 32 ? 30 + 2 * ((k - 16) >> 1) : 46 + 2 * ((k - 32) >> 2);
+}
+J40B_HD J40B_INLINE int coeff_nnz_ctx2(int q) { // q in [0, 64)
+    return q < 2 ? 0 : q == 2 ? 62 : q < 5 ? 124 : q < 9 ? 186 : q < 13 ? 246 : q < 21 ? 304 : q < 33 ? 360 : 412;
+}
+
+// Written as a state machine with exactly one symbol read per loop iteration: several groups can then be
+// decoded by the lanes of one warp (one group per lane) and stay convergent at the symbol read, whatever
+// their position inside a block is. `nonzeros`: [gh8*gw8][3] bytes of per-group scratch.
 J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
                                      const DFrame &f, const uint8_t *arena, const DLfGroup &g, DGroup &grp,
-                                     int32_t ctxoff, DToken *tokens /* image token array */, int8_t *nonzeros /* [gh8*gw8][3] */) {
+                                     int32_t ctxoff, DToken *tokens /* image token array */, int8_t *nonzeros) {
     const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
     const int lfidx_size = (f.nb_lf_thr[0] + 1) * (f.nb_lf_thr[1] + 1) * (f.nb_lf_thr[2] + 1);
+    const int bctxc = 13 * (f.nb_qf_thr + 1) * lfidx_size;
     const uint8_t *block_ctx_map = arena + f.block_ctx_map_off;
     const int n8 = g.width8 * g.height8;
-    uint32_t tok = grp.tok_first, tok_end = grp.tok_first + grp.tok_cap;
-    const int8_t FREQ_CTX[64] = { // CoeffFreqContext, pre-multiplied by 2 (index 0 unused)
-        -1, 0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28,
-        30, 30, 32, 32, 34, 34, 36, 36, 38, 38, 40, 40, 42, 42, 44, 44,
-        46, 46, 46, 46, 48, 48, 48, 48, 50, 50, 50, 50, 52, 52, 52, 52,
-        54, 54, 54, 54, 56, 56, 56, 56, 58, 58, 58, 58, 60, 60, 60, 60,
-    };
-    const int16_t NNZ_CTX[64] = { // CoeffNumNonzeroContext, pre-multiplied by 2
-        0, 0, 62, 124, 124, 186, 186, 186, 186, 246, 246, 246, 246, 304, 304, 304,
-        304, 304, 304, 304, 304, 360, 360, 360, 360, 360, 360, 360, 360, 360, 360, 360,
-        360, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412,
-        412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412, 412,
-    };
-    for (int y8 = 0; y8 < gh8; ++y8) for (int x8 = 0; x8 < gw8; ++x8) {
-        int ggx8 = x8 + grp.gx8, ggy8 = y8 + grp.gy8, nzpos = y8 * gw8 + x8;
-        int32_t voff = g.blocks[ggy8 * g.width8 + ggx8], dctsel = voff >> 20;
-        if (dctsel < 2) continue;
-        dctsel -= 2;
-        voff &= 0xfffff;
-        DctSelectInfo d = dct_select_info(dctsel);
-        const int log_size = d.log_rows + d.log_columns;
-        const DVarblock &vb = g.varblocks[voff];
-        int lfidx = g.lfidx[ggy8 * g.width8 + ggx8];
-        int bctx0 = (d.order_idx * (f.nb_qf_thr + 1) + vb.qfidx) * lfidx_size + lfidx;
-        int bctxc = 13 * (f.nb_qf_thr + 1) * lfidx_size;
-        for (int c_yxb = 0; c_yxb < 3; ++c_yxb) {
-            const int c = c_yxb == 0 ? 1 : c_yxb == 1 ? 0 : 2;
-            const int32_t *order = f.order[d.order_idx][c];
-            int bctx = block_ctx_map[bctx0 + bctxc * c_yxb];
-            int nz = x8 > 0 ? (y8 > 0 ? (nonzeros[(nzpos - 1) * 3 + c] + nonzeros[(nzpos - gw8) * 3 + c] + 1) >> 1
-                                       : nonzeros[(nzpos - 1) * 3 + c])
-                            : (y8 > 0 ? nonzeros[(nzpos - gw8) * 3 + c] : 32);
-            int nzctx = ctxoff + bctx + (nz < 8 ? nz : 4 + nz / 2) * f.nb_block_ctx;
-            nz = code(br, es, cc, cs, nzctx, 0);
-            if (es.err) return;
-            if (!(nz <= (63 << (log_size - 6)))) { es.set(br, E_COEF); return; }
-            int qnz = ceil_div(nz, 1 << (log_size - 6));
-            for (int i = 0; i < (1 << (d.log_rows - 3)); ++i) for (int j = 0; j < (1 << (d.log_columns - 3)); ++j) {
-                nonzeros[(nzpos + i * gw8 + j) * 3 + c] = (int8_t) qnz;
-            }
-            int cctx = ctxoff + 458 * bctx + 37 * f.nb_block_ctx;
-            int prev = nz <= (1 << (log_size - 4));
-            uint32_t first = tok;
-            for (int i = 1 << (log_size - 6); nz > 0 && i < (1 << log_size); ++i) {
-                int ctx = cctx + NNZ_CTX[ceil_div(nz, 1 << (log_size - 6))] + FREQ_CTX[i >> (log_size - 6)] + prev;
-                int32_t ucoeff = code(br, es, cc, cs, ctx, 0);
-                if (es.err) return;
-                if (ucoeff) {
-                    if (tok >= tok_end) { es.set_raw(E_TOKV); return; }
-                    DToken t;
-                    t.pos = (uint32_t) order[i];
-                    t.val = unpack_signed(ucoeff);
-                    tokens[tok++] = t;
+    uint32_t tok = grp.tok_first;
+    const uint32_t tok_end = grp.tok_first + grp.tok_cap;
+    // scan position and per-block / per-channel state
+    int cell = -1;            // raster index of the current varblock's top-left cell inside the group
+    int c_yxb = 2;            // channel being decoded, in Y, X, B order
+    int nz = 0;               // non-zero coefficients still to come in this channel
+    int i = 0, size = 0, log_first = 0, prev = 0, cctx = 0, c = 0, bctx0 = 0, order_idx = 0, log_rows = 0, log_columns = 0;
+    int32_t voff = 0;
+    uint32_t first_tok = 0;
+    const int32_t *order = 0;
+    for (;;) {
+        int ctx;
+        const bool reading_nnz = nz == 0;
+        if (reading_nnz) {
+            // next channel, or the next varblock in raster order of top-left cells
+            if (++c_yxb == 3) {
+                c_yxb = 0;
+                int32_t b = 0;
+                for (++cell; cell < gw8 * gh8; ++cell) {
+                    int y8 = cell / gw8, x8 = cell - y8 * gw8;
+                    b = g.blocks[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
+                    if ((b >> 20) >= 2) break;
                 }
-                nz -= prev = (ucoeff != 0);
+                if (cell >= gw8 * gh8) break; // group finished
+                int dctsel = (b >> 20) - 2;
+                voff = b & 0xfffff;
+                DctSelectInfo d = dct_select_info(dctsel);
+                log_rows = d.log_rows; log_columns = d.log_columns; order_idx = d.order_idx;
+                size = 1 << (log_rows + log_columns);
+                log_first = log_rows + log_columns - 6;
+                int y8 = cell / gw8, x8 = cell - y8 * gw8;
+                int lfidx = g.lfidx[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
+                bctx0 = (order_idx * (f.nb_qf_thr + 1) + g.varblocks[voff].qfidx) * lfidx_size + lfidx;
             }
-            if (nz != 0) { es.set(br, E_COEF); return; }
-            g.vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first;
-            g.vb_tok[((size_t) c * n8 + voff) * 2 + 1] = tok - first;
+            c = c_yxb == 0 ? 1 : c_yxb == 1 ? 0 : 2;
+            order = f.order[order_idx][c];
+            const int bctx = block_ctx_map[bctx0 + bctxc * c_yxb];
+            const int y8 = cell / gw8, x8 = cell - y8 * gw8;
+            int pred = x8 > 0 ? (y8 > 0 ? (nonzeros[(cell - 1) * 3 + c] + nonzeros[(cell - gw8) * 3 + c] + 1) >> 1
+                                         : nonzeros[(cell - 1) * 3 + c])
+                              : (y8 > 0 ? nonzeros[(cell - gw8) * 3 + c] : 32);
+            ctx = ctxoff + bctx + (pred < 8 ? pred : 4 + pred / 2) * f.nb_block_ctx;
+            cctx = ctxoff + 458 * bctx + 37 * f.nb_block_ctx;
+        } else {
+            ctx = cctx + coeff_nnz_ctx2((nz + (1 << log_first) - 1) >> log_first) + coeff_freq_ctx2(i >> log_first) + prev;
+        }
+        // ---- the one symbol read of this iteration
+        const int32_t v = code(br, es, cc, cs, ctx, 0);
+        if (es.err) return;
+        if (reading_nnz) {
+            nz = v;
+            if (!(nz <= (63 << log_first))) { es.set(br, E_COEF); return; }
+            const int qnz = (nz + (1 << log_first) - 1) >> log_first;
+            for (int a = 0; a < (1 << (log_rows - 3)); ++a) for (int bb = 0; bb < (1 << (log_columns - 3)); ++bb) {
+                nonzeros[(cell + a * gw8 + bb) * 3 + c] = (int8_t) qnz;
+            }
+            prev = nz <= (size >> 4);
+            i = 1 << log_first;
+            first_tok = tok;
+            if (nz == 0) {
+                g.vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
+                g.vb_tok[((size_t) c * n8 + voff) * 2 + 1] = 0;
+            }
+        } else {
+            if (v) {
+                if (tok >= tok_end) { es.set_raw(E_TOKV); return; }
+                DToken t;
+                t.pos = (uint32_t) order[i];
+                t.val = unpack_signed(v);
+                tokens[tok++] = t;
+            }
+            prev = v != 0;
+            nz -= prev;
+            ++i;
+            if (nz == 0) {
+                g.vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
+                g.vb_tok[((size_t) c * n8 + voff) * 2 + 1] = tok - first_tok;
+            } else if (i >= size) { es.set(br, E_COEF); return; }
         }
     }
     grp.tok_used = tok - grp.tok_first;

@@ -20,23 +20,29 @@ struct HostEmuBackend {
     void dev_memset(void *d, int v, size_t n) { memset(d, v, n); }
     void sync() {}
     void launch_lf(const LfWork *w, int n) {
-        for (int i = 0; i < n; ++i) { LfShared sh; lf_group_body(w[i], sh, 0, 1, NoSync()); }
+        std::vector<uint8_t> copy(40 * 1024);
+        for (int i = 0; i < n; ++i) { SerialShared sh; lf_group_body(w[i], sh, (i & 1) ? copy.data() : nullptr, (uint32_t) copy.size(), 0, 1, NoSync()); }
     }
     void launch_hf(const HfWork *w, int n) {
-        std::vector<int8_t> nz(3 * 1024);
-        for (int i = 0; i < n; ++i) hf_group_body(w[i], nz.data());
+        std::vector<uint8_t> copy(40 * 1024);
+        for (int i = 0; i < n; ++i) {
+            // like the device kernel: every other "warp" gets a staged copy of the code spec tables
+            bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->coeff_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
+            hf_group_body(w[i], staged ? copy.data() : nullptr, w[i].arena);
+        }
     }
     void launch_back(const BackWork *w, int n) {
-        std::vector<float> smem(4 * 4096), big(4 * 65536);
+        std::vector<float> coef(3 * 4096), big(4 * 65536);
         for (int i = 0; i < n; ++i) {
+            for (int t = 0; t < 16; ++t) { TileShared ts; back_tile_body(w[i], t & 3, t >> 2, coef.data(), ts, 0, 1, NoSync()); }
             BackWork bw = w[i];
             bw.big_scratch = big.data();
-            back_body(bw, smem.data(), 0, 0, 1, NoSync());
-            back_body(bw, smem.data(), 1, 0, 1, NoSync());
+            back_generic_body(bw, 0, 1, NoSync());
         }
     }
     void launch_mod(ModWork *w, int n) {
-        for (int i = 0; i < n; ++i) { ModShared sh; modular_body(w[i], sh, 0, 1, NoSync()); }
+        std::vector<uint8_t> copy(40 * 1024);
+        for (int i = 0; i < n; ++i) { SerialShared sh; modular_body(w[i], sh, (i & 1) ? nullptr : copy.data(), (uint32_t) copy.size(), 0, 1, NoSync()); }
     }
     void launch_render(const RenderWork *w, int width, int height) {
         for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) render_px(*w, x, y);
