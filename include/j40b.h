@@ -52,6 +52,14 @@ float j40b_batch_kernel_ms(const j40b_batch *b, int which);
  * 3 compressed bytes, 4 pixels */
 int64_t j40b_batch_stat(const j40b_batch *b, int what);
 
+/* Timing several batches in flight at once (each batch owns a CUDA stream; decodes of different batches
+ * overlap, e.g. the latency-bound LF-group kernel of one with the HF/back kernels of another):
+ *   j40b_batch_mark(b0, 0); enqueue decodes on any batches; j40b_batch_join(b0, bi) for every other batch;
+ *   j40b_batch_mark(b0, 1); wait for all batches; j40b_batch_mark_ms(b0) = device time of the region. */
+int j40b_batch_mark(j40b_batch *b, int which);
+int j40b_batch_join(j40b_batch *b, j40b_batch *other);
+float j40b_batch_mark_ms(j40b_batch *b);
+
 /* 1 if a CUDA device is usable by this library, else 0 */
 int j40b_gpu_available(void);
 

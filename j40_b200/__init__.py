@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "j40b_batch_create", "j40b_batch_destroy", "j40b_batch_add", "j40b_batch_upload", "j40b_batch_decode",
     "j40b_batch_wait", "j40b_batch_count", "j40b_batch_error", "j40b_batch_info", "j40b_batch_device_pixels",
     "j40b_batch_read_pixels", "j40b_batch_last_decode_ms", "j40b_batch_kernel_ms", "j40b_batch_stat", "j40b_gpu_available",
+    "j40b_batch_mark", "j40b_batch_join", "j40b_batch_mark_ms",
 ]
 
 
@@ -95,6 +96,12 @@ def lib():
         L.j40b_batch_stat.restype = C.c_int64
         L.j40b_batch_stat.argtypes = [C.c_void_p, C.c_int]
         L.j40b_gpu_available.restype = C.c_int
+        L.j40b_batch_mark.restype = C.c_int
+        L.j40b_batch_mark.argtypes = [C.c_void_p, C.c_int]
+        L.j40b_batch_join.restype = C.c_int
+        L.j40b_batch_join.argtypes = [C.c_void_p, C.c_void_p]
+        L.j40b_batch_mark_ms.restype = C.c_float
+        L.j40b_batch_mark_ms.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -233,6 +240,15 @@ class Batch:
 
     def stat(self, what):
         return int(lib().j40b_batch_stat(self._h, what))
+
+    def mark(self, which):
+        lib().j40b_batch_mark(self._h, which)
+
+    def join(self, other):
+        lib().j40b_batch_join(self._h, other._h)
+
+    def mark_ms(self):
+        return float(lib().j40b_batch_mark_ms(self._h))
 
     def close(self):
         if self._h:

@@ -68,20 +68,24 @@ J40B_HD J40B_INLINE void idct_strided_dispatch(float *p, int stride, int log_n) 
 
 struct TileVb {
     int32_t voff;        // varblock index inside the LF group
-    uint16_t chunk_off;  // offset (floats) of this varblock's coefficients in each channel's 4096-float buffer
-    uint8_t dctsel, log_rows, log_cols;
-    uint8_t cx, cy;      // top-left cell inside the tile
-    uint8_t special;
-    float hfmul_inv, kx_hf, kb_hf;
     int32_t coeffoff;
+    uint16_t chunk_off;  // offset (floats) of this varblock's coefficients in each channel's 4096-float buffer
+    uint8_t dctsel, log_rows, log_cols, param_idx;
+    uint8_t cx, cy;      // top-left cell inside the tile
+    uint8_t special, pad;
+    float m[3];          // dequantisation multipliers mult[c] of j40__dequant_hf
+    float kx_hf, kb_hf;
 };
 
 struct TileShared {
     int32_t nvb;
     TileVb vb[64];
-    uint8_t cover[64];     // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
-    uint8_t chunk_vb[64];  // 64-float chunk -> index into vb[]
+    int32_t cell_voff[64];  // per cell: varblock index if the cell is a top-left handled here, else -1
+    uint8_t cell_size64[64];
+    uint8_t cover[64];      // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
+    uint8_t chunk_vb[64];   // 64-float chunk -> index into vb[]
     float thr[255];
+    uint8_t lut[1028];
 };
 
 // tile (tx, ty) of group w.grp; coef = 3 * 4096 floats of shared memory
@@ -96,38 +100,61 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     const int n8 = g.width8 * g.height8;
     float *coefx = coef, *coefy = coef + 4096, *coefb = coef + 8192;
 
-    // ---- 0. varblocks of this tile (thread 0), thresholds, zeroed coefficients
-    for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
-    for (int i = tid; i < 3 * 4096; i += nth) coef[i] = 0.0f;
-    if (tid == 0) {
-        int n = 0, off = 0;
-        for (int c = 0; c < 64; ++c) ts.cover[c] = 0xff;
-        for (int cy = 0; cy < 8; ++cy) for (int cx = 0; cx < 8; ++cx) {
-            int x8 = tx * 8 + cx, y8 = ty * 8 + cy;
-            if (x8 >= gw8 || y8 >= gh8) continue;
+    // ---- 0. which varblocks start in this tile (one cell per thread), thresholds, zeroed coefficients
+    for (int c = tid; c < 64; c += nth) {
+        int cx = c & 7, cy = c >> 3;
+        int x8 = tx * 8 + cx, y8 = ty * 8 + cy;
+        int32_t voff = -1;
+        int size64 = 0;
+        if (x8 < gw8 && y8 < gh8) {
             int32_t b = g.blocks[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
-            if ((b >> 20) < 2) continue;
-            int32_t voff = b & 0xfffff;
-            const DVarblock &vb = g.varblocks[voff];
-            if (vb.pad & 1) continue; // generic path
+            if ((b >> 20) >= 2 && !(g.varblocks[b & 0xfffff].pad & 1)) {
+                voff = b & 0xfffff;
+                DctSelectInfo d = dct_select_info((b >> 20) - 2);
+                size64 = 1 << (d.log_rows + d.log_columns - 6);
+            }
+        }
+        ts.cell_voff[c] = voff;
+        ts.cell_size64[c] = (uint8_t) size64;
+        ts.cover[c] = 0xff;
+    }
+    for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
+    for (int i = tid; i < 1028 / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
+    for (int i = tid; i < 3 * 4096; i += nth) coef[i] = 0.0f;
+    sync();
+    // ---- 0b. compact them in raster order (each top-left cell computes its own rank and chunk offset)
+    {
+        const float gs = J40B_FDIV(65536.0f, (float) f.global_scale);
+        for (int c = tid; c < 64; c += nth) {
+            if (c == 63) {
+                int n = 0;
+                for (int k = 0; k < 64; ++k) n += ts.cell_voff[k] >= 0;
+                ts.nvb = n;
+            }
+            const int32_t voff = ts.cell_voff[c];
+            if (voff < 0) continue;
+            int rank = 0, off64 = 0;
+            for (int k = 0; k < c; ++k) { rank += ts.cell_voff[k] >= 0; off64 += ts.cell_size64[k]; }
+            const DVarblock vb = g.varblocks[voff];
             DctSelectInfo d = dct_select_info(vb.dctsel);
-            TileVb &t = ts.vb[n];
+            TileVb &t = ts.vb[rank];
             t.voff = voff;
-            t.chunk_off = (uint16_t) off;
-            t.dctsel = vb.dctsel; t.log_rows = (uint8_t) d.log_rows; t.log_cols = (uint8_t) d.log_columns;
-            t.cx = (uint8_t) cx; t.cy = (uint8_t) cy;
-            t.special = is_special_8x8(vb.dctsel) ? 1 : 0;
-            t.hfmul_inv = vb.hfmul_inv;
             t.coeffoff = vb.coeffoff;
+            t.chunk_off = (uint16_t) (off64 * 64);
+            t.dctsel = vb.dctsel; t.log_rows = (uint8_t) d.log_rows; t.log_cols = (uint8_t) d.log_columns; t.param_idx = (uint8_t) d.param_idx;
+            t.cx = (uint8_t) (c & 7); t.cy = (uint8_t) (c >> 3);
+            t.special = is_special_8x8(vb.dctsel) ? 1 : 0;
+            t.pad = 0;
+            t.m[1] = J40B_FMUL(gs, vb.hfmul_inv);
+            t.m[0] = J40B_FMUL(t.m[1], f.x_qm_mult);
+            t.m[2] = J40B_FMUL(t.m[1], f.b_qm_mult);
             t.kx_hf = J40B_FADD(f.base_corr_x, J40B_FMUL(f.inv_colour_factor, (float) g.xfromy[(vb.y8 / 8) * g.width64 + (vb.x8 / 8)]));
             t.kb_hf = J40B_FADD(f.base_corr_b, J40B_FMUL(f.inv_colour_factor, (float) g.bfromy[(vb.y8 / 8) * g.width64 + (vb.x8 / 8)]));
-            int size = 1 << (d.log_rows + d.log_columns);
-            for (int k = 0; k < size / 64; ++k) ts.chunk_vb[off / 64 + k] = (uint8_t) n;
-            for (int i = 0; i < (1 << (d.log_rows - 3)); ++i) for (int j = 0; j < (1 << (d.log_columns - 3)); ++j) ts.cover[(cy + i) * 8 + cx + j] = (uint8_t) n;
-            off += size;
-            ++n;
+            for (int k = 0; k < ts.cell_size64[c]; ++k) ts.chunk_vb[off64 + k] = (uint8_t) rank;
+            for (int i = 0; i < (1 << (d.log_rows - 3)); ++i) for (int j = 0; j < (1 << (d.log_columns - 3)); ++j) {
+                ts.cover[((c >> 3) + i) * 8 + (c & 7) + j] = (uint8_t) rank;
+            }
         }
-        ts.nvb = n;
     }
     sync();
     const int nvb = ts.nvb;
@@ -152,22 +179,20 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
 
     // ---- 2. dequantise + chroma from luma (element-wise; j40.h:7078-7094, 7155-7175)
     {
-        const float gs = J40B_FDIV(65536.0f, (float) f.global_scale);
+        const float qb0 = f.quant_bias[0], qb1 = f.quant_bias[1], qb2 = f.quant_bias[2], qbn = f.quant_bias_num;
         int total = 0;
         { const TileVb &last = ts.vb[nvb - 1]; total = last.chunk_off + (1 << (last.log_rows + last.log_cols)); }
         for (int e = tid; e < total; e += nth) {
             const TileVb &t = ts.vb[ts.chunk_vb[e >> 6]];
             const int i = e - t.chunk_off;
-            const float *dq = f.dq[dct_select_info(t.dctsel).param_idx] + (size_t) i * 3;
-            float m1 = J40B_FMUL(gs, t.hfmul_inv);
-            float m0 = J40B_FMUL(m1, f.x_qm_mult), m2 = J40B_FMUL(m1, f.b_qm_mult);
+            const float *dq = f.dq[t.param_idx] + (size_t) i * 3;
             float vx = coefx[e], vy = coefy[e], vb_ = coefb[e];
-            vx = (-1.0f <= vx && vx <= 1.0f) ? J40B_FMUL(vx, f.quant_bias[0]) : J40B_FSUB(vx, J40B_FDIV(f.quant_bias_num, vx));
-            vy = (-1.0f <= vy && vy <= 1.0f) ? J40B_FMUL(vy, f.quant_bias[1]) : J40B_FSUB(vy, J40B_FDIV(f.quant_bias_num, vy));
-            vb_ = (-1.0f <= vb_ && vb_ <= 1.0f) ? J40B_FMUL(vb_, f.quant_bias[2]) : J40B_FSUB(vb_, J40B_FDIV(f.quant_bias_num, vb_));
-            vx = J40B_FMUL(vx, J40B_FDIV(m0, dq[0]));
-            vy = J40B_FMUL(vy, J40B_FDIV(m1, dq[1]));
-            vb_ = J40B_FMUL(vb_, J40B_FDIV(m2, dq[2]));
+            vx = (-1.0f <= vx && vx <= 1.0f) ? J40B_FMUL(vx, qb0) : J40B_FSUB(vx, J40B_FDIV(qbn, vx));
+            vy = (-1.0f <= vy && vy <= 1.0f) ? J40B_FMUL(vy, qb1) : J40B_FSUB(vy, J40B_FDIV(qbn, vy));
+            vb_ = (-1.0f <= vb_ && vb_ <= 1.0f) ? J40B_FMUL(vb_, qb2) : J40B_FSUB(vb_, J40B_FDIV(qbn, vb_));
+            vx = J40B_FMUL(vx, J40B_FDIV(t.m[0], dq[0]));
+            vy = J40B_FMUL(vy, J40B_FDIV(t.m[1], dq[1]));
+            vb_ = J40B_FMUL(vb_, J40B_FDIV(t.m[2], dq[2]));
             coefx[e] = J40B_FADD(vx, J40B_FMUL(vy, t.kx_hf));
             coefy[e] = vy;
             coefb[e] = J40B_FADD(vb_, J40B_FMUL(vy, t.kb_hf));
@@ -175,20 +200,23 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     }
     sync();
     // ---- 3. LLF corner from the LF image (j40.h:7158-7172)
-    for (int slot = tid; slot < nvb * 64; slot += nth) {
-        const TileVb &t = ts.vb[slot >> 6];
-        const int e = slot & 63;
-        const int lmin = t.log_rows < t.log_cols ? t.log_rows : t.log_cols, lmax = t.log_rows < t.log_cols ? t.log_cols : t.log_rows;
-        const int vh8 = 1 << (lmin - 3), vw8 = 1 << (lmax - 3);
-        if (e >= vh8 * vw8) continue;
-        int y = e / vw8, x = e - y * vw8;
-        int p = t.chunk_off + y * vw8 * 8 + x;
-        float l0 = g.llf[(size_t) 0 * n8 + (t.coeffoff >> 6) + e];
-        float l1 = g.llf[(size_t) 1 * n8 + (t.coeffoff >> 6) + e];
-        float l2 = g.llf[(size_t) 2 * n8 + (t.coeffoff >> 6) + e];
-        coefx[p] = J40B_FADD(l0, J40B_FMUL(l1, f.kx_lf));
-        coefy[p] = l1;
-        coefb[p] = J40B_FADD(l2, J40B_FMUL(l1, f.kb_lf));
+    {
+        const float kx_lf = f.kx_lf, kb_lf = f.kb_lf;
+        for (int slot = tid; slot < nvb * 64; slot += nth) {
+            const TileVb &t = ts.vb[slot >> 6];
+            const int e = slot & 63;
+            const int lmin = t.log_rows < t.log_cols ? t.log_rows : t.log_cols, lmax = t.log_rows < t.log_cols ? t.log_cols : t.log_rows;
+            const int vh8 = 1 << (lmin - 3), vw8 = 1 << (lmax - 3);
+            if (e >= vh8 * vw8) continue;
+            int y = e / vw8, x = e - y * vw8;
+            int p = t.chunk_off + y * vw8 * 8 + x;
+            float l0 = g.llf[(size_t) 0 * n8 + (t.coeffoff >> 6) + e];
+            float l1 = g.llf[(size_t) 1 * n8 + (t.coeffoff >> 6) + e];
+            float l2 = g.llf[(size_t) 2 * n8 + (t.coeffoff >> 6) + e];
+            coefx[p] = J40B_FADD(l0, J40B_FMUL(l1, kx_lf));
+            coefy[p] = l1;
+            coefb[p] = J40B_FADD(l2, J40B_FMUL(l1, kb_lf));
+        }
     }
     sync();
     // ---- 4. pass A: 1-D inverse DCTs along the horizontal frequency u; special 8x8 transforms whole
@@ -229,10 +257,17 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     sync();
     // ---- 6. XYB -> sRGB -> RGBA8 (j40.h:7208-7237, 7941-7952), one thread per pixel, row-major
     const int gx0 = g.left + (grp.gx8 + tx * 8) * 8, gy0 = g.top + (grp.gy8 + ty * 8) * 8;
+    const int fw = f.width, fh = f.height;
+    const float cb0 = f.cbrt_opsin_bias[0], cb1 = f.cbrt_opsin_bias[1], cb2 = f.cbrt_opsin_bias[2];
+    const float ob0 = f.opsin_bias[0], ob1 = f.opsin_bias[1], ob2 = f.opsin_bias[2], itscale = f.itscale;
+    float om[9];
+    for (int i = 0; i < 9; ++i) om[i] = f.opsin_inv_mat[i];
+    uint8_t *rgba = w.rgba;
+    const size_t rgba_stride = (size_t) w.rgba_stride;
     for (int pix = tid; pix < 4096; pix += nth) {
         const int py = pix >> 6, px = pix & 63;
         const int X = gx0 + px, Y = gy0 + py;
-        if (X >= f.width || Y >= f.height) continue;
+        if (X >= fw || Y >= fh) continue;
         const uint8_t vi = ts.cover[(py >> 3) * 8 + (px >> 3)];
         if (vi == 0xff) continue;
         const TileVb &t = ts.vb[vi];
@@ -241,19 +276,17 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         // special transforms and wide blocks end as [y][x]; square / tall DCT blocks as [x][y]
         const int idx = t.chunk_off + ((t.special || t.log_cols > t.log_rows) ? ly * C + lx : lx * R + ly);
         float sx = coefx[idx], sy = coefy[idx], sb = coefb[idx];
-        float p[3] = {J40B_FADD(sy, sx), J40B_FSUB(sy, sx), sb};
-        float lin[3];
-        for (int c = 0; c < 3; ++c) {
-            float pp = J40B_FSUB(p[c], f.cbrt_opsin_bias[c]);
-            lin[c] = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(pp, pp), pp), f.opsin_bias[c]), f.itscale);
-        }
+        float p0 = J40B_FSUB(J40B_FADD(sy, sx), cb0), p1 = J40B_FSUB(J40B_FSUB(sy, sx), cb1), p2 = J40B_FSUB(sb, cb2);
+        float l0 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p0, p0), p0), ob0), itscale);
+        float l1 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p1, p1), p1), ob1), itscale);
+        float l2 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p2, p2), p2), ob2), itscale);
         uint32_t out = 0xff000000u;
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float v = J40B_FADD(J40B_FADD(J40B_FMUL(lin[0], f.opsin_inv_mat[c * 3 + 0]), J40B_FMUL(lin[1], f.opsin_inv_mat[c * 3 + 1])),
-                                J40B_FMUL(lin[2], f.opsin_inv_mat[c * 3 + 2]));
-            out |= (uint32_t) srgb_u8_from_linear(ts.thr, v) << (8 * c);
+            float v = J40B_FADD(J40B_FADD(J40B_FMUL(l0, om[c * 3 + 0]), J40B_FMUL(l1, om[c * 3 + 1])), J40B_FMUL(l2, om[c * 3 + 2]));
+            out |= (uint32_t) srgb_u8_lut(ts.thr, ts.lut, v) << (8 * c);
         }
-        *(uint32_t *) (w.rgba + (size_t) Y * (size_t) w.rgba_stride + (size_t) X * 4) = out;
+        *(uint32_t *) (rgba + (size_t) Y * rgba_stride + (size_t) X * 4) = out;
     }
 }
 

@@ -34,18 +34,26 @@ __global__ void __launch_bounds__(128) k_lf_group(const LfWork *items) {
 // list is ordered image by image, so a warp's lanes nearly always share one image, whose coefficient code
 // spec (cluster map + alias tables / prefix LUTs) is staged in shared memory; lanes of another image (at
 // image boundaries) and specs that do not fit read the tables from global memory instead.
-__global__ void __launch_bounds__(32) k_hf_group(const HfWork *items, int n) {
+// `lanes` (<= 32) groups per warp: with small batches fewer lanes per warp give more warps (latency hiding)
+// and less divergence; the host picks it from the number of groups (CudaBackend::launch_hf).
+enum { HF_WARPS = 4 };
+__global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items, int n, int lanes) {
     extern __shared__ __align__(16) uint8_t spec_copy[];
-    const int first = (int) blockIdx.x * 32;
+    __shared__ uint16_t ctx_lut[128];
+    const int per_block = HF_WARPS * lanes;
+    const int first = (int) blockIdx.x * per_block;
     const HfWork &w0 = items[first];
-    const bool staged = stage_spec_blob(w0.arena, w0.f->coeff_spec_off, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, 32);
-    __syncwarp();
-    const int i = first + (int) threadIdx.x;
-    if (i < n) hf_group_body(items[i], staged ? spec_copy : nullptr, w0.arena);
+    const bool staged = stage_spec_blob(w0.arena, w0.f->coeff_spec_off, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, 32 * HF_WARPS);
+    if (threadIdx.x < 64) ctx_lut[threadIdx.x] = (uint16_t) coeff_nnz_ctx2((int) threadIdx.x);
+    else if (threadIdx.x < 128) ctx_lut[threadIdx.x] = (uint16_t) (threadIdx.x == 64 ? 0 : coeff_freq_ctx2((int) threadIdx.x - 64));
+    __syncthreads();
+    const int warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
+    const int i = first + warp * lanes + lane;
+    if (lane < lanes && i < n) hf_group_body(items[i], staged ? spec_copy : nullptr, w0.arena, ctx_lut);
 }
 
 // one block per 64x64-pixel tile of a group (blockIdx.y = tile index inside the 256x256 group)
-__global__ void __launch_bounds__(256, 2) k_back_tile(const BackWork *items) {
+__global__ void __launch_bounds__(256, 3) k_back_tile(const BackWork *items) {
     extern __shared__ __align__(16) float tile_coef[];
     __shared__ TileShared ts;
     back_tile_body(items[blockIdx.x], (int) (blockIdx.y & 3), (int) (blockIdx.y >> 2), tile_coef, ts, (int) threadIdx.x, (int) blockDim.x, BlockSync());
@@ -128,7 +136,12 @@ struct CudaBackend {
         ++launches;
     }
     void launch_hf(const HfWork *w, int n) {
-        k_hf_group<<<(n + 31) / 32, 32, SPEC_COPY_BYTES, stream>>>(w, n);
+        // lanes per warp: aim at ~8 warps per SM before filling warps completely
+        int lanes = (n + num_sms * 8 - 1) / (num_sms * 8);
+        lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
+        if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
+        const int per_block = HF_WARPS * lanes;
+        k_hf_group<<<(n + per_block - 1) / per_block, 32 * HF_WARPS, SPEC_COPY_BYTES, stream>>>(w, n, lanes);
         cudaEventRecord(ev[2], stream);
         ++launches;
     }
@@ -165,7 +178,7 @@ struct j40b_batch {
     Batch<CudaBackend> *batch = nullptr;
     std::vector<std::pair<const uint8_t *, size_t>> inputs;
     bool uploaded = false, decoded = false;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, m[2] = {nullptr, nullptr}, jev = nullptr;
     float last_ms = 0;
     int64_t last_launches = 0;
 };
@@ -190,6 +203,9 @@ EXPORT void j40b_batch_destroy(j40b_batch *b) {
     delete b->batch;
     if (b->t0) cudaEventDestroy(b->t0);
     if (b->t1) cudaEventDestroy(b->t1);
+    if (b->m[0]) cudaEventDestroy(b->m[0]);
+    if (b->m[1]) cudaEventDestroy(b->m[1]);
+    if (b->jev) cudaEventDestroy(b->jev);
     b->be.destroy();
     delete b;
 }
@@ -287,6 +303,32 @@ EXPORT int j40b_batch_read_pixels(j40b_batch *b, int i, void *dst) {
     return 0;
 }
 EXPORT float j40b_batch_last_decode_ms(const j40b_batch *b) { return b ? b->last_ms : 0.0f; }
+
+// Several batches (each with its own stream) can be in flight at once, e.g. to overlap the latency-bound
+// LF-group decode of one batch with the HF / back kernels of another. These three calls time such a
+// region on the device: mark(b, 0) ... enqueue on any batches ... join(b, other) for every other batch,
+// mark(b, 1); after the batches have been waited for, j40b_batch_mark_ms(b) is the elapsed device time.
+EXPORT int j40b_batch_mark(j40b_batch *b, int which) {
+    if (!b || which < 0 || which > 1) return -1;
+    cudaSetDevice(b->be.device);
+    if (!b->m[which]) cudaEventCreate(&b->m[which]);
+    return cudaEventRecord(b->m[which], b->be.stream) == cudaSuccess ? 0 : -1;
+}
+EXPORT int j40b_batch_join(j40b_batch *b, j40b_batch *other) {
+    if (!b || !other || b->be.device != other->be.device) return -1;
+    cudaSetDevice(b->be.device);
+    if (!other->jev) cudaEventCreateWithFlags(&other->jev, cudaEventDisableTiming);
+    cudaEventRecord(other->jev, other->be.stream);
+    return cudaStreamWaitEvent(b->be.stream, other->jev, 0) == cudaSuccess ? 0 : -1;
+}
+EXPORT float j40b_batch_mark_ms(j40b_batch *b) {
+    float ms = 0;
+    if (!b || !b->m[0] || !b->m[1]) return 0;
+    cudaSetDevice(b->be.device);
+    cudaEventSynchronize(b->m[1]);
+    cudaEventElapsedTime(&ms, b->m[0], b->m[1]);
+    return ms;
+}
 EXPORT float j40b_batch_kernel_ms(const j40b_batch *b, int which) { return b && which >= 0 && which < 6 ? b->be.kernel_ms[which] : 0.0f; }
 EXPORT int64_t j40b_batch_stat(const j40b_batch *b, int what) {
     if (!b) return 0;

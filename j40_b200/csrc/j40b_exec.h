@@ -208,7 +208,7 @@ J40B_HD inline void lf_group_body(const LfWork &w, SerialShared &sh, uint8_t *sp
 // One group per *thread*: the 32 lanes of a warp decode 32 groups side by side (the decoder is a state
 // machine with one symbol read per iteration, so the lanes reconverge at every read). `spec_copy` is an
 // optional shared-memory copy of the coefficient code spec of image `copy_arena` (null = none).
-J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, const uint8_t *copy_arena) {
+J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, const uint8_t *copy_arena, const uint16_t *ctx_lut) {
     if (*w.lf_err) return;
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
@@ -230,7 +230,7 @@ J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, con
         // contexts beyond the code spec: the reference reads out of bounds here; treat as corrupt
         es.set(br, E_COEF);
     } else {
-        hf_coeffs_tokens(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros);
+        hf_coeffs_tokens(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros, ctx_lut);
     }
     if (!es.err) {
         if (grp.sec_start_bit == ~0ull) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // single-section frame: real check

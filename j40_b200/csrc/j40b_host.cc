@@ -1440,6 +1440,11 @@ const GlobalTables &GlobalTables::get() {
         static const int8_t ORDER_LOG[13][2] = {{3, 3}, {3, 3}, {4, 4}, {5, 5}, {3, 4}, {3, 5}, {4, 5}, {6, 6}, {5, 6}, {7, 7}, {6, 7}, {8, 8}, {7, 8}};
         for (int i = 0; i < 13; ++i) t->order[i] = compute_natural_order(ORDER_LOG[i][0], ORDER_LOG[i][1]);
         compute_srgb_thresholds(8, t->srgb_thr);
+        for (int b = 0; b <= 1024; ++b) {
+            int n = 0;
+            while (n < 255 && t->srgb_thr[n] <= (float) b / 1024.0f) ++n;
+            t->srgb_lut[b] = (uint8_t) n;
+        }
         g = t;
     });
     return *g;

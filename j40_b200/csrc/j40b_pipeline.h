@@ -54,6 +54,7 @@ public:
         for (int i = 0; i < 17; ++i) gt_dq[i] = up_alloc(gt.dq[i].size() * 4);
         for (int i = 0; i < 13; ++i) gt_order[i] = up_alloc(gt.order[i].size() * 4);
         gt_thr = up_alloc(255 * 4);
+        size_t gt_lut = up_alloc(1028);
         size_t work = 0;                    // device-only area cursor (follows the upload blob)
         auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
         size_t n_lf = 0, n_hf = 0, n_mod = 0;
@@ -159,6 +160,7 @@ public:
         for (int i = 0; i < 17; ++i) memcpy(staging + gt_dq[i], gt.dq[i].data(), gt.dq[i].size() * 4);
         for (int i = 0; i < 13; ++i) memcpy(staging + gt_order[i], gt.order[i].data(), gt.order[i].size() * 4);
         memcpy(staging + gt_thr, gt.srgb_thr, 255 * 4);
+        memcpy(staging + gt_lut, gt.srgb_lut, 1028);
         LfWork *lfw = (LfWork *) (staging + lfw_off);
         HfWork *hfw = (HfWork *) (staging + hfw_off);
         BackWork *bkw = (BackWork *) (staging + bkw_off);
@@ -177,6 +179,7 @@ public:
                 d.order[i][c] = (const int32_t *) (p.custom_order_off[i][c] ? dev + im.arena_off + p.custom_order_off[i][c] : dev + gt_order[i]);
             }
             d.srgb_thr = (const float *) (dev + gt_thr);
+            d.srgb_lut = dev + gt_lut;
             memcpy(staging + im.frame_off, &d, sizeof(d));
             memcpy(staging + im.arena_off, p.arena.bytes.data(), p.arena.bytes.size());
             memcpy(staging + im.cs_off, p.cs, p.cs_size);

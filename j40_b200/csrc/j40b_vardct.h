@@ -78,6 +78,7 @@ struct DFrame {
     const float *dq[17];             // float[n][3] per parameter set
     const int32_t *order[13][3];     // int32_t[size] per order and channel
     const float *srgb_thr;           // float[255]: smallest v whose 8-bit output is >= k+1
+    const uint8_t *srgb_lut;         // uint8[1025]: number of thresholds <= b / 1024
     int32_t global_tree_uses_wp, have_global_tree;
     // modular frames
     int32_t num_channels, num_gm_channels, alpha_channel; // alpha_channel < 0: opaque
@@ -558,19 +559,26 @@ J40B_HD J40B_INLINE int coeff_nnz_ctx2(int q) { // q in [0, 64)
 
 // Written as a state machine with exactly one symbol read per loop iteration: several groups can then be
 // decoded by the lanes of one warp (one group per lane) and stay convergent at the symbol read, whatever
-// their position inside a block is. `nonzeros`: [gh8*gw8][3] bytes of per-group scratch.
+// their position inside a block is. `nonzeros`: [gh8*gw8][3] bytes of per-group scratch. `ctx_lut`: optional
+// 128-entry table (shared memory on the device): [q] = coeff_nnz_ctx2(q), [64 + k] = coeff_freq_ctx2(k).
 J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
                                      const DFrame &f, const uint8_t *arena, const DLfGroup &g, DGroup &grp,
-                                     int32_t ctxoff, DToken *tokens /* image token array */, int8_t *nonzeros) {
+                                     int32_t ctxoff, DToken *tokens /* image token array */, int8_t *nonzeros,
+                                     const uint16_t *ctx_lut) {
     const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
+    const int nb_block_ctx = f.nb_block_ctx, qf_count = f.nb_qf_thr + 1;
     const int lfidx_size = (f.nb_lf_thr[0] + 1) * (f.nb_lf_thr[1] + 1) * (f.nb_lf_thr[2] + 1);
-    const int bctxc = 13 * (f.nb_qf_thr + 1) * lfidx_size;
+    const int bctxc = 13 * qf_count * lfidx_size;
     const uint8_t *block_ctx_map = arena + f.block_ctx_map_off;
-    const int n8 = g.width8 * g.height8;
+    const int n8 = g.width8 * g.height8, w8 = g.width8;
+    const int32_t *blocks = g.blocks + grp.gy8 * w8 + grp.gx8;
+    const uint8_t *lfidx_map = g.lfidx + grp.gy8 * w8 + grp.gx8;
+    const DVarblock *varblocks = g.varblocks;
+    uint32_t *vb_tok = g.vb_tok;
     uint32_t tok = grp.tok_first;
     const uint32_t tok_end = grp.tok_first + grp.tok_cap;
     // scan position and per-block / per-channel state
-    int cell = -1;            // raster index of the current varblock's top-left cell inside the group
+    int x8 = -1, y8 = 0, cell = -1; // current varblock's top-left cell inside the group (cell = y8 * gw8 + x8)
     int c_yxb = 2;            // channel being decoded, in Y, X, B order
     int nz = 0;               // non-zero coefficients still to come in this channel
     int i = 0, size = 0, log_first = 0, prev = 0, cctx = 0, c = 0, bctx0 = 0, order_idx = 0, log_rows = 0, log_columns = 0;
@@ -585,33 +593,32 @@ J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &
             if (++c_yxb == 3) {
                 c_yxb = 0;
                 int32_t b = 0;
-                for (++cell; cell < gw8 * gh8; ++cell) {
-                    int y8 = cell / gw8, x8 = cell - y8 * gw8;
-                    b = g.blocks[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
+                for (;;) {
+                    ++cell;
+                    if (++x8 == gw8) { x8 = 0; ++y8; }
+                    if (y8 >= gh8) break;
+                    b = blocks[y8 * w8 + x8];
                     if ((b >> 20) >= 2) break;
                 }
-                if (cell >= gw8 * gh8) break; // group finished
-                int dctsel = (b >> 20) - 2;
+                if (y8 >= gh8) break; // group finished
                 voff = b & 0xfffff;
-                DctSelectInfo d = dct_select_info(dctsel);
+                DctSelectInfo d = dct_select_info((b >> 20) - 2);
                 log_rows = d.log_rows; log_columns = d.log_columns; order_idx = d.order_idx;
                 size = 1 << (log_rows + log_columns);
                 log_first = log_rows + log_columns - 6;
-                int y8 = cell / gw8, x8 = cell - y8 * gw8;
-                int lfidx = g.lfidx[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
-                bctx0 = (order_idx * (f.nb_qf_thr + 1) + g.varblocks[voff].qfidx) * lfidx_size + lfidx;
+                bctx0 = (order_idx * qf_count + varblocks[voff].qfidx) * lfidx_size + lfidx_map[y8 * w8 + x8];
             }
             c = c_yxb == 0 ? 1 : c_yxb == 1 ? 0 : 2;
             order = f.order[order_idx][c];
             const int bctx = block_ctx_map[bctx0 + bctxc * c_yxb];
-            const int y8 = cell / gw8, x8 = cell - y8 * gw8;
             int pred = x8 > 0 ? (y8 > 0 ? (nonzeros[(cell - 1) * 3 + c] + nonzeros[(cell - gw8) * 3 + c] + 1) >> 1
                                          : nonzeros[(cell - 1) * 3 + c])
                               : (y8 > 0 ? nonzeros[(cell - gw8) * 3 + c] : 32);
-            ctx = ctxoff + bctx + (pred < 8 ? pred : 4 + pred / 2) * f.nb_block_ctx;
-            cctx = ctxoff + 458 * bctx + 37 * f.nb_block_ctx;
+            ctx = ctxoff + bctx + (pred < 8 ? pred : 4 + pred / 2) * nb_block_ctx;
+            cctx = ctxoff + 458 * bctx + 37 * nb_block_ctx;
         } else {
-            ctx = cctx + coeff_nnz_ctx2((nz + (1 << log_first) - 1) >> log_first) + coeff_freq_ctx2(i >> log_first) + prev;
+            const int q = (nz + (1 << log_first) - 1) >> log_first, k = i >> log_first;
+            ctx = cctx + prev + (ctx_lut ? (int) ctx_lut[q] + (int) ctx_lut[64 + k] : coeff_nnz_ctx2(q) + coeff_freq_ctx2(k));
         }
         // ---- the one symbol read of this iteration
         const int32_t v = code(br, es, cc, cs, ctx, 0);
@@ -619,16 +626,20 @@ J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &
         if (reading_nnz) {
             nz = v;
             if (!(nz <= (63 << log_first))) { es.set(br, E_COEF); return; }
-            const int qnz = (nz + (1 << log_first) - 1) >> log_first;
-            for (int a = 0; a < (1 << (log_rows - 3)); ++a) for (int bb = 0; bb < (1 << (log_columns - 3)); ++bb) {
-                nonzeros[(cell + a * gw8 + bb) * 3 + c] = (int8_t) qnz;
+            const int8_t qnz = (int8_t) ((nz + (1 << log_first) - 1) >> log_first);
+            if (log_first == 0) {
+                nonzeros[cell * 3 + c] = qnz;
+            } else {
+                for (int a = 0; a < (1 << (log_rows - 3)); ++a) for (int bb = 0; bb < (1 << (log_columns - 3)); ++bb) {
+                    nonzeros[(cell + a * gw8 + bb) * 3 + c] = qnz;
+                }
             }
             prev = nz <= (size >> 4);
             i = 1 << log_first;
             first_tok = tok;
             if (nz == 0) {
-                g.vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
-                g.vb_tok[((size_t) c * n8 + voff) * 2 + 1] = 0;
+                vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
+                vb_tok[((size_t) c * n8 + voff) * 2 + 1] = 0;
             }
         } else {
             if (v) {
@@ -642,8 +653,8 @@ J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &
             nz -= prev;
             ++i;
             if (nz == 0) {
-                g.vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
-                g.vb_tok[((size_t) c * n8 + voff) * 2 + 1] = tok - first_tok;
+                vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
+                vb_tok[((size_t) c * n8 + voff) * 2 + 1] = tok - first_tok;
             } else if (i >= size) { es.set(br, E_COEF); return; }
         }
     }
@@ -662,6 +673,16 @@ J40B_HD J40B_INLINE int srgb_u8_from_linear(const float *thr, float v) {
         if (thr[mid] <= v) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// Same result through a 1025-entry start table: lut[b] = number of thresholds <= b / 1024 (b = floor(1024 v)
+// clamped to [0, 1024]), then at most a few steps up; used by the tile kernel
+J40B_HD J40B_INLINE int srgb_u8_lut(const float *thr, const uint8_t *lut, float v) {
+    if (!(v > 0.0f)) return 0; // thr[0] > 0; NaN also lands here (the reference's cast gives 0 after clamping)
+    int b = v >= 1.0f ? 1024 : (int) J40B_FMUL(v, 1024.0f);
+    int code = lut[b];
+    while (code < 255 && thr[code] <= v) ++code;
+    return code;
 }
 
 // Working buffers: coef[3] (X, Y, B) each `size` floats, scratch `size` floats; `size` = R*C.

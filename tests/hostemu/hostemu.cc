@@ -28,7 +28,9 @@ struct HostEmuBackend {
         for (int i = 0; i < n; ++i) {
             // like the device kernel: every other "warp" gets a staged copy of the code spec tables
             bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->coeff_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
-            hf_group_body(w[i], staged ? copy.data() : nullptr, w[i].arena);
+            uint16_t lut[128];
+            for (int k = 0; k < 64; ++k) { lut[k] = (uint16_t) coeff_nnz_ctx2(k); lut[64 + k] = (uint16_t) (k ? coeff_freq_ctx2(k) : 0); }
+            hf_group_body(w[i], staged ? copy.data() : nullptr, w[i].arena, (i & 2) ? lut : nullptr);
         }
     }
     void launch_back(const BackWork *w, int n) {
