@@ -23,11 +23,56 @@ struct BlockSync { __device__ void operator()() const { __syncthreads(); } };
 
 // dynamic shared memory of the serial-decoder kernels: a copy of the code spec's tables
 enum { SPEC_COPY_BYTES = 40 * 1024 };
+// widest channel the shared-memory row path of the serial decoders takes: LF groups are at most 256 cells
+// wide; modular groups at most 1024 pixels
+enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
 
-__global__ void __launch_bounds__(128) k_lf_group(const LfWork *items) {
-    __shared__ SerialShared sh;
-    extern __shared__ __align__(16) uint8_t spec_copy[];
-    lf_group_body(items[blockIdx.x], sh, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+// Serial modular decoders (LF image, HF metadata, modular groups): one *warp* per work item. Lane 0 runs
+// the decoder; the other lanes keep its per-sample working set (sample rows, weighted-predictor error rows,
+// reference-channel rows) in shared memory. The CTA's warps share one staged copy of the code spec (work
+// lists are ordered image by image, so they nearly always belong to the same image).
+struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
+
+__host__ __device__ inline size_t warp_slice_bytes(int cap) {
+    size_t n = sizeof(WarpScratch);
+    n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + MOD_STAGED_REFS * 2 * 2);
+    return (n + 15) & ~(size_t) 15;
+}
+
+__device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws) {
+    ws = (WarpScratch *) base;
+    ModSmem ms;
+    ms.wp = (int32_t *) (base + sizeof(WarpScratch));
+    ms.rows = (int16_t *) (ms.wp + (size_t) cap * 10);
+    ms.refs = ms.rows + (size_t) cap * 3;
+    ms.info = ws->info;
+    ms.cap = cap;
+    return ms;
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, int cap) {
+    __shared__ int32_t div24[64];
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warps = (int) blockDim.x >> 5, warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
+    const LfWork &w0 = items[(int) blockIdx.x * warps];
+    const bool staged = stage_spec_blob(w0.arena, w0.f->global_spec_off, smem, SPEC_COPY_BYTES, (int) threadIdx.x, (int) blockDim.x);
+    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
+    __syncthreads();
+    const int i = (int) blockIdx.x * warps + warp;
+    if (i >= n) return;
+    WarpScratch *ws;
+    ModSmem ms = carve_warp_slice(smem + SPEC_COPY_BYTES + (size_t) warp * warp_slice_bytes(cap), cap, ws);
+    if (STAGE == 1) lf_decode1_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
+    else lf_decode2_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
+}
+
+__global__ void __launch_bounds__(256) k_lf_post(const LfWork *items) {
+    lf_post_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+
+__global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
+    lf_llf_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
 }
 
 // HF coefficient entropy decode, SIMT: one warp per 32 consecutive groups (one group per lane). The work
@@ -70,11 +115,16 @@ __global__ void __launch_bounds__(256) k_back_generic(const BackWork *items, int
     }
 }
 
-__global__ void __launch_bounds__(32) k_modular(ModWork *items) {
-    __shared__ SerialShared sh;
-    extern __shared__ __align__(16) uint8_t spec_copy[];
-    struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
-    modular_body(items[blockIdx.x], sh, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, (int) blockDim.x, WarpSync());
+__global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap) {
+    __shared__ int32_t div24[64];
+    extern __shared__ __align__(16) uint8_t smem[];
+    ModWork &w = items[blockIdx.x];
+    const bool staged = stage_spec_blob(w.arena, w.f->global_spec_off, smem, SPEC_COPY_BYTES, (int) threadIdx.x, 32);
+    fill_div24(div24, (int) threadIdx.x, 32);
+    __syncwarp();
+    WarpScratch *ws;
+    ModSmem ms = carve_warp_slice(smem + SPEC_COPY_BYTES, cap, ws);
+    modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
 }
 
 __global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height) {
@@ -108,6 +158,10 @@ struct CudaBackend {
         if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
         if (!cuda_ok(cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4))) return false;
+        const int lf_smem = (int) (SPEC_COPY_BYTES + 4 * warp_slice_bytes(LF_ROW_CAP)), mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
+        if (!cuda_ok(cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem))) return false;
+        if (!cuda_ok(cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem))) return false;
+        if (!cuda_ok(cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem))) return false;
         ok = true;
         return true;
     }
@@ -130,10 +184,17 @@ struct CudaBackend {
     void sync() { cudaStreamSynchronize(stream); }
 
     void launch_lf(const LfWork *w, int n) {
+        int warps = 1;
+        if (const char *e = getenv("J40B_LF_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 4) warps = v; }
+        const size_t smem = SPEC_COPY_BYTES + (size_t) warps * warp_slice_bytes(LF_ROW_CAP);
+        const int blocks = (n + warps - 1) / warps;
         cudaEventRecord(ev[0], stream);
-        k_lf_group<<<n, 128, SPEC_COPY_BYTES, stream>>>(w);
+        k_lf_decode<1><<<blocks, 32 * warps, smem, stream>>>(w, n, LF_ROW_CAP);
+        k_lf_post<<<n, 256, 0, stream>>>(w);
+        k_lf_decode<2><<<blocks, 32 * warps, smem, stream>>>(w, n, LF_ROW_CAP);
+        k_lf_llf<<<n, 128, 0, stream>>>(w);
         cudaEventRecord(ev[1], stream);
-        ++launches;
+        launches += 4;
     }
     void launch_hf(const HfWork *w, int n) {
         // lanes per warp: aim at ~8 warps per SM before filling warps completely
@@ -160,7 +221,7 @@ struct CudaBackend {
         cudaEventRecord(ev[4], stream);
     }
     void launch_mod(ModWork *w, int n) {
-        k_modular<<<n, 32, SPEC_COPY_BYTES, stream>>>(w);
+        k_modular<<<n, 32, SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP), stream>>>(w, MOD_ROW_CAP);
         ++launches;
     }
     void launch_render(const RenderWork *w, int width, int height) {

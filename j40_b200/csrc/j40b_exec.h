@@ -1,13 +1,22 @@
-// j40-b200: kernel bodies. Each *_body function is what one CUDA thread block executes for one work
-// item; the __global__ wrappers live in j40b_cuda.cu. The CPU kernel-logic tests (tests/hostemu) call
-// the same bodies with nth = 1. Serial bitstream work is done by thread 0, everything else by all
-// threads, separated by `sync` (block barrier on the device).
+// j40-b200: kernel bodies. Each *_body function is what one CUDA warp or thread block executes for one
+// work item; the __global__ wrappers live in j40b_cuda.cu. The CPU kernel-logic tests (tests/hostemu) call
+// the same bodies with a single "thread" (lane 0 of 1 / tid 0 of 1).
+//
+// VarDCT frame, per step (all images of the batch in each launch):
+//   lf_decode1   warp per LF group   serial: LF image (3 modular channels)              [latency-bound]
+//   lf_post      block per LF group  parallel: inverse RCT, dequantise, LF indices, adaptive smoothing
+//   lf_decode2   warp per LF group   serial: HF metadata (4 modular channels) + varblock placement
+//   lf_llf       block per LF group  parallel: LLF coefficients (forward DCT of LF patches)
+//   hf_group     thread per group    serial per lane: HF coefficient entropy decode -> token lists
+//   back_tile    block per 64x64 tile  parallel: dequant, CfL, IDCT, XYB->sRGB, RGBA8 store
+//   back_generic persistent blocks   varblocks larger than 64x64 / straddling tiles
+// Modular frame: modular (warp per group) -> render (thread per pixel).
 #pragma once
 #include "j40b_vardct.h"
 
 namespace j40b {
 
-// one work item per thread block; all pointers are device pointers
+// one work item per LF group / group; all pointers are device pointers
 struct LfWork {
     const DFrame *f;
     const uint8_t *arena;   // per-image table arena
@@ -69,18 +78,16 @@ namespace j40b {
 
 enum { PTREE_CAP = 192 };
 
-// block-shared scratch of the serial decoders: pruned tree, WP divisor table, optional copy of the code
-// spec's tables (cluster map, alias / prefix LUTs) so that the symbol loop never leaves the SM
-struct SerialShared {
-    uint32_t err;
-    int32_t extra_prec;
-    int32_t div24[64];
+// per-warp scratch of the serial decoders (shared memory on the device)
+struct WarpScratch {
     DTreeNode ptree[PTREE_CAP];
     ModImage m;
+    int32_t info[4];
 };
 
 // cooperative staging of a code spec's blob into `dst` (cap bytes); returns true if it fits
 J40B_HD inline bool stage_spec_blob(const uint8_t *arena, uint32_t spec_off, uint8_t *dst, uint32_t cap, int tid, int nth) {
+    if (!spec_off) return false;
     const DCodeSpec *spec = (const DCodeSpec *) (arena + spec_off);
     uint32_t lo = spec->blob_lo, hi = spec->blob_hi;
     if (!dst || hi - lo > cap) return false;
@@ -90,30 +97,35 @@ J40B_HD inline bool stage_spec_blob(const uint8_t *arena, uint32_t spec_off, uin
     return true;
 }
 
+J40B_HD inline void fill_div24(int32_t *div24, int tid, int nth) {
+    for (int i = tid; i < 64; i += nth) div24[i] = (int32_t) (0x1000000u / (uint32_t) (i + 1));
+}
+
+J40B_HD inline void init_code_ctx(CodeCtx &cc, const uint8_t *arena, uint32_t spec_off, const uint8_t *spec_copy, const uint8_t *copy_arena) {
+    if (spec_copy && copy_arena == arena) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (arena + spec_off))->blob_lo, spec_off);
+    else cc.init(arena, spec_off);
+}
+
 // ---------------------------------------------------------------------------------------------
+// LF group, stage 1 (one warp): LfQuant, the 3-channel modular LF image (j40.h:6739-6757)
 template <class Sync>
-J40B_HD inline void lf_group_body(const LfWork &w, SerialShared &sh, uint8_t *spec_copy, uint32_t spec_copy_cap, int tid, int nth, Sync sync) {
+J40B_HD inline void lf_decode1_body(const LfWork &w, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
+                                    const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
     const int n8 = g.width8 * g.height8;
-    for (int i = tid; i < n8; i += nth) g.blocks[i] = 0;
-    for (int i = tid; i < 64; i += nth) sh.div24[i] = (int32_t) (0x1000000u / (uint32_t) (i + 1));
-    const bool staged = f.global_spec_off && stage_spec_blob(w.arena, f.global_spec_off, spec_copy, spec_copy_cap, tid, nth);
-    sync();
-    // thread-0 state that lives across the barriers
     BitReader br;
     ErrSlot es;
     CodeCtx cc;
     CodeState cs;
     es.err = 0;
+    br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
+    init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
+    cs.init(g.lz_window, (1u << 18) - 1);
     const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
-    if (tid == 0) {
-        sh.err = 0;
-        br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
-        if (staged) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (w.arena + f.global_spec_off))->blob_lo, f.global_spec_off);
-        else cc.init(w.arena, f.global_spec_off);
-        sh.extra_prec = (int32_t) br.u(2);
-        ModImage &m = sh.m;
+    ModImage &m = ws.m;
+    if (lane == 0) {
+        g.extra_prec = (int32_t) br.u(2);
         m.num_channels = 3;
         for (int c = 0; c < 3; ++c) {
             m.ch[c].px = g.lfq + (size_t) c * n8;
@@ -121,60 +133,105 @@ J40B_HD inline void lf_group_body(const LfWork &w, SerialShared &sh, uint8_t *sp
             m.ch[c].hshift = m.ch[c].vshift = 0;
         }
         modular_header(br, es, f.have_global_tree != 0, m);
-        if (!es.err) {
-            cs.init(g.lz_window, (1u << 18) - 1);
-            for (int c = 0; c < 3 && !es.err; ++c) {
-                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, sh.div24, sh.ptree, PTREE_CAP, m, c, 1 + g.idx);
-            }
-            if (!es.err) finish_code(br, es, cc, cs);
-        }
-        sh.err = es.err;
+        ws.info[3] = (int32_t) es.err;
     }
     sync();
-    if (sh.err) { if (tid == 0) *w.err = sh.err; return; }
-    for (int t = sh.m.nb_transforms - 1; t >= 0; --t) {
-        ModImage one = sh.m;
+    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    for (int c = 0; c < 3; ++c) {
+        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, 1 + g.idx, lane, nlanes, sync);
+        if (lane == 0) ws.info[3] = (int32_t) es.err;
+        sync();
+        if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    }
+    if (lane == 0) {
+        finish_code(br, es, cc, cs);
+        g.mid_bit = br.bits_consumed();
+        g.nb_tr1 = m.nb_transforms;
+        for (int t = 0; t < m.nb_transforms; ++t) g.tr1[t] = m.tr[t];
+        if (es.err) *w.err = es.err;
+    }
+}
+
+// LF group, stage 2 (one block): inverse transforms, dequantisation, LF indices, smoothing (j40.h:6544-6583)
+template <class Sync>
+J40B_HD inline void lf_post_body(const LfWork &w, int tid, int nth, Sync sync) {
+    if (*w.err) return;
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    const int n8 = g.width8 * g.height8;
+    for (int i = tid; i < n8; i += nth) g.blocks[i] = 0;
+    for (int t = g.nb_tr1 - 1; t >= 0; --t) {
+        ModImage one;
+        one.num_channels = 3;
+        for (int c = 0; c < 3; ++c) {
+            one.ch[c].px = g.lfq + (size_t) c * n8;
+            one.ch[c].stride = g.width8; one.ch[c].w = g.width8; one.ch[c].h = g.height8;
+            one.ch[c].hshift = one.ch[c].vshift = 0;
+        }
         one.nb_transforms = 1;
-        one.tr[0] = sh.m.tr[t];
+        one.tr[0] = g.tr1[t];
         inverse_transforms(one, tid, nth);
         sync();
     }
-    lf_dequant(f, g, sh.extra_prec, tid, nth);
+    lf_dequant(f, g, g.extra_prec, tid, nth);
     sync();
-    if (!f.skip_adapt_lf_smooth) { lf_smooth(f, g, tid, nth); sync(); }
-    if (tid == 0) {
+    if (!f.skip_adapt_lf_smooth) lf_smooth(f, g, tid, nth);
+}
+
+// LF group, stage 3 (one warp): HF metadata image + varblock placement (j40.h:6766-6777, 6585-6720)
+template <class Sync>
+J40B_HD inline void lf_decode2_body(const LfWork &w, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
+                                    const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
+    if (*w.err) return;
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    const int n8 = g.width8 * g.height8;
+    BitReader br;
+    ErrSlot es;
+    CodeCtx cc;
+    CodeState cs;
+    es.err = 0;
+    br.init(w.cs + g.sec_off, g.sec_size, g.mid_bit);
+    init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
+    cs.init(g.lz_window, (1u << 18) - 1);
+    const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+    ModImage &m = ws.m;
+    if (lane == 0) {
         int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
         g.nb_varblocks = nvb;
-        if (!es.err) {
-            ModImage &m = sh.m;
-            m.num_channels = 4;
-            m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
-            m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
-            m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
-            m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
-            for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
-            modular_header(br, es, f.have_global_tree != 0, m);
-            if (!es.err) {
-                cs.init(g.lz_window, (1u << 18) - 1);
-                for (int c = 0; c < 4 && !es.err; ++c) {
-                    modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, sh.div24, sh.ptree, PTREE_CAP, m, c,
-                                    1 + 2 * f.num_lf_groups + g.idx);
-                }
-                if (!es.err) finish_code(br, es, cc, cs);
-            }
-        }
-        sh.err = es.err;
+        m.num_channels = 4;
+        m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
+        m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
+        m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
+        m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
+        for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
+        modular_header(br, es, f.have_global_tree != 0, m);
+        ws.info[3] = (int32_t) es.err;
     }
     sync();
-    if (sh.err) { if (tid == 0) *w.err = sh.err; return; }
-    for (int t = sh.m.nb_transforms - 1; t >= 0; --t) {
-        ModImage one = sh.m;
+    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    for (int c = 0; c < 4; ++c) {
+        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c,
+                             1 + 2 * f.num_lf_groups + g.idx, lane, nlanes, sync);
+        if (lane == 0) ws.info[3] = (int32_t) es.err;
+        sync();
+        if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    }
+    if (lane == 0) {
+        finish_code(br, es, cc, cs);
+        ws.info[3] = (int32_t) es.err;
+    }
+    sync();
+    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    // inverse transforms (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide)
+    for (int t = m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = m;
         one.nb_transforms = 1;
-        one.tr[0] = sh.m.tr[t];
-        inverse_transforms(one, tid, nth);
+        one.tr[0] = m.tr[t];
+        inverse_transforms(one, lane, nlanes);
         sync();
     }
-    if (tid == 0) {
+    if (lane == 0) {
         place_varblocks(f, g, es, br);
         if (!es.err) {
             // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
@@ -182,11 +239,15 @@ J40B_HD inline void lf_group_body(const LfWork &w, SerialShared &sh, uint8_t *sp
             if (br.overrun()) es.set_raw(E_SHRT);
             g.end_bit = br.bits_consumed();
         }
-        sh.err = es.err;
+        if (es.err) *w.err = es.err;
     }
-    sync();
-    if (sh.err) { if (tid == 0) *w.err = sh.err; return; }
-    // LLF coefficients: one thread per varblock for patches up to 8x8 cells, the rest by thread 0
+}
+
+// LF group, stage 4 (one block): LLF coefficients of every varblock (j40.h:6669-6683)
+template <class Sync>
+J40B_HD inline void lf_llf_body(const LfWork &w, int tid, int nth, Sync sync) {
+    if (*w.err) return;
+    DLfGroup &g = *w.g;
     for (int v = tid; v < g.nb_varblocks; v += nth) {
         const DVarblock &vb = g.varblocks[v];
         DctSelectInfo d = dct_select_info(vb.dctsel);
@@ -205,7 +266,7 @@ J40B_HD inline void lf_group_body(const LfWork &w, SerialShared &sh, uint8_t *sp
 }
 
 // ---------------------------------------------------------------------------------------------
-// One group per *thread*: the 32 lanes of a warp decode 32 groups side by side (the decoder is a state
+// One group per *thread*: the lanes of a warp decode several groups side by side (the decoder is a state
 // machine with one symbol read per iteration, so the lanes reconverge at every read). `spec_copy` is an
 // optional shared-memory copy of the coefficient code spec of image `copy_arena` (null = none).
 J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, const uint8_t *copy_arena, const uint16_t *ctx_lut) {
@@ -220,8 +281,7 @@ J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, con
     uint64_t start_bit = grp.sec_start_bit == ~0ull ? g.end_bit : grp.sec_start_bit;
     br.init(w.cs + grp.sec_off, grp.sec_size, start_bit);
     CodeCtx cc;
-    if (spec_copy && copy_arena == w.arena) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (w.arena + f.coeff_spec_off))->blob_lo, f.coeff_spec_off);
-    else cc.init(w.arena, f.coeff_spec_off);
+    init_code_ctx(cc, w.arena, f.coeff_spec_off, spec_copy, copy_arena);
     CodeState cs;
     cs.init(grp.lz_window, (1u << 18) - 1);
     int32_t preset = (int32_t) br.u(ceil_lg32((uint32_t) f.num_hf_presets));
@@ -234,7 +294,7 @@ J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, con
     }
     if (!es.err) {
         if (grp.sec_start_bit == ~0ull) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // single-section frame: real check
-        else if (br.overrun()) es.set_raw(E_SHRT); // see lf_group_body
+        else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
     }
     if (es.err) *w.err = es.err;
 }
@@ -263,45 +323,50 @@ J40B_HD inline void back_generic_body(const BackWork &w, int tid, int nth, Sync 
 }
 
 // ---------------------------------------------------------------------------------------------
+// one warp per modular sub-bitstream
 template <class Sync>
-J40B_HD inline void modular_body(ModWork &w, SerialShared &sh, uint8_t *spec_copy, uint32_t spec_copy_cap, int tid, int nth, Sync sync) {
+J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
+                                 const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
     const DFrame &f = *w.f;
-    for (int i = tid; i < 64; i += nth) sh.div24[i] = (int32_t) (0x1000000u / (uint32_t) (i + 1));
-    const bool staged = f.global_spec_off && stage_spec_blob(w.arena, f.global_spec_off, spec_copy, spec_copy_cap, tid, nth);
+    BitReader br;
+    ErrSlot es;
+    CodeCtx cc;
+    CodeState cs;
+    es.err = 0;
+    br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
+    init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
+    cs.init(w.lz_window, w.lz_mask);
+    const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+    ModImage &m = ws.m;
+    if (lane == 0) {
+        m = w.m;
+        if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, m);
+        ws.info[3] = (int32_t) es.err;
+    }
     sync();
-    if (tid == 0) {
-        BitReader br;
-        ErrSlot es;
-        es.err = 0;
-        br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
-        CodeCtx cc;
-        if (staged) cc.init_from_copy(spec_copy, ((const DCodeSpec *) (w.arena + f.global_spec_off))->blob_lo, f.global_spec_off);
-        else cc.init(w.arena, f.global_spec_off);
-        CodeState cs;
-        sh.m = w.m;
-        if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, sh.m);
-        if (!es.err) {
-            cs.init(w.lz_window, w.lz_mask);
-            const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
-            for (int c = 0; c < sh.m.num_channels && !es.err; ++c) {
-                modular_channel(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, sh.div24, sh.ptree, PTREE_CAP, sh.m, c, w.sidx);
-            }
-            if (!es.err) finish_code(br, es, cc, cs);
-        }
+    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    for (int c = 0; c < m.num_channels; ++c) {
+        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, w.sidx, lane, nlanes, sync);
+        if (lane == 0) ws.info[3] = (int32_t) es.err;
+        sync();
+        if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    }
+    if (lane == 0) {
+        finish_code(br, es, cc, cs);
         if (!es.err) {
             if (w.header_parsed) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
-            else if (br.overrun()) es.set_raw(E_SHRT); // see lf_group_body
+            else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
         }
-        sh.err = es.err;
+        ws.info[3] = (int32_t) es.err;
         if (es.err) *w.err = es.err;
     }
     sync();
-    if (sh.err || w.header_parsed) return; // global transforms are applied by the render step
-    for (int t = sh.m.nb_transforms - 1; t >= 0; --t) {
-        ModImage one = sh.m;
+    if (ws.info[3] || w.header_parsed) return; // global transforms are applied by the render step
+    for (int t = m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = m;
         one.nb_transforms = 1;
-        one.tr[0] = sh.m.tr[t];
-        inverse_transforms(one, tid, nth);
+        one.tr[0] = m.tr[t];
+        inverse_transforms(one, lane, nlanes);
         sync();
     }
 }

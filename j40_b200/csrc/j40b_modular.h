@@ -263,6 +263,199 @@ J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &c
     else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative variant: lane 0 is the (inherently serial) decoder, the other lanes keep everything it
+// touches per sample in shared memory: a ring of the last three sample rows, the weighted predictor's two
+// error rows, and the current / previous row of up to two reference channels (properties >= 16). The
+// per-sample dependency chain then never leaves the SM. Same arithmetic as modular_channel_t.
+enum { MOD_STAGED_REFS = 2 };
+struct ModSmem {
+    int16_t *rows;   // [3][cap]
+    int32_t *wp;     // [2][cap][5]
+    int16_t *refs;   // [MOD_STAGED_REFS][2][cap]
+    int32_t *info;   // [4]: uses_wp, refs staged, use row path, abort
+    int32_t cap;     // widest channel the row path can take
+};
+
+template <bool USE_WP, class Sync>
+J40B_HD inline void modular_channel_rows(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                         const DTreeNode *tree, const ModSmem &ms, const int32_t *div24,
+                                         const ModImage &m, int32_t cidx, int32_t sidx, int nstaged,
+                                         int lane, int nlanes, Sync sync) {
+    const ModChannel &c = m.ch[cidx];
+    const int32_t width = c.w, height = c.h, stride = c.stride, cap = ms.cap;
+    const int32_t dist_mult = m.dist_mult;
+    const WPParams wpp = m.wp;
+    WPState wp;
+    wp.errors = ms.wp;
+    wp.width = width;
+    for (int i = 0; i < 5; ++i) wp.pred[i] = 0;
+    wp.trueerrw = wp.trueerrn = wp.trueerrnw = wp.trueerrne = 0;
+    int32_t refcmap[MOD_MAX_CH], nref = 0;
+    for (int32_t i = cidx - 1; i >= 0; --i) {
+        const ModChannel &r = m.ch[i];
+        if (c.w != r.w || c.h != r.h || c.hshift != r.hshift || c.vshift != r.vshift) continue;
+        refcmap[nref++] = i;
+    }
+    if (nstaged > nref) nstaged = nref;
+    if (USE_WP) for (int32_t i = lane; i < width * 2 * 5; i += nlanes) ms.wp[i] = 0;
+    for (int32_t y = 0; y < height; ++y) {
+        // all lanes: row y of the staged reference channels (row y-1 is still there from the last round)
+        for (int r = 0; r < nstaged; ++r) {
+            const ModChannel &rc = m.ch[refcmap[r]];
+            const int16_t *src = rc.px + (size_t) y * (size_t) rc.stride;
+            int16_t *dst = ms.refs + (size_t) (r * 2 + (y & 1)) * cap;
+            for (int32_t x = lane; x < width; x += nlanes) dst[x] = src[x];
+        }
+        sync();
+        if (lane == 0) {
+            int16_t *row = c.px + (size_t) y * (size_t) stride;
+            int16_t *cur = ms.rows + (size_t) (y % 3) * cap;
+            const int16_t *nrow = ms.rows + (size_t) ((y + 2) % 3) * cap, *nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
+            int32_t prev = 0, prev2 = 0;
+            for (int32_t x = 0; x < width; ++x) {
+                int32_t pw = x > 0 ? prev : y > 0 ? nrow[x] : 0;
+                int32_t pn = y > 0 ? nrow[x] : pw;
+                int32_t pnw = x > 0 && y > 0 ? nrow[x - 1] : pw;
+                int32_t pne = x + 1 < width && y > 0 ? nrow[x + 1] : pn;
+                int32_t pnn = y > 1 ? nnrow[x] : pn;
+                int32_t pnee = x + 2 < width && y > 0 ? nrow[x + 2] : pne;
+                int32_t pww = x > 1 ? prev2 : pw;
+                int32_t pnww = x > 1 && y > 0 ? nrow[x - 2] : pww;
+                if (USE_WP) wp_before_predict(wp, wpp, div24, x, y, pw, pn, pnw, pne, pnn);
+
+                const DTreeNode *n = tree;
+                while (n->a < 0) {
+                    int32_t prop = -1 - n->a, val;
+                    switch (prop) {
+                    case 0: val = cidx; break;
+                    case 1: val = sidx; break;
+                    case 2: val = y; break;
+                    case 3: val = x; break;
+                    case 4: val = iabs(pn); break;
+                    case 5: val = iabs(pw); break;
+                    case 6: val = pn; break;
+                    case 7: val = pw; break;
+                    case 8: val = x > 0 ? pw - (pww + pnw - pnww) : pw; break;
+                    case 9: val = pw + pn - pnw; break;
+                    case 10: val = pw - pnw; break;
+                    case 11: val = pnw - pn; break;
+                    case 12: val = pn - pne; break;
+                    case 13: val = pn - pnn; break;
+                    case 14: val = pw - pww; break;
+                    case 15:
+                        val = wp.trueerrw;
+                        if (iabs(val) < iabs(wp.trueerrn)) val = wp.trueerrn;
+                        if (iabs(val) < iabs(wp.trueerrnw)) val = wp.trueerrnw;
+                        if (iabs(val) < iabs(wp.trueerrne)) val = wp.trueerrne;
+                        break;
+                    default: {
+                        int32_t refcidx = (prop - 16) / 4;
+                        if (refcidx >= nref) { es.set(br, E_TREC); break; }
+                        int32_t rw, rn, rnw;
+                        if (refcidx < nstaged) {
+                            const int16_t *ry = ms.refs + (size_t) (refcidx * 2 + (y & 1)) * cap;
+                            const int16_t *rp = ms.refs + (size_t) (refcidx * 2 + ((y & 1) ^ 1)) * cap;
+                            val = ry[x];
+                            rw = x > 0 ? ry[x - 1] : 0;
+                            rn = y > 0 ? rp[x] : rw;
+                            rnw = x > 0 && y > 0 ? rp[x - 1] : rw;
+                        } else {
+                            const ModChannel &r = m.ch[refcmap[refcidx]];
+                            const int16_t *rp = r.px + (size_t) y * (size_t) r.stride + x;
+                            val = rp[0];
+                            rw = x > 0 ? rp[-1] : 0;
+                            rn = y > 0 ? rp[-r.stride] : rw;
+                            rnw = x > 0 && y > 0 ? rp[-1 - r.stride] : rw;
+                        }
+                        if (prop & 2) val -= mod_gradient(rw, rn, rnw);
+                        if (prop & 1) val = iabs(val);
+                        break;
+                    }
+                    }
+                    if (es.err) break;
+                    n = tree + (val > n->b ? n->c : n->d);
+                }
+                if (es.err) break;
+
+                int32_t val = code(br, es, cc, cs, n->a, dist_mult);
+                val = unpack_signed(val) * n->d + n->c;
+                int32_t pred = 0;
+                switch (n->b) {
+                case 0: pred = 0; break;
+                case 1: pred = pw; break;
+                case 2: pred = pn; break;
+                case 3: pred = (pw + pn) / 2; break;
+                case 4: pred = iabs(pn - pnw) < iabs(pw - pnw) ? pw : pn; break;
+                case 5: pred = mod_gradient(pw, pn, pnw); break;
+                case 6: pred = (wp.pred[4] + 3) >> 3; break;
+                case 7: pred = pne; break;
+                case 8: pred = pnw; break;
+                case 9: pred = pww; break;
+                case 10: pred = (pw + pnw) / 2; break;
+                case 11: pred = (pn + pnw) / 2; break;
+                case 12: pred = (pn + pne) / 2; break;
+                case 13: pred = (6 * pn - 2 * pnn + 7 * pw + pww + pnee + 3 * pne + 8) / 16; break;
+                default: es.set(br, E_PRED); break;
+                }
+                val += pred;
+                if (es.err) break;
+                if (val < -32768 || val > 32767) { es.set(br, E_POVF); break; }
+                row[x] = (int16_t) val;
+                cur[x] = (int16_t) val;
+                prev2 = prev;
+                prev = val;
+                if (USE_WP) wp_after_predict(wp, x, y, val);
+            }
+            ms.info[3] = es.err ? 1 : 0;
+        }
+        sync();
+        if (ms.info[3]) return;
+    }
+}
+
+// Entry point for a warp: decides (lane 0) between the row path above and the plain path, then all lanes
+// follow. Every lane must call this with the same arguments; only lane 0's br / es / cs are meaningful.
+template <class Sync>
+J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                         const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch, const int32_t *div24,
+                                         DTreeNode *ptree, int ptree_cap, const ModSmem &ms,
+                                         const ModImage &m, int32_t cidx, int32_t sidx, int lane, int nlanes, Sync sync) {
+    const ModChannel &c = m.ch[cidx];
+    if (c.w <= 0 || c.h <= 0) return;
+    if (lane == 0) {
+        bool uses_wp = tree_uses_wp;
+        int n = ptree_cap > 0 ? prune_tree(tree, cidx, sidx, ptree, ptree_cap, &uses_wp) : 0;
+        if (n == 0) uses_wp = tree_uses_wp;
+        int maxprop = 0;
+        const DTreeNode *t = n ? ptree : tree;
+        if (n) for (int i = 0; i < n; ++i) { if (t[i].a < 0 && -1 - t[i].a > maxprop) maxprop = -1 - t[i].a; }
+        else maxprop = 16 + 4 * MOD_STAGED_REFS - 1; // unknown: stage what we can
+        int want = maxprop >= 16 ? (maxprop - 16) / 4 + 1 : 0;
+        ms.info[0] = uses_wp;
+        ms.info[1] = want < MOD_STAGED_REFS ? want : MOD_STAGED_REFS;
+        ms.info[2] = (ms.rows && c.w <= ms.cap && n > 0) ? 1 : 0;
+        ms.info[3] = 0;
+    }
+    sync();
+    const bool uses_wp = ms.info[0] != 0;
+    const int nstaged = ms.info[1];
+    if (ms.info[2]) {
+        if (uses_wp) modular_channel_rows<true>(br, es, cc, cs, ptree, ms, div24, m, cidx, sidx, nstaged, lane, nlanes, sync);
+        else modular_channel_rows<false>(br, es, cc, cs, ptree, ms, div24, m, cidx, sidx, nstaged, lane, nlanes, sync);
+    } else {
+        if (lane == 0) {
+            // wide channels (or trees too large to prune into shared memory): plain path through global memory
+            const DTreeNode *t = tree;
+            bool wpf = tree_uses_wp;
+            if (ptree_cap > 0 && prune_tree(tree, cidx, sidx, ptree, ptree_cap, &wpf) > 0) t = ptree; else wpf = tree_uses_wp;
+            if (wpf) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
+            else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
+        }
+        sync();
+    }
+}
+
 // ModularHeader as far as the device understands it (global tree only; RCT transforms only).
 // Mirrors the checks of j40.h:3729-3759, 3816.
 J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_tree, ModImage &m) {

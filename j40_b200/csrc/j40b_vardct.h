@@ -116,6 +116,11 @@ struct DLfGroup {
     int32_t has_big;      // written by the kernel: some varblock is larger than 64x64
     uint64_t end_bit;     // written by the kernel (single-section frames continue from here)
     uint32_t *vb_tok;     // [3][h8*w8][2] {first token, count}, written by the pass-group kernel
+    // hand-over between the LF kernels (decode LF image -> post-process -> decode HF metadata -> LLF)
+    uint64_t mid_bit;     // bit position after the LF image
+    int32_t extra_prec;
+    int32_t nb_tr1, nb_tr2;               // transforms of the LF image / of the HF metadata image
+    ModTransform tr1[MOD_MAX_TRANSFORMS], tr2[MOD_MAX_TRANSFORMS];
 };
 
 struct DToken { uint32_t pos; int32_t val; };

@@ -19,9 +19,31 @@ struct HostEmuBackend {
     void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void dev_memset(void *d, int v, size_t n) { memset(d, v, n); }
     void sync() {}
+    // shared memory of one warp of the serial decoders
+    struct WarpMem {
+        WarpScratch ws;
+        std::vector<int32_t> wp;
+        std::vector<int16_t> rows, refs;
+        int32_t div24[64];
+        ModSmem ms;
+        explicit WarpMem(int cap) : wp((size_t) cap * 10 + 1), rows((size_t) cap * 3 + 1), refs((size_t) cap * MOD_STAGED_REFS * 2 + 1) {
+            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refs = refs.data(); ms.info = ws.info; ms.cap = cap;
+            fill_div24(div24, 0, 1);
+        }
+    };
+    // HOSTEMU_ROW_CAP overrides the row-path width limit (0 = always take the plain path)
+    static int row_cap(int dflt) { const char *e = getenv("HOSTEMU_ROW_CAP"); return e ? atoi(e) : dflt; }
     void launch_lf(const LfWork *w, int n) {
         std::vector<uint8_t> copy(40 * 1024);
-        for (int i = 0; i < n; ++i) { SerialShared sh; lf_group_body(w[i], sh, (i & 1) ? copy.data() : nullptr, (uint32_t) copy.size(), 0, 1, NoSync()); }
+        WarpMem wm(row_cap(256));
+        for (int i = 0; i < n; ++i) {
+            bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->global_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
+            const uint8_t *sc = staged ? copy.data() : nullptr;
+            lf_decode1_body(w[i], wm.ws, wm.ms, wm.div24, sc, w[i].arena, 0, 1, NoSync());
+            lf_post_body(w[i], 0, 1, NoSync());
+            lf_decode2_body(w[i], wm.ws, wm.ms, wm.div24, sc, w[i].arena, 0, 1, NoSync());
+            lf_llf_body(w[i], 0, 1, NoSync());
+        }
     }
     void launch_hf(const HfWork *w, int n) {
         std::vector<uint8_t> copy(40 * 1024);
@@ -44,7 +66,11 @@ struct HostEmuBackend {
     }
     void launch_mod(ModWork *w, int n) {
         std::vector<uint8_t> copy(40 * 1024);
-        for (int i = 0; i < n; ++i) { SerialShared sh; modular_body(w[i], sh, (i & 1) ? nullptr : copy.data(), (uint32_t) copy.size(), 0, 1, NoSync()); }
+        WarpMem wm(row_cap(1024));
+        for (int i = 0; i < n; ++i) {
+            bool staged = !(i & 1) && stage_spec_blob(w[i].arena, w[i].f->global_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
+            modular_body(w[i], wm.ws, wm.ms, wm.div24, staged ? copy.data() : nullptr, w[i].arena, 0, 1, NoSync());
+        }
     }
     void launch_render(const RenderWork *w, int width, int height) {
         for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) render_px(*w, x, y);
