@@ -24,11 +24,17 @@ j40b_batch *j40b_batch_create(int device);
 void j40b_batch_destroy(j40b_batch *b);
 
 /* host-side parse of one image (container, headers, TOC, LfGlobal, HfGlobal: the part the reference does in
- * j40.h:8175-8192). `buf` must stay valid until j40b_batch_upload returns. Returns the image index or -1. */
+ * j40.h:8175-8192). `buf` must stay valid until j40b_batch_wait has returned for the decode that uses it (or the
+ * batch is reset / destroyed). Returns the image index or -1. */
 int j40b_batch_add(j40b_batch *b, const void *buf, size_t size);
 
-/* copies codestreams + tables of all added images to the device (one H2D transfer). 0 on success. */
+/* lays the added images out and enqueues ONE H2D transfer of codestreams + tables on the batch's stream
+ * (asynchronous; the staging buffer is pinned memory owned by the batch). 0 on success. */
 int j40b_batch_upload(j40b_batch *b);
+
+/* forgets all images but keeps the device and pinned allocations, so that a batch object can be reused for
+ * the next set of images without cudaMalloc / cudaHostAlloc. Waits for work in flight. */
+int j40b_batch_reset(j40b_batch *b);
 
 /* enqueues all decode kernels (asynchronous). May be called repeatedly on the same uploaded batch. */
 int j40b_batch_decode(j40b_batch *b);
@@ -41,6 +47,10 @@ uint32_t j40b_batch_error(const j40b_batch *b, int index);            /* four-ch
 int j40b_batch_info(const j40b_batch *b, int index, int32_t *width, int32_t *height, int32_t *stride_bytes);
 const void *j40b_batch_device_pixels(const j40b_batch *b, int index); /* RGBA8 in device memory */
 int j40b_batch_read_pixels(j40b_batch *b, int index, void *dst);     /* D2H of stride*height bytes */
+/* enqueues, behind the decode kernels on the batch's stream, the D2H copy of every image to dst + index*pitch
+ * (stride*height bytes each, clipped to pitch). Asynchronous when dst is pinned; complete after j40b_batch_wait.
+ * With several batch objects in flight the copies of one overlap the kernels of the others. */
+int j40b_batch_read_all_async(j40b_batch *b, void *dst, size_t pitch);
 
 /* device time in milliseconds of the most recent j40b_batch_decode, measured with CUDA events on the
  * batch's stream (valid after j40b_batch_wait) */

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "j40b_batch_create", "j40b_batch_destroy", "j40b_batch_add", "j40b_batch_upload", "j40b_batch_decode",
     "j40b_batch_wait", "j40b_batch_count", "j40b_batch_error", "j40b_batch_info", "j40b_batch_device_pixels",
     "j40b_batch_read_pixels", "j40b_batch_last_decode_ms", "j40b_batch_kernel_ms", "j40b_batch_stat", "j40b_gpu_available",
-    "j40b_batch_mark", "j40b_batch_join", "j40b_batch_mark_ms",
+    "j40b_batch_mark", "j40b_batch_join", "j40b_batch_mark_ms", "j40b_batch_reset", "j40b_batch_read_all_async",
 ]
 
 
@@ -98,6 +98,10 @@ def lib():
         L.j40b_gpu_available.restype = C.c_int
         L.j40b_batch_mark.restype = C.c_int
         L.j40b_batch_mark.argtypes = [C.c_void_p, C.c_int]
+        L.j40b_batch_reset.restype = C.c_int
+        L.j40b_batch_reset.argtypes = [C.c_void_p]
+        L.j40b_batch_read_all_async.restype = C.c_int
+        L.j40b_batch_read_all_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.j40b_batch_join.restype = C.c_int
         L.j40b_batch_join.argtypes = [C.c_void_p, C.c_void_p]
         L.j40b_batch_mark_ms.restype = C.c_float
@@ -203,6 +207,19 @@ class Batch:
     def upload(self):
         if lib().j40b_batch_upload(self._h) != 0:
             raise RuntimeError("j40_b200: upload failed")
+
+    def reset(self):
+        """Forget the images, keep the device and pinned allocations (waits for work in flight)."""
+        lib().j40b_batch_reset(self._h)
+        self._bufs = []
+
+    def read_all_async(self, out):
+        """Enqueue the D2H copy of every image into `out` (uint8 array [n, pitch], ideally pinned) behind the
+        decode kernels; complete after wait()."""
+        assert out.ndim >= 2 and out.dtype == np.uint8
+        pitch = out.strides[0]
+        if lib().j40b_batch_read_all_async(self._h, out.ctypes.data, pitch) != 0:
+            raise RuntimeError("j40_b200: read_all_async before decode")
 
     def decode(self):
         lib().j40b_batch_decode(self._h)

@@ -180,6 +180,7 @@ struct CudaBackend {
     bool pinned = false;
     void h2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream); }
     void d2h(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); }
+    void d2h_async(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); }
     void dev_memset(void *d, int v, size_t n) { cudaMemsetAsync(d, v, n, stream); }
     void sync() { cudaStreamSynchronize(stream); }
 
@@ -242,6 +243,8 @@ struct j40b_batch {
     cudaEvent_t t0 = nullptr, t1 = nullptr, m[2] = {nullptr, nullptr}, jev = nullptr;
     float last_ms = 0;
     int64_t last_launches = 0;
+    uint8_t *read_dst = nullptr; // pending j40b_batch_read_all_async target (re-issued if the decode is retried)
+    size_t read_pitch = 0;
 };
 
 EXPORT int j40b_gpu_available(void) {
@@ -279,13 +282,35 @@ EXPORT int j40b_batch_add(j40b_batch *b, const void *buf, size_t size) {
     return (int) b->batch->plans.size() - 1;
 }
 
+EXPORT int j40b_batch_reset(j40b_batch *b) {
+    if (!b) return -1;
+    cudaSetDevice(b->be.device);
+    b->be.sync();
+    b->batch->reset();
+    b->batch->full_token_cap = false;
+    b->inputs.clear();
+    b->uploaded = b->decoded = false;
+    b->read_dst = nullptr;
+    return 0;
+}
+
 EXPORT int j40b_batch_upload(j40b_batch *b) {
     if (!b) return -1;
     cudaSetDevice(b->be.device);
-    b->batch->upload();
-    b->be.sync();
-    b->uploaded = true;
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    bool ok = b->batch->upload();
+    b->uploaded = ok;
+    b->decoded = false;
+    b->read_dst = nullptr;
+    return ok && cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+EXPORT int j40b_batch_read_all_async(j40b_batch *b, void *dst, size_t pitch) {
+    if (!b || !dst || !b->decoded) return -1;
+    cudaSetDevice(b->be.device);
+    b->read_dst = (uint8_t *) dst;
+    b->read_pitch = pitch;
+    b->batch->download_all_async(b->read_dst, pitch);
+    return 0;
 }
 
 EXPORT int j40b_batch_decode(j40b_batch *b) {
@@ -326,8 +351,10 @@ EXPORT int j40b_batch_wait(j40b_batch *b) {
     for (auto &r : b->batch->results) if (r.err == E_TOKV) retry = true;
     if (retry && !b->batch->full_token_cap) {
         b->batch->full_token_cap = true;
-        b->batch->upload();
-        b->batch->execute();
+        if (b->batch->upload()) {
+            b->batch->execute();
+            if (b->read_dst) b->batch->download_all_async(b->read_dst, b->read_pitch);
+        }
         b->batch->collect_errors();
     }
     int failed = 0;

@@ -40,9 +40,11 @@ public:
         plans.push_back(std::move(p));
     }
 
-    // ---- step 2: lay out + upload
-    void upload() {
-        release();
+    // forgets the images but keeps the device / pinned allocations for the next upload()
+    void reset() { plans.clear(); results.clear(); img.clear(); num_lf = num_hf = 0; }
+
+    // ---- step 2: lay out + upload (asynchronous on the backend's stream). Returns false when out of memory.
+    bool upload() {
         const GlobalTables &gt = GlobalTables::get();
         size_t n = plans.size();
         results.assign(n, ImageResult());
@@ -152,8 +154,23 @@ public:
         num_lf = n_lf; num_hf = n_hf;
         upload_bytes = align_up(up, 256);
         work_bytes = align_up(work, 256);
-        dev = (uint8_t *) be.dev_alloc(upload_bytes + work_bytes);
-        staging = (uint8_t *) be.host_alloc(upload_bytes);
+        if (upload_bytes + work_bytes > dev_cap) {
+            if (dev) be.dev_free(dev);
+            dev_cap = upload_bytes + work_bytes;
+            dev = (uint8_t *) be.dev_alloc(dev_cap);
+        }
+        if (upload_bytes > staging_cap) {
+            if (staging) be.host_free(staging);
+            staging_cap = upload_bytes + upload_bytes / 8;
+            staging = (uint8_t *) be.host_alloc(staging_cap);
+        }
+        if (!dev || !staging) {
+            release();
+            for (size_t k = 0; k < n; ++k) if (!results[k].err) results[k].err = E_MEM;
+            for (size_t k = 0; k < n; ++k) if (!plans[k]->err) plans[k]->err = E_MEM;
+            num_lf = num_hf = 0;
+            return false;
+        }
         memset(staging, 0, upload_bytes);
         uint8_t *dwork = dev + upload_bytes;
         // ---- fill the staging blob with device addresses
@@ -272,10 +289,12 @@ public:
             }
         }
         be.h2d(dev, staging, upload_bytes);
+        return true;
     }
 
     // ---- step 3: kernels (can be repeated: all state they depend on is re-initialised here)
     void execute() {
+        if (!dev) return;
         uint8_t *dwork = dev + upload_bytes;
         for (size_t k = 0; k < plans.size(); ++k) {
             FramePlan &p = *plans[k];
@@ -300,6 +319,7 @@ public:
     // ---- step 4: errors (synchronises)
     void collect_errors() {
         be.sync();
+        if (!dev) return;
         uint8_t *dwork = dev + upload_bytes;
         for (size_t k = 0; k < plans.size(); ++k) {
             FramePlan &p = *plans[k];
@@ -338,11 +358,23 @@ public:
         be.d2h(dst, dev + r.rgba_off, (size_t) r.stride * (size_t) r.height);
     }
     uint8_t *device_pixels(size_t k) { return dev + results[k].rgba_off; }
+    // enqueues the D2H copy of every image (pitch bytes apart in dst) behind the kernels; truly asynchronous
+    // when dst is pinned host memory
+    void download_all_async(uint8_t *dst, size_t pitch) {
+        if (!dev) return;
+        for (size_t k = 0; k < results.size(); ++k) {
+            const ImageResult &r = results[k];
+            if (plans[k]->err || !r.height) continue;
+            size_t bytes = (size_t) r.stride * (size_t) r.height;
+            be.d2h_async(dst + k * pitch, dev + r.rgba_off, bytes < pitch ? bytes : pitch);
+        }
+    }
 
     void release() {
         if (dev) be.dev_free(dev);
         if (staging) be.host_free(staging);
         dev = staging = nullptr;
+        dev_cap = staging_cap = 0;
     }
 
     size_t device_bytes() const { return upload_bytes + work_bytes; }
@@ -362,7 +394,7 @@ private:
     };
     std::vector<Img> img;
     uint8_t *dev = nullptr, *staging = nullptr;
-    size_t upload_bytes = 0, work_bytes = 0;
+    size_t upload_bytes = 0, work_bytes = 0, dev_cap = 0, staging_cap = 0;
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, num_lf = 0, num_hf = 0;
 };
 

@@ -17,6 +17,7 @@ struct HostEmuBackend {
     void host_free(void *p) { free(p); }
     void h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); }
+    void d2h_async(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void dev_memset(void *d, int v, size_t n) { memset(d, v, n); }
     void sync() {}
     // shared memory of one warp of the serial decoders

@@ -94,3 +94,27 @@ def test_no_cpu_fallback_without_gpu(gen):
         assert False, "Batch must refuse to exist without a GPU"
     except RuntimeError:
         pass
+
+
+DJ40 = os.path.join(ROOT, "oracle", "_ref", "dj40_b200")
+
+
+def test_reference_dj40_builds_unchanged_and_fails_loudly_without_gpu(tmp_path, gen):
+    """oracle/Makefile compiles the reference's own dj40.c, unmodified, against include/j40.h and links it to
+    libj40b200.so. Without a CUDA device the decode must fail with the `!gpu` message rather than
+    fall back to anything."""
+    import subprocess
+    if not os.path.exists(DJ40):
+        import pytest
+        pytest.skip("dj40_b200 not built (no /root/reference in this environment)")
+    p = tmp_path / "a.jxl"
+    p.write_bytes(gen.vardct(64, 64, seed=1)[0])
+    r = subprocess.run([DJ40, str(p), str(tmp_path / "a.png")], capture_output=True, text=True)
+    if J.gpu_available():
+        assert r.returncode == 0 and "64x64 frame read." in r.stderr
+    else:
+        assert r.returncode == 1
+        assert "No usable CUDA device" in r.stderr and "during j40_next_frame" in r.stderr
+        assert not (tmp_path / "a.png").exists() or (tmp_path / "a.png").stat().st_size < 2000  # placeholder only
+    r = subprocess.run([DJ40, str(tmp_path / "missing.jxl")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Failed to open file during j40_from_file" in r.stderr

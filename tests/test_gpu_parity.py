@@ -113,3 +113,59 @@ def test_error_codes_on_corrupt_streams(oracle, gen):
             elif ea != eb:
                 mismatches += 1
     assert mismatches <= total // 10, (mismatches, total)
+
+
+def test_batch_reuse_and_async_readback(oracle, gen):
+    """j40b_batch_reset keeps the allocations; j40b_batch_read_all_async copies every image behind the kernels.
+    Two batch objects in flight at once (the pipelined serving pattern bench.py's e2e figure uses)."""
+    import torch
+    sets = [[streams.make(gen, "vardct", 264 + 8 * k, 200, 40 + 3 * k + i, dict(mix=1, tree=1)) for i in range(3)] for k in range(4)]
+    objs = [J.Batch(0), J.Batch(0)]
+    outs = [torch.empty((3, 300 * 4 * 300), dtype=torch.uint8, pin_memory=True).numpy() for _ in objs]
+    for rnd in range(2):
+        for k, b in enumerate(objs):
+            b.reset()
+            for d in sets[2 * rnd + k]:
+                b.add(d)
+            b.upload()
+            b.decode()
+            b.read_all_async(outs[k])
+        for k, b in enumerate(objs):
+            assert b.wait() == 0
+            for i, d in enumerate(sets[2 * rnd + k]):
+                a, ea, _, sa = oracle.decode(d)
+                w, h, s = b.info(i)
+                assert (w, h, s) == (a.shape[1], a.shape[0], sa)
+                got = outs[k][i][: h * s].reshape(h, s)[:, : w * 4].reshape(h, w, 4)
+                assert np.array_equal(got, a), (rnd, k, i)
+    for b in objs:
+        b.close()
+
+
+def test_sharded_decode_two_ranks_one_gpu(oracle, gen):
+    """the sharding helper with the real GPU decoder: two 'ranks' (sequential here) cover the list once"""
+    import hashlib
+    from j40_b200.sharding import decode_shard, gpu_decode_batch
+    datas = [streams.make(gen, "vardct", 136, 72 + 8 * i, 60 + i, dict(mix=1)) for i in range(5)]
+    st = sorted(decode_shard(datas, 0, 2, gpu_decode_batch(0)) + decode_shard(datas, 1, 2, gpu_decode_batch(0)))
+    assert [i for i, _, _ in st] == list(range(5))
+    for i, err, digest in st:
+        a, ea, _, _ = oracle.decode(datas[i])
+        assert err == ea == "" and digest == hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def test_reference_dj40_unchanged_writes_the_oracle_pixels(oracle, gen, tmp_path):
+    """the reference's own CLI, built unchanged against include/j40.h (oracle/Makefile), on the GPU"""
+    import os, subprocess
+    from PIL import Image
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "dj40_b200")
+    if not os.path.exists(exe):
+        pytest.skip("dj40_b200 not built")
+    data = streams.make(gen, "vardct", 520, 392, 77, dict(mix=1, tree=1))
+    (tmp_path / "a.jxl").write_bytes(data)
+    r = subprocess.run([exe, str(tmp_path / "a.jxl"), str(tmp_path / "a.png")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "520x392 frame read." in r.stderr
+    a, ea, _, _ = oracle.decode(data)
+    got = np.array(Image.open(tmp_path / "a.png").convert("RGBA"))
+    assert np.array_equal(got, a)
