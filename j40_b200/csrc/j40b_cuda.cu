@@ -34,35 +34,37 @@ enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
 struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
 
 __host__ __device__ inline size_t warp_slice_bytes(int cap) {
-    size_t n = sizeof(WarpScratch);
-    n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + MOD_STAGED_REFS * 2 * 2);
+    size_t n = sizeof(WarpScratch) + sizeof(SimtLane) * SIMT_LANES;
+    n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + SIMT_REF_SLOTS * 4);
     return (n + 15) & ~(size_t) 15;
 }
 
 __device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws) {
     ws = (WarpScratch *) base;
     ModSmem ms;
-    ms.wp = (int32_t *) (base + sizeof(WarpScratch));
-    ms.rows = (int16_t *) (ms.wp + (size_t) cap * 10);
-    ms.refs = ms.rows + (size_t) cap * 3;
+    ms.tab = (SimtLane *) (base + sizeof(WarpScratch));
+    ms.wp = (int32_t *) (ms.tab + SIMT_LANES);
+    ms.refp = ms.wp + (size_t) cap * 10;
+    ms.rows = cap ? (int16_t *) (ms.refp + (size_t) cap * SIMT_REF_SLOTS) : nullptr;
     ms.info = ws->info;
     ms.cap = cap;
     return ms;
 }
 
+// `spec_cap`: bytes of dynamic shared memory reserved for the staged code spec (0 = read the tables through L1)
 template <int STAGE>
-__global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, int cap) {
+__global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, int cap, int spec_cap) {
     __shared__ int32_t div24[64];
     extern __shared__ __align__(16) uint8_t smem[];
     const int warps = (int) blockDim.x >> 5, warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
     const LfWork &w0 = items[(int) blockIdx.x * warps];
-    const bool staged = stage_spec_blob(w0.arena, w0.f->global_spec_off, smem, SPEC_COPY_BYTES, (int) threadIdx.x, (int) blockDim.x);
+    const bool staged = spec_cap > 0 && stage_spec_blob(w0.arena, w0.f->global_spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, (int) blockDim.x);
     fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
     __syncthreads();
     const int i = (int) blockIdx.x * warps + warp;
     if (i >= n) return;
     WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem + SPEC_COPY_BYTES + (size_t) warp * warp_slice_bytes(cap), cap, ws);
+    ModSmem ms = carve_warp_slice(smem + spec_cap + (size_t) warp * warp_slice_bytes(cap), cap, ws);
     if (STAGE == 1) lf_decode1_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
     else lf_decode2_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
 }
@@ -82,13 +84,13 @@ __global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
 // `lanes` (<= 32) groups per warp: with small batches fewer lanes per warp give more warps (latency hiding)
 // and less divergence; the host picks it from the number of groups (CudaBackend::launch_hf).
 enum { HF_WARPS = 4 };
-__global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items, int n, int lanes) {
+__global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items, int n, int lanes, int spec_cap) {
     extern __shared__ __align__(16) uint8_t spec_copy[];
     __shared__ uint16_t ctx_lut[128];
     const int per_block = HF_WARPS * lanes;
     const int first = (int) blockIdx.x * per_block;
     const HfWork &w0 = items[first];
-    const bool staged = stage_spec_blob(w0.arena, w0.f->coeff_spec_off, spec_copy, SPEC_COPY_BYTES, (int) threadIdx.x, 32 * HF_WARPS);
+    const bool staged = spec_cap > 0 && stage_spec_blob(w0.arena, w0.f->coeff_spec_off, spec_copy, (uint32_t) spec_cap, (int) threadIdx.x, 32 * HF_WARPS);
     if (threadIdx.x < 64) ctx_lut[threadIdx.x] = (uint16_t) coeff_nnz_ctx2((int) threadIdx.x);
     else if (threadIdx.x < 128) ctx_lut[threadIdx.x] = (uint16_t) (threadIdx.x == 64 ? 0 : coeff_freq_ctx2((int) threadIdx.x - 64));
     __syncthreads();
@@ -184,26 +186,31 @@ struct CudaBackend {
     void dev_memset(void *d, int v, size_t n) { cudaMemsetAsync(d, v, n, stream); }
     void sync() { cudaStreamSynchronize(stream); }
 
-    void launch_lf(const LfWork *w, int n) {
-        int warps = 1;
+    // `spec_bytes`: largest code-spec blob among the batch's images (sizes the staging area)
+    void launch_lf(const LfWork *w, int n, size_t spec_bytes) {
+        int warps = 1, cap = LF_ROW_CAP, stage = 1;
         if (const char *e = getenv("J40B_LF_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 4) warps = v; }
-        const size_t smem = SPEC_COPY_BYTES + (size_t) warps * warp_slice_bytes(LF_ROW_CAP);
+        if (const char *e = getenv("J40B_LF_CAP")) { int v = atoi(e); if (v == 0 || v == LF_ROW_CAP) cap = v; }
+        if (const char *e = getenv("J40B_LF_STAGE")) stage = atoi(e);
+        const int spec_cap = stage && spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
+        const size_t smem = (size_t) spec_cap + (size_t) warps * warp_slice_bytes(cap);
         const int blocks = (n + warps - 1) / warps;
         cudaEventRecord(ev[0], stream);
-        k_lf_decode<1><<<blocks, 32 * warps, smem, stream>>>(w, n, LF_ROW_CAP);
+        k_lf_decode<1><<<blocks, 32 * warps, smem, stream>>>(w, n, cap, spec_cap);
         k_lf_post<<<n, 256, 0, stream>>>(w);
-        k_lf_decode<2><<<blocks, 32 * warps, smem, stream>>>(w, n, LF_ROW_CAP);
+        k_lf_decode<2><<<blocks, 32 * warps, smem, stream>>>(w, n, cap, spec_cap);
         k_lf_llf<<<n, 128, 0, stream>>>(w);
         cudaEventRecord(ev[1], stream);
         launches += 4;
     }
-    void launch_hf(const HfWork *w, int n) {
+    void launch_hf(const HfWork *w, int n, size_t spec_bytes) {
+        const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
         // lanes per warp: aim at ~8 warps per SM before filling warps completely
         int lanes = (n + num_sms * 8 - 1) / (num_sms * 8);
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
         const int per_block = HF_WARPS * lanes;
-        k_hf_group<<<(n + per_block - 1) / per_block, 32 * HF_WARPS, SPEC_COPY_BYTES, stream>>>(w, n, lanes);
+        k_hf_group<<<(n + per_block - 1) / per_block, 32 * HF_WARPS, (size_t) spec_cap, stream>>>(w, n, lanes, spec_cap);
         cudaEventRecord(ev[2], stream);
         ++launches;
     }

@@ -82,7 +82,7 @@ enum { PTREE_CAP = 192 };
 struct WarpScratch {
     DTreeNode ptree[PTREE_CAP];
     ModImage m;
-    int32_t info[4];
+    int32_t info[8];
 };
 
 // cooperative staging of a code spec's blob into `dst` (cap bytes); returns true if it fits
@@ -123,28 +123,24 @@ J40B_HD inline void lf_decode1_body(const LfWork &w, WarpScratch &ws, const ModS
     init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
     cs.init(g.lz_window, (1u << 18) - 1);
     const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+    // every lane runs the decoder on identical state (see modular_channel_warp); identical values are written
+    // to the shared ModImage by all of them
     ModImage &m = ws.m;
-    if (lane == 0) {
-        g.extra_prec = (int32_t) br.u(2);
-        m.num_channels = 3;
-        for (int c = 0; c < 3; ++c) {
-            m.ch[c].px = g.lfq + (size_t) c * n8;
-            m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
-            m.ch[c].hshift = m.ch[c].vshift = 0;
-        }
-        modular_header(br, es, f.have_global_tree != 0, m);
-        ws.info[3] = (int32_t) es.err;
-    }
-    sync();
-    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+    const int32_t extra_prec = (int32_t) br.u(2);
+    m.num_channels = 3;
     for (int c = 0; c < 3; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, 1 + g.idx, lane, nlanes, sync);
-        if (lane == 0) ws.info[3] = (int32_t) es.err;
-        sync();
-        if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
+        m.ch[c].px = g.lfq + (size_t) c * n8;
+        m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
+        m.ch[c].hshift = m.ch[c].vshift = 0;
     }
+    modular_header(br, es, f.have_global_tree != 0, m);
+    sync();
+    for (int c = 0; c < 3 && !es.err; ++c) {
+        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, 1 + g.idx, lane, nlanes, sync);
+    }
+    if (!es.err) finish_code(br, es, cc, cs);
     if (lane == 0) {
-        finish_code(br, es, cc, cs);
+        g.extra_prec = extra_prec;
         g.mid_bit = br.bits_consumed();
         g.nb_tr1 = m.nb_transforms;
         for (int t = 0; t < m.nb_transforms; ++t) g.tr1[t] = m.tr[t];
@@ -196,33 +192,23 @@ J40B_HD inline void lf_decode2_body(const LfWork &w, WarpScratch &ws, const ModS
     cs.init(g.lz_window, (1u << 18) - 1);
     const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
     ModImage &m = ws.m;
-    if (lane == 0) {
-        int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
-        g.nb_varblocks = nvb;
-        m.num_channels = 4;
-        m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
-        m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
-        m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
-        m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
-        for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
-        modular_header(br, es, f.have_global_tree != 0, m);
-        ws.info[3] = (int32_t) es.err;
-    }
+    const int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
+    if (lane == 0) g.nb_varblocks = nvb;
+    m.num_channels = 4;
+    m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
+    m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
+    m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
+    m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
+    for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
+    modular_header(br, es, f.have_global_tree != 0, m);
     sync();
-    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 4 && !es.err; ++c) {
         modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c,
                              1 + 2 * f.num_lf_groups + g.idx, lane, nlanes, sync);
-        if (lane == 0) ws.info[3] = (int32_t) es.err;
-        sync();
-        if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
     }
-    if (lane == 0) {
-        finish_code(br, es, cc, cs);
-        ws.info[3] = (int32_t) es.err;
-    }
+    if (!es.err) finish_code(br, es, cc, cs);
+    if (es.err) { if (lane == 0) *w.err = es.err; return; }
     sync();
-    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
     // inverse transforms (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide)
     for (int t = m.nb_transforms - 1; t >= 0; --t) {
         ModImage one = m;
@@ -338,30 +324,20 @@ J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms,
     cs.init(w.lz_window, w.lz_mask);
     const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
     ModImage &m = ws.m;
-    if (lane == 0) {
-        m = w.m;
-        if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, m);
-        ws.info[3] = (int32_t) es.err;
-    }
+    m = w.m;
+    if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, m);
     sync();
-    if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
-    for (int c = 0; c < m.num_channels; ++c) {
+    for (int c = 0; c < m.num_channels && !es.err; ++c) {
         modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, w.sidx, lane, nlanes, sync);
-        if (lane == 0) ws.info[3] = (int32_t) es.err;
-        sync();
-        if (ws.info[3]) { if (lane == 0) *w.err = (uint32_t) ws.info[3]; return; }
     }
-    if (lane == 0) {
-        finish_code(br, es, cc, cs);
-        if (!es.err) {
-            if (w.header_parsed) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
-            else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
-        }
-        ws.info[3] = (int32_t) es.err;
-        if (es.err) *w.err = es.err;
+    if (!es.err) finish_code(br, es, cc, cs);
+    if (!es.err) {
+        if (w.header_parsed) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
+        else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
     }
+    if (es.err && lane == 0) *w.err = es.err;
     sync();
-    if (ws.info[3] || w.header_parsed) return; // global transforms are applied by the render step
+    if (es.err || w.header_parsed) return; // global transforms are applied by the render step
     for (int t = m.nb_transforms - 1; t >= 0; --t) {
         ModImage one = m;
         one.nb_transforms = 1;

@@ -264,158 +264,312 @@ J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-cooperative variant: lane 0 is the (inherently serial) decoder, the other lanes keep everything it
-// touches per sample in shared memory: a ring of the last three sample rows, the weighted predictor's two
-// error rows, and the current / previous row of up to two reference channels (properties >= 16). The
-// per-sample dependency chain then never leaves the SM. Same arithmetic as modular_channel_t.
-enum { MOD_STAGED_REFS = 2 };
+// Warp variant ("SIMT-uniform" decoding). The serial decoder is executed by ALL lanes of a warp in lockstep on
+// identical state (bit reader, ANS state, neighbours): redundant uniform work costs no extra issue slots, and it
+// lets the lanes split the parts of a sample that are parallel:
+//   * the MA tree is evaluated without walking it: lane j computes the decision of inner node j (every
+//     property is a small linear form of the neighbours, see SimtLane), one ballot collects the decision bits
+//     and a second one finds the leaf whose path matches (lane j also owns leaf j);
+//   * the weighted predictor's four sub-predictor weights / error updates are computed by lanes 0..3 (+4 for
+//     the signed true error), gathered with shuffles;
+//   * at the start of each row all lanes compute the row's reference-channel properties (they depend on
+//     finished channels only) and the sample rows / error rows live in shared memory.
+// On the CPU (kernel-logic tests) the same code runs with one "lane" and loops over the lane-indexed parts.
+// Same integer arithmetic as modular_channel_t (j40.h:3965-4229).
+enum { SIMT_LANES = 32, SIMT_REF_SLOTS = 4 };
+
+struct SimtLane {       // lane j: decision node j and leaf j of the compiled (pruned) tree
+    int32_t c[7];       // coefficients of pn, pw, pnw, pne, pnn, pww, pnww
+    int32_t cx, cy, ce; // coefficients of x, y and the weighted predictor's max true error (property 15)
+    int32_t refslot;    // >= 0: the value is refp[refslot][x] (property >= 16)
+    int32_t flags;      // bit 0: absolute value; bit 1: property 8 (is pw at x == 0); bit 2: node present
+    int32_t thr;        // decision: value > thr
+    uint32_t care, want; // leaf j is selected iff (decisions & care) == want
+    int32_t leaf_node;  // index of leaf j in the pruned tree, -1 if none
+};
+
 struct ModSmem {
-    int16_t *rows;   // [3][cap]
-    int32_t *wp;     // [2][cap][5]
-    int16_t *refs;   // [MOD_STAGED_REFS][2][cap]
-    int32_t *info;   // [4]: uses_wp, refs staged, use row path, abort
-    int32_t cap;     // widest channel the row path can take
+    int16_t *rows;   // [3][cap]  ring of the last three sample rows (null: no SIMT path)
+    int32_t *wp;     // [2][cap][5] weighted predictor error rows
+    int32_t *refp;   // [SIMT_REF_SLOTS][cap] reference-channel property values of the current row
+    SimtLane *tab;   // [SIMT_LANES]
+    int32_t *info;   // [8] scratch flags shared by the lanes
+    int32_t cap;     // widest channel the SIMT path can take
+};
+
+// Compiles the pruned tree into per-lane decision forms. Returns false if it does not fit (more than 32 inner
+// nodes or leaves, more than SIMT_REF_SLOTS distinct reference properties, a reference property without its
+// channel): the caller then walks the tree instead. refprops[s] = property number of slot s.
+J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, SimtLane *tab, int32_t *refprops, int32_t *nslots) {
+    int inner_of[192], ni = 0, nl = 0, ns = 0;
+    if (n <= 0 || n > 192) return false;
+    for (int i = 0; i < SIMT_LANES; ++i) {
+        SimtLane &L = tab[i];
+        for (int k = 0; k < 7; ++k) L.c[k] = 0;
+        L.cx = L.cy = L.ce = 0; L.refslot = -1; L.flags = 0; L.thr = 0; L.care = 0; L.want = 0xffffffffu; L.leaf_node = -1;
+    }
+    for (int i = 0; i < n; ++i) {
+        inner_of[i] = -1;
+        if (t[i].a >= 0) { if (++nl > SIMT_LANES) return false; continue; }
+        if (ni >= SIMT_LANES) return false;
+        inner_of[i] = ni;
+        SimtLane &L = tab[ni++];
+        const int prop = -1 - t[i].a;
+        L.flags = 4;
+        L.thr = t[i].b;
+        // neighbours: 0 pn, 1 pw, 2 pnw, 3 pne, 4 pnn, 5 pww, 6 pnww
+        switch (prop) {
+        case 2: L.cy = 1; break;
+        case 3: L.cx = 1; break;
+        case 4: L.c[0] = 1; L.flags |= 1; break;
+        case 5: L.c[1] = 1; L.flags |= 1; break;
+        case 6: L.c[0] = 1; break;
+        case 7: L.c[1] = 1; break;
+        case 8: L.c[1] = 1; L.c[5] = -1; L.c[2] = -1; L.c[6] = 1; L.flags |= 2; break;
+        case 9: L.c[1] = 1; L.c[0] = 1; L.c[2] = -1; break;
+        case 10: L.c[1] = 1; L.c[2] = -1; break;
+        case 11: L.c[2] = 1; L.c[0] = -1; break;
+        case 12: L.c[0] = 1; L.c[3] = -1; break;
+        case 13: L.c[0] = 1; L.c[4] = -1; break;
+        case 14: L.c[1] = 1; L.c[5] = -1; break;
+        case 15: L.ce = 1; break;
+        default: {
+            if (prop < 16 || (prop - 16) / 4 >= nref) return false; // (static properties 0/1 were pruned away)
+            int slot = -1;
+            for (int k = 0; k < ns; ++k) if (refprops[k] == prop) slot = k;
+            if (slot < 0) { if (ns >= SIMT_REF_SLOTS) return false; refprops[ns] = prop; slot = ns++; }
+            L.refslot = slot;
+            break;
+        }
+        }
+    }
+    // leaves: path masks by walking down from the root with an explicit stack
+    int32_t stack_node[64]; uint32_t stack_care[64], stack_want[64];
+    int sp = 0, leaf = 0;
+    stack_node[sp] = 0; stack_care[sp] = 0; stack_want[sp] = 0; ++sp;
+    while (sp > 0) {
+        --sp;
+        int i = stack_node[sp]; uint32_t care = stack_care[sp], want = stack_want[sp];
+        if (t[i].a >= 0) { tab[leaf].care = care; tab[leaf].want = want; tab[leaf].leaf_node = i; ++leaf; continue; }
+        if (sp + 2 > 64) return false;
+        uint32_t bit = 1u << inner_of[i];
+        stack_node[sp] = t[i].c; stack_care[sp] = care | bit; stack_want[sp] = want | bit; ++sp; // value > threshold
+        stack_node[sp] = t[i].d; stack_care[sp] = care | bit; stack_want[sp] = want; ++sp;
+    }
+    *nslots = ns;
+    return true;
+}
+
+J40B_HD J40B_INLINE bool simt_decision(const SimtLane &L, int32_t x, int32_t y, int32_t pn, int32_t pw, int32_t pnw, int32_t pne,
+                                       int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr, const int32_t *refp, int32_t cap) {
+    int32_t v = L.c[0] * pn + L.c[1] * pw + L.c[2] * pnw + L.c[3] * pne + L.c[4] * pnn + L.c[5] * pww + L.c[6] * pnww
+              + L.cx * x + L.cy * y + L.ce * maxerr;
+    if (L.refslot >= 0) v = refp[(size_t) L.refslot * cap + x];
+    if ((L.flags & 2) && x == 0) v = pw;
+    if (L.flags & 1) v = iabs(v);
+    return (L.flags & 4) && v > L.thr;
+}
+
+// index (in the pruned tree) of the leaf the current sample falls into
+J40B_HD J40B_INLINE int32_t simt_tree_leaf(const SimtLane *tab, const SimtLane &mine, int32_t x, int32_t y, int32_t pn, int32_t pw,
+                                           int32_t pnw, int32_t pne, int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr,
+                                           const int32_t *refp, int32_t cap) {
+#ifdef __CUDA_ARCH__
+    const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision(mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
+    const uint32_t hit = __ballot_sync(0xffffffffu, mine.leaf_node >= 0 && (dec & mine.care) == mine.want);
+    return __shfl_sync(0xffffffffu, mine.leaf_node, __ffs((int) hit) - 1);
+#else
+    uint32_t dec = 0;
+    for (int j = 0; j < SIMT_LANES; ++j) dec |= (uint32_t) simt_decision(tab[j], x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap) << j;
+    for (int j = 0; j < SIMT_LANES; ++j) if (tab[j].leaf_node >= 0 && (dec & tab[j].care) == tab[j].want) return tab[j].leaf_node;
+    return -1;
+#endif
+}
+
+// Weighted predictor with the lane-indexed parts split out. NL = lane-indexed values this thread holds:
+// 1 on the device (lane i = min(lane, 4) holds index i), 5 on the CPU (all of them).
+#ifdef __CUDA_ARCH__
+enum { WP_NL = 1 };
+#else
+enum { WP_NL = 5 };
+#endif
+struct WpSimt {
+    int32_t e_n[WP_NL], e_nw[WP_NL], e_ne[WP_NL], e_w[WP_NL], e_ww[WP_NL]; // error window, index i per lane
+    int32_t te_w, te_n, te_nw, te_ne;                                       // true errors (index 4), uniform
+    int32_t pred[5];
 };
 
 template <bool USE_WP, class Sync>
-J40B_HD inline void modular_channel_rows(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
-                                         const DTreeNode *tree, const ModSmem &ms, const int32_t *div24,
-                                         const ModImage &m, int32_t cidx, int32_t sidx, int nstaged,
+J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                         const DTreeNode *tree, const ModSmem &ms, const int32_t *refprops, int nslots,
+                                         const int32_t *div24, const ModImage &m, int32_t cidx, int32_t sidx,
                                          int lane, int nlanes, Sync sync) {
     const ModChannel &c = m.ch[cidx];
     const int32_t width = c.w, height = c.h, stride = c.stride, cap = ms.cap;
     const int32_t dist_mult = m.dist_mult;
     const WPParams wpp = m.wp;
-    WPState wp;
-    wp.errors = ms.wp;
-    wp.width = width;
-    for (int i = 0; i < 5; ++i) wp.pred[i] = 0;
-    wp.trueerrw = wp.trueerrn = wp.trueerrnw = wp.trueerrne = 0;
     int32_t refcmap[MOD_MAX_CH], nref = 0;
     for (int32_t i = cidx - 1; i >= 0; --i) {
         const ModChannel &r = m.ch[i];
         if (c.w != r.w || c.h != r.h || c.hshift != r.hshift || c.vshift != r.vshift) continue;
         refcmap[nref++] = i;
     }
-    if (nstaged > nref) nstaged = nref;
-    if (USE_WP) for (int32_t i = lane; i < width * 2 * 5; i += nlanes) ms.wp[i] = 0;
+    const SimtLane mine = ms.tab[lane & (SIMT_LANES - 1)];
+    const int my_i = lane < 4 ? lane : 4; // this lane's weighted-predictor index (device)
+    (void) my_i;
+    WpSimt wp;
     for (int32_t y = 0; y < height; ++y) {
-        // all lanes: row y of the staged reference channels (row y-1 is still there from the last round)
-        for (int r = 0; r < nstaged; ++r) {
-            const ModChannel &rc = m.ch[refcmap[r]];
-            const int16_t *src = rc.px + (size_t) y * (size_t) rc.stride;
-            int16_t *dst = ms.refs + (size_t) (r * 2 + (y & 1)) * cap;
-            for (int32_t x = lane; x < width; x += nlanes) dst[x] = src[x];
-        }
-        sync();
-        if (lane == 0) {
-            int16_t *row = c.px + (size_t) y * (size_t) stride;
-            int16_t *cur = ms.rows + (size_t) (y % 3) * cap;
-            const int16_t *nrow = ms.rows + (size_t) ((y + 2) % 3) * cap, *nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
-            int32_t prev = 0, prev2 = 0;
-            for (int32_t x = 0; x < width; ++x) {
-                int32_t pw = x > 0 ? prev : y > 0 ? nrow[x] : 0;
-                int32_t pn = y > 0 ? nrow[x] : pw;
-                int32_t pnw = x > 0 && y > 0 ? nrow[x - 1] : pw;
-                int32_t pne = x + 1 < width && y > 0 ? nrow[x + 1] : pn;
-                int32_t pnn = y > 1 ? nnrow[x] : pn;
-                int32_t pnee = x + 2 < width && y > 0 ? nrow[x + 2] : pne;
-                int32_t pww = x > 1 ? prev2 : pw;
-                int32_t pnww = x > 1 && y > 0 ? nrow[x - 2] : pww;
-                if (USE_WP) wp_before_predict(wp, wpp, div24, x, y, pw, pn, pnw, pne, pnn);
-
-                const DTreeNode *n = tree;
-                while (n->a < 0) {
-                    int32_t prop = -1 - n->a, val;
-                    switch (prop) {
-                    case 0: val = cidx; break;
-                    case 1: val = sidx; break;
-                    case 2: val = y; break;
-                    case 3: val = x; break;
-                    case 4: val = iabs(pn); break;
-                    case 5: val = iabs(pw); break;
-                    case 6: val = pn; break;
-                    case 7: val = pw; break;
-                    case 8: val = x > 0 ? pw - (pww + pnw - pnww) : pw; break;
-                    case 9: val = pw + pn - pnw; break;
-                    case 10: val = pw - pnw; break;
-                    case 11: val = pnw - pn; break;
-                    case 12: val = pn - pne; break;
-                    case 13: val = pn - pnn; break;
-                    case 14: val = pw - pww; break;
-                    case 15:
-                        val = wp.trueerrw;
-                        if (iabs(val) < iabs(wp.trueerrn)) val = wp.trueerrn;
-                        if (iabs(val) < iabs(wp.trueerrnw)) val = wp.trueerrnw;
-                        if (iabs(val) < iabs(wp.trueerrne)) val = wp.trueerrne;
-                        break;
-                    default: {
-                        int32_t refcidx = (prop - 16) / 4;
-                        if (refcidx >= nref) { es.set(br, E_TREC); break; }
-                        int32_t rw, rn, rnw;
-                        if (refcidx < nstaged) {
-                            const int16_t *ry = ms.refs + (size_t) (refcidx * 2 + (y & 1)) * cap;
-                            const int16_t *rp = ms.refs + (size_t) (refcidx * 2 + ((y & 1) ^ 1)) * cap;
-                            val = ry[x];
-                            rw = x > 0 ? ry[x - 1] : 0;
-                            rn = y > 0 ? rp[x] : rw;
-                            rnw = x > 0 && y > 0 ? rp[x - 1] : rw;
-                        } else {
-                            const ModChannel &r = m.ch[refcmap[refcidx]];
-                            const int16_t *rp = r.px + (size_t) y * (size_t) r.stride + x;
-                            val = rp[0];
-                            rw = x > 0 ? rp[-1] : 0;
-                            rn = y > 0 ? rp[-r.stride] : rw;
-                            rnw = x > 0 && y > 0 ? rp[-1 - r.stride] : rw;
-                        }
-                        if (prop & 2) val -= mod_gradient(rw, rn, rnw);
-                        if (prop & 1) val = iabs(val);
-                        break;
-                    }
-                    }
-                    if (es.err) break;
-                    n = tree + (val > n->b ? n->c : n->d);
+        // ---- all lanes: this row's reference-channel property values
+        for (int sl = 0; sl < nslots; ++sl) {
+            const int prop = refprops[sl];
+            const ModChannel &r = m.ch[refcmap[(prop - 16) / 4]];
+            const int16_t *rrow = r.px + (size_t) y * (size_t) r.stride;
+            int32_t *dst = ms.refp + (size_t) sl * cap;
+            for (int32_t x = lane; x < width; x += nlanes) {
+                int32_t val = rrow[x];
+                if (prop & 2) {
+                    int32_t rw = x > 0 ? rrow[x - 1] : 0;
+                    int32_t rn = y > 0 ? rrow[x - r.stride] : rw;
+                    int32_t rnw = x > 0 && y > 0 ? rrow[x - 1 - r.stride] : rw;
+                    val -= mod_gradient(rw, rn, rnw);
                 }
-                if (es.err) break;
-
-                int32_t val = code(br, es, cc, cs, n->a, dist_mult);
-                val = unpack_signed(val) * n->d + n->c;
-                int32_t pred = 0;
-                switch (n->b) {
-                case 0: pred = 0; break;
-                case 1: pred = pw; break;
-                case 2: pred = pn; break;
-                case 3: pred = (pw + pn) / 2; break;
-                case 4: pred = iabs(pn - pnw) < iabs(pw - pnw) ? pw : pn; break;
-                case 5: pred = mod_gradient(pw, pn, pnw); break;
-                case 6: pred = (wp.pred[4] + 3) >> 3; break;
-                case 7: pred = pne; break;
-                case 8: pred = pnw; break;
-                case 9: pred = pww; break;
-                case 10: pred = (pw + pnw) / 2; break;
-                case 11: pred = (pn + pnw) / 2; break;
-                case 12: pred = (pn + pne) / 2; break;
-                case 13: pred = (6 * pn - 2 * pnn + 7 * pw + pww + pnee + 3 * pne + 8) / 16; break;
-                default: es.set(br, E_PRED); break;
-                }
-                val += pred;
-                if (es.err) break;
-                if (val < -32768 || val > 32767) { es.set(br, E_POVF); break; }
-                row[x] = (int16_t) val;
-                cur[x] = (int16_t) val;
-                prev2 = prev;
-                prev = val;
-                if (USE_WP) wp_after_predict(wp, x, y, val);
+                if (prop & 1) val = iabs(val);
+                dst[x] = val;
             }
-            ms.info[3] = es.err ? 1 : 0;
         }
-        sync();
-        if (ms.info[3]) return;
+        sync(); // also orders the previous row's error stores before this row's loads
+        int16_t *grow = c.px + (size_t) y * (size_t) stride;
+        int16_t *cur = ms.rows + (size_t) (y % 3) * cap;
+        const int16_t *nrow = ms.rows + (size_t) ((y + 2) % 3) * cap, *nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
+        int32_t *err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
+        const int32_t *nerr = ms.wp + (size_t) ((y & 1) ? 0 : width) * 5;
+        int32_t prev = 0, prev2 = 0;
+        // sliding windows over the row above
+        int32_t n_ww = 0, n_w = 0, n_c = y > 0 ? nrow[0] : 0, n_e = y > 0 && width > 1 ? nrow[1] : n_c;
+        if (USE_WP) {
+            for (int k = 0; k < WP_NL; ++k) {
+                const int i = WP_NL == 1 ? my_i : k;
+                wp.e_w[k] = wp.e_ww[k] = 0;
+                wp.e_n[k] = y > 0 ? nerr[i] : 0;
+                wp.e_nw[k] = wp.e_n[k];
+                wp.e_ne[k] = y > 0 && width > 1 ? nerr[5 + i] : wp.e_n[k];
+            }
+            wp.te_w = 0;
+            wp.te_n = y > 0 ? nerr[4] : 0;
+            wp.te_nw = wp.te_n;
+            wp.te_ne = y > 0 && width > 1 ? nerr[5 + 4] : wp.te_n;
+        }
+        for (int32_t x = 0; x < width; ++x) {
+            const int32_t n_ee = y > 0 && x + 2 < width ? nrow[x + 2] : n_e;
+            const int32_t pw = x > 0 ? prev : n_c;                 // (n_c is 0 in the first row)
+            const int32_t pn = y > 0 ? n_c : pw;
+            const int32_t pnw = x > 0 && y > 0 ? n_w : pw;
+            const int32_t pne = y > 0 ? n_e : pn;                   // n_e already equals n_c at the right edge
+            const int32_t pnn = y > 1 ? nnrow[x] : pn;
+            const int32_t pnee = y > 0 ? n_ee : pne;
+            const int32_t pww = x > 1 ? prev2 : pw;
+            const int32_t pnww = x > 1 && y > 0 ? n_ww : pww;
+            int32_t maxerr = 0;
+            if (USE_WP) {
+                // j40.h:4011-4072
+                wp.pred[0] = (pw + pne - pn) * 8;
+                wp.pred[1] = pn * 8 - (((wp.te_w + wp.te_n + wp.te_ne) * wpp.p1) >> 5);
+                wp.pred[2] = pw * 8 - (((wp.te_w + wp.te_n + wp.te_nw) * wpp.p2) >> 5);
+                wp.pred[3] = pn * 8 - ((wp.te_nw * wpp.p3[0] + wp.te_n * wpp.p3[1] + wp.te_ne * wpp.p3[2] +
+                                        (pnn - pn) * 8 * wpp.p3[3] + (pnw - pw) * 8 * wpp.p3[4]) >> 5);
+                int32_t w[4];
+#ifdef __CUDA_ARCH__
+                {
+                    const int i = my_i & 3;
+                    int32_t errsum = wp.e_n[0] + wp.e_w[0] + wp.e_nw[0] + wp.e_ww[0] + wp.e_ne[0] + (x + 1 < width ? 0 : wp.e_w[0]);
+                    int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
+                    int32_t wi = (int32_t) (4 + (((int64_t) wpp.w[i] * div24[errsum >> shift]) >> shift));
+                    for (int k = 0; k < 4; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k);
+                }
+#else
+                for (int i = 0; i < 4; ++i) {
+                    int32_t errsum = wp.e_n[i] + wp.e_w[i] + wp.e_nw[i] + wp.e_ww[i] + wp.e_ne[i] + (x + 1 < width ? 0 : wp.e_w[i]);
+                    int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
+                    w[i] = (int32_t) (4 + (((int64_t) wpp.w[i] * div24[errsum >> shift]) >> shift));
+                }
+#endif
+                int32_t logw = floor_lg32((uint32_t) (w[0] + w[1] + w[2] + w[3])) - 4;
+                int32_t wsum = 0, sum = 0;
+                for (int i = 0; i < 4; ++i) {
+                    w[i] >>= logw;
+                    wsum += w[i];
+                    sum += wp.pred[i] * w[i];
+                }
+                wp.pred[4] = (int32_t) ((((int64_t) sum + (wsum >> 1) - 1) * div24[wsum - 1]) >> 24);
+                if (((wp.te_n ^ wp.te_w) | (wp.te_n ^ wp.te_nw)) <= 0) {
+                    int32_t lo = imin(pw, imin(pn, pne)) * 8;
+                    int32_t hi = imax(pw, imax(pn, pne)) * 8;
+                    wp.pred[4] = imin(imax(lo, wp.pred[4]), hi);
+                }
+                maxerr = wp.te_w;
+                if (iabs(maxerr) < iabs(wp.te_n)) maxerr = wp.te_n;
+                if (iabs(maxerr) < iabs(wp.te_nw)) maxerr = wp.te_nw;
+                if (iabs(maxerr) < iabs(wp.te_ne)) maxerr = wp.te_ne;
+            }
+
+            const int32_t li = simt_tree_leaf(ms.tab, mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, ms.refp, cap);
+            const DTreeNode leaf = tree[li];
+            int32_t val = code(br, es, cc, cs, leaf.a, dist_mult);
+            val = unpack_signed(val) * leaf.d + leaf.c;
+            int32_t pred = 0;
+            switch (leaf.b) {
+            case 0: pred = 0; break;
+            case 1: pred = pw; break;
+            case 2: pred = pn; break;
+            case 3: pred = (pw + pn) / 2; break;
+            case 4: pred = iabs(pn - pnw) < iabs(pw - pnw) ? pw : pn; break;
+            case 5: pred = mod_gradient(pw, pn, pnw); break;
+            case 6: pred = (wp.pred[4] + 3) >> 3; break;
+            case 7: pred = pne; break;
+            case 8: pred = pnw; break;
+            case 9: pred = pww; break;
+            case 10: pred = (pw + pnw) / 2; break;
+            case 11: pred = (pn + pnw) / 2; break;
+            case 12: pred = (pn + pne) / 2; break;
+            case 13: pred = (6 * pn - 2 * pnn + 7 * pw + pww + pnee + 3 * pne + 8) / 16; break;
+            default: es.set(br, E_PRED); break;
+            }
+            val += pred;
+            if (es.err) return; // uniform: every lane sees the same error
+            if (val < -32768 || val > 32767) { es.set(br, E_POVF); return; }
+            grow[x] = (int16_t) val;
+            cur[x] = (int16_t) val;
+            prev2 = prev;
+            prev = val;
+            n_ww = n_w; n_w = n_c; n_c = n_e; n_e = n_ee;
+            if (USE_WP) {
+                // j40.h:4103-4111, then slide the error windows
+                const int32_t v8 = val * 8;
+                const int32_t te = wp.pred[4] - v8;
+                for (int k = 0; k < WP_NL; ++k) {
+                    const int i = WP_NL == 1 ? my_i : k;
+                    const int32_t psel = i == 0 ? wp.pred[0] : i == 1 ? wp.pred[1] : i == 2 ? wp.pred[2] : wp.pred[3];
+                    const int32_t e = i < 4 ? (iabs(psel - v8) + 3) >> 3 : te;
+                    err[(size_t) x * 5 + i] = e;
+                    wp.e_ww[k] = wp.e_w[k];
+                    wp.e_w[k] = e;
+                    wp.e_nw[k] = wp.e_n[k];
+                    wp.e_n[k] = wp.e_ne[k];
+                    wp.e_ne[k] = y > 0 && x + 2 < width ? nerr[(size_t) (x + 2) * 5 + i] : wp.e_ne[k];
+                }
+                wp.te_w = te;
+                wp.te_nw = wp.te_n;
+                wp.te_n = wp.te_ne;
+                wp.te_ne = y > 0 && x + 2 < width ? nerr[(size_t) (x + 2) * 5 + 4] : wp.te_ne;
+            }
+        }
     }
+    sync();
 }
 
-// Entry point for a warp: decides (lane 0) between the row path above and the plain path, then all lanes
-// follow. Every lane must call this with the same arguments; only lane 0's br / es / cs are meaningful.
+// Entry point for a warp; every lane calls it with identical arguments and identical decoder state, and leaves
+// it with identical state. Chooses between the SIMT path above and walking the tree (wide channels, trees that
+// do not compile); the latter is executed redundantly by all lanes so that their state stays in step.
 template <class Sync>
 J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
                                          const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch, const int32_t *div24,
@@ -423,35 +577,35 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
                                          const ModImage &m, int32_t cidx, int32_t sidx, int lane, int nlanes, Sync sync) {
     const ModChannel &c = m.ch[cidx];
     if (c.w <= 0 || c.h <= 0) return;
+    sync(); // the previous channel's readers of ptree / tab are done
     if (lane == 0) {
         bool uses_wp = tree_uses_wp;
         int n = ptree_cap > 0 ? prune_tree(tree, cidx, sidx, ptree, ptree_cap, &uses_wp) : 0;
         if (n == 0) uses_wp = tree_uses_wp;
-        int maxprop = 0;
-        const DTreeNode *t = n ? ptree : tree;
-        if (n) for (int i = 0; i < n; ++i) { if (t[i].a < 0 && -1 - t[i].a > maxprop) maxprop = -1 - t[i].a; }
-        else maxprop = 16 + 4 * MOD_STAGED_REFS - 1; // unknown: stage what we can
-        int want = maxprop >= 16 ? (maxprop - 16) / 4 + 1 : 0;
+        int nref = 0;
+        for (int32_t i = cidx - 1; i >= 0; --i) {
+            const ModChannel &r = m.ch[i];
+            if (c.w == r.w && c.h == r.h && c.hshift == r.hshift && c.vshift == r.vshift) ++nref;
+        }
+        int32_t nslots = 0;
+        bool simt = ms.rows && c.w <= ms.cap && n > 0 && simt_compile_tree(ptree, n, nref, ms.tab, ms.info + 4, &nslots);
         ms.info[0] = uses_wp;
-        ms.info[1] = want < MOD_STAGED_REFS ? want : MOD_STAGED_REFS;
-        ms.info[2] = (ms.rows && c.w <= ms.cap && n > 0) ? 1 : 0;
-        ms.info[3] = 0;
+        ms.info[1] = nslots;
+        ms.info[2] = simt;
+        ms.info[3] = n;
     }
     sync();
     const bool uses_wp = ms.info[0] != 0;
-    const int nstaged = ms.info[1];
+    const int n = ms.info[3];
     if (ms.info[2]) {
-        if (uses_wp) modular_channel_rows<true>(br, es, cc, cs, ptree, ms, div24, m, cidx, sidx, nstaged, lane, nlanes, sync);
-        else modular_channel_rows<false>(br, es, cc, cs, ptree, ms, div24, m, cidx, sidx, nstaged, lane, nlanes, sync);
+        int32_t refprops[SIMT_REF_SLOTS];
+        for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
+        if (uses_wp) modular_channel_simt<true>(br, es, cc, cs, ptree, ms, refprops, ms.info[1], div24, m, cidx, sidx, lane, nlanes, sync);
+        else modular_channel_simt<false>(br, es, cc, cs, ptree, ms, refprops, ms.info[1], div24, m, cidx, sidx, lane, nlanes, sync);
     } else {
-        if (lane == 0) {
-            // wide channels (or trees too large to prune into shared memory): plain path through global memory
-            const DTreeNode *t = tree;
-            bool wpf = tree_uses_wp;
-            if (ptree_cap > 0 && prune_tree(tree, cidx, sidx, ptree, ptree_cap, &wpf) > 0) t = ptree; else wpf = tree_uses_wp;
-            if (wpf) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
-            else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
-        }
+        const DTreeNode *t = n > 0 ? ptree : tree;
+        if (uses_wp) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
+        else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
         sync();
     }
 }

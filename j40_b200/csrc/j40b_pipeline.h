@@ -60,6 +60,7 @@ public:
         size_t work = 0;                    // device-only area cursor (follows the upload blob)
         auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
         size_t n_lf = 0, n_hf = 0, n_mod = 0;
+        max_global_blob = max_coeff_blob = 0;
         for (size_t k = 0; k < n; ++k) {
             FramePlan &p = *plans[k];
             Img &im = img[k];
@@ -74,6 +75,12 @@ public:
             im.rgba_off = wk_alloc((size_t) results[k].stride * (size_t) d.height);
             results[k].rgba_off = im.rgba_off; // relative to the work area for now
             if (!d.is_modular) {
+                if (d.global_spec_off) {
+                    const DCodeSpec *gs = (const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off);
+                    max_global_blob = std::max(max_global_blob, (size_t) (gs->blob_hi - gs->blob_lo));
+                }
+                const DCodeSpec *cs_ = (const DCodeSpec *) (p.arena.bytes.data() + d.coeff_spec_off);
+                max_coeff_blob = std::max(max_coeff_blob, (size_t) (cs_->blob_hi - cs_->blob_lo));
                 im.nlf = p.lfg_sec.size(); im.ng = p.pg_sec.size();
                 im.lfg_off = up_alloc(sizeof(DLfGroup) * im.nlf);
                 im.grp_off = up_alloc(sizeof(DGroup) * im.ng);
@@ -304,8 +311,8 @@ public:
             be.dev_memset(dwork + im.err_off, 0, 4 * nerr);
             if (!p.df.is_modular) for (const LfBuf &b : im.lf) be.dev_memset(dwork + b.vb_tok, 0, 4 * 2 * 3 * (size_t) b.w8 * b.h8);
         }
-        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf);
-        if (num_hf) be.launch_hf((const HfWork *) (dev + hfw_off), (int) num_hf);
+        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob);
+        if (num_hf) be.launch_hf((const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
         if (num_hf) be.launch_back((const BackWork *) (dev + bkw_off), (int) num_hf);
         for (size_t k = 0; k < plans.size(); ++k) {
             FramePlan &p = *plans[k];
@@ -396,6 +403,7 @@ private:
     uint8_t *dev = nullptr, *staging = nullptr;
     size_t upload_bytes = 0, work_bytes = 0, dev_cap = 0, staging_cap = 0;
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, num_lf = 0, num_hf = 0;
+    size_t max_global_blob = 0, max_coeff_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
 };
 
 } // namespace j40b

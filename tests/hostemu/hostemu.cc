@@ -23,18 +23,19 @@ struct HostEmuBackend {
     // shared memory of one warp of the serial decoders
     struct WarpMem {
         WarpScratch ws;
-        std::vector<int32_t> wp;
-        std::vector<int16_t> rows, refs;
+        std::vector<int32_t> wp, refp;
+        std::vector<int16_t> rows;
+        SimtLane tab[SIMT_LANES];
         int32_t div24[64];
         ModSmem ms;
-        explicit WarpMem(int cap) : wp((size_t) cap * 10 + 1), rows((size_t) cap * 3 + 1), refs((size_t) cap * MOD_STAGED_REFS * 2 + 1) {
-            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refs = refs.data(); ms.info = ws.info; ms.cap = cap;
+        explicit WarpMem(int cap) : wp((size_t) cap * 10 + 1), refp((size_t) cap * SIMT_REF_SLOTS + 1), rows((size_t) cap * 3 + 1) {
+            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = refp.data(); ms.tab = tab; ms.info = ws.info; ms.cap = cap;
             fill_div24(div24, 0, 1);
         }
     };
     // HOSTEMU_ROW_CAP overrides the row-path width limit (0 = always take the plain path)
     static int row_cap(int dflt) { const char *e = getenv("HOSTEMU_ROW_CAP"); return e ? atoi(e) : dflt; }
-    void launch_lf(const LfWork *w, int n) {
+    void launch_lf(const LfWork *w, int n, size_t) {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(256));
         for (int i = 0; i < n; ++i) {
@@ -46,7 +47,7 @@ struct HostEmuBackend {
             lf_llf_body(w[i], 0, 1, NoSync());
         }
     }
-    void launch_hf(const HfWork *w, int n) {
+    void launch_hf(const HfWork *w, int n, size_t) {
         std::vector<uint8_t> copy(40 * 1024);
         for (int i = 0; i < n; ++i) {
             // like the device kernel: every other "warp" gets a staged copy of the code spec tables
