@@ -85,7 +85,7 @@ struct TileShared {
     uint8_t cover[64];      // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
     uint8_t chunk_vb[64];   // 64-float chunk -> index into vb[]
     float thr[255];
-    uint8_t lut[1028];
+    uint8_t lut[SRGB_LUT_BYTES];
 };
 
 // tile (tx, ty) of group w.grp; coef = 3 * 4096 floats of shared memory
@@ -119,7 +119,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         ts.cover[c] = 0xff;
     }
     for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
-    for (int i = tid; i < 1028 / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
+    for (int i = tid; i < SRGB_LUT_BYTES / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
     for (int i = tid; i < 3 * 4096; i += nth) coef[i] = 0.0f;
     sync();
     // ---- 0b. compact them in raster order (each top-left cell computes its own rank and chunk offset)

@@ -80,7 +80,7 @@ struct HybridCfg {
     int32_t max_token;
 };
 
-struct DCluster {
+struct alignas(16) DCluster {
     HybridCfg cfg;
     uint32_t table_off; // ANS: uint64_t[1 << log_alpha_size]; prefix: uint32_t[] two-level LUT
     int16_t root_bits;  // prefix only: index width of the first-level LUT (0 = zero-length code)

@@ -34,7 +34,7 @@ enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
 struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
 
 __host__ __device__ inline size_t warp_slice_bytes(int cap) {
-    size_t n = sizeof(WarpScratch) + sizeof(SimtLane) * SIMT_LANES;
+    size_t n = sizeof(WarpScratch) + (sizeof(SimtLane) + sizeof(SimtLeaf)) * SIMT_LANES;
     n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + SIMT_REF_SLOTS * 4);
     return (n + 15) & ~(size_t) 15;
 }
@@ -42,7 +42,8 @@ __host__ __device__ inline size_t warp_slice_bytes(int cap) {
 __device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws) {
     ws = (WarpScratch *) base;
     ModSmem ms;
-    ms.tab = (SimtLane *) (base + sizeof(WarpScratch));
+    ms.leaves = (SimtLeaf *) (base + sizeof(WarpScratch));
+    ms.tab = (SimtLane *) (ms.leaves + SIMT_LANES);
     ms.wp = (int32_t *) (ms.tab + SIMT_LANES);
     ms.refp = ms.wp + (size_t) cap * 10;
     ms.rows = cap ? (int16_t *) (ms.refp + (size_t) cap * SIMT_REF_SLOTS) : nullptr;

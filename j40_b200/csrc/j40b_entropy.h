@@ -156,11 +156,15 @@ J40B_HD J40B_INLINE int32_t hybrid_int(BitReader &br, ErrSlot &es, int32_t token
     return (int32_t) (((uint32_t) (top | hi) << (midbits + c.lsb_in_token)) | (((uint32_t) mid << c.lsb_in_token) | (uint32_t) lo));
 }
 
+// INIT_CHECK = false: the caller has already seeded the state (ans_seed) before its first symbol
+J40B_HD J40B_INLINE void ans_seed(BitReader &br, uint32_t &state) {
+    state = br.u(16);
+    state |= br.u(16) << 16;
+}
+
+template <bool INIT_CHECK = true>
 J40B_HD J40B_INLINE int32_t ans_symbol(BitReader &br, uint32_t &state, int log_bucket_size, const uint64_t *table) {
-    if (state == 0) {
-        state = br.u(16);
-        state |= br.u(16) << 16;
-    }
+    if (INIT_CHECK && state == 0) ans_seed(br, state);
     uint32_t idx = state & 0xfff;
     uint32_t i = idx >> log_bucket_size;
     uint32_t p = idx & ((1u << log_bucket_size) - 1);
@@ -191,22 +195,31 @@ struct CodeCtx { // everything a symbol read needs besides the state
     const DCodeSpec *spec;
     const uint8_t *cluster_map;
     const DCluster *clusters;
+    // per-symbol fields of the spec, kept in registers
+    int32_t min_symbol;   // INT32_MAX when LZ77 is off, so that one compare decides
+    int32_t log_bucket;   // ANS: 12 - log_alpha_size
+    bool prefix, lz77;
     J40B_HD void init(const uint8_t *arena_, uint32_t spec_off) {
         arena = arena_;
         spec = (const DCodeSpec *) (arena_ + spec_off);
         cluster_map = arena_ + spec->cluster_map_off;
         clusters = (const DCluster *) (arena_ + spec->clusters_off);
+        prefix = spec->use_prefix_code != 0;
+        lz77 = spec->lz77_enabled != 0;
+        min_symbol = lz77 ? spec->min_symbol : 0x7fffffff;
+        log_bucket = 12 - spec->log_alpha_size;
     }
     // `copy` holds the bytes [blob_lo, blob_hi) of the arena (cluster map, clusters, tables, spec): all
     // table offsets keep working relative to (copy - blob_lo)
     J40B_HD void init_from_copy(const uint8_t *copy, uint32_t blob_lo, uint32_t spec_off) { init(copy - blob_lo, spec_off); }
 };
 
-J40B_HD J40B_INLINE int32_t cluster_symbol(BitReader &br, const CodeCtx &cc, const DCluster *cl, uint32_t &ans_state) {
-    if (cc.spec->use_prefix_code) {
-        return prefix_symbol(br, cl->root_bits, (const uint32_t *) (cc.arena + cl->table_off));
+template <bool INIT_CHECK = true>
+J40B_HD J40B_INLINE int32_t cluster_symbol(BitReader &br, const CodeCtx &cc, const DCluster &cl, uint32_t &ans_state) {
+    if (cc.prefix) {
+        return prefix_symbol(br, cl.root_bits, (const uint32_t *) (cc.arena + cl.table_off));
     } else {
-        return ans_symbol(br, ans_state, 12 - cc.spec->log_alpha_size, (const uint64_t *) (cc.arena + cl->table_off));
+        return ans_symbol<INIT_CHECK>(br, ans_state, cc.log_bucket, (const uint64_t *) (cc.arena + cl.table_off));
     }
 }
 
@@ -228,23 +241,17 @@ J40B_HD J40B_INLINE int32_t special_distance(int idx) {
     return (int32_t) T[idx];
 }
 
-// one decoded integer (aka DecodeHybridVarLenUint); mirrors j40__code incl. its LZ77 quirks
-J40B_HD J40B_INLINE int32_t code(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs, int32_t ctx, int32_t dist_mult) {
-    const DCodeSpec *spec = cc.spec;
-    if (cs.num_to_copy > 0) {
-        --cs.num_to_copy;
-        int32_t v = cs.copy_pos == cs.num_decoded ? 0 : cs.window[(uint32_t) cs.copy_pos & cs.window_mask];
-        ++cs.copy_pos;
-        cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = v;
-        return v;
-    }
-    const DCluster *cl = &cc.clusters[cc.cluster_map[ctx]];
-    int32_t token = cluster_symbol(br, cc, cl, cs.ans_state);
-    if (token >= spec->min_symbol) { // only possible when LZ77 is enabled
-        const DCluster *lz = &cc.clusters[cc.cluster_map[spec->num_dist - 1]];
+// one decoded integer (aka DecodeHybridVarLenUint) whose context has already been resolved to cluster `cl`;
+// mirrors j40__code incl. its LZ77 quirks
+template <bool INIT_CHECK = true>
+J40B_HD J40B_INLINE int32_t code_cluster(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs, const DCluster &cl, int32_t dist_mult) {
+    int32_t token = cluster_symbol<INIT_CHECK>(br, cc, cl, cs.ans_state);
+    if (token >= cc.min_symbol) { // only possible when LZ77 is enabled
+        const DCodeSpec *spec = cc.spec;
+        const DCluster lz = cc.clusters[cc.cluster_map[spec->num_dist - 1]];
         int32_t num_to_copy = hybrid_int(br, es, token - spec->min_symbol, spec->lz_len_cfg) + spec->min_length;
-        token = cluster_symbol(br, cc, lz, cs.ans_state);
-        int32_t distance = hybrid_int(br, es, token, lz->cfg);
+        token = cluster_symbol<INIT_CHECK>(br, cc, lz, cs.ans_state);
+        int32_t distance = hybrid_int(br, es, token, lz.cfg);
         if (es.err) return 0;
         if (!dist_mult) {
             ++distance;
@@ -262,15 +269,32 @@ J40B_HD J40B_INLINE int32_t code(BitReader &br, ErrSlot &es, const CodeCtx &cc, 
         cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = v;
         return v;
     }
-    token = hybrid_int(br, es, token, cl->cfg);
+    token = hybrid_int(br, es, token, cl.cfg);
     if (es.err) return 0;
-    if (spec->lz77_enabled) cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = token;
+    if (cc.lz77) cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = token;
     return token;
+}
+
+// the LZ77 copy in progress, if any (the part of j40__code that precedes the symbol read)
+J40B_HD J40B_INLINE bool code_copy(CodeState &cs, int32_t &v) {
+    if (cs.num_to_copy <= 0) return false;
+    --cs.num_to_copy;
+    v = cs.copy_pos == cs.num_decoded ? 0 : cs.window[(uint32_t) cs.copy_pos & cs.window_mask];
+    ++cs.copy_pos;
+    cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = v;
+    return true;
+}
+
+J40B_HD J40B_INLINE int32_t code(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs, int32_t ctx, int32_t dist_mult) {
+    int32_t v;
+    if (code_copy(cs, v)) return v;
+    const DCluster cl = cc.clusters[cc.cluster_map[ctx]];
+    return code_cluster(br, es, cc, cs, cl, dist_mult);
 }
 
 // end of one entropy-coded stream (j40__finish_and_free_code): the rANS state must be back at its seed
 J40B_HD J40B_INLINE void finish_code(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs) {
-    if (!cc.spec->use_prefix_code) {
+    if (!cc.prefix) {
         if (cs.ans_state) {
             if (cs.ans_state != 0x130000u) es.set(br, E_ANS);
         } else {

@@ -79,7 +79,7 @@ namespace j40b {
 enum { PTREE_CAP = 192 };
 
 // per-warp scratch of the serial decoders (shared memory on the device)
-struct WarpScratch {
+struct alignas(16) WarpScratch {
     DTreeNode ptree[PTREE_CAP];
     ModImage m;
     int32_t info[8];

@@ -3,6 +3,8 @@
 // acceptance rules and four-character error codes as the reference (file:line citations below), emitting
 // device-ready tables. Compiled with -ffp-contract=off: the float tables must match the reference bit for bit.
 #include "j40b_host.h"
+#include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -507,7 +509,7 @@ struct Parser {
         spec.blob_lo = blob_lo;
         spec.cluster_map_off = arena.alloc(map.size(), 8);
         memcpy(arena.at<uint8_t>(spec.cluster_map_off), map.data(), map.size());
-        spec.clusters_off = arena.alloc(clusters.size() * sizeof(DCluster), 8);
+        spec.clusters_off = arena.alloc(clusters.size() * sizeof(DCluster), 16);
         memcpy(arena.at<uint8_t>(spec.clusters_off), clusters.data(), clusters.size() * sizeof(DCluster));
         uint32_t off = arena.alloc(sizeof(DCodeSpec), 16);
         spec.blob_hi = off + (uint32_t) sizeof(DCodeSpec);
@@ -1440,10 +1442,13 @@ const GlobalTables &GlobalTables::get() {
         static const int8_t ORDER_LOG[13][2] = {{3, 3}, {3, 3}, {4, 4}, {5, 5}, {3, 4}, {3, 5}, {4, 5}, {6, 6}, {5, 6}, {7, 7}, {6, 7}, {8, 8}, {7, 8}};
         for (int i = 0; i < 13; ++i) t->order[i] = compute_natural_order(ORDER_LOG[i][0], ORDER_LOG[i][1]);
         compute_srgb_thresholds(8, t->srgb_thr);
-        for (int b = 0; b <= 1024; ++b) {
+        memset(t->srgb_lut, 0, sizeof(t->srgb_lut));
+        for (int b = 0; b <= SRGB_LUT_N; ++b) {
             int n = 0;
-            while (n < 255 && t->srgb_thr[n] <= (float) b / 1024.0f) ++n;
+            while (n < 255 && t->srgb_thr[n] <= (float) b / (float) SRGB_LUT_N) ++n;
             t->srgb_lut[b] = (uint8_t) n;
+            // srgb_u8_lut() takes at most two steps inside a bucket
+            if (b > 0 && n - t->srgb_lut[b - 1] > 2) { fprintf(stderr, "j40_b200: sRGB start table too coarse\n"); abort(); }
         }
         g = t;
     });

@@ -75,7 +75,7 @@ struct GlobalTables {
     std::vector<float> dq[17];        // [n][3]
     std::vector<int32_t> order[13];
     float srgb_thr[255];
-    uint8_t srgb_lut[1028];
+    uint8_t srgb_lut[4100]; // SRGB_LUT_BYTES
     static const GlobalTables &get();
 };
 

@@ -288,11 +288,17 @@ struct SimtLane {       // lane j: decision node j and leaf j of the compiled (p
     int32_t leaf_node;  // index of leaf j in the pruned tree, -1 if none
 };
 
+struct alignas(16) SimtLeaf { // leaf j with its context already resolved to a cluster
+    DCluster cl;
+    int32_t predictor, offset, multiplier, pad;
+};
+
 struct ModSmem {
     int16_t *rows;   // [3][cap]  ring of the last three sample rows (null: no SIMT path)
     int32_t *wp;     // [2][cap][5] weighted predictor error rows
     int32_t *refp;   // [SIMT_REF_SLOTS][cap] reference-channel property values of the current row
     SimtLane *tab;   // [SIMT_LANES]
+    SimtLeaf *leaves; // [SIMT_LANES]
     int32_t *info;   // [8] scratch flags shared by the lanes
     int32_t cap;     // widest channel the SIMT path can take
 };
@@ -300,7 +306,8 @@ struct ModSmem {
 // Compiles the pruned tree into per-lane decision forms. Returns false if it does not fit (more than 32 inner
 // nodes or leaves, more than SIMT_REF_SLOTS distinct reference properties, a reference property without its
 // channel): the caller then walks the tree instead. refprops[s] = property number of slot s.
-J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, SimtLane *tab, int32_t *refprops, int32_t *nslots) {
+J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, const CodeCtx &cc, SimtLane *tab, SimtLeaf *leaves,
+                                      int32_t *refprops, int32_t *nslots) {
     int inner_of[192], ni = 0, nl = 0, ns = 0;
     if (n <= 0 || n > 192) return false;
     for (int i = 0; i < SIMT_LANES; ++i) {
@@ -350,7 +357,14 @@ J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, SimtL
     while (sp > 0) {
         --sp;
         int i = stack_node[sp]; uint32_t care = stack_care[sp], want = stack_want[sp];
-        if (t[i].a >= 0) { tab[leaf].care = care; tab[leaf].want = want; tab[leaf].leaf_node = i; ++leaf; continue; }
+        if (t[i].a >= 0) {
+            tab[leaf].care = care; tab[leaf].want = want; tab[leaf].leaf_node = i;
+            SimtLeaf &lf = leaves[leaf];
+            lf.cl = cc.clusters[cc.cluster_map[t[i].a]];
+            lf.predictor = t[i].b; lf.offset = t[i].c; lf.multiplier = t[i].d; lf.pad = 0;
+            ++leaf;
+            continue;
+        }
         if (sp + 2 > 64) return false;
         uint32_t bit = 1u << inner_of[i];
         stack_node[sp] = t[i].c; stack_care[sp] = care | bit; stack_want[sp] = want | bit; ++sp; // value > threshold
@@ -370,18 +384,18 @@ J40B_HD J40B_INLINE bool simt_decision(const SimtLane &L, int32_t x, int32_t y, 
     return (L.flags & 4) && v > L.thr;
 }
 
-// index (in the pruned tree) of the leaf the current sample falls into
+// index (into ModSmem::leaves) of the leaf the current sample falls into
 J40B_HD J40B_INLINE int32_t simt_tree_leaf(const SimtLane *tab, const SimtLane &mine, int32_t x, int32_t y, int32_t pn, int32_t pw,
                                            int32_t pnw, int32_t pne, int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr,
                                            const int32_t *refp, int32_t cap) {
 #ifdef __CUDA_ARCH__
     const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision(mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
     const uint32_t hit = __ballot_sync(0xffffffffu, mine.leaf_node >= 0 && (dec & mine.care) == mine.want);
-    return __shfl_sync(0xffffffffu, mine.leaf_node, __ffs((int) hit) - 1);
+    return __ffs((int) hit) - 1;
 #else
     uint32_t dec = 0;
     for (int j = 0; j < SIMT_LANES; ++j) dec |= (uint32_t) simt_decision(tab[j], x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap) << j;
-    for (int j = 0; j < SIMT_LANES; ++j) if (tab[j].leaf_node >= 0 && (dec & tab[j].care) == tab[j].want) return tab[j].leaf_node;
+    for (int j = 0; j < SIMT_LANES; ++j) if (tab[j].leaf_node >= 0 && (dec & tab[j].care) == tab[j].want) return j;
     return -1;
 #endif
 }
@@ -418,7 +432,16 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
     const int my_i = lane < 4 ? lane : 4; // this lane's weighted-predictor index (device)
     (void) my_i;
     WpSimt wp;
+    // the first call below always reads a symbol (or continues an LZ77 copy that an earlier channel began):
+    // seed the rANS state here so that the per-sample path does not have to test for it
+    if (!cc.prefix && cs.ans_state == 0 && cs.num_to_copy <= 0) ans_seed(br, cs.ans_state);
     for (int32_t y = 0; y < height; ++y) {
+        // ---- all lanes: the finished previous row goes to global memory, coalesced
+        if (y > 0) {
+            const int16_t *done = ms.rows + (size_t) ((y + 2) % 3) * cap;
+            int16_t *gdst = c.px + (size_t) (y - 1) * (size_t) stride;
+            for (int32_t x = lane; x < width; x += nlanes) gdst[x] = done[x];
+        }
         // ---- all lanes: this row's reference-channel property values
         for (int sl = 0; sl < nslots; ++sl) {
             const int prop = refprops[sl];
@@ -438,7 +461,6 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
             }
         }
         sync(); // also orders the previous row's error stores before this row's loads
-        int16_t *grow = c.px + (size_t) y * (size_t) stride;
         int16_t *cur = ms.rows + (size_t) (y % 3) * cap;
         const int16_t *nrow = ms.rows + (size_t) ((y + 2) % 3) * cap, *nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
         int32_t *err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
@@ -513,11 +535,12 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
             }
 
             const int32_t li = simt_tree_leaf(ms.tab, mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, ms.refp, cap);
-            const DTreeNode leaf = tree[li];
-            int32_t val = code(br, es, cc, cs, leaf.a, dist_mult);
-            val = unpack_signed(val) * leaf.d + leaf.c;
+            const SimtLeaf leaf = ms.leaves[li];
+            int32_t val;
+            if (!code_copy(cs, val)) val = code_cluster<false>(br, es, cc, cs, leaf.cl, dist_mult);
+            val = unpack_signed(val) * leaf.multiplier + leaf.offset;
             int32_t pred = 0;
-            switch (leaf.b) {
+            switch (leaf.predictor) {
             case 0: pred = 0; break;
             case 1: pred = pw; break;
             case 2: pred = pn; break;
@@ -537,7 +560,6 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
             val += pred;
             if (es.err) return; // uniform: every lane sees the same error
             if (val < -32768 || val > 32767) { es.set(br, E_POVF); return; }
-            grow[x] = (int16_t) val;
             cur[x] = (int16_t) val;
             prev2 = prev;
             prev = val;
@@ -565,6 +587,12 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
         }
     }
     sync();
+    {
+        const int16_t *done = ms.rows + (size_t) ((height - 1) % 3) * cap;
+        int16_t *gdst = c.px + (size_t) (height - 1) * (size_t) stride;
+        for (int32_t x = lane; x < width; x += nlanes) gdst[x] = done[x];
+    }
+    sync();
 }
 
 // Entry point for a warp; every lane calls it with identical arguments and identical decoder state, and leaves
@@ -588,7 +616,7 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
             if (c.w == r.w && c.h == r.h && c.hshift == r.hshift && c.vshift == r.vshift) ++nref;
         }
         int32_t nslots = 0;
-        bool simt = ms.rows && c.w <= ms.cap && n > 0 && simt_compile_tree(ptree, n, nref, ms.tab, ms.info + 4, &nslots);
+        bool simt = ms.rows && c.w <= ms.cap && n > 0 && simt_compile_tree(ptree, n, nref, cc, ms.tab, ms.leaves, ms.info + 4, &nslots);
         ms.info[0] = uses_wp;
         ms.info[1] = nslots;
         ms.info[2] = simt;

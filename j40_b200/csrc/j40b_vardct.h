@@ -78,7 +78,7 @@ struct DFrame {
     const float *dq[17];             // float[n][3] per parameter set
     const int32_t *order[13][3];     // int32_t[size] per order and channel
     const float *srgb_thr;           // float[255]: smallest v whose 8-bit output is >= k+1
-    const uint8_t *srgb_lut;         // uint8[1025]: number of thresholds <= b / 1024
+    const uint8_t *srgb_lut;         // uint8[SRGB_LUT_N + 1]: number of thresholds <= b / SRGB_LUT_N
     int32_t global_tree_uses_wp, have_global_tree;
     // modular frames
     int32_t num_channels, num_gm_channels, alpha_channel; // alpha_channel < 0: opaque
@@ -680,13 +680,17 @@ J40B_HD J40B_INLINE int srgb_u8_from_linear(const float *thr, float v) {
     return lo;
 }
 
-// Same result through a 1025-entry start table: lut[b] = number of thresholds <= b / 1024 (b = floor(1024 v)
-// clamped to [0, 1024]), then at most a few steps up; used by the tile kernel
+// Same result through a start table of SRGB_LUT_N + 1 entries: lut[b] = number of thresholds <= b / SRGB_LUT_N
+// (b = floor(SRGB_LUT_N v) clamped to [0, SRGB_LUT_N]). The thresholds are at least 1 / (255 * 12.92) apart, wider
+// than a bucket, so at most one more lies inside bucket b (the host checks "at most two" when it builds the
+// table); two branch-free steps finish the search. Used by the tile kernel.
+enum { SRGB_LUT_N = 4096, SRGB_LUT_BYTES = 4100 };
 J40B_HD J40B_INLINE int srgb_u8_lut(const float *thr, const uint8_t *lut, float v) {
     if (!(v > 0.0f)) return 0; // thr[0] > 0; NaN also lands here (the reference's cast gives 0 after clamping)
-    int b = v >= 1.0f ? 1024 : (int) J40B_FMUL(v, 1024.0f);
+    int b = v >= 1.0f ? SRGB_LUT_N : (int) J40B_FMUL(v, (float) SRGB_LUT_N);
     int code = lut[b];
-    while (code < 255 && thr[code] <= v) ++code;
+    code += (code < 255 && thr[code < 255 ? code : 254] <= v) ? 1 : 0;
+    code += (code < 255 && thr[code < 255 ? code : 254] <= v) ? 1 : 0;
     return code;
 }
 

@@ -23,6 +23,7 @@ def lib():
         L.hostemu_srgb_thresholds.argtypes = [C.c_int, C.c_void_p]
         L.hostemu_srgb_lookup.restype = C.c_int
         L.hostemu_srgb_lookup.argtypes = [C.c_void_p, C.c_float]
+        L.hostemu_srgb_lut_lookup.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hostemu_inverse_transform.argtypes = [C.c_int, C.c_void_p]
         L.hostemu_forward_llf.argtypes = [C.c_void_p, C.c_int, C.c_int]
         _LIB = L

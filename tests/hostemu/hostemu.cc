@@ -26,10 +26,11 @@ struct HostEmuBackend {
         std::vector<int32_t> wp, refp;
         std::vector<int16_t> rows;
         SimtLane tab[SIMT_LANES];
+        SimtLeaf leaves[SIMT_LANES];
         int32_t div24[64];
         ModSmem ms;
         explicit WarpMem(int cap) : wp((size_t) cap * 10 + 1), refp((size_t) cap * SIMT_REF_SLOTS + 1), rows((size_t) cap * 3 + 1) {
-            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = refp.data(); ms.tab = tab; ms.info = ws.info; ms.cap = cap;
+            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = refp.data(); ms.tab = tab; ms.leaves = leaves; ms.info = ws.info; ms.cap = cap;
             fill_div24(div24, 0, 1);
         }
     };
@@ -124,6 +125,11 @@ __attribute__((visibility("default"))) int hostemu_natural_order(int log_rows, i
 }
 __attribute__((visibility("default"))) void hostemu_srgb_thresholds(int bpp, float *thr) { compute_srgb_thresholds(bpp, thr); }
 __attribute__((visibility("default"))) int hostemu_srgb_lookup(const float *thr, float v) { return srgb_u8_from_linear(thr, v); }
+// the tile kernel's two-step table search, on the library's global tables
+__attribute__((visibility("default"))) void hostemu_srgb_lut_lookup(const float *v, int n, uint8_t *out) {
+    const GlobalTables &gt = GlobalTables::get();
+    for (int i = 0; i < n; ++i) out[i] = (uint8_t) srgb_u8_lut(gt.srgb_thr, gt.srgb_lut, v[i]);
+}
 __attribute__((visibility("default"))) void hostemu_inverse_transform(int dctsel, float *buf) {
     DctSelectInfo d = dct_select_info(dctsel);
     if (is_special_8x8(dctsel)) { inverse_special(dctsel, buf); return; }

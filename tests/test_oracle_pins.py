@@ -53,10 +53,20 @@ def test_srgb_threshold_table_matches_reference_quantiser(oracle, emu):
         np.nextafter(thr, np.float32(-np.inf)), thr, np.nextafter(thr, np.float32(np.inf)),
     ])
     L = emu.lib()
-    for v in vals:
-        want = min(max(int(oracle.lib().ref_srgb_quant(float(v), 8)), 0), 255)
+    # bucket edges of the tile kernel's start table (j40b_vardct.h srgb_u8_lut) and their neighbours
+    edges = (np.arange(0, 4097, dtype=np.float32) / np.float32(4096.0)).astype(np.float32)
+    vals = np.concatenate([vals, edges, np.nextafter(edges, np.float32(-np.inf)), np.nextafter(edges, np.float32(np.inf)),
+                           np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1.0, 2.0, 1e30], np.float32)]).astype(np.float32)
+    lut_out = np.zeros(vals.size, np.uint8)
+    L.hostemu_srgb_lut_lookup(vals.ctypes.data, int(vals.size), lut_out.ctypes.data)
+    for k, v in enumerate(vals):
+        if np.isfinite(v) and v < 100.0:
+            want = min(max(int(oracle.lib().ref_srgb_quant(float(v), 8)), 0), 255)
+        else:
+            want = 255 if v > 0 else 0   # saturating device behaviour; the reference's int16 cast is undefined here
         got = L.hostemu_srgb_lookup(thr.ctypes.data, float(v))
         assert got == want, (float(v), got, want)
+        assert int(lut_out[k]) == want, (float(v), int(lut_out[k]), want)
 
 
 @pytest.mark.parametrize("dctsel", list(range(27)))

@@ -11,12 +11,10 @@ except Exception as e:
     print("$name failed", e); print(open("gpurun_out/x_$name.err").read()[-800:])
 PY
 }
-ARGS="--steps 12 --warmup 3 --streams 6 --skip-e2e"
-run s6_default A=1
-run s6_nostage_nocap J40B_LF_STAGE=0 J40B_LF_CAP=0
-run s6_nostage_cap J40B_LF_STAGE=0 J40B_LF_CAP=256
-run s6_warps4 J40B_LF_WARPS=4
-ARGS="--steps 12 --warmup 3 --streams 3 --skip-e2e"
-run s3_nostage_nocap J40B_LF_STAGE=0 J40B_LF_CAP=0
 ARGS="--steps 6 --warmup 3 --streams 3"
-run full_default A=1
+run v6_s3_full A=1
+ARGS="--steps 6 --warmup 3 --streams 3 --skip-e2e"
+run v6_s3_nostage J40B_LF_STAGE=0
+ARGS="--steps 12 --warmup 3 --streams 6 --skip-e2e"
+run v6_s6_nostage J40B_LF_STAGE=0
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_lf_decode|k_back_tile" -c 3 -o gpurun_out/prof_v6 python bench.py --steps 1 --warmup 1 --frames-per-gpu 8 --skip-e2e --streams 1 > gpurun_out/ncu_v6.log 2>&1; tail -1 gpurun_out/ncu_v6.log | cut -c1-200
