@@ -47,32 +47,49 @@ template <> struct Idct1D<2> {
 };
 template <> struct Idct1D<1> { J40B_HD static J40B_INLINE void run(float *) {} };
 
-template <int N>
-J40B_HD J40B_INLINE void idct_strided(float *p, int stride) {
-    float v[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = p[i * stride];
-    Idct1D<N>::run(v);
-#pragma unroll
-    for (int i = 0; i < N; ++i) p[i * stride] = v[i];
+// Shared-memory layout of one varblock's coefficients: the stored index i = a * M + b (a = major, b = minor,
+// M = 1 << mlog = the longer side, so a < M) lives at a * M + (b ^ a). Both IDCT passes then touch 32
+// different banks from the 32 lanes of a warp (lanes differ in the fixed index of a 1-D transform), instead of
+// the 4 banks of the plain layout when each lane walks 8 consecutive floats.
+J40B_HD J40B_INLINE int tile_swz(int i, int mlog) {
+    const int a = i >> mlog;
+    return i ^ (a & ((1 << mlog) - 1));
 }
 
-J40B_HD J40B_INLINE void idct_strided_dispatch(float *p, int stride, int log_n) {
+// 1-D transform number f of a pass over a block: ALONG_MINOR walks b with a = f fixed, else walks a with b = f
+template <int N, bool ALONG_MINOR>
+J40B_HD J40B_INLINE void idct_swz(float *blk, int f, int mlog) {
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = ALONG_MINOR ? blk[(f << mlog) + (i ^ f)] : blk[(i << mlog) + (f ^ i)];
+    Idct1D<N>::run(v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { if (ALONG_MINOR) blk[(f << mlog) + (i ^ f)] = v[i]; else blk[(i << mlog) + (f ^ i)] = v[i]; }
+}
+
+template <bool ALONG_MINOR>
+J40B_HD J40B_INLINE void idct_swz_dispatch(float *blk, int f, int mlog, int log_n) {
     switch (log_n) {
-    case 3: idct_strided<8>(p, stride); break;
-    case 4: idct_strided<16>(p, stride); break;
-    case 5: idct_strided<32>(p, stride); break;
-    case 6: idct_strided<64>(p, stride); break;
+    case 3: idct_swz<8, ALONG_MINOR>(blk, f, mlog); break;
+    case 4: idct_swz<16, ALONG_MINOR>(blk, f, mlog); break;
+    case 5: idct_swz<32, ALONG_MINOR>(blk, f, mlog); break;
+    case 6: idct_swz<64, ALONG_MINOR>(blk, f, mlog); break;
     }
 }
+
+// floats per channel buffer: 4096 coefficients + the per-varblock skew (8 floats per varblock and 8 more per
+// started row of eight, see chunk_off) that spreads neighbouring varblocks over the banks
+enum { TILE_CH = 4672 };
 
 struct TileVb {
     int32_t voff;        // varblock index inside the LF group
     int32_t coeffoff;
-    uint16_t chunk_off;  // offset (floats) of this varblock's coefficients in each channel's 4096-float buffer
+    uint16_t chunk_off;  // offset (floats) of this varblock's coefficients in each channel's buffer
+    uint16_t log_off;    // the same without the bank skew: position in the tile's raster order of 64-float chunks
     uint8_t dctsel, log_rows, log_cols, param_idx;
     uint8_t cx, cy;      // top-left cell inside the tile
-    uint8_t special, pad;
+    uint8_t special;
+    uint8_t mlog;        // log2 of the swizzled layout's row length (longer side); 0 = plain layout (special 8x8)
     float m[3];          // dequantisation multipliers mult[c] of j40__dequant_hf
     float kx_hf, kb_hf;
 };
@@ -88,7 +105,7 @@ struct TileShared {
     uint8_t lut[SRGB_LUT_BYTES];
 };
 
-// tile (tx, ty) of group w.grp; coef = 3 * 4096 floats of shared memory
+// tile (tx, ty) of group w.grp; coef = 3 * TILE_CH floats of shared memory
 template <class Sync>
 J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coef, TileShared &ts, int tid, int nth, Sync sync) {
     if (*w.lf_err || *w.hf_err) return;
@@ -98,7 +115,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
     if (tx * 8 >= gw8 || ty * 8 >= gh8) return;
     const int n8 = g.width8 * g.height8;
-    float *coefx = coef, *coefy = coef + 4096, *coefb = coef + 8192;
+    float *coefx = coef, *coefy = coef + TILE_CH, *coefb = coef + 2 * TILE_CH;
 
     // ---- 0. which varblocks start in this tile (one cell per thread), thresholds, zeroed coefficients
     for (int c = tid; c < 64; c += nth) {
@@ -120,7 +137,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     }
     for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
     for (int i = tid; i < SRGB_LUT_BYTES / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
-    for (int i = tid; i < 3 * 4096; i += nth) coef[i] = 0.0f;
+    for (int i = tid; i < 3 * TILE_CH; i += nth) coef[i] = 0.0f;
     sync();
     // ---- 0b. compact them in raster order (each top-left cell computes its own rank and chunk offset)
     {
@@ -140,11 +157,12 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             TileVb &t = ts.vb[rank];
             t.voff = voff;
             t.coeffoff = vb.coeffoff;
-            t.chunk_off = (uint16_t) (off64 * 64);
+            t.log_off = (uint16_t) (off64 * 64);
+            t.chunk_off = (uint16_t) (off64 * 64 + 8 * rank + 8 * (rank >> 3));
             t.dctsel = vb.dctsel; t.log_rows = (uint8_t) d.log_rows; t.log_cols = (uint8_t) d.log_columns; t.param_idx = (uint8_t) d.param_idx;
             t.cx = (uint8_t) (c & 7); t.cy = (uint8_t) (c >> 3);
             t.special = is_special_8x8(vb.dctsel) ? 1 : 0;
-            t.pad = 0;
+            t.mlog = t.special ? 0 : (uint8_t) (d.log_rows > d.log_columns ? d.log_rows : d.log_columns);
             t.m[1] = J40B_FMUL(gs, vb.hfmul_inv);
             t.m[0] = J40B_FMUL(t.m[1], f.x_qm_mult);
             t.m[2] = J40B_FMUL(t.m[1], f.b_qm_mult);
@@ -168,10 +186,12 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             int v = pair / 3, c = pair - v * 3;
             const TileVb &t = ts.vb[v];
             uint32_t first = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 0], cnt = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 1];
-            float *dst = coef + c * 4096 + t.chunk_off;
+            float *dst = coef + c * TILE_CH + t.chunk_off;
+            const int mlog = t.mlog;
             for (uint32_t k = (uint32_t) lane; k < cnt; k += (uint32_t) lanes) {
                 DToken tk = w.tokens[first + k];
-                dst[tk.pos] = J40B_FADD(dst[tk.pos], (float) tk.val);
+                const int p = tile_swz(tk.pos, mlog);
+                dst[p] = J40B_FADD(dst[p], (float) tk.val);
             }
         }
     }
@@ -181,10 +201,11 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     {
         const float qb0 = f.quant_bias[0], qb1 = f.quant_bias[1], qb2 = f.quant_bias[2], qbn = f.quant_bias_num;
         int total = 0;
-        { const TileVb &last = ts.vb[nvb - 1]; total = last.chunk_off + (1 << (last.log_rows + last.log_cols)); }
-        for (int e = tid; e < total; e += nth) {
-            const TileVb &t = ts.vb[ts.chunk_vb[e >> 6]];
-            const int i = e - t.chunk_off;
+        { const TileVb &last = ts.vb[nvb - 1]; total = last.log_off + (1 << (last.log_rows + last.log_cols)); }
+        for (int q = tid; q < total; q += nth) {
+            const TileVb &t = ts.vb[ts.chunk_vb[q >> 6]];
+            const int i = q - t.log_off;
+            const int e = t.chunk_off + tile_swz(i, t.mlog);
             const float *dq = f.dq[t.param_idx] + (size_t) i * 3;
             float vx = coefx[e], vy = coefy[e], vb_ = coefb[e];
             vx = (-1.0f <= vx && vx <= 1.0f) ? J40B_FMUL(vx, qb0) : J40B_FSUB(vx, J40B_FDIV(qbn, vx));
@@ -209,7 +230,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             const int vh8 = 1 << (lmin - 3), vw8 = 1 << (lmax - 3);
             if (e >= vh8 * vw8) continue;
             int y = e / vw8, x = e - y * vw8;
-            int p = t.chunk_off + y * vw8 * 8 + x;
+            int p = t.chunk_off + tile_swz(y * vw8 * 8 + x, t.mlog);
             float l0 = g.llf[(size_t) 0 * n8 + (t.coeffoff >> 6) + e];
             float l1 = g.llf[(size_t) 1 * n8 + (t.coeffoff >> 6) + e];
             float l2 = g.llf[(size_t) 2 * n8 + (t.coeffoff >> 6) + e];
@@ -229,14 +250,13 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const TileVb &t = ts.vb[vi];
         if (t.cx != cx) continue; // not the leftmost cell of this varblock
         const int r = r64 - t.cy * 8; // row inside the varblock (vertical frequency index v at this stage)
-        float *blk = coef + c * 4096 + t.chunk_off;
+        float *blk = coef + c * TILE_CH + t.chunk_off;
         if (t.special) {
             if (r == 0) inverse_special(t.dctsel, blk);
             continue;
         }
-        const int R = 1 << t.log_rows, C = 1 << t.log_cols;
-        if (t.log_cols > t.log_rows) idct_strided_dispatch(blk + r * C, 1, t.log_cols);       // [v][u], contiguous
-        else idct_strided_dispatch(blk + r, R, t.log_cols);                                 // [u][v], stride R
+        if (t.log_cols > t.log_rows) idct_swz_dispatch<true>(blk, r, t.mlog, t.log_cols);    // [v][u]: row v = r, along u
+        else idct_swz_dispatch<false>(blk, r, t.mlog, t.log_cols);                          // [u][v]: column v = r, along u
     }
     sync();
     // ---- 5. pass B: 1-D inverse DCTs along the vertical frequency v
@@ -249,10 +269,9 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const TileVb &t = ts.vb[vi];
         if (t.cy != cy || t.special) continue;
         const int x = x64 - t.cx * 8;
-        float *blk = coef + c * 4096 + t.chunk_off;
-        const int R = 1 << t.log_rows, C = 1 << t.log_cols;
-        if (t.log_cols > t.log_rows) idct_strided_dispatch(blk + x, C, t.log_rows);          // [v][x] -> [y][x]
-        else idct_strided_dispatch(blk + x * R, 1, t.log_rows);                              // [x][v] -> [x][y]
+        float *blk = coef + c * TILE_CH + t.chunk_off;
+        if (t.log_cols > t.log_rows) idct_swz_dispatch<false>(blk, x, t.mlog, t.log_rows);   // [v][x] -> [y][x]: column x, along v
+        else idct_swz_dispatch<true>(blk, x, t.mlog, t.log_rows);                           // [x][v] -> [x][y]: row x, along v
     }
     sync();
     // ---- 6. XYB -> sRGB -> RGBA8 (j40.h:7208-7237, 7941-7952), one thread per pixel, row-major
@@ -274,7 +293,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const int ly = py - t.cy * 8, lx = px - t.cx * 8;
         const int R = 1 << t.log_rows, C = 1 << t.log_cols;
         // special transforms and wide blocks end as [y][x]; square / tall DCT blocks as [x][y]
-        const int idx = t.chunk_off + ((t.special || t.log_cols > t.log_rows) ? ly * C + lx : lx * R + ly);
+        const int idx = t.chunk_off + tile_swz((t.special || t.log_cols > t.log_rows) ? ly * C + lx : lx * R + ly, t.mlog);
         float sx = coefx[idx], sy = coefy[idx], sb = coefb[idx];
         float p0 = J40B_FSUB(J40B_FADD(sy, sx), cb0), p1 = J40B_FSUB(J40B_FSUB(sy, sx), cb1), p2 = J40B_FSUB(sb, cb2);
         float l0 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p0, p0), p0), ob0), itscale);

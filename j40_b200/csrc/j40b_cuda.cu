@@ -160,7 +160,7 @@ struct CudaBackend {
         num_sms = prop.multiProcessorCount;
         if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
-        if (!cuda_ok(cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4096 * 4))) return false;
+        if (!cuda_ok(cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4))) return false;
         const int lf_smem = (int) (SPEC_COPY_BYTES + 4 * warp_slice_bytes(LF_ROW_CAP)), mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
         if (!cuda_ok(cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem))) return false;
         if (!cuda_ok(cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem))) return false;
@@ -216,7 +216,7 @@ struct CudaBackend {
         ++launches;
     }
     void launch_back(const BackWork *w, int n) {
-        k_back_tile<<<dim3((unsigned) n, 16), 256, 3 * 4096 * 4, stream>>>(w);
+        k_back_tile<<<dim3((unsigned) n, 16), 256, 3 * TILE_CH * 4, stream>>>(w);
         cudaEventRecord(ev[3], stream);
         ++launches;
         if (!big_pool) {

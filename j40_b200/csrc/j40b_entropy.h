@@ -214,9 +214,10 @@ struct CodeCtx { // everything a symbol read needs besides the state
     J40B_HD void init_from_copy(const uint8_t *copy, uint32_t blob_lo, uint32_t spec_off) { init(copy - blob_lo, spec_off); }
 };
 
-template <bool INIT_CHECK = true>
+// MODE 0: read the spec's flags at run time; MODE 1: the caller knows this is rANS without LZ77
+template <bool INIT_CHECK = true, int MODE = 0>
 J40B_HD J40B_INLINE int32_t cluster_symbol(BitReader &br, const CodeCtx &cc, const DCluster &cl, uint32_t &ans_state) {
-    if (cc.prefix) {
+    if (MODE == 0 && cc.prefix) {
         return prefix_symbol(br, cl.root_bits, (const uint32_t *) (cc.arena + cl.table_off));
     } else {
         return ans_symbol<INIT_CHECK>(br, ans_state, cc.log_bucket, (const uint64_t *) (cc.arena + cl.table_off));
@@ -243,10 +244,10 @@ J40B_HD J40B_INLINE int32_t special_distance(int idx) {
 
 // one decoded integer (aka DecodeHybridVarLenUint) whose context has already been resolved to cluster `cl`;
 // mirrors j40__code incl. its LZ77 quirks
-template <bool INIT_CHECK = true>
+template <bool INIT_CHECK = true, int MODE = 0>
 J40B_HD J40B_INLINE int32_t code_cluster(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs, const DCluster &cl, int32_t dist_mult) {
-    int32_t token = cluster_symbol<INIT_CHECK>(br, cc, cl, cs.ans_state);
-    if (token >= cc.min_symbol) { // only possible when LZ77 is enabled
+    int32_t token = cluster_symbol<INIT_CHECK, MODE>(br, cc, cl, cs.ans_state);
+    if (MODE == 0 && token >= cc.min_symbol) { // only possible when LZ77 is enabled
         const DCodeSpec *spec = cc.spec;
         const DCluster lz = cc.clusters[cc.cluster_map[spec->num_dist - 1]];
         int32_t num_to_copy = hybrid_int(br, es, token - spec->min_symbol, spec->lz_len_cfg) + spec->min_length;
@@ -271,7 +272,7 @@ J40B_HD J40B_INLINE int32_t code_cluster(BitReader &br, ErrSlot &es, const CodeC
     }
     token = hybrid_int(br, es, token, cl.cfg);
     if (es.err) return 0;
-    if (cc.lz77) cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = token;
+    if (MODE == 0 && cc.lz77) cs.window[(uint32_t) cs.num_decoded++ & cs.window_mask] = token;
     return token;
 }
 

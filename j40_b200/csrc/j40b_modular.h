@@ -413,15 +413,142 @@ struct WpSimt {
     int32_t pred[5];
 };
 
-template <bool USE_WP, class Sync>
+// everything one sample of the SIMT path reads and updates (lives in registers; pointers are shared memory)
+struct SimtCtx {
+    const SimtLane *tab; const SimtLeaf *leaves; const int32_t *refp; const int32_t *div24;
+    int32_t cap, width, y, dist_mult, my_i;
+    int16_t *cur; const int16_t *nrow, *nnrow;
+    int32_t *err; const int32_t *nerr;
+    int32_t prev, prev2, n_ww, n_w, n_c, n_e; // the two samples to the left; sliding window over the row above
+    WPParams wpp;
+    WpSimt wp;
+};
+
+J40B_HD J40B_INLINE int32_t mod_predict(int32_t predictor, int32_t pw, int32_t pn, int32_t pnw, int32_t pne, int32_t pnn,
+                                        int32_t pww, int32_t pnee, int32_t wp_pred, bool *bad) {
+    switch (predictor) {
+    case 0: return 0;
+    case 1: return pw;
+    case 2: return pn;
+    case 3: return (pw + pn) / 2;
+    case 4: return iabs(pn - pnw) < iabs(pw - pnw) ? pw : pn;
+    case 5: return mod_gradient(pw, pn, pnw);
+    case 6: return (wp_pred + 3) >> 3;
+    case 7: return pne;
+    case 8: return pnw;
+    case 9: return pww;
+    case 10: return (pw + pnw) / 2;
+    case 11: return (pn + pnw) / 2;
+    case 12: return (pn + pne) / 2;
+    case 13: return (6 * pn - 2 * pnn + 7 * pw + pww + pnee + 3 * pne + 8) / 16;
+    default: *bad = true; return 0;
+    }
+}
+
+// One sample. PRED >= 0: every leaf of the compiled tree uses that predictor (no dispatch); MODE: see
+// code_cluster; INTERIOR: y >= 2 and 2 <= x < width - 2, so no neighbour falls off the image.
+// Returns false on error (uniform across the lanes).
+template <bool USE_WP, int PRED, int MODE, bool INTERIOR>
+J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs, int32_t x) {
+    const int32_t y = S.y, width = S.width;
+    const int32_t n_ee = INTERIOR ? S.nrow[x + 2] : (y > 0 && x + 2 < width ? S.nrow[x + 2] : S.n_e);
+    const int32_t pw = INTERIOR ? S.prev : (x > 0 ? S.prev : S.n_c);   // (n_c is 0 in the first row)
+    const int32_t pn = INTERIOR ? S.n_c : (y > 0 ? S.n_c : pw);
+    const int32_t pnw = INTERIOR ? S.n_w : (x > 0 && y > 0 ? S.n_w : pw);
+    const int32_t pne = INTERIOR ? S.n_e : (y > 0 ? S.n_e : pn);        // n_e already equals n_c at the right edge
+    const int32_t pnn = INTERIOR ? S.nnrow[x] : (y > 1 ? S.nnrow[x] : pn);
+    const int32_t pnee = INTERIOR ? n_ee : (y > 0 ? n_ee : pne);
+    const int32_t pww = INTERIOR ? S.prev2 : (x > 1 ? S.prev2 : pw);
+    const int32_t pnww = INTERIOR ? S.n_ww : (x > 1 && y > 0 ? S.n_ww : pww);
+    WpSimt &wp = S.wp;
+    int32_t maxerr = 0;
+    if (USE_WP) {
+        // j40.h:4011-4072
+        const WPParams &wpp = S.wpp;
+        wp.pred[0] = (pw + pne - pn) * 8;
+        wp.pred[1] = pn * 8 - (((wp.te_w + wp.te_n + wp.te_ne) * wpp.p1) >> 5);
+        wp.pred[2] = pw * 8 - (((wp.te_w + wp.te_n + wp.te_nw) * wpp.p2) >> 5);
+        wp.pred[3] = pn * 8 - ((wp.te_nw * wpp.p3[0] + wp.te_n * wpp.p3[1] + wp.te_ne * wpp.p3[2] +
+                                (pnn - pn) * 8 * wpp.p3[3] + (pnw - pw) * 8 * wpp.p3[4]) >> 5);
+        int32_t w[4];
+#ifdef __CUDA_ARCH__
+        {
+            const int i = S.my_i & 3;
+            int32_t errsum = wp.e_n[0] + wp.e_w[0] + wp.e_nw[0] + wp.e_ww[0] + wp.e_ne[0] + (INTERIOR || x + 1 < width ? 0 : wp.e_w[0]);
+            int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
+            int32_t wi = (int32_t) (4 + (((int64_t) wpp.w[i] * S.div24[errsum >> shift]) >> shift));
+            for (int k = 0; k < 4; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k);
+        }
+#else
+        for (int i = 0; i < 4; ++i) {
+            int32_t errsum = wp.e_n[i] + wp.e_w[i] + wp.e_nw[i] + wp.e_ww[i] + wp.e_ne[i] + (INTERIOR || x + 1 < width ? 0 : wp.e_w[i]);
+            int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
+            w[i] = (int32_t) (4 + (((int64_t) wpp.w[i] * S.div24[errsum >> shift]) >> shift));
+        }
+#endif
+        int32_t logw = floor_lg32((uint32_t) (w[0] + w[1] + w[2] + w[3])) - 4;
+        int32_t wsum = 0, sum = 0;
+        for (int i = 0; i < 4; ++i) {
+            w[i] >>= logw;
+            wsum += w[i];
+            sum += wp.pred[i] * w[i];
+        }
+        wp.pred[4] = (int32_t) ((((int64_t) sum + (wsum >> 1) - 1) * S.div24[wsum - 1]) >> 24);
+        if (((wp.te_n ^ wp.te_w) | (wp.te_n ^ wp.te_nw)) <= 0) {
+            int32_t lo = imin(pw, imin(pn, pne)) * 8;
+            int32_t hi = imax(pw, imax(pn, pne)) * 8;
+            wp.pred[4] = imin(imax(lo, wp.pred[4]), hi);
+        }
+        maxerr = wp.te_w;
+        if (iabs(maxerr) < iabs(wp.te_n)) maxerr = wp.te_n;
+        if (iabs(maxerr) < iabs(wp.te_nw)) maxerr = wp.te_nw;
+        if (iabs(maxerr) < iabs(wp.te_ne)) maxerr = wp.te_ne;
+    }
+
+    const int32_t li = simt_tree_leaf(S.tab, mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
+    const SimtLeaf leaf = S.leaves[li];
+    int32_t val;
+    if (MODE == 1 || !code_copy(cs, val)) val = code_cluster<false, MODE>(br, es, cc, cs, leaf.cl, S.dist_mult);
+    val = unpack_signed(val) * leaf.multiplier + leaf.offset;
+    bool bad = false;
+    val += mod_predict(PRED >= 0 ? PRED : leaf.predictor, pw, pn, pnw, pne, pnn, pww, pnee, USE_WP ? wp.pred[4] : 0, &bad);
+    if (bad) es.set(br, E_PRED);
+    if (es.err) return false; // uniform: every lane sees the same error
+    if (val < -32768 || val > 32767) { es.set(br, E_POVF); return false; }
+    S.cur[x] = (int16_t) val;
+    S.prev2 = S.prev;
+    S.prev = val;
+    S.n_ww = S.n_w; S.n_w = S.n_c; S.n_c = S.n_e; S.n_e = n_ee;
+    if (USE_WP) {
+        // j40.h:4103-4111, then slide the error windows
+        const int32_t v8 = val * 8;
+        const int32_t te = wp.pred[4] - v8;
+        for (int k = 0; k < WP_NL; ++k) {
+            const int i = WP_NL == 1 ? S.my_i : k;
+            const int32_t psel = i == 0 ? wp.pred[0] : i == 1 ? wp.pred[1] : i == 2 ? wp.pred[2] : wp.pred[3];
+            const int32_t e = i < 4 ? (iabs(psel - v8) + 3) >> 3 : te;
+            S.err[(size_t) x * 5 + i] = e;
+            wp.e_ww[k] = wp.e_w[k];
+            wp.e_w[k] = e;
+            wp.e_nw[k] = wp.e_n[k];
+            wp.e_n[k] = wp.e_ne[k];
+            wp.e_ne[k] = INTERIOR || (y > 0 && x + 2 < width) ? S.nerr[(size_t) (x + 2) * 5 + i] : wp.e_ne[k];
+        }
+        wp.te_w = te;
+        wp.te_nw = wp.te_n;
+        wp.te_n = wp.te_ne;
+        wp.te_ne = INTERIOR || (y > 0 && x + 2 < width) ? S.nerr[(size_t) (x + 2) * 5 + 4] : wp.te_ne;
+    }
+    return true;
+}
+
+template <bool USE_WP, int PRED, int MODE, class Sync>
 J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
-                                         const DTreeNode *tree, const ModSmem &ms, const int32_t *refprops, int nslots,
-                                         const int32_t *div24, const ModImage &m, int32_t cidx, int32_t sidx,
+                                         const ModSmem &ms, const int32_t *refprops, int nslots,
+                                         const int32_t *div24, const ModImage &m, int32_t cidx,
                                          int lane, int nlanes, Sync sync) {
     const ModChannel &c = m.ch[cidx];
     const int32_t width = c.w, height = c.h, stride = c.stride, cap = ms.cap;
-    const int32_t dist_mult = m.dist_mult;
-    const WPParams wpp = m.wp;
     int32_t refcmap[MOD_MAX_CH], nref = 0;
     for (int32_t i = cidx - 1; i >= 0; --i) {
         const ModChannel &r = m.ch[i];
@@ -429,9 +556,12 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
         refcmap[nref++] = i;
     }
     const SimtLane mine = ms.tab[lane & (SIMT_LANES - 1)];
-    const int my_i = lane < 4 ? lane : 4; // this lane's weighted-predictor index (device)
-    (void) my_i;
-    WpSimt wp;
+    SimtCtx S;
+    S.tab = ms.tab; S.leaves = ms.leaves; S.refp = ms.refp; S.div24 = div24;
+    S.cap = cap; S.width = width; S.dist_mult = m.dist_mult;
+    S.my_i = lane < 4 ? lane : 4; // this lane's weighted-predictor index (device)
+    S.wpp = m.wp;
+    WpSimt &wp = S.wp;
     // the first call below always reads a symbol (or continues an LZ77 copy that an earlier channel began):
     // seed the rANS state here so that the per-sample path does not have to test for it
     if (!cc.prefix && cs.ans_state == 0 && cs.num_to_copy <= 0) ans_seed(br, cs.ans_state);
@@ -461,130 +591,35 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
             }
         }
         sync(); // also orders the previous row's error stores before this row's loads
-        int16_t *cur = ms.rows + (size_t) (y % 3) * cap;
-        const int16_t *nrow = ms.rows + (size_t) ((y + 2) % 3) * cap, *nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
-        int32_t *err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
-        const int32_t *nerr = ms.wp + (size_t) ((y & 1) ? 0 : width) * 5;
-        int32_t prev = 0, prev2 = 0;
-        // sliding windows over the row above
-        int32_t n_ww = 0, n_w = 0, n_c = y > 0 ? nrow[0] : 0, n_e = y > 0 && width > 1 ? nrow[1] : n_c;
+        S.y = y;
+        S.cur = ms.rows + (size_t) (y % 3) * cap;
+        S.nrow = ms.rows + (size_t) ((y + 2) % 3) * cap;
+        S.nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
+        S.err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
+        S.nerr = ms.wp + (size_t) ((y & 1) ? 0 : width) * 5;
+        S.prev = S.prev2 = 0;
+        S.n_ww = S.n_w = 0;
+        S.n_c = y > 0 ? S.nrow[0] : 0;
+        S.n_e = y > 0 && width > 1 ? S.nrow[1] : S.n_c;
         if (USE_WP) {
             for (int k = 0; k < WP_NL; ++k) {
-                const int i = WP_NL == 1 ? my_i : k;
+                const int i = WP_NL == 1 ? S.my_i : k;
                 wp.e_w[k] = wp.e_ww[k] = 0;
-                wp.e_n[k] = y > 0 ? nerr[i] : 0;
+                wp.e_n[k] = y > 0 ? S.nerr[i] : 0;
                 wp.e_nw[k] = wp.e_n[k];
-                wp.e_ne[k] = y > 0 && width > 1 ? nerr[5 + i] : wp.e_n[k];
+                wp.e_ne[k] = y > 0 && width > 1 ? S.nerr[5 + i] : wp.e_n[k];
             }
             wp.te_w = 0;
-            wp.te_n = y > 0 ? nerr[4] : 0;
+            wp.te_n = y > 0 ? S.nerr[4] : 0;
             wp.te_nw = wp.te_n;
-            wp.te_ne = y > 0 && width > 1 ? nerr[5 + 4] : wp.te_n;
+            wp.te_ne = y > 0 && width > 1 ? S.nerr[5 + 4] : wp.te_n;
         }
-        for (int32_t x = 0; x < width; ++x) {
-            const int32_t n_ee = y > 0 && x + 2 < width ? nrow[x + 2] : n_e;
-            const int32_t pw = x > 0 ? prev : n_c;                 // (n_c is 0 in the first row)
-            const int32_t pn = y > 0 ? n_c : pw;
-            const int32_t pnw = x > 0 && y > 0 ? n_w : pw;
-            const int32_t pne = y > 0 ? n_e : pn;                   // n_e already equals n_c at the right edge
-            const int32_t pnn = y > 1 ? nnrow[x] : pn;
-            const int32_t pnee = y > 0 ? n_ee : pne;
-            const int32_t pww = x > 1 ? prev2 : pw;
-            const int32_t pnww = x > 1 && y > 0 ? n_ww : pww;
-            int32_t maxerr = 0;
-            if (USE_WP) {
-                // j40.h:4011-4072
-                wp.pred[0] = (pw + pne - pn) * 8;
-                wp.pred[1] = pn * 8 - (((wp.te_w + wp.te_n + wp.te_ne) * wpp.p1) >> 5);
-                wp.pred[2] = pw * 8 - (((wp.te_w + wp.te_n + wp.te_nw) * wpp.p2) >> 5);
-                wp.pred[3] = pn * 8 - ((wp.te_nw * wpp.p3[0] + wp.te_n * wpp.p3[1] + wp.te_ne * wpp.p3[2] +
-                                        (pnn - pn) * 8 * wpp.p3[3] + (pnw - pw) * 8 * wpp.p3[4]) >> 5);
-                int32_t w[4];
-#ifdef __CUDA_ARCH__
-                {
-                    const int i = my_i & 3;
-                    int32_t errsum = wp.e_n[0] + wp.e_w[0] + wp.e_nw[0] + wp.e_ww[0] + wp.e_ne[0] + (x + 1 < width ? 0 : wp.e_w[0]);
-                    int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
-                    int32_t wi = (int32_t) (4 + (((int64_t) wpp.w[i] * div24[errsum >> shift]) >> shift));
-                    for (int k = 0; k < 4; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k);
-                }
-#else
-                for (int i = 0; i < 4; ++i) {
-                    int32_t errsum = wp.e_n[i] + wp.e_w[i] + wp.e_nw[i] + wp.e_ww[i] + wp.e_ne[i] + (x + 1 < width ? 0 : wp.e_w[i]);
-                    int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
-                    w[i] = (int32_t) (4 + (((int64_t) wpp.w[i] * div24[errsum >> shift]) >> shift));
-                }
-#endif
-                int32_t logw = floor_lg32((uint32_t) (w[0] + w[1] + w[2] + w[3])) - 4;
-                int32_t wsum = 0, sum = 0;
-                for (int i = 0; i < 4; ++i) {
-                    w[i] >>= logw;
-                    wsum += w[i];
-                    sum += wp.pred[i] * w[i];
-                }
-                wp.pred[4] = (int32_t) ((((int64_t) sum + (wsum >> 1) - 1) * div24[wsum - 1]) >> 24);
-                if (((wp.te_n ^ wp.te_w) | (wp.te_n ^ wp.te_nw)) <= 0) {
-                    int32_t lo = imin(pw, imin(pn, pne)) * 8;
-                    int32_t hi = imax(pw, imax(pn, pne)) * 8;
-                    wp.pred[4] = imin(imax(lo, wp.pred[4]), hi);
-                }
-                maxerr = wp.te_w;
-                if (iabs(maxerr) < iabs(wp.te_n)) maxerr = wp.te_n;
-                if (iabs(maxerr) < iabs(wp.te_nw)) maxerr = wp.te_nw;
-                if (iabs(maxerr) < iabs(wp.te_ne)) maxerr = wp.te_ne;
-            }
-
-            const int32_t li = simt_tree_leaf(ms.tab, mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, ms.refp, cap);
-            const SimtLeaf leaf = ms.leaves[li];
-            int32_t val;
-            if (!code_copy(cs, val)) val = code_cluster<false>(br, es, cc, cs, leaf.cl, dist_mult);
-            val = unpack_signed(val) * leaf.multiplier + leaf.offset;
-            int32_t pred = 0;
-            switch (leaf.predictor) {
-            case 0: pred = 0; break;
-            case 1: pred = pw; break;
-            case 2: pred = pn; break;
-            case 3: pred = (pw + pn) / 2; break;
-            case 4: pred = iabs(pn - pnw) < iabs(pw - pnw) ? pw : pn; break;
-            case 5: pred = mod_gradient(pw, pn, pnw); break;
-            case 6: pred = (wp.pred[4] + 3) >> 3; break;
-            case 7: pred = pne; break;
-            case 8: pred = pnw; break;
-            case 9: pred = pww; break;
-            case 10: pred = (pw + pnw) / 2; break;
-            case 11: pred = (pn + pnw) / 2; break;
-            case 12: pred = (pn + pne) / 2; break;
-            case 13: pred = (6 * pn - 2 * pnn + 7 * pw + pww + pnee + 3 * pne + 8) / 16; break;
-            default: es.set(br, E_PRED); break;
-            }
-            val += pred;
-            if (es.err) return; // uniform: every lane sees the same error
-            if (val < -32768 || val > 32767) { es.set(br, E_POVF); return; }
-            cur[x] = (int16_t) val;
-            prev2 = prev;
-            prev = val;
-            n_ww = n_w; n_w = n_c; n_c = n_e; n_e = n_ee;
-            if (USE_WP) {
-                // j40.h:4103-4111, then slide the error windows
-                const int32_t v8 = val * 8;
-                const int32_t te = wp.pred[4] - v8;
-                for (int k = 0; k < WP_NL; ++k) {
-                    const int i = WP_NL == 1 ? my_i : k;
-                    const int32_t psel = i == 0 ? wp.pred[0] : i == 1 ? wp.pred[1] : i == 2 ? wp.pred[2] : wp.pred[3];
-                    const int32_t e = i < 4 ? (iabs(psel - v8) + 3) >> 3 : te;
-                    err[(size_t) x * 5 + i] = e;
-                    wp.e_ww[k] = wp.e_w[k];
-                    wp.e_w[k] = e;
-                    wp.e_nw[k] = wp.e_n[k];
-                    wp.e_n[k] = wp.e_ne[k];
-                    wp.e_ne[k] = y > 0 && x + 2 < width ? nerr[(size_t) (x + 2) * 5 + i] : wp.e_ne[k];
-                }
-                wp.te_w = te;
-                wp.te_nw = wp.te_n;
-                wp.te_n = wp.te_ne;
-                wp.te_ne = y > 0 && x + 2 < width ? nerr[(size_t) (x + 2) * 5 + 4] : wp.te_ne;
-            }
+        int32_t x = 0;
+        if (y >= 2 && width >= 5) {
+            for (; x < 2; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
+            for (; x < width - 2; ++x) if (!simt_sample<USE_WP, PRED, MODE, true>(S, mine, br, es, cc, cs, x)) return;
         }
+        for (; x < width; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
     }
     sync();
     {
@@ -617,9 +652,17 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
         }
         int32_t nslots = 0;
         bool simt = ms.rows && c.w <= ms.cap && n > 0 && simt_compile_tree(ptree, n, nref, cc, ms.tab, ms.leaves, ms.info + 4, &nslots);
+        // fast variants: rANS without LZ77 and one predictor (gradient or weighted) shared by all leaves
+        int variant = 0;
+        if (simt && !cc.prefix && !cc.lz77) {
+            int common = -2;
+            for (int i = 0; i < n; ++i) if (ptree[i].a >= 0) common = common == -2 || common == ptree[i].b ? ptree[i].b : -1;
+            if (common == 5) variant = 1;
+            else if (common == 6) variant = 2;
+        }
         ms.info[0] = uses_wp;
         ms.info[1] = nslots;
-        ms.info[2] = simt;
+        ms.info[2] = simt ? 1 + variant : 0;
         ms.info[3] = n;
     }
     sync();
@@ -628,8 +671,12 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
     if (ms.info[2]) {
         int32_t refprops[SIMT_REF_SLOTS];
         for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
-        if (uses_wp) modular_channel_simt<true>(br, es, cc, cs, ptree, ms, refprops, ms.info[1], div24, m, cidx, sidx, lane, nlanes, sync);
-        else modular_channel_simt<false>(br, es, cc, cs, ptree, ms, refprops, ms.info[1], div24, m, cidx, sidx, lane, nlanes, sync);
+        const int variant = ms.info[2] - 1, ns = ms.info[1];
+        if (variant == 2) modular_channel_simt<true, 6, 1>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (variant == 1 && uses_wp) modular_channel_simt<true, 5, 1>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (variant == 1) modular_channel_simt<false, 5, 1>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (uses_wp) modular_channel_simt<true, -1, 0>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else modular_channel_simt<false, -1, 0>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else {
         const DTreeNode *t = n > 0 ? ptree : tree;
         if (uses_wp) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);

@@ -59,7 +59,7 @@ struct HostEmuBackend {
         }
     }
     void launch_back(const BackWork *w, int n) {
-        std::vector<float> coef(3 * 4096), big(4 * 65536);
+        std::vector<float> coef(3 * TILE_CH), big(4 * 65536);
         for (int i = 0; i < n; ++i) {
             for (int t = 0; t < 16; ++t) { TileShared ts; back_tile_body(w[i], t & 3, t >> 2, coef.data(), ts, 0, 1, NoSync()); }
             BackWork bw = w[i];
