@@ -125,7 +125,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=64)
     ap.add_argument("--distinct", type=int, default=8, help="distinct streams per rank (cycled to fill the batch)")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="batch objects (CUDA streams) the timed steps are pipelined over")
+    ap.add_argument("--streams", type=int, default=6, help="batch objects (CUDA streams) the timed steps are pipelined over")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -234,7 +234,7 @@ def main():
     # pipelined over them so that the parse / H2D / D2H of one step overlap the kernels of its neighbours.
     e2e = None
     if not args.skip_e2e:
-        E = min(len(batches), 3)
+        E = min(len(batches), 4)
         pitch = h * b.info(0)[2]
         host_out = [torch.empty((F, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(E)]
         out_np = [t_.numpy() for t_ in host_out]

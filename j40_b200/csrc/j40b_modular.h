@@ -374,27 +374,28 @@ J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, const
     return true;
 }
 
-J40B_HD J40B_INLINE bool simt_decision(const SimtLane &L, int32_t x, int32_t y, int32_t pn, int32_t pw, int32_t pnw, int32_t pne,
+// `xs` = x relative to the start of the current segment of the row (refp holds one segment)
+J40B_HD J40B_INLINE bool simt_decision(const SimtLane &L, int32_t x, int32_t xs, int32_t y, int32_t pn, int32_t pw, int32_t pnw, int32_t pne,
                                        int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr, const int32_t *refp, int32_t cap) {
     int32_t v = L.c[0] * pn + L.c[1] * pw + L.c[2] * pnw + L.c[3] * pne + L.c[4] * pnn + L.c[5] * pww + L.c[6] * pnww
               + L.cx * x + L.cy * y + L.ce * maxerr;
-    if (L.refslot >= 0) v = refp[(size_t) L.refslot * cap + x];
+    if (L.refslot >= 0) v = refp[(size_t) L.refslot * cap + xs];
     if ((L.flags & 2) && x == 0) v = pw;
     if (L.flags & 1) v = iabs(v);
     return (L.flags & 4) && v > L.thr;
 }
 
 // index (into ModSmem::leaves) of the leaf the current sample falls into
-J40B_HD J40B_INLINE int32_t simt_tree_leaf(const SimtLane *tab, const SimtLane &mine, int32_t x, int32_t y, int32_t pn, int32_t pw,
+J40B_HD J40B_INLINE int32_t simt_tree_leaf(const SimtLane *tab, const SimtLane &mine, int32_t x, int32_t xs, int32_t y, int32_t pn, int32_t pw,
                                            int32_t pnw, int32_t pne, int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr,
                                            const int32_t *refp, int32_t cap) {
 #ifdef __CUDA_ARCH__
-    const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision(mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
+    const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision(mine, x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
     const uint32_t hit = __ballot_sync(0xffffffffu, mine.leaf_node >= 0 && (dec & mine.care) == mine.want);
     return __ffs((int) hit) - 1;
 #else
     uint32_t dec = 0;
-    for (int j = 0; j < SIMT_LANES; ++j) dec |= (uint32_t) simt_decision(tab[j], x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap) << j;
+    for (int j = 0; j < SIMT_LANES; ++j) dec |= (uint32_t) simt_decision(tab[j], x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap) << j;
     for (int j = 0; j < SIMT_LANES; ++j) if (tab[j].leaf_node >= 0 && (dec & tab[j].care) == tab[j].want) return j;
     return -1;
 #endif
@@ -416,7 +417,7 @@ struct WpSimt {
 // everything one sample of the SIMT path reads and updates (lives in registers; pointers are shared memory)
 struct SimtCtx {
     const SimtLane *tab; const SimtLeaf *leaves; const int32_t *refp; const int32_t *div24;
-    int32_t cap, width, y, dist_mult, my_i;
+    int32_t cap, width, y, seg0, dist_mult, my_i;
     int16_t *cur; const int16_t *nrow, *nnrow;
     int32_t *err; const int32_t *nerr;
     int32_t prev, prev2, n_ww, n_w, n_c, n_e; // the two samples to the left; sliding window over the row above
@@ -505,7 +506,7 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
         if (iabs(maxerr) < iabs(wp.te_ne)) maxerr = wp.te_ne;
     }
 
-    const int32_t li = simt_tree_leaf(S.tab, mine, x, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
+    const int32_t li = simt_tree_leaf(S.tab, mine, x, x - S.seg0, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
     const SimtLeaf leaf = S.leaves[li];
     int32_t val;
     if (MODE == 1 || !code_copy(cs, val)) val = code_cluster<false, MODE>(br, es, cc, cs, leaf.cl, S.dist_mult);
@@ -542,9 +543,12 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
     return true;
 }
 
-template <bool USE_WP, int PRED, int MODE, class Sync>
+// WIDE: the channel is wider than the shared-memory rows (HF metadata's block-info channel: 2 x up to 65536).
+// Sample and error rows then stay in global memory (read through L1) and the reference properties are
+// computed one segment of `cap` samples at a time.
+template <bool USE_WP, int PRED, int MODE, bool WIDE, class Sync>
 J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
-                                         const ModSmem &ms, const int32_t *refprops, int nslots,
+                                         const ModSmem &ms, int32_t *wp_scratch, const int32_t *refprops, int nslots,
                                          const int32_t *div24, const ModImage &m, int32_t cidx,
                                          int lane, int nlanes, Sync sync) {
     const ModChannel &c = m.ch[cidx];
@@ -567,62 +571,78 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
     if (!cc.prefix && cs.ans_state == 0 && cs.num_to_copy <= 0) ans_seed(br, cs.ans_state);
     for (int32_t y = 0; y < height; ++y) {
         // ---- all lanes: the finished previous row goes to global memory, coalesced
-        if (y > 0) {
+        if (!WIDE && y > 0) {
             const int16_t *done = ms.rows + (size_t) ((y + 2) % 3) * cap;
             int16_t *gdst = c.px + (size_t) (y - 1) * (size_t) stride;
             for (int32_t x = lane; x < width; x += nlanes) gdst[x] = done[x];
         }
-        // ---- all lanes: this row's reference-channel property values
-        for (int sl = 0; sl < nslots; ++sl) {
-            const int prop = refprops[sl];
-            const ModChannel &r = m.ch[refcmap[(prop - 16) / 4]];
-            const int16_t *rrow = r.px + (size_t) y * (size_t) r.stride;
-            int32_t *dst = ms.refp + (size_t) sl * cap;
-            for (int32_t x = lane; x < width; x += nlanes) {
-                int32_t val = rrow[x];
-                if (prop & 2) {
-                    int32_t rw = x > 0 ? rrow[x - 1] : 0;
-                    int32_t rn = y > 0 ? rrow[x - r.stride] : rw;
-                    int32_t rnw = x > 0 && y > 0 ? rrow[x - 1 - r.stride] : rw;
-                    val -= mod_gradient(rw, rn, rnw);
-                }
-                if (prop & 1) val = iabs(val);
-                dst[x] = val;
-            }
-        }
-        sync(); // also orders the previous row's error stores before this row's loads
         S.y = y;
-        S.cur = ms.rows + (size_t) (y % 3) * cap;
-        S.nrow = ms.rows + (size_t) ((y + 2) % 3) * cap;
-        S.nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
-        S.err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
-        S.nerr = ms.wp + (size_t) ((y & 1) ? 0 : width) * 5;
-        S.prev = S.prev2 = 0;
-        S.n_ww = S.n_w = 0;
-        S.n_c = y > 0 ? S.nrow[0] : 0;
-        S.n_e = y > 0 && width > 1 ? S.nrow[1] : S.n_c;
-        if (USE_WP) {
-            for (int k = 0; k < WP_NL; ++k) {
-                const int i = WP_NL == 1 ? S.my_i : k;
-                wp.e_w[k] = wp.e_ww[k] = 0;
-                wp.e_n[k] = y > 0 ? S.nerr[i] : 0;
-                wp.e_nw[k] = wp.e_n[k];
-                wp.e_ne[k] = y > 0 && width > 1 ? S.nerr[5 + i] : wp.e_n[k];
+        if (WIDE) {
+            S.cur = c.px + (size_t) y * (size_t) stride;
+            S.nrow = S.cur - (y > 0 ? stride : 0);
+            S.nnrow = S.cur - (y > 1 ? 2 * stride : 0);
+            S.err = wp_scratch + (size_t) ((y & 1) ? width : 0) * 5;
+            S.nerr = wp_scratch + (size_t) ((y & 1) ? 0 : width) * 5;
+        } else {
+            S.cur = ms.rows + (size_t) (y % 3) * cap;
+            S.nrow = ms.rows + (size_t) ((y + 2) % 3) * cap;
+            S.nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
+            S.err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
+            S.nerr = ms.wp + (size_t) ((y & 1) ? 0 : width) * 5;
+        }
+        for (int32_t seg0 = 0; seg0 < width; seg0 += cap) {
+            const int32_t seg1 = seg0 + cap < width ? seg0 + cap : width;
+            // ---- all lanes: this segment's reference-channel property values
+            if (seg0 > 0) sync();
+            for (int sl = 0; sl < nslots; ++sl) {
+                const int prop = refprops[sl];
+                const ModChannel &r = m.ch[refcmap[(prop - 16) / 4]];
+                const int16_t *rrow = r.px + (size_t) y * (size_t) r.stride;
+                int32_t *dst = ms.refp + (size_t) sl * cap;
+                for (int32_t x = seg0 + lane; x < seg1; x += nlanes) {
+                    int32_t val = rrow[x];
+                    if (prop & 2) {
+                        int32_t rw = x > 0 ? rrow[x - 1] : 0;
+                        int32_t rn = y > 0 ? rrow[x - r.stride] : rw;
+                        int32_t rnw = x > 0 && y > 0 ? rrow[x - 1 - r.stride] : rw;
+                        val -= mod_gradient(rw, rn, rnw);
+                    }
+                    if (prop & 1) val = iabs(val);
+                    dst[x - seg0] = val;
+                }
             }
-            wp.te_w = 0;
-            wp.te_n = y > 0 ? S.nerr[4] : 0;
-            wp.te_nw = wp.te_n;
-            wp.te_ne = y > 0 && width > 1 ? S.nerr[5 + 4] : wp.te_n;
+            sync(); // also orders the previous row's sample / error stores before this row's loads
+            S.seg0 = seg0;
+            if (seg0 == 0) {
+                S.prev = S.prev2 = 0;
+                S.n_ww = S.n_w = 0;
+                S.n_c = y > 0 ? S.nrow[0] : 0;
+                S.n_e = y > 0 && width > 1 ? S.nrow[1] : S.n_c;
+                if (USE_WP) {
+                    for (int k = 0; k < WP_NL; ++k) {
+                        const int i = WP_NL == 1 ? S.my_i : k;
+                        wp.e_w[k] = wp.e_ww[k] = 0;
+                        wp.e_n[k] = y > 0 ? S.nerr[i] : 0;
+                        wp.e_nw[k] = wp.e_n[k];
+                        wp.e_ne[k] = y > 0 && width > 1 ? S.nerr[5 + i] : wp.e_n[k];
+                    }
+                    wp.te_w = 0;
+                    wp.te_n = y > 0 ? S.nerr[4] : 0;
+                    wp.te_nw = wp.te_n;
+                    wp.te_ne = y > 0 && width > 1 ? S.nerr[5 + 4] : wp.te_n;
+                }
+            }
+            int32_t x = seg0;
+            if (y >= 2 && width >= 5) {
+                const int32_t e0 = seg1 < 2 ? seg1 : 2, e1 = seg1 < width - 2 ? seg1 : width - 2;
+                for (; x < e0; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
+                for (; x < e1; ++x) if (!simt_sample<USE_WP, PRED, MODE, true>(S, mine, br, es, cc, cs, x)) return;
+            }
+            for (; x < seg1; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
         }
-        int32_t x = 0;
-        if (y >= 2 && width >= 5) {
-            for (; x < 2; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
-            for (; x < width - 2; ++x) if (!simt_sample<USE_WP, PRED, MODE, true>(S, mine, br, es, cc, cs, x)) return;
-        }
-        for (; x < width; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
     }
     sync();
-    {
+    if (!WIDE) {
         const int16_t *done = ms.rows + (size_t) ((height - 1) % 3) * cap;
         int16_t *gdst = c.px + (size_t) (height - 1) * (size_t) stride;
         for (int32_t x = lane; x < width; x += nlanes) gdst[x] = done[x];
@@ -651,7 +671,7 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
             if (c.w == r.w && c.h == r.h && c.hshift == r.hshift && c.vshift == r.vshift) ++nref;
         }
         int32_t nslots = 0;
-        bool simt = ms.rows && c.w <= ms.cap && n > 0 && simt_compile_tree(ptree, n, nref, cc, ms.tab, ms.leaves, ms.info + 4, &nslots);
+        bool simt = ms.rows && n > 0 && (c.w <= ms.cap || !uses_wp || wp_scratch) && simt_compile_tree(ptree, n, nref, cc, ms.tab, ms.leaves, ms.info + 4, &nslots);
         // fast variants: rANS without LZ77 and one predictor (gradient or weighted) shared by all leaves
         int variant = 0;
         if (simt && !cc.prefix && !cc.lz77) {
@@ -672,11 +692,15 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
         int32_t refprops[SIMT_REF_SLOTS];
         for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
         const int variant = ms.info[2] - 1, ns = ms.info[1];
-        if (variant == 2) modular_channel_simt<true, 6, 1>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (variant == 1 && uses_wp) modular_channel_simt<true, 5, 1>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (variant == 1) modular_channel_simt<false, 5, 1>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (uses_wp) modular_channel_simt<true, -1, 0>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else modular_channel_simt<false, -1, 0>(br, es, cc, cs, ms, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        if (c.w > ms.cap) { // wide channels: generic variants only
+            if (uses_wp) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+            else modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        }
+        else if (variant == 2) modular_channel_simt<true, 6, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (variant == 1 && uses_wp) modular_channel_simt<true, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (variant == 1) modular_channel_simt<false, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (uses_wp) modular_channel_simt<true, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else modular_channel_simt<false, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else {
         const DTreeNode *t = n > 0 ? ptree : tree;
         if (uses_wp) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);

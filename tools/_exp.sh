@@ -11,9 +11,8 @@ except Exception as e:
     print("$name failed", e); print(open("gpurun_out/x_$name.err").read()[-800:])
 PY
 }
-ARGS="--steps 6 --warmup 3 --streams 3"
-run v7_s3_full A=1
-ARGS="--steps 12 --warmup 3 --streams 6 --skip-e2e"
-run v7_s6_nostage J40B_LF_STAGE=0
-run v7_s6_stage A=1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_lf_decode|k_back_tile" -c 3 -o gpurun_out/prof_v7 python bench.py --steps 1 --warmup 1 --frames-per-gpu 8 --skip-e2e --streams 1 > gpurun_out/ncu_v7.log 2>&1; tail -1 gpurun_out/ncu_v7.log | cut -c1-200
+ARGS="--steps 12 --warmup 3"
+run v8_default A=1
+ARGS="--steps 5 --warmup 3"
+run v8_default_s5 A=1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_lf_decode" -c 2 -o gpurun_out/prof_v8 python bench.py --steps 1 --warmup 1 --frames-per-gpu 8 --skip-e2e --streams 1 > gpurun_out/ncu_v8.log 2>&1; tail -1 gpurun_out/ncu_v8.log | cut -c1-200
