@@ -178,8 +178,12 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     const int nvb = ts.nvb;
     if (nvb == 0) return;
 
-    // ---- 1. scatter the decoded coefficients (one warp-sized stripe of threads per varblock-channel)
+    // ---- 1. scatter + dequantise the decoded coefficients (one warp-sized stripe of threads per
+    // varblock-channel; j40.h:7078-7094). Only non-zero coefficients have tokens (one per position: a single
+    // pass), and a zero coefficient dequantises to +0 whatever its weight, so the dense loop of the reference
+    // reduces to the token list: q = |c| <= 1 ? c * bias : c - bias_num / c; q *= mult / weight.
     {
+        const float qbn = f.quant_bias_num;
         const int lanes = nth < 32 ? nth : 32, groups = nth / lanes;
         const int lane = tid % lanes, grp_id = tid / lanes;
         for (int pair = grp_id; pair < nvb * 3; pair += groups) {
@@ -188,35 +192,33 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             uint32_t first = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 0], cnt = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 1];
             float *dst = coef + c * TILE_CH + t.chunk_off;
             const int mlog = t.mlog;
+            const float qb = f.quant_bias[c], m = t.m[c];
+            const float *dq = f.dq[t.param_idx] + c;
             for (uint32_t k = (uint32_t) lane; k < cnt; k += (uint32_t) lanes) {
                 DToken tk = w.tokens[first + k];
-                const int p = tile_swz(tk.pos, mlog);
-                dst[p] = J40B_FADD(dst[p], (float) tk.val);
+                float q = (float) tk.val;
+                q = (-1.0f <= q && q <= 1.0f) ? J40B_FMUL(q, qb) : J40B_FSUB(q, J40B_FDIV(qbn, q));
+                q = J40B_FMUL(q, J40B_FDIV(m, dq[(size_t) tk.pos * 3]));
+                dst[tile_swz(tk.pos, mlog)] = q;
             }
         }
     }
     sync();
-
-    // ---- 2. dequantise + chroma from luma (element-wise; j40.h:7078-7094, 7155-7175)
+    // ---- 2. chroma from luma (j40.h:7155-7175): x += y * kx, b += y * kb; a no-op wherever y is zero, so
+    // again only the Y tokens are visited
     {
-        const float qb0 = f.quant_bias[0], qb1 = f.quant_bias[1], qb2 = f.quant_bias[2], qbn = f.quant_bias_num;
-        int total = 0;
-        { const TileVb &last = ts.vb[nvb - 1]; total = last.log_off + (1 << (last.log_rows + last.log_cols)); }
-        for (int q = tid; q < total; q += nth) {
-            const TileVb &t = ts.vb[ts.chunk_vb[q >> 6]];
-            const int i = q - t.log_off;
-            const int e = t.chunk_off + tile_swz(i, t.mlog);
-            const float *dq = f.dq[t.param_idx] + (size_t) i * 3;
-            float vx = coefx[e], vy = coefy[e], vb_ = coefb[e];
-            vx = (-1.0f <= vx && vx <= 1.0f) ? J40B_FMUL(vx, qb0) : J40B_FSUB(vx, J40B_FDIV(qbn, vx));
-            vy = (-1.0f <= vy && vy <= 1.0f) ? J40B_FMUL(vy, qb1) : J40B_FSUB(vy, J40B_FDIV(qbn, vy));
-            vb_ = (-1.0f <= vb_ && vb_ <= 1.0f) ? J40B_FMUL(vb_, qb2) : J40B_FSUB(vb_, J40B_FDIV(qbn, vb_));
-            vx = J40B_FMUL(vx, J40B_FDIV(t.m[0], dq[0]));
-            vy = J40B_FMUL(vy, J40B_FDIV(t.m[1], dq[1]));
-            vb_ = J40B_FMUL(vb_, J40B_FDIV(t.m[2], dq[2]));
-            coefx[e] = J40B_FADD(vx, J40B_FMUL(vy, t.kx_hf));
-            coefy[e] = vy;
-            coefb[e] = J40B_FADD(vb_, J40B_FMUL(vy, t.kb_hf));
+        const int lanes = nth < 32 ? nth : 32, groups = nth / lanes;
+        const int lane = tid % lanes, grp_id = tid / lanes;
+        for (int v = grp_id; v < nvb; v += groups) {
+            const TileVb &t = ts.vb[v];
+            uint32_t first = g.vb_tok[((size_t) 1 * n8 + t.voff) * 2 + 0], cnt = g.vb_tok[((size_t) 1 * n8 + t.voff) * 2 + 1];
+            const int mlog = t.mlog;
+            for (uint32_t k = (uint32_t) lane; k < cnt; k += (uint32_t) lanes) {
+                const int p = t.chunk_off + tile_swz(w.tokens[first + k].pos, mlog);
+                const float vy = coefy[p];
+                coefx[p] = J40B_FADD(coefx[p], J40B_FMUL(vy, t.kx_hf));
+                coefb[p] = J40B_FADD(coefb[p], J40B_FMUL(vy, t.kb_hf));
+            }
         }
     }
     sync();

@@ -217,8 +217,11 @@ J40B_HD inline void lf_decode2_body(const LfWork &w, WarpScratch &ws, const ModS
         inverse_transforms(one, lane, nlanes);
         sync();
     }
+    // the weighted predictor's shared-memory rows are free now: 8 words per row of cells serve as the
+    // occupancy bitmap of the placement (needs 256 * 8 words)
+    if (ms.rows && ms.cap >= 256) place_varblocks_warp(f, g, es, br, (uint32_t *) ms.wp, lane, nlanes, sync);
+    else if (lane == 0) place_varblocks(f, g, es, br);
     if (lane == 0) {
-        place_varblocks(f, g, es, br);
         if (!es.err) {
             // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
             // on the per-section state and never copied back, j40.h:7791-7798); running short is still an error

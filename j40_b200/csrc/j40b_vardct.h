@@ -237,6 +237,75 @@ J40B_HD inline void place_varblocks(const DFrame &f, DLfGroup &g, ErrSlot &es, c
     if (voff != nvb) es.set(br, E_VBLK);
 }
 
+// The same with an occupancy bitmap in shared memory (`bitmap`: height8 rows of 8 words, zeroed here) instead of
+// reading the `blocks` map back from global memory: a group is 32 cells wide, i.e. one bitmap word, and a
+// varblock may not cross a group boundary, so a varblock's cells of one row always lie in one word. Lane 0
+// places the varblocks (position, coefficient offset, `blocks` cells; the order of the stores is the
+// reference's, so overlapping varblocks of malformed streams end up the same); then all lanes fill in the
+// per-varblock attributes.
+template <class Sync>
+J40B_HD inline void place_varblocks_warp(const DFrame &f, DLfGroup &g, ErrSlot &es, const BitReader &br, uint32_t *bitmap,
+                                         int lane, int nlanes, Sync sync) {
+    const int w8 = g.width8, h8 = g.height8, nvb = g.nb_varblocks;
+    const int words = (w8 + 31) >> 5;
+    for (int i = lane; i < h8 * 8; i += nlanes) bitmap[i] = 0;
+    sync();
+    if (lane == 0) {
+        const int log_gsize8 = f.group_size_shift - 3;
+        const int16_t *info0 = g.blockinfo;
+        int voff = 0, coeffoff = 0, big = 0;
+        for (int y0 = 0; y0 < h8 && !es.err; ++y0) for (int wi = 0; wi < words && !es.err; ++wi) {
+            const int nbits = w8 - wi * 32 < 32 ? w8 - wi * 32 : 32;
+            const uint32_t valid = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1);
+            for (;;) {
+                const uint32_t freeb = ~bitmap[y0 * 8 + wi] & valid;
+                if (!freeb) break;
+                const int x0 = wi * 32 + floor_lg32(freeb & (0u - freeb));
+                if (voff >= nvb) { es.set(br, E_VBLK); break; }
+                const int dctsel = info0[voff];
+                if (dctsel < 0 || dctsel >= 27) { es.set(br, E_DCT); break; }
+                const DctSelectInfo d = dct_select_info(dctsel);
+                const int vw8 = 1 << (d.log_columns - 3), vh8 = 1 << (d.log_rows - 3);
+                const int x1 = x0 + vw8 - 1, y1 = y0 + vh8 - 1;
+                if (!(x1 < w8 && (x0 >> log_gsize8) == (x1 >> log_gsize8))) { es.set(br, E_VBLK); break; }
+                if (!(y1 < h8 && (y0 >> log_gsize8) == (y1 >> log_gsize8))) { es.set(br, E_VBLK); break; }
+                const uint32_t mask = (vw8 >= 32 ? 0xffffffffu : ((1u << vw8) - 1)) << (x0 & 31);
+                for (int i = 0; i < vh8; ++i) {
+                    bitmap[(y0 + i) * 8 + wi] |= mask;
+                    int32_t *row = g.blocks + (size_t) (y0 + i) * w8 + x0;
+                    for (int j = 0; j < vw8; ++j) row[j] = 1 << 20 | voff;
+                }
+                g.blocks[y0 * w8 + x0] = (dctsel + 2) << 20 | voff;
+                DVarblock vb;
+                vb.coeffoff = coeffoff;
+                vb.qfidx = 0;
+                vb.hfmul_inv = 0.0f;
+                vb.x8 = (uint16_t) x0; vb.y8 = (uint16_t) y0;
+                vb.dctsel = (uint8_t) dctsel;
+                // bit 0: not handled by the tile kernel (larger than 64x64, or straddling a 64x64-pixel tile)
+                vb.pad = (uint16_t) ((d.log_columns + d.log_rows > 12 || (x0 & 7) + vw8 > 8 || (y0 & 7) + vh8 > 8) ? 1 : 0);
+                g.varblocks[voff] = vb;
+                big |= vb.pad & 1;
+                coeffoff += 1 << (d.log_columns + d.log_rows);
+                ++voff;
+            }
+        }
+        if (!es.err && voff != nvb) es.set(br, E_VBLK);
+        g.has_big = big;
+        bitmap[0] = es.err; // hand the outcome to the other lanes
+    }
+    sync();
+    if (bitmap[0]) { if (lane != 0) es.set_raw(bitmap[0]); return; }
+    const int16_t *info1 = g.blockinfo + nvb;
+    for (int v = lane; v < nvb; v += nlanes) {
+        const int m1 = info1[v];
+        int qf = 0;
+        for (int j = 0; j < f.nb_qf_thr; ++j) qf += m1 >= f.qf_thr[j];
+        g.varblocks[v].qfidx = (uint8_t) qf;
+        g.varblocks[v].hfmul_inv = J40B_FDIV(1.0f, J40B_FADD((float) m1, 1.0f));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 1-D transforms over `rep` interleaved columns (element i of column r at [i * rep + r])
 
