@@ -234,15 +234,14 @@ def main():
     # pipelined over them so that the parse / H2D / D2H of one step overlap the kernels of its neighbours.
     e2e = None
     if not args.skip_e2e:
-        E = min(len(batches), 4)
+        E = len(batches)
         pitch = h * b.info(0)[2]
         host_out = [torch.empty((F, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(E)]
         out_np = [t_.numpy() for t_ in host_out]
 
         def submit(bm, k):
             bm.reset()
-            for d in frames:
-                bm.add(d)
+            bm.add_many(frames)
             bm.upload()
             bm.decode()
             bm.read_all_async(out_np[k])

@@ -28,6 +28,10 @@ void j40b_batch_destroy(j40b_batch *b);
  * batch is reset / destroyed). Returns the image index or -1. */
 int j40b_batch_add(j40b_batch *b, const void *buf, size_t size);
 
+/* the same for n images at once, parsed on `threads` host threads (<= 0: all cores, at most 16); the thread
+ * count is also used for the copies into the staging buffer at upload. Returns the index of the first. */
+int j40b_batch_add_many(j40b_batch *b, const void *const *bufs, const size_t *sizes, int n, int threads);
+
 /* lays the added images out and enqueues ONE H2D transfer of codestreams + tables on the batch's stream
  * (asynchronous; the staging buffer is pinned memory owned by the batch). 0 on success. */
 int j40b_batch_upload(j40b_batch *b);

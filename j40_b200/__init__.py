@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "j40b_batch_wait", "j40b_batch_count", "j40b_batch_error", "j40b_batch_info", "j40b_batch_device_pixels",
     "j40b_batch_read_pixels", "j40b_batch_last_decode_ms", "j40b_batch_kernel_ms", "j40b_batch_stat", "j40b_gpu_available",
     "j40b_batch_mark", "j40b_batch_join", "j40b_batch_mark_ms", "j40b_batch_reset", "j40b_batch_read_all_async",
+    "j40b_batch_add_many",
 ]
 
 
@@ -98,6 +99,8 @@ def lib():
         L.j40b_gpu_available.restype = C.c_int
         L.j40b_batch_mark.restype = C.c_int
         L.j40b_batch_mark.argtypes = [C.c_void_p, C.c_int]
+        L.j40b_batch_add_many.restype = C.c_int
+        L.j40b_batch_add_many.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int]
         L.j40b_batch_reset.restype = C.c_int
         L.j40b_batch_reset.argtypes = [C.c_void_p]
         L.j40b_batch_read_all_async.restype = C.c_int
@@ -203,6 +206,16 @@ class Batch:
         buf = C.create_string_buffer(bytes(data), len(data))
         self._bufs.append(buf)
         return lib().j40b_batch_add(self._h, C.cast(buf, C.c_void_p), len(data))
+
+    def add_many(self, datas, threads=0):
+        """Parse many images on `threads` host threads (0 = all cores, at most 16). `datas`: bytes objects, kept
+        alive by this object until reset()/close()."""
+        n = len(datas)
+        keep = [d if isinstance(d, bytes) else bytes(d) for d in datas]
+        ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(d), C.c_void_p) for d in keep])
+        sizes = (C.c_size_t * n)(*[len(d) for d in keep])
+        self._bufs.extend(keep)
+        return lib().j40b_batch_add_many(self._h, ptrs, sizes, n, threads)
 
     def upload(self):
         if lib().j40b_batch_upload(self._h) != 0:

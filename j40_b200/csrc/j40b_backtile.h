@@ -221,7 +221,8 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             }
         }
     }
-    sync();
+    // (no barrier: the LLF corner below is disjoint from every token position -- the coefficient scan starts
+    // behind the LLF coefficients, j40.h:6978, and custom orders leave that prefix in place)
     // ---- 3. LLF corner from the LF image (j40.h:7158-7172)
     {
         const float kx_lf = f.kx_lf, kb_lf = f.kb_lf;

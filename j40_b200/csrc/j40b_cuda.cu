@@ -206,7 +206,8 @@ struct CudaBackend {
     }
     void launch_hf(const HfWork *w, int n, size_t spec_bytes) {
         const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
-        // lanes per warp: aim at ~8 warps per SM before filling warps completely
+        // lanes per warp: aim at ~8 warps per SM before filling warps completely (measured: 8 lanes at 8640 groups is
+        // the latency optimum; with several batches in flight the choice no longer matters)
         int lanes = (n + num_sms * 8 - 1) / (num_sms * 8);
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
@@ -288,6 +289,17 @@ EXPORT int j40b_batch_add(j40b_batch *b, const void *buf, size_t size) {
     b->batch->add((const uint8_t *) buf, size);
     b->uploaded = false;
     return (int) b->batch->plans.size() - 1;
+}
+
+EXPORT int j40b_batch_add_many(j40b_batch *b, const void *const *bufs, const size_t *sizes, int n, int threads) {
+    if (!b || !bufs || !sizes || n < 0) return -1;
+    for (int i = 0; i < n; ++i) if (!bufs[i]) return -1;
+    const int first = (int) b->batch->plans.size();
+    for (int i = 0; i < n; ++i) b->inputs.push_back({(const uint8_t *) bufs[i], sizes[i]});
+    b->batch->host_threads = threads;
+    b->batch->add_many((const uint8_t *const *) bufs, sizes, (size_t) n, threads);
+    b->uploaded = false;
+    return first;
 }
 
 EXPORT int j40b_batch_reset(j40b_batch *b) {

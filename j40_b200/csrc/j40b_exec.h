@@ -279,7 +279,14 @@ J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, con
         // contexts beyond the code spec: the reference reads out of bounds here; treat as corrupt
         es.set(br, E_COEF);
     } else {
-        hf_coeffs_tokens(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros, ctx_lut);
+        if (!cc.prefix && !cc.lz77) {
+            // every group reads at least one symbol (its first varblock's non-zero count): seed the rANS state
+            // now, so that the symbol loop need not test for it
+            ans_seed(br, cs.ans_state);
+            hf_coeffs_tokens<1>(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros, ctx_lut);
+        } else {
+            hf_coeffs_tokens<0>(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros, ctx_lut);
+        }
     }
     if (!es.err) {
         if (grp.sec_start_bit == ~0ull) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // single-section frame: real check

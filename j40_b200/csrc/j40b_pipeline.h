@@ -11,6 +11,8 @@
 #include <memory>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 namespace j40b {
 
@@ -39,6 +41,29 @@ public:
         parse_frame(data, size, *p);
         plans.push_back(std::move(p));
     }
+
+    // host parse of many images on `threads` host threads (frames are independent; parse_frame touches only its
+    // own FramePlan and the immutable global tables)
+    void add_many(const uint8_t *const *bufs, const size_t *sizes, size_t n, int threads) {
+        const size_t first = plans.size();
+        for (size_t i = 0; i < n; ++i) plans.emplace_back(new FramePlan);
+        parallel_for(n, threads, [&](size_t i) { parse_frame(bufs[i], sizes[i], *plans[first + i]); });
+    }
+
+    // runs fn(0..n-1) on up to `threads` host threads (<= 0: as many as the machine offers, at most 16)
+    template <class F>
+    static void parallel_for(size_t n, int threads, F fn) {
+        if (threads <= 0) threads = (int) std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+        threads = (int) std::min<size_t>((size_t) threads, n);
+        if (threads <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+        std::atomic<size_t> next(0);
+        std::vector<std::thread> pool;
+        auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); };
+        for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    }
+    int host_threads = 0; // for upload()'s copies into the staging buffer
 
     // forgets the images but keeps the device / pinned allocations for the next upload()
     void reset() { plans.clear(); results.clear(); img.clear(); num_lf = num_hf = 0; }
@@ -178,7 +203,24 @@ public:
             num_lf = num_hf = 0;
             return false;
         }
-        memset(staging, 0, upload_bytes);
+        // zero everything but the codestream / arena payloads (those are overwritten below, in parallel)
+        {
+            size_t pos = 0;
+            for (size_t k = 0; k < n; ++k) {
+                if (plans[k]->err) continue;
+                const Img &im = img[k];
+                memset(staging + pos, 0, im.arena_off - pos);
+                pos = im.cs_off + plans[k]->cs_size; // arena and codestream are adjacent allocations
+                memset(staging + im.arena_off + plans[k]->arena.bytes.size(), 0, im.cs_off - (im.arena_off + plans[k]->arena.bytes.size()));
+            }
+            memset(staging + pos, 0, upload_bytes - pos);
+        }
+        parallel_for(n, host_threads, [&](size_t k) {
+            const FramePlan &p = *plans[k];
+            if (p.err) return;
+            memcpy(staging + img[k].arena_off, p.arena.bytes.data(), p.arena.bytes.size());
+            memcpy(staging + img[k].cs_off, p.cs, p.cs_size);
+        });
         uint8_t *dwork = dev + upload_bytes;
         // ---- fill the staging blob with device addresses
         for (int i = 0; i < 17; ++i) memcpy(staging + gt_dq[i], gt.dq[i].data(), gt.dq[i].size() * 4);
@@ -205,8 +247,6 @@ public:
             d.srgb_thr = (const float *) (dev + gt_thr);
             d.srgb_lut = dev + gt_lut;
             memcpy(staging + im.frame_off, &d, sizeof(d));
-            memcpy(staging + im.arena_off, p.arena.bytes.data(), p.arena.bytes.size());
-            memcpy(staging + im.cs_off, p.cs, p.cs_size);
             const DFrame *dframe = (const DFrame *) (dev + im.frame_off);
             const uint8_t *darena = dev + im.arena_off, *dcs = dev + im.cs_off;
             uint32_t *derr = (uint32_t *) (dwork + im.err_off);

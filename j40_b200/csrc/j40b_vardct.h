@@ -635,6 +635,8 @@ J40B_HD J40B_INLINE int coeff_nnz_ctx2(int q) { // q in [0, 64)
 // decoded by the lanes of one warp (one group per lane) and stay convergent at the symbol read, whatever
 // their position inside a block is. `nonzeros`: [gh8*gw8][3] bytes of per-group scratch. `ctx_lut`: optional
 // 128-entry table (shared memory on the device): [q] = coeff_nnz_ctx2(q), [64 + k] = coeff_freq_ctx2(k).
+// MODE 1: the code spec is rANS without LZ77 and the caller has seeded the state (see code_cluster).
+template <int MODE>
 J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
                                      const DFrame &f, const uint8_t *arena, const DLfGroup &g, DGroup &grp,
                                      int32_t ctxoff, DToken *tokens /* image token array */, int8_t *nonzeros,
@@ -695,7 +697,9 @@ J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &
             ctx = cctx + prev + (ctx_lut ? (int) ctx_lut[q] + (int) ctx_lut[64 + k] : coeff_nnz_ctx2(q) + coeff_freq_ctx2(k));
         }
         // ---- the one symbol read of this iteration
-        const int32_t v = code(br, es, cc, cs, ctx, 0);
+        int32_t v;
+        if (MODE == 1) v = code_cluster<false, 1>(br, es, cc, cs, cc.clusters[cc.cluster_map[ctx]], 0);
+        else v = code(br, es, cc, cs, ctx, 0);
         if (es.err) return;
         if (reading_nnz) {
             nz = v;

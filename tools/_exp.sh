@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 run() { # name, env..., args
   name=$1; shift
   env "$@" timeout 280 python bench.py $ARGS > gpurun_out/x_$name.json 2> gpurun_out/x_$name.err
@@ -12,7 +12,10 @@ except Exception as e:
 PY
 }
 ARGS="--steps 12 --warmup 3"
-run v8_default A=1
-ARGS="--steps 5 --warmup 3"
-run v8_default_s5 A=1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_lf_decode" -c 2 -o gpurun_out/prof_v8 python bench.py --steps 1 --warmup 1 --frames-per-gpu 8 --skip-e2e --streams 1 > gpurun_out/ncu_v8.log 2>&1; tail -1 gpurun_out/ncu_v8.log | cut -c1-200
+run v10_default A=1
+ARGS="--steps 12 --warmup 3 --skip-e2e"
+run v10_lanes24 J40B_HF_LANES=24
+run v10_lanes32 J40B_HF_LANES=32
+run v10_lanes8 J40B_HF_LANES=8
+ARGS="--steps 16 --warmup 3 --skip-e2e --streams 8"
+run v10_s8 A=1
