@@ -1,7 +1,6 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-run() { # name, env..., args
+run() { # name, args
   name=$1; shift
-  env "$@" timeout 280 python bench.py $ARGS > gpurun_out/x_$name.json 2> gpurun_out/x_$name.err
+  timeout 280 python bench.py "$@" > gpurun_out/x_$name.json 2> gpurun_out/x_$name.err
   python - <<PY
 import json
 try:
@@ -11,11 +10,8 @@ except Exception as e:
     print("$name failed", e); print(open("gpurun_out/x_$name.err").read()[-800:])
 PY
 }
-ARGS="--steps 12 --warmup 3"
-run v10_default A=1
-ARGS="--steps 12 --warmup 3 --skip-e2e"
-run v10_lanes24 J40B_HF_LANES=24
-run v10_lanes32 J40B_HF_LANES=32
-run v10_lanes8 J40B_HF_LANES=8
-ARGS="--steps 16 --warmup 3 --skip-e2e --streams 8"
-run v10_s8 A=1
+run s3 --steps 12 --warmup 3 --skip-e2e --streams 3
+run s12 --steps 24 --warmup 3 --skip-e2e --streams 12
+run f32s12 --steps 24 --warmup 3 --skip-e2e --streams 12 --frames-per-gpu 32
+run f128s6 --steps 12 --warmup 3 --skip-e2e --streams 6 --frames-per-gpu 128
+run f16s24 --steps 48 --warmup 3 --skip-e2e --streams 24 --frames-per-gpu 16
