@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=8, help="distinct streams per rank (cycled to fill the batch)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=6, help="batch objects (CUDA streams) the timed steps are pipelined over")
+    ap.add_argument("--lag", type=int, default=-1, help="step s starts its LF stage when step s-lag has finished its own "
+                    "(keeps the batches in flight out of phase); 0 = no phase control, -1 = streams/2")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,6 +191,14 @@ def main():
     # LF-group kernel of one step overlaps the HF / back kernels of its neighbours. All K steps run inside the
     # region; device time is taken with CUDA events on stream 0 after joining every stream.
     M = max(1, min(args.streams, args.steps))
+    lag = M // 2 if args.lag < 0 else min(args.lag, M - 1)
+
+    def submit_decode(s_):
+        # phase control: without it all batches in flight run their LF stages together, then their HF stages ...
+        if lag and s_ >= lag:
+            batches[s_ % M].after(batches[(s_ - lag) % M], 0)
+        batches[s_ % M].decode()
+
     batches = [b]
     for m in range(1, M):
         bm = J.Batch(local_rank)
@@ -197,8 +207,8 @@ def main():
         bm.upload()
         batches.append(bm)
     for _ in range(args.warmup):
-        for bm in batches:
-            bm.decode()
+        for k in range(M):
+            submit_decode(k)
         for bm in batches:
             assert bm.wait() == 0
     sampler = ClockSampler(local_rank)
@@ -208,7 +218,7 @@ def main():
     torch.cuda.synchronize()
     b.mark(0)
     for s_ in range(args.steps):
-        batches[s_ % M].decode()
+        submit_decode(s_)
     for bm in batches[1:]:
         b.join(bm)
     b.mark(1)
@@ -216,6 +226,11 @@ def main():
         assert bm.wait() == 0
     torch.cuda.synchronize()
     total_ms = b.mark_ms()
+    if os.environ.get("J40B_TIMELINE"):
+        # when each stage of the last decode on every batch object ended, relative to the start of the region
+        for k, bm in enumerate(batches):
+            print("timeline batch %d: " % k + " ".join("%s=%.1f" % (n, bm.event_ms(b, i)) for n, i in
+                  [("lf0", 0), ("lfimg", 5), ("hfmeta", 6), ("lf", 1), ("hf", 2), ("tiles", 3), ("end", 4)]), file=sys.stderr)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     launches = launches_per_step * args.steps
@@ -318,7 +333,7 @@ def main():
                    "compressed_bytes_per_gpu": comp_bytes, "bits_per_pixel": 8.0 * comp_bytes / pixels,
                    "hf_symbols_per_pixel": sum(s["hf_symbols"] for s in stats) / (len(stats) * w * h),
                    "l2": "inputs+outputs per step (%.1f GB) exceed L2" % ((comp_bytes + 4 * pixels) / 1e9),
-                   "pipelining": f"{args.steps} steps over {M} batch objects / CUDA streams",
+                   "pipelining": f"{args.steps} steps over {M} batch objects / CUDA streams, LF stage of step s gated on step s-{lag}",
                    "parallelism": f"batch-sharded x{world}, no collective"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.result(), "device_bytes": int(dev_bytes),

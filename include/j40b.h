@@ -74,6 +74,16 @@ int j40b_batch_mark(j40b_batch *b, int which);
 int j40b_batch_join(j40b_batch *b, j40b_batch *other);
 float j40b_batch_mark_ms(j40b_batch *b);
 
+/* Phase control for a serving loop with several batches in flight: work enqueued on b after this call waits
+ * until `other`'s most recently enqueued decode has finished stage `stage` (0 LF-group stage, 1 pass-group
+ * entropy decode, 2 everything). Keeping half of the batches one stage behind the others lets the serial,
+ * latency-bound LF decoders of one half run under the throughput kernels of the other half. */
+int j40b_batch_after(j40b_batch *b, j40b_batch *other, int stage);
+
+/* diagnostic: device time in ms from `ref`'s mark 0 to event `which` of b's most recent decode (0 LF start,
+ * 5 LF image decoded, 6 HF metadata decoded, 1 LF stage done, 2 HF done, 3 tiles done, 4 all done); -1 if unknown */
+float j40b_batch_event_ms(const j40b_batch *b, const j40b_batch *ref, int which);
+
 /* 1 if a CUDA device is usable by this library, else 0 */
 int j40b_gpu_available(void);
 

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "j40b_batch_wait", "j40b_batch_count", "j40b_batch_error", "j40b_batch_info", "j40b_batch_device_pixels",
     "j40b_batch_read_pixels", "j40b_batch_last_decode_ms", "j40b_batch_kernel_ms", "j40b_batch_stat", "j40b_gpu_available",
     "j40b_batch_mark", "j40b_batch_join", "j40b_batch_mark_ms", "j40b_batch_reset", "j40b_batch_read_all_async",
-    "j40b_batch_add_many",
+    "j40b_batch_add_many", "j40b_batch_event_ms", "j40b_batch_after",
 ]
 
 
@@ -94,6 +94,10 @@ def lib():
         L.j40b_batch_last_decode_ms.argtypes = [C.c_void_p]
         L.j40b_batch_kernel_ms.restype = C.c_float
         L.j40b_batch_kernel_ms.argtypes = [C.c_void_p, C.c_int]
+        L.j40b_batch_after.restype = C.c_int
+        L.j40b_batch_after.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.j40b_batch_event_ms.restype = C.c_float
+        L.j40b_batch_event_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.j40b_batch_stat.restype = C.c_int64
         L.j40b_batch_stat.argtypes = [C.c_void_p, C.c_int]
         L.j40b_gpu_available.restype = C.c_int
@@ -276,6 +280,12 @@ class Batch:
 
     def join(self, other):
         lib().j40b_batch_join(self._h, other._h)
+
+    def after(self, other, stage=0):
+        return int(lib().j40b_batch_after(self._h, other._h, stage))
+
+    def event_ms(self, ref, which):
+        return float(lib().j40b_batch_event_ms(self._h, ref._h, which))
 
     def mark_ms(self):
         return float(lib().j40b_batch_mark_ms(self._h))

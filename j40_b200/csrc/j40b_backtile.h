@@ -19,33 +19,14 @@
 
 namespace j40b {
 
-// 1-D inverse DCT of N points in place, the recursion of j40__inverse_dct_core (j40.h:5802-5841) unrolled
-template <int N> struct Idct1D {
-    J40B_HD static J40B_INLINE void run(float *v) {
-        float a[N / 2], b[N / 2];
-#pragma unroll
-        for (int i = 0; i < N / 2; ++i) a[i] = v[2 * i];
-        b[0] = J40B_FMUL(J40B_SQRT2, v[1]);
-#pragma unroll
-        for (int i = 1; i < N / 2; ++i) b[i] = J40B_FADD(v[2 * i - 1], v[2 * i + 1]);
-        Idct1D<N / 2>::run(a);
-        Idct1D<N / 2>::run(b);
-#pragma unroll
-        for (int i = 0; i < N / 2; ++i) {
-            float t = J40B_FMUL(b[i], J40B_HALF_SECANT(N / 2 + i));
-            v[i] = J40B_FADD(a[i], t);
-            v[N - 1 - i] = J40B_FSUB(a[i], t);
-        }
-    }
-};
-template <> struct Idct1D<2> {
-    J40B_HD static J40B_INLINE void run(float *v) {
-        float x = v[0], y = v[1];
-        v[0] = J40B_FADD(x, y);
-        v[1] = J40B_FSUB(x, y);
-    }
-};
-template <> struct Idct1D<1> { J40B_HD static J40B_INLINE void run(float *) {} };
+// per-phase cycle counters of the tile kernel (diagnostic builds only: make PHASE_CLOCKS=1)
+#if defined(__CUDA_ARCH__) && defined(J40B_PHASE_CLOCKS) && defined(J40B_KERN_BACK_TU) // ts.phase: set by k_back_tile
+#define J40B_PHASE(i) do { if (tid == 0) { long long now_ = clock64(); atomicAdd(&ts.phase[i], (unsigned long long) (now_ - phase_t0_)); phase_t0_ = now_; } } while (0)
+#define J40B_PHASE_BEGIN long long phase_t0_ = clock64()
+#else
+#define J40B_PHASE(i) do {} while (0)
+#define J40B_PHASE_BEGIN do {} while (0)
+#endif
 
 // Shared-memory layout of one varblock's coefficients: the stored index i = a * M + b (a = major, b = minor,
 // M = 1 << mlog = the longer side, so a < M) lives at a * M + (b ^ a). Both IDCT passes then touch 32
@@ -54,6 +35,15 @@ template <> struct Idct1D<1> { J40B_HD static J40B_INLINE void run(float *) {} }
 J40B_HD J40B_INLINE int tile_swz(int i, int mlog) {
     const int a = i >> mlog;
     return i ^ (a & ((1 << mlog) - 1));
+}
+
+// *p += v on a coefficient buffer that other threads of the block may be adding to as well
+J40B_HD J40B_INLINE void tile_add(float *p, float v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p = *p + v;
+#endif
 }
 
 // 1-D transform number f of a pass over a block: ALONG_MINOR walks b with a = f fixed, else walks a with b = f
@@ -91,19 +81,98 @@ struct TileVb {
     uint8_t special;
     uint8_t mlog;        // log2 of the swizzled layout's row length (longer side); 0 = plain layout (special 8x8)
     float m[3];          // dequantisation multipliers mult[c] of j40__dequant_hf
-    float kx_hf, kb_hf;
+    uint32_t first[3];   // first token of channel c (X, Y, B) in the image's token array
+    uint16_t cnt[3];     // number of tokens of channel c
 };
 
 struct TileShared {
+    unsigned long long *phase; // diagnostic builds: global per-phase cycle counters
     int32_t nvb;
     TileVb vb[64];
     int32_t cell_voff[64];  // per cell: varblock index if the cell is a top-left handled here, else -1
+    uint32_t cell_first[64][3]; // per cell: first token / token count per channel of the varblock starting there
+    uint16_t cell_cnt[64][3];
+    uint16_t tstart[65];    // per compacted varblock: start of its tokens in the tile's flattened token list
+    // 1-D transform tasks of the two IDCT passes, listed per transform type so that the lanes of a warp run the
+    // same code: pstart[pass][type][v] = tasks of that type in varblocks before v, [64] = their total.
+    // type = 2 * (log2 N - 3) + ALONG_MINOR (see idct_swz)
+    uint16_t pstart[2][8][65];
+    float kx_hf, kb_hf;     // chroma-from-luma factors of this tile (one 64x64 cell of the XFromY / BFromY maps)
     uint8_t cell_size64[64];
     uint8_t cover[64];      // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
     uint8_t chunk_vb[64];   // 64-float chunk -> index into vb[]
     float thr[255];
     uint8_t lut[SRGB_LUT_BYTES];
 };
+
+// number of 1-D transforms of `type` that varblock t contributes to pass 0 (along u) / pass 1 (along v)
+J40B_HD J40B_INLINE int tile_task_count(const TileVb &t, int pass, int type) {
+    if (t.special) return 0;
+    const bool wide = t.log_cols > t.log_rows;
+    const int log_n = pass == 0 ? t.log_cols : t.log_rows;
+    const int minor = pass == 0 ? (wide ? 1 : 0) : (wide ? 0 : 1);
+    if (2 * (log_n - 3) + minor != type) return 0;
+    return 3 << (pass == 0 ? t.log_rows : t.log_cols);
+}
+
+// exclusive prefix sums of the task counts over the compacted varblocks, one (pass, type) pair per warp
+J40B_HD inline void tile_type_scan(TileShared &ts, int nvb, int tid, int nth) {
+#if defined(__CUDA_ARCH__)
+    if (nth >= 32 && !(nth & 31)) {
+        const int lane = tid & 31;
+        for (int pair = tid >> 5; pair < 16; pair += nth >> 5) {
+            const int pass = pair >> 3, type = pair & 7;
+            int carry = 0;
+            for (int base = 0; base < 64; base += 32) {
+                const int v = base + lane;
+                const int cnt = v < nvb ? tile_task_count(ts.vb[v], pass, type) : 0;
+                int x = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+                ts.pstart[pass][type][v] = (uint16_t) (carry + x - cnt);
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) ts.pstart[pass][type][64] = (uint16_t) carry;
+        }
+        return;
+    }
+#endif
+    for (int pair = tid; pair < 16; pair += nth) {
+        const int pass = pair >> 3, type = pair & 7;
+        int sum = 0;
+        for (int v = 0; v < 64; ++v) {
+            ts.pstart[pass][type][v] = (uint16_t) sum;
+            if (v < nvb) sum += tile_task_count(ts.vb[v], pass, type);
+        }
+        ts.pstart[pass][type][64] = (uint16_t) sum;
+    }
+}
+
+// all 1-D transforms of one type in one pass: task k -> (varblock, channel, transform number)
+template <int LOGN, bool MINOR>
+J40B_HD J40B_INLINE void tile_pass_type(float *coef, const TileShared &ts, int pass, int nvb, int tid, int nth) {
+    const uint16_t *start = ts.pstart[pass][2 * (LOGN - 3) + (MINOR ? 1 : 0)];
+    const int total = start[64];
+    for (int k = tid; k < total; k += nth) {
+        int lo = 0, hi = nvb - 1; // last varblock whose first task is <= k (varblocks of other types have none)
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int) start[mid] <= k) lo = mid; else hi = mid - 1; }
+        const TileVb &t = ts.vb[lo];
+        const int j = k - (int) start[lo];
+        const int lcnt = pass == 0 ? t.log_rows : t.log_cols;
+        idct_swz<(1 << LOGN), MINOR>(coef + (j >> lcnt) * TILE_CH + t.chunk_off, j & ((1 << lcnt) - 1), t.mlog);
+    }
+}
+
+J40B_HD J40B_INLINE void tile_pass(float *coef, const TileShared &ts, int pass, int nvb, int tid, int nth) {
+    tile_pass_type<6, false>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<6, true>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<5, false>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<5, true>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<4, false>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<4, true>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<3, false>(coef, ts, pass, nvb, tid, nth);
+    tile_pass_type<3, true>(coef, ts, pass, nvb, tid, nth);
+}
 
 // tile (tx, ty) of group w.grp; coef = 3 * TILE_CH floats of shared memory
 template <class Sync>
@@ -116,6 +185,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     if (tx * 8 >= gw8 || ty * 8 >= gh8) return;
     const int n8 = g.width8 * g.height8;
     float *coefx = coef, *coefy = coef + TILE_CH, *coefb = coef + 2 * TILE_CH;
+    J40B_PHASE_BEGIN;
 
     // ---- 0. which varblocks start in this tile (one cell per thread), thresholds, zeroed coefficients
     for (int c = tid; c < 64; c += nth) {
@@ -125,33 +195,54 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         int size64 = 0;
         if (x8 < gw8 && y8 < gh8) {
             int32_t b = g.blocks[(y8 + grp.gy8) * g.width8 + x8 + grp.gx8];
-            if ((b >> 20) >= 2 && !(g.varblocks[b & 0xfffff].pad & 1)) {
-                voff = b & 0xfffff;
-                DctSelectInfo d = dct_select_info((b >> 20) - 2);
-                size64 = 1 << (d.log_rows + d.log_columns - 6);
+            if ((b >> 20) >= 2) {
+                // the varblock record and its three token ranges are fetched together (one round trip to L2)
+                const int32_t vo = b & 0xfffff;
+                const uint16_t pad = g.varblocks[vo].pad;
+                const uint64_t r0 = *(const uint64_t *) (g.vb_tok + ((size_t) 0 * n8 + vo) * 2);
+                const uint64_t r1 = *(const uint64_t *) (g.vb_tok + ((size_t) 1 * n8 + vo) * 2);
+                const uint64_t r2 = *(const uint64_t *) (g.vb_tok + ((size_t) 2 * n8 + vo) * 2);
+                if (!(pad & 1)) {
+                    voff = vo;
+                    DctSelectInfo d = dct_select_info((b >> 20) - 2);
+                    size64 = 1 << (d.log_rows + d.log_columns - 6);
+                    ts.cell_first[c][0] = (uint32_t) r0; ts.cell_first[c][1] = (uint32_t) r1; ts.cell_first[c][2] = (uint32_t) r2;
+                    ts.cell_cnt[c][0] = (uint16_t) (r0 >> 32); ts.cell_cnt[c][1] = (uint16_t) (r1 >> 32); ts.cell_cnt[c][2] = (uint16_t) (r2 >> 32);
+                }
             }
         }
         ts.cell_voff[c] = voff;
         ts.cell_size64[c] = (uint8_t) size64;
         ts.cover[c] = 0xff;
     }
+    if (tid == 0) {
+        // every varblock that starts in this tile lies in the same 64x64 cell of the colour-correlation maps
+        const int m64 = ((grp.gy8 >> 3) + ty) * g.width64 + (grp.gx8 >> 3) + tx;
+        ts.kx_hf = J40B_FADD(f.base_corr_x, J40B_FMUL(f.inv_colour_factor, (float) g.xfromy[m64]));
+        ts.kb_hf = J40B_FADD(f.base_corr_b, J40B_FMUL(f.inv_colour_factor, (float) g.bfromy[m64]));
+    }
     for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
     for (int i = tid; i < SRGB_LUT_BYTES / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
     for (int i = tid; i < 3 * TILE_CH; i += nth) coef[i] = 0.0f;
     sync();
+    J40B_PHASE(0);
     // ---- 0b. compact them in raster order (each top-left cell computes its own rank and chunk offset)
     {
         const float gs = J40B_FDIV(65536.0f, (float) f.global_scale);
         for (int c = tid; c < 64; c += nth) {
             if (c == 63) {
-                int n = 0;
-                for (int k = 0; k < 64; ++k) n += ts.cell_voff[k] >= 0;
+                int n = 0, tt = 0;
+                for (int k = 0; k < 64; ++k) if (ts.cell_voff[k] >= 0) { ++n; tt += ts.cell_cnt[k][0] + ts.cell_cnt[k][1] + ts.cell_cnt[k][2]; }
                 ts.nvb = n;
+                ts.tstart[n] = (uint16_t) tt;
             }
             const int32_t voff = ts.cell_voff[c];
             if (voff < 0) continue;
-            int rank = 0, off64 = 0;
-            for (int k = 0; k < c; ++k) { rank += ts.cell_voff[k] >= 0; off64 += ts.cell_size64[k]; }
+            int rank = 0, off64 = 0, tstart = 0;
+            for (int k = 0; k < c; ++k) if (ts.cell_voff[k] >= 0) {
+                ++rank; off64 += ts.cell_size64[k];
+                tstart += ts.cell_cnt[k][0] + ts.cell_cnt[k][1] + ts.cell_cnt[k][2];
+            }
             const DVarblock vb = g.varblocks[voff];
             DctSelectInfo d = dct_select_info(vb.dctsel);
             TileVb &t = ts.vb[rank];
@@ -166,8 +257,8 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             t.m[1] = J40B_FMUL(gs, vb.hfmul_inv);
             t.m[0] = J40B_FMUL(t.m[1], f.x_qm_mult);
             t.m[2] = J40B_FMUL(t.m[1], f.b_qm_mult);
-            t.kx_hf = J40B_FADD(f.base_corr_x, J40B_FMUL(f.inv_colour_factor, (float) g.xfromy[(vb.y8 / 8) * g.width64 + (vb.x8 / 8)]));
-            t.kb_hf = J40B_FADD(f.base_corr_b, J40B_FMUL(f.inv_colour_factor, (float) g.bfromy[(vb.y8 / 8) * g.width64 + (vb.x8 / 8)]));
+            for (int k = 0; k < 3; ++k) { t.first[k] = ts.cell_first[c][k]; t.cnt[k] = ts.cell_cnt[c][k]; }
+            ts.tstart[rank] = (uint16_t) tstart;
             for (int k = 0; k < ts.cell_size64[c]; ++k) ts.chunk_vb[off64 + k] = (uint8_t) rank;
             for (int i = 0; i < (1 << (d.log_rows - 3)); ++i) for (int j = 0; j < (1 << (d.log_columns - 3)); ++j) {
                 ts.cover[((c >> 3) + i) * 8 + (c & 7) + j] = (uint8_t) rank;
@@ -175,52 +266,48 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         }
     }
     sync();
+    J40B_PHASE(1);
     const int nvb = ts.nvb;
     if (nvb == 0) return;
+    tile_type_scan(ts, nvb, tid, nth); // read by the IDCT passes, behind the barrier that ends the scatter phase
 
-    // ---- 1. scatter + dequantise the decoded coefficients (one warp-sized stripe of threads per
-    // varblock-channel; j40.h:7078-7094). Only non-zero coefficients have tokens (one per position: a single
-    // pass), and a zero coefficient dequantises to +0 whatever its weight, so the dense loop of the reference
-    // reduces to the token list: q = |c| <= 1 ? c * bias : c - bias_num / c; q *= mult / weight.
+    // ---- 1+2. scatter, dequantise (j40.h:7078-7094) and chroma from luma (j40.h:7155-7175), one thread per
+    // token over the tile's flattened token list, so that every global load of the phase (token, then its
+    // dequantisation weight) is in flight for 256 tokens at once instead of one varblock-channel per warp.
+    // Only non-zero coefficients have tokens (one per position: a single pass), and a zero coefficient
+    // dequantises to +0 whatever its weight, so the dense loop of the reference reduces to the token list:
+    // q = |c| <= 1 ? c * bias : c - bias_num / c; q *= mult / weight. Chroma from luma, x += y * kx and
+    // b += y * kb, is a no-op wherever y is zero: it is applied from the Y tokens. A position of the X (B)
+    // buffer thus receives at most two addends on top of the initial +0, its own coefficient and the luma
+    // term; float addition is commutative and 0 + a is exact, so adding them in either order (shared-memory
+    // atomics, which keep denormals) gives the reference's x + y * kx bit for bit.
     {
         const float qbn = f.quant_bias_num;
-        const int lanes = nth < 32 ? nth : 32, groups = nth / lanes;
-        const int lane = tid % lanes, grp_id = tid / lanes;
-        for (int pair = grp_id; pair < nvb * 3; pair += groups) {
-            int v = pair / 3, c = pair - v * 3;
-            const TileVb &t = ts.vb[v];
-            uint32_t first = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 0], cnt = g.vb_tok[((size_t) c * n8 + t.voff) * 2 + 1];
-            float *dst = coef + c * TILE_CH + t.chunk_off;
-            const int mlog = t.mlog;
-            const float qb = f.quant_bias[c], m = t.m[c];
-            const float *dq = f.dq[t.param_idx] + c;
-            for (uint32_t k = (uint32_t) lane; k < cnt; k += (uint32_t) lanes) {
-                DToken tk = w.tokens[first + k];
-                float q = (float) tk.val;
-                q = (-1.0f <= q && q <= 1.0f) ? J40B_FMUL(q, qb) : J40B_FSUB(q, J40B_FDIV(qbn, q));
-                q = J40B_FMUL(q, J40B_FDIV(m, dq[(size_t) tk.pos * 3]));
-                dst[tile_swz(tk.pos, mlog)] = q;
+        const float kx_hf = ts.kx_hf, kb_hf = ts.kb_hf;
+        const int total = ts.tstart[nvb];
+        for (int k = tid; k < total; k += nth) {
+            int lo = 0, hi = nvb - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int) ts.tstart[mid] <= k) lo = mid; else hi = mid - 1; }
+            const TileVb &t = ts.vb[lo];
+            int j = k - (int) ts.tstart[lo];
+            // tokens of a varblock were written in decoding order: Y, X, B
+            int c = 1;
+            if (j >= (int) t.cnt[1]) { j -= t.cnt[1]; c = 0; if (j >= (int) t.cnt[0]) { j -= t.cnt[0]; c = 2; } }
+            const DToken tk = w.tokens[t.first[c] + (uint32_t) j];
+            float q = (float) tk.val;
+            q = (-1.0f <= q && q <= 1.0f) ? J40B_FMUL(q, f.quant_bias[c]) : J40B_FSUB(q, J40B_FDIV(qbn, q));
+            q = J40B_FMUL(q, J40B_FDIV(t.m[c], f.dq[t.param_idx][(size_t) tk.pos * 3 + c]));
+            const int p = t.chunk_off + tile_swz(tk.pos, t.mlog);
+            if (c == 1) {
+                coefy[p] = q;
+                tile_add(&coefx[p], J40B_FMUL(q, kx_hf));
+                tile_add(&coefb[p], J40B_FMUL(q, kb_hf));
+            } else {
+                tile_add(c == 0 ? &coefx[p] : &coefb[p], q);
             }
         }
     }
-    sync();
-    // ---- 2. chroma from luma (j40.h:7155-7175): x += y * kx, b += y * kb; a no-op wherever y is zero, so
-    // again only the Y tokens are visited
-    {
-        const int lanes = nth < 32 ? nth : 32, groups = nth / lanes;
-        const int lane = tid % lanes, grp_id = tid / lanes;
-        for (int v = grp_id; v < nvb; v += groups) {
-            const TileVb &t = ts.vb[v];
-            uint32_t first = g.vb_tok[((size_t) 1 * n8 + t.voff) * 2 + 0], cnt = g.vb_tok[((size_t) 1 * n8 + t.voff) * 2 + 1];
-            const int mlog = t.mlog;
-            for (uint32_t k = (uint32_t) lane; k < cnt; k += (uint32_t) lanes) {
-                const int p = t.chunk_off + tile_swz(w.tokens[first + k].pos, mlog);
-                const float vy = coefy[p];
-                coefx[p] = J40B_FADD(coefx[p], J40B_FMUL(vy, t.kx_hf));
-                coefb[p] = J40B_FADD(coefb[p], J40B_FMUL(vy, t.kb_hf));
-            }
-        }
-    }
+    J40B_PHASE(2);
     // (no barrier: the LLF corner below is disjoint from every token position -- the coefficient scan starts
     // behind the LLF coefficients, j40.h:6978, and custom orders leave that prefix in place)
     // ---- 3. LLF corner from the LF image (j40.h:7158-7172)
@@ -243,40 +330,22 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         }
     }
     sync();
-    // ---- 4. pass A: 1-D inverse DCTs along the horizontal frequency u; special 8x8 transforms whole
-    // slot = (channel, tile pixel row, tile cell column); active where the cell starts a varblock's row of cells
-    for (int slot = tid; slot < 3 * 64 * 8; slot += nth) {
-        const int c = slot / 512, r64 = slot & 63, cx = (slot >> 6) & 7;
-        const int cell = (r64 >> 3) * 8 + cx;
-        const uint8_t vi = ts.cover[cell];
-        if (vi == 0xff) continue;
-        const TileVb &t = ts.vb[vi];
-        if (t.cx != cx) continue; // not the leftmost cell of this varblock
-        const int r = r64 - t.cy * 8; // row inside the varblock (vertical frequency index v at this stage)
-        float *blk = coef + c * TILE_CH + t.chunk_off;
-        if (t.special) {
-            if (r == 0) inverse_special(t.dctsel, blk);
-            continue;
-        }
-        if (t.log_cols > t.log_rows) idct_swz_dispatch<true>(blk, r, t.mlog, t.log_cols);    // [v][u]: row v = r, along u
-        else idct_swz_dispatch<false>(blk, r, t.mlog, t.log_cols);                          // [u][v]: column v = r, along u
+    J40B_PHASE(3);
+    // ---- 4. pass A: 1-D inverse DCTs along the horizontal frequency u (square / tall blocks keep [u][v]:
+    // column v = r, along u; wide blocks keep [v][u]: row v = r, along u); special 8x8 transforms whole,
+    // one thread per block and channel, issued first because they are the longest tasks of the pass
+    for (int sp = tid; sp < nvb * 3; sp += nth) {
+        const TileVb &t = ts.vb[sp / 3];
+        if (t.special) inverse_special(t.dctsel, coef + (sp % 3) * TILE_CH + t.chunk_off);
     }
+    tile_pass(coef, ts, 0, nvb, tid, nth);
     sync();
-    // ---- 5. pass B: 1-D inverse DCTs along the vertical frequency v
-    // slot = (channel, tile pixel column, tile cell row); active where the cell starts a varblock's column of cells
-    for (int slot = tid; slot < 3 * 64 * 8; slot += nth) {
-        const int c = slot / 512, x64 = slot & 63, cy = (slot >> 6) & 7;
-        const int cell = cy * 8 + (x64 >> 3);
-        const uint8_t vi = ts.cover[cell];
-        if (vi == 0xff) continue;
-        const TileVb &t = ts.vb[vi];
-        if (t.cy != cy || t.special) continue;
-        const int x = x64 - t.cx * 8;
-        float *blk = coef + c * TILE_CH + t.chunk_off;
-        if (t.log_cols > t.log_rows) idct_swz_dispatch<false>(blk, x, t.mlog, t.log_rows);   // [v][x] -> [y][x]: column x, along v
-        else idct_swz_dispatch<true>(blk, x, t.mlog, t.log_rows);                           // [x][v] -> [x][y]: row x, along v
-    }
+    J40B_PHASE(4);
+    // ---- 5. pass B: 1-D inverse DCTs along the vertical frequency v ([v][x] -> [y][x]: column x, along v;
+    // [x][v] -> [x][y]: row x, along v)
+    tile_pass(coef, ts, 1, nvb, tid, nth);
     sync();
+    J40B_PHASE(5);
     // ---- 6. XYB -> sRGB -> RGBA8 (j40.h:7208-7237, 7941-7952), one thread per pixel, row-major
     const int gx0 = g.left + (grp.gx8 + tx * 8) * 8, gy0 = g.top + (grp.gy8 + ty * 8) * 8;
     const int fw = f.width, fh = f.height;
@@ -310,6 +379,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         }
         *(uint32_t *) (rgba + (size_t) Y * rgba_stride + (size_t) X * 4) = out;
     }
+    J40B_PHASE(6);
 }
 
 } // namespace j40b

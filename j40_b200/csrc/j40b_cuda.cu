@@ -2,7 +2,7 @@
 // the ten j40_* entry points of the reference (include/j40.h) plus the j40b_* batch extension
 // (include/j40b.h). There is no CPU decoding path in this library: without a usable GPU every decode
 // fails loudly with the error code "!gpu".
-#include "j40b_pipeline.h"
+#include "j40b_kernels.h"
 #include "../../include/j40.h"
 #include "../../include/j40b.h"
 #include <cuda_runtime.h>
@@ -16,132 +16,11 @@ using namespace j40b;
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
-// ---------------------------------------------------------------------------------------------
-// kernels: thin wrappers around the bodies in j40b_exec.h
-
-struct BlockSync { __device__ void operator()() const { __syncthreads(); } };
-
-// dynamic shared memory of the serial-decoder kernels: a copy of the code spec's tables
-enum { SPEC_COPY_BYTES = 40 * 1024 };
-// widest channel the shared-memory row path of the serial decoders takes: LF groups are at most 256 cells
-// wide; modular groups at most 1024 pixels
-enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
-
-// Serial modular decoders (LF image, HF metadata, modular groups): one *warp* per work item. Lane 0 runs
-// the decoder; the other lanes keep its per-sample working set (sample rows, weighted-predictor error rows,
-// reference-channel rows) in shared memory. The CTA's warps share one staged copy of the code spec (work
-// lists are ordered image by image, so they nearly always belong to the same image).
-struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
-
-__host__ __device__ inline size_t warp_slice_bytes(int cap) {
-    size_t n = sizeof(WarpScratch) + (sizeof(SimtLane) + sizeof(SimtLeaf)) * SIMT_LANES;
-    n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + SIMT_REF_SLOTS * 4);
-    return (n + 15) & ~(size_t) 15;
-}
-
-__device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws) {
-    ws = (WarpScratch *) base;
-    ModSmem ms;
-    ms.leaves = (SimtLeaf *) (base + sizeof(WarpScratch));
-    ms.tab = (SimtLane *) (ms.leaves + SIMT_LANES);
-    ms.wp = (int32_t *) (ms.tab + SIMT_LANES);
-    ms.refp = ms.wp + (size_t) cap * 10;
-    ms.rows = cap ? (int16_t *) (ms.refp + (size_t) cap * SIMT_REF_SLOTS) : nullptr;
-    ms.info = ws->info;
-    ms.cap = cap;
-    return ms;
-}
-
-// `spec_cap`: bytes of dynamic shared memory reserved for the staged code spec (0 = read the tables through L1)
-template <int STAGE>
-__global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, int cap, int spec_cap) {
-    __shared__ int32_t div24[64];
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int warps = (int) blockDim.x >> 5, warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
-    const LfWork &w0 = items[(int) blockIdx.x * warps];
-    const bool staged = spec_cap > 0 && stage_spec_blob(w0.arena, w0.f->global_spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, (int) blockDim.x);
-    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
-    __syncthreads();
-    const int i = (int) blockIdx.x * warps + warp;
-    if (i >= n) return;
-    WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem + spec_cap + (size_t) warp * warp_slice_bytes(cap), cap, ws);
-    if (STAGE == 1) lf_decode1_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
-    else lf_decode2_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
-}
-
-__global__ void __launch_bounds__(256) k_lf_post(const LfWork *items) {
-    lf_post_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
-}
-
-__global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
-    lf_llf_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
-}
-
-// HF coefficient entropy decode, SIMT: one warp per 32 consecutive groups (one group per lane). The work
-// list is ordered image by image, so a warp's lanes nearly always share one image, whose coefficient code
-// spec (cluster map + alias tables / prefix LUTs) is staged in shared memory; lanes of another image (at
-// image boundaries) and specs that do not fit read the tables from global memory instead.
-// `lanes` (<= 32) groups per warp: with small batches fewer lanes per warp give more warps (latency hiding)
-// and less divergence; the host picks it from the number of groups (CudaBackend::launch_hf).
-enum { HF_WARPS = 4 };
-__global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items, int n, int lanes, int spec_cap) {
-    extern __shared__ __align__(16) uint8_t spec_copy[];
-    __shared__ uint16_t ctx_lut[128];
-    const int per_block = HF_WARPS * lanes;
-    const int first = (int) blockIdx.x * per_block;
-    const HfWork &w0 = items[first];
-    const bool staged = spec_cap > 0 && stage_spec_blob(w0.arena, w0.f->coeff_spec_off, spec_copy, (uint32_t) spec_cap, (int) threadIdx.x, 32 * HF_WARPS);
-    if (threadIdx.x < 64) ctx_lut[threadIdx.x] = (uint16_t) coeff_nnz_ctx2((int) threadIdx.x);
-    else if (threadIdx.x < 128) ctx_lut[threadIdx.x] = (uint16_t) (threadIdx.x == 64 ? 0 : coeff_freq_ctx2((int) threadIdx.x - 64));
-    __syncthreads();
-    const int warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
-    const int i = first + warp * lanes + lane;
-    if (lane < lanes && i < n) hf_group_body(items[i], staged ? spec_copy : nullptr, w0.arena, ctx_lut);
-}
-
-// one block per 64x64-pixel tile of a group (blockIdx.y = tile index inside the 256x256 group)
-__global__ void __launch_bounds__(256, 3) k_back_tile(const BackWork *items) {
-    extern __shared__ __align__(16) float tile_coef[];
-    __shared__ TileShared ts;
-    back_tile_body(items[blockIdx.x], (int) (blockIdx.y & 3), (int) (blockIdx.y >> 2), tile_coef, ts, (int) threadIdx.x, (int) blockDim.x, BlockSync());
-}
-
-// varblocks the tile kernel leaves out: persistent blocks, each with its own 1 MiB slice of scratch
-__global__ void __launch_bounds__(256) k_back_generic(const BackWork *items, int n, float *scratch_pool) {
-    float *scratch = scratch_pool + (size_t) blockIdx.x * 4 * 65536;
-    for (int i = (int) blockIdx.x; i < n; i += (int) gridDim.x) {
-        BackWork w = items[i];
-        w.big_scratch = scratch;
-        back_generic_body(w, (int) threadIdx.x, (int) blockDim.x, BlockSync());
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap) {
-    __shared__ int32_t div24[64];
-    extern __shared__ __align__(16) uint8_t smem[];
-    ModWork &w = items[blockIdx.x];
-    const bool staged = stage_spec_blob(w.arena, w.f->global_spec_off, smem, SPEC_COPY_BYTES, (int) threadIdx.x, 32);
-    fill_div24(div24, (int) threadIdx.x, 32);
-    __syncwarp();
-    WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem + SPEC_COPY_BYTES, cap, ws);
-    modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
-}
-
-__global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height) {
-    int x = (int) (blockIdx.x * blockDim.x + threadIdx.x), y = (int) blockIdx.y;
-    if (x < width && y < height) render_px(*w, x, y);
-}
-
-// ---------------------------------------------------------------------------------------------
-
 static bool cuda_ok(cudaError_t e) { return e == cudaSuccess; }
 
 struct CudaBackend {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream_lo = nullptr;
     bool ok = false;
     int num_sms = 148;
     float *big_pool = nullptr;
@@ -158,13 +37,13 @@ struct CudaBackend {
         cudaDeviceProp prop;
         if (!cuda_ok(cudaGetDeviceProperties(&prop, dev))) return false;
         num_sms = prop.multiProcessorCount;
-        if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char *pe = getenv("J40B_PRIO"); // 1: back kernels on a lowest-priority side stream
+        if (!cuda_ok(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pe && atoi(pe) ? prio_hi : 0))) return false;
+        if (pe && atoi(pe) == 1 && !cuda_ok(cudaStreamCreateWithPriority(&stream_lo, cudaStreamNonBlocking, prio_lo))) return false;
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
-        if (!cuda_ok(cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4))) return false;
-        const int lf_smem = (int) (SPEC_COPY_BYTES + 4 * warp_slice_bytes(LF_ROW_CAP)), mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
-        if (!cuda_ok(cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem))) return false;
-        if (!cuda_ok(cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem))) return false;
-        if (!cuda_ok(cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem))) return false;
+        if (!kl_init_lf() || !kl_init_back() || !kl_init_mod()) return false;
         ok = true;
         return true;
     }
@@ -174,6 +53,7 @@ struct CudaBackend {
         if (big_pool) cudaFree(big_pool);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (stream_lo) cudaStreamDestroy(stream_lo);
         ok = false;
     }
     void *dev_alloc(size_t n) { void *p = nullptr; cudaSetDevice(device); if (!cuda_ok(cudaMalloc(&p, n ? n : 1))) return nullptr; return p; }
@@ -197,10 +77,12 @@ struct CudaBackend {
         const size_t smem = (size_t) spec_cap + (size_t) warps * warp_slice_bytes(cap);
         const int blocks = (n + warps - 1) / warps;
         cudaEventRecord(ev[0], stream);
-        k_lf_decode<1><<<blocks, 32 * warps, smem, stream>>>(w, n, cap, spec_cap);
-        k_lf_post<<<n, 256, 0, stream>>>(w);
-        k_lf_decode<2><<<blocks, 32 * warps, smem, stream>>>(w, n, cap, spec_cap);
-        k_lf_llf<<<n, 128, 0, stream>>>(w);
+        kl_lf_decode(1, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
+        cudaEventRecord(ev[5], stream);
+        kl_lf_post(n, stream, w);
+        kl_lf_decode(2, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
+        cudaEventRecord(ev[6], stream);
+        kl_lf_llf(n, stream, w);
         cudaEventRecord(ev[1], stream);
         launches += 4;
     }
@@ -212,12 +94,25 @@ struct CudaBackend {
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
         const int per_block = HF_WARPS * lanes;
-        k_hf_group<<<(n + per_block - 1) / per_block, 32 * HF_WARPS, (size_t) spec_cap, stream>>>(w, n, lanes, spec_cap);
+        kl_hf_group((n + per_block - 1) / per_block, (size_t) spec_cap, stream, w, n, lanes, spec_cap);
         cudaEventRecord(ev[2], stream);
         ++launches;
     }
     void launch_back(const BackWork *w, int n) {
-        k_back_tile<<<dim3((unsigned) n, 16), 256, 3 * TILE_CH * 4, stream>>>(w);
+        cudaStream_t main_stream = stream;
+        if (stream_lo) { // the short-block throughput kernels yield block slots to the latency-bound serial decoders
+            cudaEventRecord(ev[7], stream);
+            cudaStreamWaitEvent(stream_lo, ev[7], 0);
+            stream = stream_lo;
+        }
+        launch_back_on(w, n);
+        if (stream_lo) {
+            stream = main_stream;
+            cudaStreamWaitEvent(stream, ev[4], 0);
+        }
+    }
+    void launch_back_on(const BackWork *w, int n) {
+        kl_back_tile(n, stream, w);
         cudaEventRecord(ev[3], stream);
         ++launches;
         if (!big_pool) {
@@ -225,18 +120,17 @@ struct CudaBackend {
             if (!cuda_ok(cudaMalloc(&big_pool, (size_t) big_blocks * 4 * 65536 * sizeof(float)))) { big_pool = nullptr; big_blocks = 0; }
         }
         if (big_pool) {
-            k_back_generic<<<big_blocks < n ? big_blocks : n, 256, 0, stream>>>(w, n, big_pool);
+            kl_back_generic(big_blocks < n ? big_blocks : n, stream, w, n, big_pool);
             ++launches;
         }
         cudaEventRecord(ev[4], stream);
     }
     void launch_mod(ModWork *w, int n) {
-        k_modular<<<n, 32, SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP), stream>>>(w, MOD_ROW_CAP);
+        kl_modular(n, stream, w);
         ++launches;
     }
     void launch_render(const RenderWork *w, int width, int height) {
-        dim3 grid((unsigned) ((width + 255) / 256), (unsigned) height);
-        k_render<<<grid, 256, 0, stream>>>(w, width, height);
+        kl_render(stream, w, width, height);
         ++launches;
     }
 };
@@ -366,6 +260,7 @@ EXPORT int j40b_batch_wait(j40b_batch *b) {
     b->batch->collect_errors();
     cudaError_t ce = cudaGetLastError();
     gather_times(b);
+    if (getenv("J40B_PHASE_DUMP")) kl_back_phase_dump();
     // a token arena that turned out too small is an internal condition: redo with worst-case capacity
     bool retry = false;
     for (auto &r : b->batch->results) if (r.err == E_TOKV) retry = true;
@@ -429,12 +324,30 @@ EXPORT int j40b_batch_join(j40b_batch *b, j40b_batch *other) {
     cudaEventRecord(other->jev, other->be.stream);
     return cudaStreamWaitEvent(b->be.stream, other->jev, 0) == cudaSuccess ? 0 : -1;
 }
+// Makes everything enqueued on b from now on wait until `other`'s most recently enqueued decode has finished
+// stage `stage` (0 = LF stage, 1 = HF stage, 2 = everything). A serving loop uses it to keep batches in
+// flight out of phase, so that the latency-bound LF decoders of some overlap the HF / tile kernels of others.
+EXPORT int j40b_batch_after(j40b_batch *b, j40b_batch *other, int stage) {
+    if (!b || !other || b->be.device != other->be.device || stage < 0 || stage > 2 || !other->decoded) return -1;
+    cudaSetDevice(b->be.device);
+    const int which = stage == 0 ? 1 : stage == 1 ? 2 : 4;
+    return cudaStreamWaitEvent(b->be.stream, other->be.ev[which], 0) == cudaSuccess ? 0 : -1;
+}
 EXPORT float j40b_batch_mark_ms(j40b_batch *b) {
     float ms = 0;
     if (!b || !b->m[0] || !b->m[1]) return 0;
     cudaSetDevice(b->be.device);
     cudaEventSynchronize(b->m[1]);
     cudaEventElapsedTime(&ms, b->m[0], b->m[1]);
+    return ms;
+}
+// diagnostic: device time from `ref`'s mark 0 to event `which` of b's last decode (0 LF start, 5 LF image decoded,
+// 6 HF metadata decoded, 1 LF done, 2 HF done, 3 tiles done, 4 all done); shows how batches in flight interleave
+EXPORT float j40b_batch_event_ms(const j40b_batch *b, const j40b_batch *ref, int which) {
+    float ms = -1;
+    if (!b || !ref || !ref->m[0] || which < 0 || which > 6) return ms;
+    cudaSetDevice(b->be.device);
+    if (cudaEventElapsedTime(&ms, ref->m[0], b->be.ev[which]) != cudaSuccess) { cudaGetLastError(); return -1; }
     return ms;
 }
 EXPORT float j40b_batch_kernel_ms(const j40b_batch *b, int which) { return b && which >= 0 && which < 6 ? b->be.kernel_ms[which] : 0.0f; }

@@ -1,0 +1,64 @@
+// j40-b200: kernel launch interface between the host side of the CUDA backend (j40b_cuda.cu) and the
+// translation units that hold the kernels (kern_lf.cu, kern_hf.cu, kern_back.cu, kern_mod.cu; split so that
+// they compile in parallel). Each launcher enqueues one kernel on `stream`.
+#pragma once
+#include "j40b_pipeline.h"
+#include <cuda_runtime.h>
+
+namespace j40b {
+
+#if defined(__CUDACC__)
+struct BlockSync { __device__ void operator()() const { __syncthreads(); } };
+#endif
+
+// dynamic shared memory of the serial-decoder kernels: a copy of the code spec's tables
+enum { SPEC_COPY_BYTES = 40 * 1024 };
+// widest channel the shared-memory row path of the serial decoders takes: LF groups are at most 256 cells
+// wide; modular groups at most 1024 pixels
+enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
+
+// Serial modular decoders (LF image, HF metadata, modular groups): one *warp* per work item. Lane 0 runs
+// the decoder; the other lanes keep its per-sample working set (sample rows, weighted-predictor error rows,
+// reference-channel rows) in shared memory. The CTA's warps share one staged copy of the code spec (work
+// lists are ordered image by image, so they nearly always belong to the same image).
+#if defined(__CUDACC__)
+struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
+#endif
+
+__host__ __device__ inline size_t warp_slice_bytes(int cap) {
+    size_t n = sizeof(WarpScratch) + (sizeof(SimtLane) + sizeof(SimtLeaf)) * SIMT_LANES;
+    n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + SIMT_REF_SLOTS * 4);
+    return (n + 15) & ~(size_t) 15;
+}
+
+#if defined(__CUDACC__)
+__device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws) {
+    ws = (WarpScratch *) base;
+    ModSmem ms;
+    ms.leaves = (SimtLeaf *) (base + sizeof(WarpScratch));
+    ms.tab = (SimtLane *) (ms.leaves + SIMT_LANES);
+    ms.wp = (int32_t *) (ms.tab + SIMT_LANES);
+    ms.refp = ms.wp + (size_t) cap * 10;
+    ms.rows = cap ? (int16_t *) (ms.refp + (size_t) cap * SIMT_REF_SLOTS) : nullptr;
+    ms.info = ws->info;
+    ms.cap = cap;
+    return ms;
+}
+#endif
+
+enum { HF_WARPS = 4 };
+
+bool kl_init_lf();   // raises the dynamic shared-memory limits of the kernels in that translation unit
+bool kl_init_back();
+bool kl_init_mod();
+void kl_lf_decode(int stage, int blocks, int threads, size_t smem, cudaStream_t stream, const LfWork *w, int n, int cap, int spec_cap);
+void kl_lf_post(int n, cudaStream_t stream, const LfWork *w);
+void kl_lf_llf(int n, cudaStream_t stream, const LfWork *w);
+void kl_hf_group(int blocks, size_t smem, cudaStream_t stream, const HfWork *w, int n, int lanes, int spec_cap);
+void kl_back_tile(int n, cudaStream_t stream, const BackWork *w);
+void kl_back_generic(int blocks, cudaStream_t stream, const BackWork *w, int n, float *pool);
+void kl_back_phase_dump(); // diagnostic builds (make PHASE_CLOCKS=1): prints and clears the tile kernel's phase counters
+void kl_modular(int n, cudaStream_t stream, ModWork *w);
+void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height);
+
+} // namespace j40b

@@ -231,10 +231,12 @@ public:
         HfWork *hfw = (HfWork *) (staging + hfw_off);
         BackWork *bkw = (BackWork *) (staging + bkw_off);
         size_t ilf = 0, ihf = 0;
+        std::vector<std::pair<int64_t, LfWork>> lf_sorted; // (cells, item)
         for (size_t k = 0; k < n; ++k) {
             FramePlan &p = *plans[k];
             Img &im = img[k];
             if (p.err) continue;
+            const size_t ihf_image = ihf;
             results[k].rgba_off = upload_bytes + im.rgba_off;
             DFrame d = p.df;
             // tables: per-image custom ones live in the arena, library defaults in the shared block
@@ -274,6 +276,7 @@ public:
                     w.g = (DLfGroup *) (dev + im.lfg_off) + i;
                     w.err = derr + i;
                     w.llf_scratch = (float *) (dwork + b.llf_scratch);
+                    lf_sorted.emplace_back((int64_t) b.w8 * b.h8, w);
                 }
                 for (size_t gi = 0; gi < im.ng; ++gi) {
                     const GrpBuf &gb = im.grp[gi];
@@ -301,6 +304,11 @@ public:
                     bw.rgba = dwork + im.rgba_off; bw.rgba_stride = results[k].stride;
                     bw.big_scratch = nullptr;
                 }
+                // pass groups of one image, longest section first: the lanes of a warp (one group each) then
+                // carry similar amounts of work, and the long ones start first
+                std::stable_sort(hfw + ihf_image, hfw + ihf, [&](const HfWork &a, const HfWork &b2) {
+                    return gr[a.grp - (DGroup *) (dev + im.grp_off)].sec_size > gr[b2.grp - (DGroup *) (dev + im.grp_off)].sec_size;
+                });
             } else {
                 ModWork *mw = (ModWork *) (staging + im.mod_off);
                 RenderWork *rw = (RenderWork *) (staging + im.render_off);
@@ -335,6 +343,10 @@ public:
                 }
             }
         }
+        // LF groups, largest first: a 4K frame has two big and two tiny LF groups; in image order the
+        // one-warp blocks of the serial decoders land two big ones per SM on half of the SMs
+        std::stable_sort(lf_sorted.begin(), lf_sorted.end(), [](const std::pair<int64_t, LfWork> &a, const std::pair<int64_t, LfWork> &b2) { return a.first > b2.first; });
+        for (size_t i = 0; i < lf_sorted.size(); ++i) lfw[i] = lf_sorted[i].second;
         be.h2d(dev, staging, upload_bytes);
         return true;
     }

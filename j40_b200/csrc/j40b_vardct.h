@@ -453,6 +453,49 @@ J40B_HD inline void forward_dct2d_llf(float *buf, float *scratch, int log_rows, 
     sync();
 }
 
+// 1-D inverse DCT of N points in place, the recursion of j40__inverse_dct_core (j40.h:5802-5841) unrolled
+template <int N> struct Idct1D {
+    J40B_HD static J40B_INLINE void run(float *v) {
+        float a[N / 2], b[N / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) a[i] = v[2 * i];
+        b[0] = J40B_FMUL(J40B_SQRT2, v[1]);
+#pragma unroll
+        for (int i = 1; i < N / 2; ++i) b[i] = J40B_FADD(v[2 * i - 1], v[2 * i + 1]);
+        Idct1D<N / 2>::run(a);
+        Idct1D<N / 2>::run(b);
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            float t = J40B_FMUL(b[i], J40B_HALF_SECANT(N / 2 + i));
+            v[i] = J40B_FADD(a[i], t);
+            v[N - 1 - i] = J40B_FSUB(a[i], t);
+        }
+    }
+};
+template <> struct Idct1D<2> {
+    J40B_HD static J40B_INLINE void run(float *v) {
+        float x = v[0], y = v[1];
+        v[0] = J40B_FADD(x, y);
+        v[1] = J40B_FSUB(x, y);
+    }
+};
+template <> struct Idct1D<1> { J40B_HD static J40B_INLINE void run(float *) {} };
+
+// `rep` interleaved columns (element i of column r at [i * REP + r]), each through Idct1D: what
+// idct_cols computes, as straight-line code for one thread with compile-time sizes
+template <int T, int REP>
+J40B_HD J40B_INLINE void idct_cols_fixed(float *out, const float *in) {
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+        float v[1 << T];
+#pragma unroll
+        for (int i = 0; i < (1 << T); ++i) v[i] = in[i * REP + r];
+        Idct1D<(1 << T)>::run(v);
+#pragma unroll
+        for (int i = 0; i < (1 << T); ++i) out[i * REP + r] = v[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // special 8x8 transforms (one thread each; j40.h:5992-6246)
 
@@ -468,18 +511,31 @@ J40B_HD J40B_INLINE void aux_idct2x2(float *out, const float *in, int x, int y, 
 J40B_HD inline void inverse_dct2x2_pyramid(float *buf) { // DctSelect 2
     float scratch[64];
     aux_idct2x2(buf, buf, 0, 0, 1);
+    #pragma unroll
     for (int i = 0; i < 64; ++i) scratch[i] = buf[i];
-    for (int y = 0; y < 2; ++y) for (int x = 0; x < 2; ++x) aux_idct2x2(scratch, buf, x, y, 2);
-    for (int y = 0; y < 4; ++y) for (int x = 0; x < 4; ++x) aux_idct2x2(buf, scratch, x, y, 4);
+    #pragma unroll
+    for (int y = 0; y < 2; ++y)
+        #pragma unroll
+        for (int x = 0; x < 2; ++x) aux_idct2x2(scratch, buf, x, y, 2);
+    #pragma unroll
+    for (int y = 0; y < 4; ++y)
+        #pragma unroll
+        for (int x = 0; x < 4; ++x) aux_idct2x2(buf, scratch, x, y, 4);
 }
 
 J40B_HD inline void inverse_dct4x4_quad(float *buf) { // DctSelect 3
     float scratch[64];
     aux_idct2x2(buf, buf, 0, 0, 1);
-    idct_cols(scratch, buf, 2, 16, 0, 1, NoSync());
-    for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
-    idct_cols(scratch, buf, 2, 16, 0, 1, NoSync());
-    for (int y = 0; y < 4; ++y) for (int x = 0; x < 4; ++x) {
+    idct_cols_fixed<2, 16>(scratch, buf);
+    #pragma unroll
+    for (int y = 0; y < 8; ++y)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
+    idct_cols_fixed<2, 16>(scratch, buf);
+    #pragma unroll
+    for (int y = 0; y < 4; ++y)
+        #pragma unroll
+        for (int x = 0; x < 4; ++x) {
         buf[y * 8 + x] = scratch[(y * 2) * 8 + (x * 2)];
         buf[y * 8 + (x + 4)] = scratch[(y * 2 + 1) * 8 + (x * 2)];
         buf[(y + 4) * 8 + x] = scratch[(y * 2) * 8 + (x * 2 + 1)];
@@ -489,19 +545,29 @@ J40B_HD inline void inverse_dct4x4_quad(float *buf) { // DctSelect 3
 
 J40B_HD inline void inverse_hornuss(float *buf) { // DctSelect 1
     float scratch[64];
+    #pragma unroll
     for (int i = 0; i < 64; ++i) scratch[i] = buf[i];
     aux_idct2x2(scratch, buf, 0, 0, 1);
-    for (int y = 0; y < 2; ++y) for (int x = 0; x < 2; ++x) {
+    #pragma unroll
+    for (int y = 0; y < 2; ++y)
+        #pragma unroll
+        for (int x = 0; x < 2; ++x) {
         int pos00 = y * 8 + x, pos11 = (y + 2) * 8 + (x + 2);
         float rsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        for (int iy = 0; iy < 4; ++iy) for (int ix = 0; ix < 4; ++ix) {
+        #pragma unroll
+        for (int iy = 0; iy < 4; ++iy)
+            #pragma unroll
+            for (int ix = 0; ix < 4; ++ix) {
             rsum[ix] = J40B_FADD(rsum[ix], scratch[(y + iy * 2) * 8 + (x + ix * 2)]);
         }
         float s = J40B_FSUB(J40B_FADD(J40B_FADD(J40B_FADD(rsum[0], rsum[1]), rsum[2]), rsum[3]), scratch[pos00]);
         float sample11 = J40B_FSUB(scratch[pos00], J40B_FMUL(s, 0.0625f));
         scratch[pos00] = scratch[pos11];
         scratch[pos11] = 0.0f;
-        for (int iy = 0; iy < 4; ++iy) for (int ix = 0; ix < 4; ++ix) {
+        #pragma unroll
+        for (int iy = 0; iy < 4; ++iy)
+            #pragma unroll
+            for (int ix = 0; ix < 4; ++ix) {
             buf[(4 * y + iy) * 8 + (4 * x + ix)] = J40B_FADD(scratch[(y + iy * 2) * 8 + (x + ix * 2)], sample11);
         }
     }
@@ -513,27 +579,42 @@ J40B_HD inline void inverse_dct8x4(float *buf) { // DctSelect 13 ("DCT32" in the
     buf[8] = J40B_FSUB(buf[0], buf[8]);
     buf[0] = tmp;
     // buf viewed as 4 rows x 16 columns; IDCT-4 down the 16 columns
-    idct_cols(scratch, buf, 2, 16, 0, 1, NoSync());
+    idct_cols_fixed<2, 16>(scratch, buf);
     // scratch viewed 8x8 again, transpose into buf
-    for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
-    idct_cols(scratch, buf, 3, 8, 0, 1, NoSync());
+    #pragma unroll
+    for (int y = 0; y < 8; ++y)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
+    idct_cols_fixed<3, 8>(scratch, buf);
     // columns 01234567 -> 02461357
-    for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) buf[y * 8 + (((x & 1) << 2) | (x >> 1))] = scratch[y * 8 + x];
+    #pragma unroll
+    for (int y = 0; y < 8; ++y)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) buf[y * 8 + (((x & 1) << 2) | (x >> 1))] = scratch[y * 8 + x];
 }
 
 J40B_HD inline void inverse_dct4x8(float *buf) { // DctSelect 12 ("DCT23")
     float scratch[64];
+    #pragma unroll
     for (int i = 0; i < 64; ++i) scratch[i] = buf[i];
     scratch[0] = J40B_FADD(buf[0], buf[8]);
     scratch[8] = J40B_FSUB(buf[0], buf[8]);
-    for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
-    idct_cols(scratch, buf, 3, 8, 0, 1, NoSync());
-    for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
+    #pragma unroll
+    for (int y = 0; y < 8; ++y)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
+    idct_cols_fixed<3, 8>(scratch, buf);
+    #pragma unroll
+    for (int y = 0; y < 8; ++y)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) buf[x * 8 + y] = scratch[y * 8 + x];
     // buf viewed as 4 rows x 16 columns
-    idct_cols(scratch, buf, 2, 16, 0, 1, NoSync());
+    idct_cols_fixed<2, 16>(scratch, buf);
     // rows 01234567 -> 02461357
+    #pragma unroll
     for (int y = 0; y < 8; ++y) {
         int oy = ((y & 1) << 2) | (y >> 1);
+        #pragma unroll
         for (int x = 0; x < 8; ++x) buf[oy * 8 + x] = scratch[y * 8 + x];
     }
 }
@@ -542,40 +623,58 @@ J40B_HD inline void inverse_afv(float *buf, int flipx, int flipy) { // DctSelect
     float scratch[64];
     float *bufafv = buf, *buf22 = buf + 16, *buf23 = buf + 32, *buf32 = buf23;
     float *scratchafv = scratch, *scratch22 = scratch + 16, *scratch23 = scratch + 32, *scratch32 = scratch23;
-    for (int y = 0; y < 8; y += 2) for (int x = 0; x < 8; ++x) {
+    #pragma unroll
+    for (int y = 0; y < 8; y += 2)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) {
         scratch[(x % 2) * 16 + (y / 2) * 4 + (x / 2)] = buf[y * 8 + x];
     }
-    for (int y = 1; y < 8; y += 2) for (int x = 0; x < 8; ++x) {
+    #pragma unroll
+    for (int y = 1; y < 8; y += 2)
+        #pragma unroll
+        for (int x = 0; x < 8; ++x) {
         scratch32[x * 4 + (y / 2)] = buf[y * 8 + x];
     }
     scratchafv[0] = J40B_FMUL(J40B_FADD(J40B_FADD(buf[0], buf[1]), buf[8]), 4.0f);
     scratch22[0] = J40B_FADD(J40B_FSUB(buf[0], buf[1]), buf[8]);
     scratch32[0] = J40B_FSUB(buf[0], buf[8]);
     // 16x16 basis times the 16 AFV coefficients, accumulated in index order from 0
+    #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float sum = 0.0f;
+        #pragma unroll
         for (int j = 0; j < 16; ++j) sum = J40B_FADD(sum, J40B_FMUL(scratchafv[j], J40B_AFV(i * 16 + j)));
         bufafv[i] = sum;
     }
-    idct_cols(buf22, scratch22, 2, 4, 0, 1, NoSync());
-    idct_cols(buf32, scratch32, 3, 4, 0, 1, NoSync());
+    idct_cols_fixed<2, 4>(buf22, scratch22);
+    idct_cols_fixed<3, 4>(buf32, scratch32);
+    #pragma unroll
     for (int y = 0; y < 4; ++y) {
+        #pragma unroll
         for (int x = 0; x < 4; ++x) scratchafv[y * 4 + x] = bufafv[y * 4 + x];
+        #pragma unroll
         for (int x = 0; x < 4; ++x) scratch22[x * 4 + y] = buf22[y * 4 + x];
     }
+    #pragma unroll
     for (int y = 0; y < 8; ++y) {
+        #pragma unroll
         for (int x = 0; x < 4; ++x) scratch23[x * 8 + y] = buf32[y * 4 + x];
     }
-    idct_cols(buf22, scratch22, 2, 4, 0, 1, NoSync());
-    idct_cols(buf23, scratch23, 2, 8, 0, 1, NoSync());
+    idct_cols_fixed<2, 4>(buf22, scratch22);
+    idct_cols_fixed<2, 8>(buf23, scratch23);
+    #pragma unroll
     for (int i = 16; i < 64; ++i) scratch[i] = buf[i];
+    #pragma unroll
     for (int y = 0; y < 4; ++y) {
         int fy = flipy ? 7 - y : y;
         int afv22pos = fy * 8;
         int dct22pos = (flipy * 4 + y) * 8 + (!flipx * 4);
         int dct23pos = (!flipy * 4 + y) * 8;
+        #pragma unroll
         for (int x = 0; x < 4; ++x) buf[afv22pos + (flipx ? 7 - x : x)] = scratchafv[y * 4 + x];
+        #pragma unroll
         for (int x = 0; x < 4; ++x) buf[dct22pos + x] = scratch22[y * 4 + x];
+        #pragma unroll
         for (int x = 0; x < 8; ++x) buf[dct23pos + x] = scratch23[y * 8 + x];
     }
 }

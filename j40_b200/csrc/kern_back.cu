@@ -1,0 +1,59 @@
+// j40-b200: back-end kernels (tokens -> dequantised coefficients -> inverse transforms -> RGBA8)
+#define J40B_KERN_BACK_TU
+#include "j40b_kernels.h"
+#include <stdio.h>
+
+namespace j40b {
+
+static unsigned long long *g_phase = nullptr;
+#if defined(J40B_PHASE_CLOCKS)
+void kl_back_phase_dump() {
+    unsigned long long h[16] = {0};
+    cudaError_t e1 = cudaDeviceSynchronize();
+    cudaError_t e2 = g_phase ? cudaMemcpy(h, g_phase, sizeof(h), cudaMemcpyDeviceToHost) : cudaSuccess;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) fprintf(stderr, "phase dump: %s / %s\n", cudaGetErrorString(e1), cudaGetErrorString(e2));
+    unsigned long long tot = 0;
+    for (int i = 0; i < 7; ++i) tot += h[i];
+    fprintf(stderr, "k_back_tile phase cycles (thread 0 of every block):");
+    for (int i = 0; i < 7; ++i) fprintf(stderr, " p%d=%.1f%%", i, 100.0 * (double) h[i] / (double) (tot ? tot : 1));
+    fprintf(stderr, " total=%llu\n", tot);
+    if (g_phase) cudaMemset(g_phase, 0, sizeof(h));
+}
+#else
+void kl_back_phase_dump() {}
+#endif
+
+// one block per 64x64-pixel tile of a group (blockIdx.y = tile index inside the 256x256 group)
+__global__ void __launch_bounds__(256, 3) k_back_tile(const BackWork *items, unsigned long long *phase) {
+    extern __shared__ __align__(16) float tile_coef[];
+    __shared__ TileShared ts;
+    ts.phase = phase;
+    back_tile_body(items[blockIdx.x], (int) (blockIdx.y & 3), (int) (blockIdx.y >> 2), tile_coef, ts, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+
+// varblocks the tile kernel leaves out: persistent blocks, each with its own 1 MiB slice of scratch
+__global__ void __launch_bounds__(256) k_back_generic(const BackWork *items, int n, float *scratch_pool) {
+    float *scratch = scratch_pool + (size_t) blockIdx.x * 4 * 65536;
+    for (int i = (int) blockIdx.x; i < n; i += (int) gridDim.x) {
+        BackWork w = items[i];
+        w.big_scratch = scratch;
+        back_generic_body(w, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+        __syncthreads();
+    }
+}
+
+
+bool kl_init_back() {
+    return cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4) == cudaSuccess;
+}
+void kl_back_tile(int n, cudaStream_t stream, const BackWork *w) {
+#if defined(J40B_PHASE_CLOCKS)
+    if (!g_phase) { cudaMalloc(&g_phase, 16 * sizeof(unsigned long long)); cudaMemset(g_phase, 0, 16 * sizeof(unsigned long long)); }
+#endif
+    k_back_tile<<<dim3((unsigned) n, 16), 256, 3 * TILE_CH * 4, stream>>>(w, g_phase);
+}
+void kl_back_generic(int blocks, cudaStream_t stream, const BackWork *w, int n, float *pool) {
+    k_back_generic<<<blocks, 256, 0, stream>>>(w, n, pool);
+}
+
+} // namespace j40b

@@ -1,0 +1,45 @@
+// j40-b200: LF-group kernels (serial modular decoders of the LF image and the HF metadata, parallel post stages)
+#include "j40b_kernels.h"
+
+namespace j40b {
+
+// `spec_cap`: bytes of dynamic shared memory reserved for the staged code spec (0 = read the tables through L1)
+template <int STAGE>
+__global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, int cap, int spec_cap) {
+    __shared__ int32_t div24[64];
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warps = (int) blockDim.x >> 5, warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
+    const LfWork &w0 = items[(int) blockIdx.x * warps];
+    const bool staged = spec_cap > 0 && stage_spec_blob(w0.arena, w0.f->global_spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, (int) blockDim.x);
+    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
+    __syncthreads();
+    const int i = (int) blockIdx.x * warps + warp;
+    if (i >= n) return;
+    WarpScratch *ws;
+    ModSmem ms = carve_warp_slice(smem + spec_cap + (size_t) warp * warp_slice_bytes(cap), cap, ws);
+    if (STAGE == 1) lf_decode1_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
+    else lf_decode2_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
+}
+
+__global__ void __launch_bounds__(256) k_lf_post(const LfWork *items) {
+    lf_post_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+
+__global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
+    lf_llf_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+
+
+bool kl_init_lf() {
+    const int lf_smem = (int) (SPEC_COPY_BYTES + 4 * warp_slice_bytes(LF_ROW_CAP));
+    return cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
+}
+void kl_lf_decode(int stage, int blocks, int threads, size_t smem, cudaStream_t stream, const LfWork *w, int n, int cap, int spec_cap) {
+    if (stage == 1) k_lf_decode<1><<<blocks, threads, smem, stream>>>(w, n, cap, spec_cap);
+    else k_lf_decode<2><<<blocks, threads, smem, stream>>>(w, n, cap, spec_cap);
+}
+void kl_lf_post(int n, cudaStream_t stream, const LfWork *w) { k_lf_post<<<n, 256, 0, stream>>>(w); }
+void kl_lf_llf(int n, cudaStream_t stream, const LfWork *w) { k_lf_llf<<<n, 128, 0, stream>>>(w); }
+
+} // namespace j40b

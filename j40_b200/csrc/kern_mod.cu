@@ -1,0 +1,35 @@
+// j40-b200: modular-frame kernels (group decode, inverse transforms + RGBA8 render)
+#include "j40b_kernels.h"
+
+namespace j40b {
+
+__global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap) {
+    __shared__ int32_t div24[64];
+    extern __shared__ __align__(16) uint8_t smem[];
+    ModWork &w = items[blockIdx.x];
+    const bool staged = stage_spec_blob(w.arena, w.f->global_spec_off, smem, SPEC_COPY_BYTES, (int) threadIdx.x, 32);
+    fill_div24(div24, (int) threadIdx.x, 32);
+    __syncwarp();
+    WarpScratch *ws;
+    ModSmem ms = carve_warp_slice(smem + SPEC_COPY_BYTES, cap, ws);
+    modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
+}
+
+__global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height) {
+    int x = (int) (blockIdx.x * blockDim.x + threadIdx.x), y = (int) blockIdx.y;
+    if (x < width && y < height) render_px(*w, x, y);
+}
+
+bool kl_init_mod() {
+    const int mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
+    return cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem) == cudaSuccess;
+}
+void kl_modular(int n, cudaStream_t stream, ModWork *w) {
+    k_modular<<<n, 32, SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP), stream>>>(w, MOD_ROW_CAP);
+}
+void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height) {
+    dim3 grid((unsigned) ((width + 255) / 256), (unsigned) height);
+    k_render<<<grid, 256, 0, stream>>>(w, width, height);
+}
+
+} // namespace j40b

@@ -9,9 +9,10 @@ try:
 except Exception as e:
     print("$name failed", e); print(open("gpurun_out/x_$name.err").read()[-800:])
 PY
+  grep timeline gpurun_out/x_$name.err | head -${TL:-0}
+  grep "phase" gpurun_out/x_$name.err | grep -v "total=0" | head -2
 }
-run s3 --steps 12 --warmup 3 --skip-e2e --streams 3
-run s12 --steps 24 --warmup 3 --skip-e2e --streams 12
-run f32s12 --steps 24 --warmup 3 --skip-e2e --streams 12 --frames-per-gpu 32
-run f128s6 --steps 12 --warmup 3 --skip-e2e --streams 6 --frames-per-gpu 128
-run f16s24 --steps 48 --warmup 3 --skip-e2e --streams 24 --frames-per-gpu 16
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+J40B_PHASE_DUMP=1 run s6l0 --steps 12 --warmup 3 --skip-e2e --lag 0
+J40B_LF_STAGE=1 run s6l0stage --steps 12 --warmup 3 --skip-e2e --lag 0
+run s12l0 --steps 24 --warmup 3 --skip-e2e --streams 12 --lag 0
