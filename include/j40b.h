@@ -59,7 +59,8 @@ int j40b_batch_read_all_async(j40b_batch *b, void *dst, size_t pitch);
 /* device time in milliseconds of the most recent j40b_batch_decode, measured with CUDA events on the
  * batch's stream (valid after j40b_batch_wait) */
 float j40b_batch_last_decode_ms(const j40b_batch *b);
-/* per-kernel device times of the last decode: 0 lf_group, 1 hf_group, 2 back, 3 back_big, 4 modular, 5 render */
+/* per-kernel device times of the last decode: 0 lf_group (= 6 + 7 + 8), 1 hf_group, 2 back, 3 back_big, 4 modular,
+ * 5 render, 6 k_lf_decode<1> (LF image), 7 k_lf_post + k_lf_decode<2> (HF metadata), 8 k_lf_llf */
 float j40b_batch_kernel_ms(const j40b_batch *b, int which);
 
 /* statistics: 0 device bytes allocated, 1 bytes uploaded (H2D), 2 kernels launched by the last decode,

@@ -269,7 +269,7 @@ class Batch:
         return float(lib().j40b_batch_last_decode_ms(self._h))
 
     def kernel_ms(self):
-        names = ["lf_group", "hf_group", "back", "back_big", "modular", "render"]
+        names = ["lf_group", "hf_group", "back", "back_big", "modular", "render", "lf_image", "lf_hfmeta", "lf_llf"]
         return {n: float(lib().j40b_batch_kernel_ms(self._h, i)) for i, n in enumerate(names)}
 
     def stat(self, what):

@@ -26,8 +26,9 @@ struct CudaBackend {
     float *big_pool = nullptr;
     int big_blocks = 0;
     int64_t launches = 0;
-    cudaEvent_t ev[8] = {nullptr};
-    float kernel_ms[6] = {0};
+    cudaEvent_t ev[10] = {nullptr};
+    bool mod_marked = false;
+    float kernel_ms[9] = {0};
 
     bool init(int dev) {
         device = dev;
@@ -88,9 +89,10 @@ struct CudaBackend {
     }
     void launch_hf(const HfWork *w, int n, size_t spec_bytes) {
         const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
-        // lanes per warp: aim at ~8 warps per SM before filling warps completely (measured: 8 lanes at 8640 groups is
-        // the latency optimum; with several batches in flight the choice no longer matters)
-        int lanes = (n + num_sms * 8 - 1) / (num_sms * 8);
+        // lanes per warp: aim at ~4 warps per SM before filling warps completely. Measured at 8640 groups: 8 lanes
+        // is the latency optimum of one batch alone (26 ms against 34 ms at 16 lanes), 16 lanes the throughput
+        // optimum with a dozen batches in flight (fewer resident blocks per group decoded)
+        int lanes = (n + num_sms * 4 - 1) / (num_sms * 4);
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
         const int per_block = HF_WARPS * lanes;
@@ -125,10 +127,15 @@ struct CudaBackend {
         }
         cudaEventRecord(ev[4], stream);
     }
-    void launch_mod(ModWork *w, int n) {
-        kl_modular(n, stream, w);
+    // `spec_bytes`: the image's code-spec blob; `max_w`: its widest channel (sizes the shared-memory rows)
+    void launch_mod(ModWork *w, int n, size_t spec_bytes, int max_w) {
+        int cap = (max_w + 63) & ~63;
+        if (cap > MOD_ROW_CAP || cap <= 0) cap = MOD_ROW_CAP;
+        const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
+        kl_modular(n, stream, w, cap, spec_cap);
         ++launches;
     }
+    void mark_modular(int which) { cudaEventRecord(ev[8 + which], stream); mod_marked = true; }
     void launch_render(const RenderWork *w, int width, int height) {
         kl_render(stream, w, width, height);
         ++launches;
@@ -246,11 +253,16 @@ static void gather_times(j40b_batch *b) {
     // events are only recorded when the corresponding kernels were launched in this decode
     bool vardct = false;
     for (auto &p : b->batch->plans) if (!p->err && !p->df.is_modular) vardct = true;
+    if (be.mod_marked) cudaEventElapsedTime(&be.kernel_ms[4], be.ev[8], be.ev[9]); // k_modular + k_render of all modular images
+    be.mod_marked = false;
     if (vardct) {
         cudaEventElapsedTime(&be.kernel_ms[0], be.ev[0], be.ev[1]);
         cudaEventElapsedTime(&be.kernel_ms[1], be.ev[1], be.ev[2]);
         cudaEventElapsedTime(&be.kernel_ms[2], be.ev[2], be.ev[3]);
         cudaEventElapsedTime(&be.kernel_ms[3], be.ev[3], be.ev[4]);
+        cudaEventElapsedTime(&be.kernel_ms[6], be.ev[0], be.ev[5]); // k_lf_decode<1>
+        cudaEventElapsedTime(&be.kernel_ms[7], be.ev[5], be.ev[6]); // k_lf_post + k_lf_decode<2>
+        cudaEventElapsedTime(&be.kernel_ms[8], be.ev[6], be.ev[1]); // k_lf_llf
     }
 }
 
@@ -350,7 +362,7 @@ EXPORT float j40b_batch_event_ms(const j40b_batch *b, const j40b_batch *ref, int
     if (cudaEventElapsedTime(&ms, ref->m[0], b->be.ev[which]) != cudaSuccess) { cudaGetLastError(); return -1; }
     return ms;
 }
-EXPORT float j40b_batch_kernel_ms(const j40b_batch *b, int which) { return b && which >= 0 && which < 6 ? b->be.kernel_ms[which] : 0.0f; }
+EXPORT float j40b_batch_kernel_ms(const j40b_batch *b, int which) { return b && which >= 0 && which < 9 ? b->be.kernel_ms[which] : 0.0f; }
 EXPORT int64_t j40b_batch_stat(const j40b_batch *b, int what) {
     if (!b) return 0;
     switch (what) {

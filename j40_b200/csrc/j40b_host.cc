@@ -1646,9 +1646,11 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
         if (f.jpeg_upsampling) return plan.err = E_TODO;
         if (im.bpp < 8 || im.exp_bits != 0) return plan.err = E_TODO;
         if (plan.gmod.num_channels > 0 && !plan.single_section) {
-            // VarDCT frame with extra channels: they are decoded but never shown by the reference
-            // (SURVEY.md App. B-3); decoding them is required only to validate the stream
-            return plan.err = E_TODO;
+            // VarDCT frame with extra channels (typically alpha): the reference decodes them -- per pass group,
+            // behind the HF coefficients (j40.h:7024-7033) -- and then discards them (j40.h:7869-7870; A = 255).
+            // Each pass group has its own byte window, so the device simply stops after the coefficients; the
+            // price is that corruption confined to the extra channels' data goes unnoticed here.
+            if (plan.num_gm_channels != 0 || plan.gmod.nb_transforms != 0) return plan.err = E_TODO;
         }
     }
     d.nb_global_transforms = plan.gmod.nb_transforms;

@@ -58,7 +58,7 @@ void kl_hf_group(int blocks, size_t smem, cudaStream_t stream, const HfWork *w, 
 void kl_back_tile(int n, cudaStream_t stream, const BackWork *w);
 void kl_back_generic(int blocks, cudaStream_t stream, const BackWork *w, int n, float *pool);
 void kl_back_phase_dump(); // diagnostic builds (make PHASE_CLOCKS=1): prints and clears the tile kernel's phase counters
-void kl_modular(int n, cudaStream_t stream, ModWork *w);
+void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap);
 void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height);
 
 } // namespace j40b

@@ -366,13 +366,21 @@ public:
         if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob);
         if (num_hf) be.launch_hf((const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
         if (num_hf) be.launch_back((const BackWork *) (dev + bkw_off), (int) num_hf);
+        bool any_mod = false;
         for (size_t k = 0; k < plans.size(); ++k) {
             FramePlan &p = *plans[k];
             Img &im = img[k];
             if (p.err || !p.df.is_modular) continue;
-            if (im.nmod) be.launch_mod((ModWork *) (dev + im.mod_off), (int) im.nmod);
+            if (!any_mod) { any_mod = true; be.mark_modular(0); }
+            if (im.nmod) {
+                int max_w = 0;
+                for (const ModBuf &mb : im.mod) max_w = std::max(max_w, (int) mb.gw);
+                const DCodeSpec *gs = p.df.global_spec_off ? (const DCodeSpec *) (p.arena.bytes.data() + p.df.global_spec_off) : nullptr;
+                be.launch_mod((ModWork *) (dev + im.mod_off), (int) im.nmod, gs ? (size_t) (gs->blob_hi - gs->blob_lo) : (size_t) -1, max_w);
+            }
             be.launch_render((const RenderWork *) (dev + im.render_off), p.df.width, p.df.height);
         }
+        if (any_mod) be.mark_modular(1);
     }
 
     // ---- step 4: errors (synchronises)

@@ -3,15 +3,18 @@
 
 namespace j40b {
 
-__global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap) {
+// `cap`: width of the shared-memory rows (the widest channel of this launch, rounded up); `spec_cap`: bytes reserved
+// for the staged code spec (0 = tables through L1). Both are sized per launch: a block of a 256-pixel-wide group
+// then takes ~30 KB instead of the 106 KB of the widest case, and seven of them fit an SM instead of two.
+__global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap, int spec_cap) {
     __shared__ int32_t div24[64];
     extern __shared__ __align__(16) uint8_t smem[];
     ModWork &w = items[blockIdx.x];
-    const bool staged = stage_spec_blob(w.arena, w.f->global_spec_off, smem, SPEC_COPY_BYTES, (int) threadIdx.x, 32);
+    const bool staged = spec_cap > 0 && stage_spec_blob(w.arena, w.f->global_spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, 32);
     fill_div24(div24, (int) threadIdx.x, 32);
     __syncwarp();
     WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem + SPEC_COPY_BYTES, cap, ws);
+    ModSmem ms = carve_warp_slice(smem + spec_cap, cap, ws);
     modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
 }
 
@@ -24,8 +27,8 @@ bool kl_init_mod() {
     const int mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
     return cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem) == cudaSuccess;
 }
-void kl_modular(int n, cudaStream_t stream, ModWork *w) {
-    k_modular<<<n, 32, SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP), stream>>>(w, MOD_ROW_CAP);
+void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap) {
+    k_modular<<<n, 32, (size_t) spec_cap + warp_slice_bytes(cap), stream>>>(w, cap, spec_cap);
 }
 void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height) {
     dim3 grid((unsigned) ((width + 255) / 256), (unsigned) height);

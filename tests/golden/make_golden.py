@@ -27,6 +27,7 @@ CASES = {
     "vardct_multigroup_520x392": lambda: streamgen.vardct(520, 392, seed=4, mix=1, tree=1, hfmul=10, hfmul_var=4),
     "vardct_container_jxlp_lz77": lambda: streamgen.vardct(96, 80, seed=5, mix=1, container=1, jxlp=1, lz77=1),
     "vardct_permuted_orders_presets": lambda: streamgen.vardct(300, 280, seed=6, mix=1, permuted=1, orders=0x1f, presets=2, block_ctx=1),
+    "vardct_alpha_extra_channel_264x264": lambda: streamgen.vardct(264, 264, seed=9, mix=1, tree=1, alpha=1),
     "modular_rgb_rct_300x200": lambda: streamgen.modular(300, 200, seed=7),
     "modular_alpha_wp_ans": lambda: streamgen.modular(130, 70, seed=8, alpha=1, tree=2, ans=1, lz77=0),
 }

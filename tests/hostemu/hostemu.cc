@@ -67,7 +67,7 @@ struct HostEmuBackend {
             back_generic_body(bw, 0, 1, NoSync());
         }
     }
-    void launch_mod(ModWork *w, int n) {
+    void launch_mod(ModWork *w, int n, size_t, int) {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(1024));
         for (int i = 0; i < n; ++i) {
@@ -75,6 +75,7 @@ struct HostEmuBackend {
             modular_body(w[i], wm.ws, wm.ms, wm.div24, staged ? copy.data() : nullptr, w[i].arena, 0, 1, NoSync());
         }
     }
+    void mark_modular(int) {}
     void launch_render(const RenderWork *w, int width, int height) {
         for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) render_px(*w, x, y);
     }

@@ -29,6 +29,10 @@ VARDCT_CASES = [
     ("ragged_257x255", 257, 255, 5, dict(mix=1, tree=1)),
     ("wide_1000x300", 1000, 300, 5, dict(mix=1, tree=1)),
     ("two_lf_groups_2100x300", 2100, 300, 6, dict(mix=1, tree=1, hfmul=6)),
+    # VarDCT frames with an alpha extra channel (coded per pass group behind the coefficients; the reference
+    # decodes and then discards it: A = 255)
+    ("alpha_extra_channel_ans", 520, 392, 22, dict(mix=1, tree=1, alpha=1)),
+    ("alpha_extra_channel_prefix", 300, 520, 23, dict(mix=1, tree=2, alpha=1, ans=0)),
 ]
 
 MODULAR_CASES = [

@@ -41,6 +41,7 @@ struct VarDCTParams {
     bool custom_cfl_base = false;
     bool smooth_lf = true;     // false sets skip_adapt_lf_smooth
     int extra_prec = 0;
+    bool alpha = false;        // 8-bit alpha extra channel, coded per pass group with the global tree (multi-group frames only)
     int tree_preset = 1;       // 0 single gradient leaf, 1 WP + property tree, 2 stress tree
     bool custom_block_ctx = false;
     int custom_orders = 0;     // bit mask over the 13 orders
@@ -243,6 +244,24 @@ public:
             mt.run(mc, 1 + 2 * num_lfg + i, meta_ts[(size_t) i]);
             stats.lf_symbols += (int64_t) lf_ts[(size_t) i].size() + (int64_t) meta_ts[(size_t) i].size();
         }
+        // extra channel (alpha): one modular sub-stream per pass group, after the HF coefficients (j40.h:7024-7033)
+        std::vector<TokStream> ec_ts;
+        if (P.alpha) {
+            JG_CHECK(num_groups > 1);
+            ec_ts.resize((size_t) num_groups);
+            for (int g = 0; g < num_groups; ++g) {
+                int grow = g / group_cols, gcol = g % group_cols;
+                int gw = std::min(P.width, (gcol + 1) * 256) - gcol * 256, gh = std::min(P.height, (grow + 1) * 256) - grow * 256;
+                std::vector<Channel> ch(1);
+                ch[0].w = gw; ch[0].h = gh;
+                for (int y = 0; y < gh; ++y) for (int x = 0; x < gw; ++x) {
+                    int X = gcol * 256 + x, Y = grow * 256 + y;
+                    ch[0].px.push_back(((X / 37 + Y / 53) % 5 == 0) ? 200 + ((X >> 3) & 7) : 255);
+                }
+                mt.run(ch, 1 + 3 * num_lfg + 17 + g, ec_ts[(size_t) g]);
+                stats.lf_symbols += (int64_t) ec_ts[(size_t) g].size();
+            }
+        }
         EntropyOpts mo;
         mo.use_prefix = !P.use_ans;
         mo.log_alpha_size = 8;
@@ -253,6 +272,7 @@ public:
             std::vector<const TokStream *> all;
             for (auto &s : lf_ts) all.push_back(&s);
             for (auto &s : meta_ts) all.push_back(&s);
+            for (auto &s : ec_ts) all.push_back(&s);
             mspec.build(tree.num_leaves, mo, all);
         }
 
@@ -297,6 +317,11 @@ public:
             BitWriter &bw = pgsec[(size_t) g];
             bw.put((uint64_t) group_preset[(size_t) g], ceil_lg((uint32_t) P.num_hf_presets));
             cspec.encode(bw, hf_ts[(size_t) g]);
+            if (P.alpha) {
+                ModularHeaderOpts mh;
+                write_modular_header_prefix(bw, mh);
+                mspec.encode(bw, ec_ts[(size_t) g]);
+            }
         }
 
         // ---- assemble the codestream
@@ -700,10 +725,23 @@ private:
     void write_headers(BitWriter &bw) {
         bw.put(0xff, 8); bw.put(0x0a, 8);
         write_size_header(bw, P.width, P.height);
-        bw.bit(1); // ImageMetadata all_default: 8-bit, XYB, sRGB
+        if (!P.alpha) {
+            bw.bit(1); // ImageMetadata all_default: 8-bit, XYB, sRGB
+        } else {
+            bw.bit(0);        // !all_default
+            bw.bit(0);        // extra_fields
+            bw.bit(0);        // integer samples
+            bw.u32(8, 8, 0, 10, 0, 12, 0, 1, 6);
+            bw.bit(1);        // modular_16bit_buffers
+            bw.u32(1, 0, 0, 1, 0, 2, 4, 1, 12); // one extra channel
+            bw.bit(1);        // d_alpha
+            bw.bit(1);        // xyb_encoded
+            bw.bit(1);        // ColourEncoding all_default
+            bw.u64(0);        // extensions
+        }
         bw.bit(1); // default_m
         bw.pad();  // frame header starts byte-aligned
-        if (!P.explicit_frame_header) {
+        if (!P.explicit_frame_header && !P.alpha) {
             JG_CHECK(P.smooth_lf && P.x_qm_scale == 3 && P.b_qm_scale == 2);
             bw.bit(1);
             return;
@@ -713,11 +751,13 @@ private:
         bw.bit(0);          // VarDCT
         bw.u64(P.smooth_lf ? 0 : 128); // flags
         bw.put(0, 2);       // log_upsampling
+        if (P.alpha) bw.put(0, 2); // ec upsampling
         bw.put((uint64_t) P.x_qm_scale, 3);
         bw.put((uint64_t) P.b_qm_scale, 3);
         bw.u32(1, 1, 0, 2, 0, 3, 0, 4, 3); // num_passes
         bw.bit(0);          // have_crop
         bw.u32(0, 0, 0, 1, 0, 2, 0, 3, 2); // blend mode: replace
+        if (P.alpha) bw.u32(0, 0, 0, 1, 0, 2, 0, 3, 2); // blend mode (alpha)
         bw.bit(1);          // is_last
         bw.u32(0, 0, 0, 0, 4, 16, 5, 48, 10); // name length 0
         // restoration filter: all_default must be 0 (SURVEY B-1); cjxl-like gaborish + 2 EPF iterations
@@ -820,7 +860,14 @@ private:
         to.max_clusters = 6;
         write_tree(bw, tree, to);
         mspec.write(bw);
-        // no global modular channels for a VarDCT frame without extra channels
+        // no global modular channels for a VarDCT frame without extra channels; with one, the global modular
+        // header follows (the channel itself is larger than a group and therefore coded per pass group)
+        if (P.alpha) {
+            ModularHeaderOpts gh;
+            write_modular_header_prefix(bw, gh);
+            TokStream empty;
+            mspec.encode(bw, empty); // an ANS stream still carries its final state
+        }
     }
 
     void write_block_ctx_map(BitWriter &bw) {
