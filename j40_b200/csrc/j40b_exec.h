@@ -56,7 +56,11 @@ struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, 
     uint32_t sec_off, sec_size;
     uint64_t sec_start_bit;
     int32_t sidx;
-    int32_t header_parsed;  // 1: `m` was filled by the host (global image), 0: parse the header here
+    int32_t header_parsed;  // 1: `m` was filled by the host (global image, or a header with a local tree), 0: parse it here
+    int32_t is_global;      // the frame's global image (transforms are applied by the render step)
+    uint32_t tree_off, spec_off; // MA tree and code spec of this sub-bitstream in the arena (the global ones or local ones)
+    int32_t tree_uses_wp;
+    uint32_t preset_err;    // non-zero: the host already found this sub-bitstream's header broken
     ModImage m;             // channel views into the frame planes
     int32_t *wp_scratch;    // [2 * width * 5] or null
     int32_t *lz_window;     // or null
@@ -324,30 +328,31 @@ template <class Sync>
 J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
                                  const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
     const DFrame &f = *w.f;
+    if (w.preset_err) { if (lane == 0) *w.err = w.preset_err; return; }
     BitReader br;
     ErrSlot es;
     CodeCtx cc;
     CodeState cs;
     es.err = 0;
     br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
-    init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
+    init_code_ctx(cc, w.arena, w.spec_off, spec_copy, copy_arena);
     cs.init(w.lz_window, w.lz_mask);
-    const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+    const DTreeNode *tree = (const DTreeNode *) (w.arena + w.tree_off);
     ModImage &m = ws.m;
     m = w.m;
     if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, m);
     sync();
     for (int c = 0; c < m.num_channels && !es.err; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, w.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, w.sidx, lane, nlanes, sync);
+        modular_channel_warp(br, es, cc, cs, tree, w.tree_uses_wp != 0, w.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, w.sidx, lane, nlanes, sync);
     }
     if (!es.err) finish_code(br, es, cc, cs);
     if (!es.err) {
-        if (w.header_parsed) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
+        if (w.is_global) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
         else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
     }
     if (es.err && lane == 0) *w.err = es.err;
     sync();
-    if (es.err || w.header_parsed) return; // global transforms are applied by the render step
+    if (es.err || w.is_global) return; // global transforms are applied by the render step
     for (int t = m.nb_transforms - 1; t >= 0; --t) {
         ModImage one = m;
         one.nb_transforms = 1;

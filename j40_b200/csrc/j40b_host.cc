@@ -1036,6 +1036,23 @@ struct Parser {
         for (int i = 0; i < m.num_channels; ++i) { m.ch[i].w = f.width; m.ch[i].h = f.height; m.ch[i].stride = f.width; }
     }
 
+    // ModularHeader on the host, including a local tree (j40.h:3717-3850). `m` holds the channel geometry.
+    void host_modular_header(ModImage &m, FramePlan::LocalHeader &lh) {
+        ErrSlot es = {0};
+        int local = 0;
+        modular_header(br, es, plan.df.have_global_tree != 0, m, &local);
+        if (es.err) { err = es.err; return; }
+        if (local) {
+            int64_t max_tree_size = 1024;
+            for (int i = 0; i < m.num_channels; ++i) max_tree_size = std::min<int64_t>(INT32_MAX, max_tree_size + (int64_t) m.ch[i].w * m.ch[i].h);
+            max_tree_size = std::min<int64_t>(1 << 20, max_tree_size);
+            read_tree((int32_t) max_tree_size, &lh.tree_off, &lh.spec_off, &lh.uses_wp);
+            if (err) return;
+            lh.present = true;
+            lh.hdr = m;
+        }
+    }
+
     void lf_global() { // j40.h:6257-6340
         ImageInfo &im = plan.im;
         FrameInfo &f = plan.fh;
@@ -1103,9 +1120,8 @@ struct Parser {
         }
         if (err) return;
         if (plan.gmod.num_channels > 0) {
-            ErrSlot es = {0};
-            modular_header(br, es, d.have_global_tree != 0, plan.gmod);
-            if (es.err) { err = es.err; return; }
+            host_modular_header(plan.gmod, plan.gmod_local);
+            if (err) return;
             check_overrun();
             if (err) return;
             if (f.width <= (1 << f.group_size_shift) && f.height <= (1 << f.group_size_shift)) plan.num_gm_channels = plan.gmod.num_channels;
@@ -1585,7 +1601,7 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
     if (plan.gmod_has_stream && plan.num_gm_channels == 0) {
         // no globally coded channel: the (empty) entropy stream still has to be closed (j40.h:6337)
         Parser::HostCode hc;
-        hc.begin(plan.arena, d.global_spec_off);
+        hc.begin(plan.arena, plan.gmod_local.present ? plan.gmod_local.spec_off : d.global_spec_off);
         q.hfinish(hc);
         if (q.err) return plan.err = q.err;
         plan.gmod_has_stream = false;
@@ -1608,6 +1624,30 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
         }
         for (auto &s : plan.lfg_sec) { uint64_t a = plan.cs_size > s.off ? plan.cs_size - s.off : 0; s.size = (uint32_t) std::min<uint64_t>(s.size, a); s.off = std::min<uint64_t>(s.off, plan.cs_size); }
         for (auto &s : plan.pg_sec) { uint64_t a = plan.cs_size > s.off ? plan.cs_size - s.off : 0; s.size = (uint32_t) std::min<uint64_t>(s.size, a); s.off = std::min<uint64_t>(s.off, plan.cs_size); }
+        if (f.is_modular && plan.gmod.num_channels > 0) {
+            // pass groups whose modular header (the first thing in the section) names a local tree: header,
+            // tree and code spec are read here. A section too short to hold them fails like on the device.
+            const int gsize = 1 << f.group_size_shift;
+            for (size_t g = 0; g < plan.pg_sec.size(); ++g) {
+                const SectionRef &s = plan.pg_sec[g];
+                if (s.size == 0 || (plan.cs[s.off] & 1)) continue; // use_global_tree = 1 (or nothing to read: the device reports it)
+                if (plan.pg_local.empty()) plan.pg_local.resize(plan.pg_sec.size());
+                Parser h(plan);
+                h.br.init(plan.cs + s.off, s.size);
+                ModImage m = plan.gmod;
+                const int gx = (int) (g % (size_t) f.gcolumns) * gsize, gy = (int) (g / (size_t) f.gcolumns) * gsize;
+                for (int c = 0; c < m.num_channels; ++c) { m.ch[c].w = std::min(f.width, gx + gsize) - gx; m.ch[c].h = std::min(f.height, gy + gsize) - gy; }
+                FramePlan::LocalHeader &lh = plan.pg_local[g];
+                h.host_modular_header(m, lh);
+                if (!h.err) h.check_overrun();
+                if (h.err) {
+                    // errors surface in the reference's decoding order: leave this one to the section's slot
+                    lh.present = true; lh.host_err = h.err;
+                    continue;
+                }
+                lh.start_bit = h.br.bits_consumed();
+            }
+        }
     } else {
         // single section: LfGlobal, HfGlobal, LfGroup, PassGroup back to back
         if (!f.is_modular) {

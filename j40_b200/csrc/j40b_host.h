@@ -68,6 +68,18 @@ struct FramePlan {
     int num_gm_channels = 0;
     bool gmod_has_stream = false; // an entropy-coded stream (possibly empty) follows the global header
     int rank_lf_global = 0;
+    // modular sub-bitstreams whose header names a tree of their own (j40.h:3827-3835): header, tree and code
+    // spec are read on the host; the device starts at `start_bit` with these tables
+    struct LocalHeader {
+        bool present = false;
+        ModImage hdr;            // wp parameters and transforms as parsed (channel geometry of the sub-image)
+        uint32_t tree_off = 0, spec_off = 0;
+        int32_t uses_wp = 0;
+        uint64_t start_bit = 0;  // first bit of the channel data, relative to the section start
+        uint32_t host_err = 0;   // the header failed to parse: reported through the section's error slot
+    };
+    LocalHeader gmod_local;              // the global image's
+    std::vector<LocalHeader> pg_local;   // per pass group of a modular frame (empty: none is local)
 };
 
 // process-wide immutable tables (library dequantisation matrices, natural orders, sRGB thresholds)

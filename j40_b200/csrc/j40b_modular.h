@@ -709,9 +709,11 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
     }
 }
 
-// ModularHeader as far as the device understands it (global tree only; RCT transforms only).
-// Mirrors the checks of j40.h:3729-3759, 3816.
-J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_tree, ModImage &m) {
+// ModularHeader as far as the device understands it (RCT transforms only). Mirrors the checks of
+// j40.h:3729-3759, 3816. A tree local to the sub-bitstream follows the header in the stream; reading it is the
+// host's job (`local_tree` non-null: set to 1 and left to the caller; null: the device path, which only gets
+// here for sub-bitstreams whose header the host could not reach -- LF groups of VarDCT frames -- rejects it).
+J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_tree, ModImage &m, int *local_tree = nullptr) {
     int use_global_tree = (int) br.u(1);
     if (use_global_tree && !have_global_tree) { es.set(br, E_MTRE); return; }
     int default_wp = (int) br.u(1);
@@ -746,10 +748,8 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
         }
     }
     if (!use_global_tree) {
-        // a tree local to this sub-bitstream would have to be parsed here; see DESIGN.md (out of
-        // scope for the device path in this round)
-        es.set(br, E_TODO);
-        return;
+        if (!local_tree) { es.set(br, E_TODO); return; }
+        *local_tree = 1;
     }
     m.dist_mult = 0;
     for (int i = 0; i < m.num_channels; ++i) m.dist_mult = imax(m.dist_mult, m.ch[i].w);

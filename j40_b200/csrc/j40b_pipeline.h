@@ -158,8 +158,8 @@ public:
                 int nch = d.num_channels;
                 for (int c = 0; c < nch; ++c) im.plane[c] = wk_alloc(2 * (size_t) d.width * d.height);
                 im.nmod = p.pg_sec.size() + (p.num_gm_channels > 0 ? 1 : 0);
-                bool wp = d.global_tree_uses_wp != 0;
-                bool lz = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
+                auto spec_lz = [&](uint32_t off) { return off && ((const DCodeSpec *) (p.arena.bytes.data() + off))->lz77_enabled; };
+                const bool wp_g = d.global_tree_uses_wp != 0, lz_g = spec_lz(d.global_spec_off);
                 int gsize = 1 << d.group_size_shift;
                 im.mod.resize(im.nmod);
                 for (size_t g = 0; g < im.nmod; ++g) {
@@ -168,6 +168,9 @@ public:
                     int gw = global ? d.width : std::min(d.width, ((int) (g % (size_t) d.gcolumns) + 1) * gsize) - (int) (g % (size_t) d.gcolumns) * gsize;
                     int gh = global ? d.height : std::min(d.height, ((int) (g / (size_t) d.gcolumns) + 1) * gsize) - (int) (g / (size_t) d.gcolumns) * gsize;
                     mb.gw = gw; mb.gh = gh;
+                    const FramePlan::LocalHeader *lh = global ? &p.gmod_local : (g < p.pg_local.size() ? &p.pg_local[g] : nullptr);
+                    const bool local = lh && lh->present;
+                    const bool wp = local ? lh->uses_wp != 0 : wp_g, lz = local ? spec_lz(lh->spec_off) : lz_g;
                     mb.wp = wp ? wk_alloc(4 * 2 * 5 * (size_t) gw) : (size_t) -1;
                     size_t syms = (size_t) nch * gw * gh;
                     uint32_t capl = 1;
@@ -328,6 +331,14 @@ public:
                     w.sec_off = (uint32_t) s.off; w.sec_size = s.size; w.sec_start_bit = s.start_bit;
                     w.sidx = global ? 0 : (int32_t) (1 + 3 * d.num_lf_groups + 17 + (int64_t) g);
                     w.header_parsed = global ? 1 : 0;
+                    w.is_global = global ? 1 : 0;
+                    w.tree_off = d.global_tree_off; w.spec_off = d.global_spec_off; w.tree_uses_wp = d.global_tree_uses_wp;
+                    const FramePlan::LocalHeader *lh = global ? &p.gmod_local : (g < p.pg_local.size() ? &p.pg_local[g] : nullptr);
+                    if (lh && lh->present) {
+                        w.preset_err = lh->host_err;
+                        w.tree_off = lh->tree_off; w.spec_off = lh->spec_off; w.tree_uses_wp = lh->uses_wp;
+                        if (!global) { w.header_parsed = 1; w.sec_start_bit = lh->start_bit; w.m = lh->hdr; }
+                    }
                     int gx = global ? 0 : (int) (g % (size_t) d.gcolumns) * gsize, gy = global ? 0 : (int) (g / (size_t) d.gcolumns) * gsize;
                     if (global) w.m = p.gmod;
                     w.m.num_channels = d.num_channels;
@@ -376,6 +387,7 @@ public:
                 int max_w = 0;
                 for (const ModBuf &mb : im.mod) max_w = std::max(max_w, (int) mb.gw);
                 const DCodeSpec *gs = p.df.global_spec_off ? (const DCodeSpec *) (p.arena.bytes.data() + p.df.global_spec_off) : nullptr;
+                if (p.gmod_local.present || !p.pg_local.empty()) gs = nullptr; // local code specs: no common blob to stage
                 be.launch_mod((ModWork *) (dev + im.mod_off), (int) im.nmod, gs ? (size_t) (gs->blob_hi - gs->blob_lo) : (size_t) -1, max_w);
             }
             be.launch_render((const RenderWork *) (dev + im.render_off), p.df.width, p.df.height);

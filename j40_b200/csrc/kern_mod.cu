@@ -10,7 +10,7 @@ __global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap, int spe
     __shared__ int32_t div24[64];
     extern __shared__ __align__(16) uint8_t smem[];
     ModWork &w = items[blockIdx.x];
-    const bool staged = spec_cap > 0 && stage_spec_blob(w.arena, w.f->global_spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, 32);
+    const bool staged = spec_cap > 0 && stage_spec_blob(w.arena, w.spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, 32);
     fill_div24(div24, (int) threadIdx.x, 32);
     __syncwarp();
     WarpScratch *ws;

@@ -71,7 +71,7 @@ struct HostEmuBackend {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(1024));
         for (int i = 0; i < n; ++i) {
-            bool staged = !(i & 1) && stage_spec_blob(w[i].arena, w[i].f->global_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
+            bool staged = !(i & 1) && stage_spec_blob(w[i].arena, w[i].spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
             modular_body(w[i], wm.ws, wm.ms, wm.div24, staged ? copy.data() : nullptr, w[i].arena, 0, 1, NoSync());
         }
     }

@@ -52,6 +52,10 @@ MODULAR_CASES = [
     ("single_group_8x8", 8, 8, 4, dict()),
     ("single_group_256", 256, 256, 4, dict(tree=2, ans=1, alpha=1)),
     ("ragged_257x129", 257, 129, 4, dict(tree=2, ans=1, alpha=1)),
+    # trees and code specs local to a sub-bitstream (j40.h:3827-3835), mixed with the global one / without any
+    ("local_tree_odd_groups", 600, 400, 6, dict(local_tree=1)),
+    ("local_tree_all_groups_wp_ans", 600, 400, 6, dict(local_tree=2, ans=1, lz77=0, tree=2, alpha=1)),
+    ("local_tree_single_group", 200, 100, 6, dict(local_tree=1, ans=1)),
 ]
 
 

@@ -9,8 +9,8 @@ import pytest
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 INDEX = json.load(open(os.path.join(HERE, "golden.json")))
-# accepted by the reference, documented as not built here: section-local MA trees
-UNSUPPORTED = {"ka_V1_modular_8x8_local_tree": "TODO"}
+# streams the reference accepts but this library documents as not built: none of the fixtures
+UNSUPPORTED = {}
 
 
 def _data(name):

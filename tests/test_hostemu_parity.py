@@ -20,12 +20,7 @@ def _cmp(oracle, emu, data):
 
 def test_known_answer(oracle, emu):
     for name, (hx, _) in streams.KNOWN_ANSWER.items():
-        data = bytes.fromhex(hx)
-        if "local_tree" in name:
-            # local MA trees are not decoded on the device path yet: documented gap
-            assert emu.decode(data)[1] == "TODO"
-            continue
-        _cmp(oracle, emu, data)
+        _cmp(oracle, emu, bytes.fromhex(hx))
 
 
 @pytest.mark.parametrize("case", streams.VARDCT_CASES, ids=[c[0] for c in streams.VARDCT_CASES])

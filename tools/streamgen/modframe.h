@@ -21,6 +21,8 @@ struct ModularParams {
     bool container = false;
     int smooth = 1;          // 0 = raw synthetic photo, 1 = posterise a little so that runs exist
     int max_clusters = 8;
+    int local_tree = 0;      // 1: odd pass groups (or the global image of a single-group frame) carry a tree and code
+                             // spec of their own; 2: all of them do and the frame has no global tree at all
 };
 
 class ModularFrameEncoder {
@@ -59,6 +61,7 @@ public:
         ModularTokenizer mt(tree);
         std::vector<TokStream> ts((size_t) num_groups);
         std::vector<int> gwidth((size_t) num_groups);
+        std::vector<std::vector<Channel>> group_channels((size_t) (P.local_tree ? num_groups : 0));
         for (int g = 0; g < num_groups; ++g) {
             int gx = (g % gcols) * gsize, gy = (g / gcols) * gsize;
             int gw = std::min(W, gx + gsize) - gx, gh = std::min(H, gy + gsize) - gy;
@@ -73,6 +76,7 @@ public:
             }
             int64_t sidx = single ? 0 : 1 + 3 * (int64_t) num_lfg + 17 + g;
             mt.run(ch, sidx, ts[(size_t) g]);
+            if (P.local_tree) group_channels[(size_t) g] = ch;
             stats.lf_symbols += (int64_t) ts[(size_t) g].size();
         }
         EntropyOpts eo;
@@ -93,17 +97,26 @@ public:
         // ---- LfGlobal
         BitWriter lfglobal;
         lfglobal.bit(1); // LF dequant defaults (parsed even for modular frames)
-        lfglobal.bit(1); // global tree present
+        const bool have_global_tree = P.local_tree != 2;
+        auto is_local = [&](int g) { return P.local_tree == 2 || (P.local_tree == 1 && (single || (g & 1))); };
+        lfglobal.bit(have_global_tree); // global tree present
         EntropyOpts to;
         to.use_prefix = !P.use_ans;
         to.log_alpha_size = 8;
         to.cfg = {4, 1, 0};
         to.max_clusters = 6;
-        write_tree(lfglobal, tree, to);
-        spec.write(lfglobal);
+        if (have_global_tree) {
+            write_tree(lfglobal, tree, to);
+            spec.write(lfglobal);
+        }
         ModularHeaderOpts gh;
         if (P.rct_type >= 0) gh.rcts.push_back({0, P.rct_type});
+        gh.use_global_tree = !(single ? is_local(0) : !have_global_tree);
         write_modular_header_prefix(lfglobal, gh);
+        if (!gh.use_global_tree) { // the same tree, but stored with the sub-bitstream (j40.h:3827-3835)
+            write_tree(lfglobal, tree, to);
+            spec.write(lfglobal);
+        }
         if (single) {
             spec.encode(lfglobal, ts[0]);
         } else {
@@ -161,6 +174,25 @@ public:
             for (int g = 0; g < num_groups; ++g) {
                 BitWriter &bw = secs[(size_t) (2 + num_lfg + g)];
                 ModularHeaderOpts mh;
+                if (is_local(g)) {
+                    // a different tree than the global one (single gradient leaf for every fourth group), with a
+                    // code spec built from this group's symbols alone
+                    MATree lt = tree;
+                    if ((g & 3) == 3) { lt = MATree(); lt.flatten(MATree::Leaf(5)); }
+                    ModularTokenizer lmt(lt);
+                    TokStream lts;
+                    lmt.run(group_channels[(size_t) g], 1 + 3 * (int64_t) num_lfg + 17 + g, lts);
+                    if (eo.lz77) lz77_rle(lts, eo.min_length, gwidth[(size_t) g], 4);
+                    CodeSpec ls;
+                    std::vector<const TokStream *> one{&lts};
+                    ls.build(lt.num_leaves, eo, one);
+                    mh.use_global_tree = false;
+                    write_modular_header_prefix(bw, mh);
+                    write_tree(bw, lt, to);
+                    ls.write(bw);
+                    ls.encode(bw, lts);
+                    continue;
+                }
                 write_modular_header_prefix(bw, mh);
                 spec.encode(bw, ts[(size_t) g]);
             }
