@@ -131,7 +131,12 @@ struct CudaBackend {
     void launch_mod(ModWork *w, int n, size_t spec_bytes, int max_w) {
         int cap = (max_w + 63) & ~63;
         if (cap > MOD_ROW_CAP || cap <= 0) cap = MOD_ROW_CAP;
-        const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
+        int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
+        // the staged code spec shortens each symbol a little but costs residency: when the groups do not fit the
+        // GPU in one wave with it, leave the tables to L1 (8192x8192: 1024 one-warp blocks, 4 vs 10 per SM)
+        const size_t slice = warp_slice_bytes(cap), sm_bytes = 227 * 1024;
+        const size_t fit_staged = sm_bytes / (slice + (size_t) spec_cap + 1024), fit_plain = sm_bytes / (slice + 1024);
+        if (spec_cap && (size_t) n > fit_staged * (size_t) num_sms && fit_plain > fit_staged) spec_cap = 0;
         kl_modular(n, stream, w, cap, spec_cap);
         ++launches;
     }
