@@ -58,6 +58,7 @@ struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, 
     int32_t sidx;
     int32_t header_parsed;  // 1: `m` was filled by the host (global image, or a header with a local tree), 0: parse it here
     int32_t is_global;      // the frame's global image (transforms are applied by the render step)
+    int32_t check_end;      // single-section frame: the sub-bitstream must end the section exactly
     uint32_t tree_off, spec_off; // MA tree and code spec of this sub-bitstream in the arena (the global ones or local ones)
     int32_t tree_uses_wp;
     uint32_t preset_err;    // non-zero: the host already found this sub-bitstream's header broken
@@ -347,7 +348,7 @@ J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms,
     }
     if (!es.err) finish_code(br, es, cc, cs);
     if (!es.err) {
-        if (w.is_global) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
+        if (w.check_end) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // global image of a single-section frame
         else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
     }
     if (es.err && lane == 0) *w.err = es.err;
@@ -363,14 +364,77 @@ J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms,
 }
 
 // one thread per pixel: global inverse RCTs (j40.h:8209) + j40__render_to_u8x4_rgba (j40.h:7910-7957)
+// the 72 hard-coded palette deltas (j40.h:4275-4290): entry k serves index 2k as is and 2k + 1 negated
+J40B_HD J40B_INLINE int32_t palette_delta(int32_t idx /* 0..142 */, int c) {
+    const int16_t T[72][3] = {
+        {0, 0, 0}, {4, 4, 4}, {11, 0, 0}, {0, 0, -13}, {0, -12, 0}, {-10, -10, -10},
+        {-18, -18, -18}, {-27, -27, -27}, {-18, -18, 0}, {0, 0, -32}, {-32, 0, 0}, {-37, -37, -37},
+        {0, -32, -32}, {24, 24, 45}, {50, 50, 50}, {-45, -24, -24}, {-24, -45, -45}, {0, -24, -24},
+        {-34, -34, 0}, {-24, 0, -24}, {-45, -45, -24}, {64, 64, 64}, {-32, 0, -32}, {0, -32, 0},
+        {-32, 0, 32}, {-24, -45, -24}, {45, 24, 45}, {24, -24, -45}, {-45, -24, 24}, {80, 80, 80},
+        {64, 0, 0}, {0, 0, -64}, {0, -64, -64}, {-24, -24, 45}, {96, 96, 96}, {64, 64, 0},
+        {45, -24, -24}, {34, -34, 0}, {112, 112, 112}, {24, -45, -45}, {45, 45, -24}, {0, -32, 32},
+        {24, -24, 45}, {0, 96, 96}, {45, -24, 24}, {24, -45, -24}, {-24, -45, 24}, {0, -64, 0},
+        {96, 0, 0}, {128, 128, 128}, {64, 0, 64}, {144, 144, 144}, {96, 96, 0}, {-36, -36, 36},
+        {45, -24, -45}, {45, -45, -24}, {0, 0, -96}, {0, 128, 128}, {0, 96, 0}, {45, 24, -45},
+        {-128, 0, 0}, {24, -45, 24}, {-45, 24, -45}, {64, 0, -64}, {64, -64, -64}, {96, 0, 96},
+        {45, -45, 24}, {24, 45, -45}, {64, 64, -64}, {128, 128, 0}, {0, 0, -128}, {-24, 45, -45},
+    };
+    // the reference's table has 144 rows, (x), (-x) alternating, and is entered at idx + 1
+    const int32_t v = T[(idx + 1) >> 1][c];
+    return ((idx + 1) & 1) ? -v : v;
+}
+
+// one colour of a palette entry (j40__inverse_palette without prediction, j40.h:4447-4470; 16-bit buffers)
+J40B_HD J40B_INLINE int16_t palette_value(const ModTransform &t, const int16_t *pal /* [num_c][nb_colours] */, int32_t idx_in, int i, int bpp) {
+    int16_t idx = (int16_t) idx_in, val;
+    if (idx < 0) {
+        if (i < 3) {
+            idx = (int16_t) (~idx % 143);
+            val = (int16_t) palette_delta(idx, i);
+            if (bpp > 8) val = (int16_t) (val << (imin(bpp, 24) - 8));
+        } else {
+            val = 0;
+        }
+    } else if (idx < t.nb_colours) {
+        val = pal[(size_t) i * (size_t) t.nb_colours + idx];
+    } else {
+        idx = (int16_t) (idx - t.nb_colours);
+        if (idx < 64) {
+            val = (int16_t) ((i < 3 ? idx >> (2 * i) : 0) * (((int32_t) 1 << bpp) - 1) / 4 + ((int32_t) 1 << imax(0, bpp - 3)));
+        } else {
+            val = (int16_t) (idx - 64);
+            for (int j = 0; j < i; ++j) val = (int16_t) (val / 5);
+            val = (int16_t) ((val % 5) * ((1 << bpp) - 1) / 4);
+        }
+    }
+    return val;
+}
+
 J40B_HD inline void render_px(const RenderWork &w, int x, int y) {
     const DFrame &f = *w.f;
-    int16_t v[MOD_MAX_CH];
+    int16_t v[MOD_MAX_CH + 4];
     const size_t o = (size_t) y * (size_t) f.width + (size_t) x;
-    for (int c = 0; c < f.num_channels; ++c) v[c] = w.plane[c][o];
+    // the coded channel list at this pixel; palette (meta) channels in front are tables, not samples
+    int n = f.num_channels, meta = f.nb_meta_channels;
+    for (int c = 0; c < n; ++c) v[c] = c < meta ? (int16_t) 0 : w.plane[c][o];
     for (int t = f.nb_global_transforms - 1; t >= 0; --t) {
-        int b = f.global_tr[t].begin_c;
-        inverse_rct_px(f.global_tr[t].type, v[b], v[b + 1], v[b + 2]);
+        const ModTransform &tr = f.global_tr[t];
+        if (tr.kind == 0) {
+            int b = tr.begin_c;
+            inverse_rct_px(tr.type, v[b], v[b + 1], v[b + 2]);
+        } else {
+            // every palette transform put its table in front of the list, so the one being undone (transforms are
+            // undone last to first) is the first meta channel still there
+            const int16_t *table = w.plane[f.nb_meta_channels - meta];
+            const int first = tr.begin_c + 1, last = tr.begin_c + tr.num_c;
+            const int32_t idx = v[first];
+            for (int k = n - 1; k > first; --k) v[k + (last - first)] = v[k]; // channels behind the index channel
+            n += last - first;
+            for (int i = 0; i < tr.num_c; ++i) v[first + i] = palette_value(tr, table, idx, i, f.bpp);
+            for (int k = 0; k + 1 < n; ++k) v[k] = v[k + 1]; // drop the palette channel itself
+            --n; --meta;
+        }
     }
     const int32_t maxpixel = (1 << f.bpp) - 1, half = 1 << (f.bpp - 1);
     uint8_t *out = w.rgba + (size_t) y * (size_t) w.rgba_stride + (size_t) x * 4;

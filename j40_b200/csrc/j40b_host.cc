@@ -1037,10 +1037,10 @@ struct Parser {
     }
 
     // ModularHeader on the host, including a local tree (j40.h:3717-3850). `m` holds the channel geometry.
-    void host_modular_header(ModImage &m, FramePlan::LocalHeader &lh) {
+    void host_modular_header(ModImage &m, FramePlan::LocalHeader &lh, bool allow_palette = false) {
         ErrSlot es = {0};
         int local = 0;
-        modular_header(br, es, plan.df.have_global_tree != 0, m, &local);
+        modular_header(br, es, plan.df.have_global_tree != 0, m, &local, allow_palette);
         if (es.err) { err = es.err; return; }
         if (local) {
             int64_t max_tree_size = 1024;
@@ -1120,12 +1120,12 @@ struct Parser {
         }
         if (err) return;
         if (plan.gmod.num_channels > 0) {
-            host_modular_header(plan.gmod, plan.gmod_local);
+            host_modular_header(plan.gmod, plan.gmod_local, f.is_modular);
             if (err) return;
             check_overrun();
             if (err) return;
             if (f.width <= (1 << f.group_size_shift) && f.height <= (1 << f.group_size_shift)) plan.num_gm_channels = plan.gmod.num_channels;
-            else plan.num_gm_channels = 0; // no meta channels without palette transforms
+            else plan.num_gm_channels = plan.gmod.nb_meta_channels; // palettes are always coded with the global image
             plan.gmod_has_stream = true;
             plan.gmod_sec.start_bit = br.bits_consumed(); // relative to the reader's base (set by the caller)
         }
@@ -1669,8 +1669,12 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
     // extra channels / alpha
     d.num_channels = plan.gmod.num_channels;
     d.num_gm_channels = plan.num_gm_channels;
+    d.nb_meta_channels = plan.gmod.nb_meta_channels;
+    int restored = plan.gmod.num_channels; // channel count once the global transforms are undone
+    for (int i = 0; i < plan.gmod.nb_transforms; ++i) if (plan.gmod.tr[i].kind == 1) restored += plan.gmod.tr[i].num_c - 2;
+    d.num_out_channels = restored;
     if (f.is_modular) {
-        for (int i = 3; i < plan.gmod.num_channels; ++i) {
+        for (int i = 3; i < restored; ++i) {
             const ImageInfo::EC &ec = im.ec[i - 3];
             if (ec.type == 0) {
                 if (!(ec.bpp == im.bpp && ec.exp_bits == im.exp_bits) || ec.alpha_associated) return plan.err = E_TODO;
@@ -1678,7 +1682,7 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
                 break;
             }
         }
-        if (plan.gmod.num_channels < 3) return plan.err = E_TODO; // grey modular frames (reference: assertion)
+        if (restored < 3) return plan.err = E_TODO; // grey modular frames (reference: assertion)
         if (im.bpp < 8 || im.exp_bits != 0) return plan.err = E_TODO;
     } else {
         if (f.do_ycbcr || im.cspace_grey) return plan.err = E_TODO;

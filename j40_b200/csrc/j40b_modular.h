@@ -20,7 +20,9 @@ struct ModChannel {
     int32_t hshift, vshift;
 };
 
-struct ModTransform { int32_t begin_c, type; };
+// RCT: begin_c, type. Palette (kind 1; only in the global image's header, see modular_header): begin_c, num_c,
+// nb_colours, nb_deltas, d_pred (j40.h:3762-3792)
+struct ModTransform { int32_t begin_c, type; int32_t kind, num_c, nb_colours, nb_deltas, d_pred; };
 
 struct ModImage {
     int32_t num_channels;
@@ -29,6 +31,7 @@ struct ModImage {
     int32_t nb_transforms;
     ModTransform tr[MOD_MAX_TRANSFORMS];
     int32_t dist_mult;
+    int32_t nb_meta_channels; // palette channels at the front of the list (global image only)
 };
 
 // floor(2^24 / (i + 1)), i in [0, 64): the divisor table of the weighted predictor (j40.h:3905)
@@ -713,7 +716,11 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
 // j40.h:3729-3759, 3816. A tree local to the sub-bitstream follows the header in the stream; reading it is the
 // host's job (`local_tree` non-null: set to 1 and left to the caller; null: the device path, which only gets
 // here for sub-bitstreams whose header the host could not reach -- LF groups of VarDCT frames -- rejects it).
-J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_tree, ModImage &m, int *local_tree = nullptr) {
+// `allow_palette`: palette transforms change the channel list (one meta channel nb_colours x num_c in front, the
+// num_c channels replaced by one index channel); the executor handles that for the global image only.
+J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_tree, ModImage &m, int *local_tree = nullptr,
+                                   bool allow_palette = false) {
+    m.nb_meta_channels = 0;
     int use_global_tree = (int) br.u(1);
     if (use_global_tree && !have_global_tree) { es.set(br, E_MTRE); return; }
     int default_wp = (int) br.u(1);
@@ -725,6 +732,7 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
     if (m.nb_transforms > MOD_MAX_TRANSFORMS) { es.set(br, E_XLIM); return; }
     for (int i = 0; i < m.nb_transforms; ++i) {
         uint32_t id = br.u(2);
+        m.tr[i].kind = 0; m.tr[i].num_c = m.tr[i].nb_colours = m.tr[i].nb_deltas = m.tr[i].d_pred = 0;
         if (id == 0) {
             int32_t begin_c = (int32_t) br.u32(0, 3, 8, 6, 72, 10, 1096, 13);
             int32_t type = (int32_t) br.u32(6, 0, 0, 2, 2, 4, 10, 6);
@@ -732,6 +740,8 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
             m.tr[i].type = type;
             if (type >= 42) { es.set(br, E_RCTT); return; }
             if (begin_c + 3 > m.num_channels) { es.set(br, E_RCTC); return; }
+            if (!(begin_c >= m.nb_meta_channels || begin_c + 3 <= m.nb_meta_channels)) { es.set(br, E_RCTC); return; }
+            if (begin_c < m.nb_meta_channels) { es.set(br, E_TODO); return; } // an RCT over palette channels: not built
             const ModChannel &a = m.ch[begin_c];
             for (int k = 1; k < 3; ++k) {
                 const ModChannel &b = m.ch[begin_c + k];
@@ -740,9 +750,41 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
         } else if (id == 3) {
             es.set(br, E_XFM);
             return;
+        } else if (id == 1) { // palette (j40.h:3762-3792)
+            ModTransform &t = m.tr[i];
+            t.kind = 1;
+            t.begin_c = (int32_t) br.u32(0, 3, 8, 6, 72, 10, 1096, 13);
+            t.num_c = (int32_t) br.u32(1, 0, 3, 0, 4, 0, 1, 13);
+            t.nb_colours = (int32_t) br.u32(0, 8, 256, 10, 1280, 12, 5376, 16);
+            t.nb_deltas = (int32_t) br.u32(0, 0, 1, 8, 257, 10, 1281, 16);
+            t.d_pred = (int32_t) br.u(4);
+            t.type = 0;
+            const int32_t end_c = t.begin_c + t.num_c;
+            if (t.d_pred >= 14) { es.set(br, J40B_4CC('p', 'a', 'l', 'p')); return; }
+            if (end_c > m.num_channels) { es.set(br, J40B_4CC('p', 'a', 'l', 'c')); return; }
+            if (t.begin_c < m.nb_meta_channels) {
+                if (end_c > m.nb_meta_channels) { es.set(br, J40B_4CC('p', 'a', 'l', 'c')); return; }
+                es.set(br, E_TODO); // a palette of palette channels: not built
+                return;
+            }
+            for (int k = t.begin_c + 1; k < end_c; ++k) {
+                const ModChannel &a = m.ch[t.begin_c], &b = m.ch[k];
+                if (a.w != b.w || a.h != b.h || a.hshift != b.hshift || a.vshift != b.vshift) { es.set(br, J40B_4CC('p', 'a', 'l', 'd')); return; }
+            }
+            // delta palettes predict from the restored neighbours (a serial scan per channel): not built
+            if (!allow_palette || t.nb_deltas > 0 || m.num_channels + 2 - t.num_c > MOD_MAX_CH) { es.set(br, E_TODO); return; }
+            const ModChannel input = m.ch[t.begin_c];
+            ModChannel list[MOD_MAX_CH + 1];
+            int n = 0;
+            list[n] = input; list[n].w = t.nb_colours; list[n].h = t.num_c; list[n].stride = t.nb_colours; list[n].hshift = 0; list[n].vshift = -1; list[n].px = nullptr; ++n;
+            for (int k = 0; k < t.begin_c; ++k) list[n++] = m.ch[k];
+            list[n++] = input;
+            for (int k = end_c; k < m.num_channels; ++k) list[n++] = m.ch[k];
+            m.num_channels = n;
+            for (int k = 0; k < n; ++k) m.ch[k] = list[k];
+            m.nb_meta_channels += 1;
         } else {
-            // palette and squeeze change the channel list; not decoded on the device yet (the
-            // reference itself rejects squeeze, j40.h:3812)
+            // squeeze: the reference itself rejects it (j40.h:3812)
             es.set(br, E_TODO);
             return;
         }
@@ -752,7 +794,7 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
         *local_tree = 1;
     }
     m.dist_mult = 0;
-    for (int i = 0; i < m.num_channels; ++i) m.dist_mult = imax(m.dist_mult, m.ch[i].w);
+    for (int i = m.nb_meta_channels; i < m.num_channels; ++i) m.dist_mult = imax(m.dist_mult, m.ch[i].w);
     m.dist_mult = imin(m.dist_mult, 1 << 21);
 }
 

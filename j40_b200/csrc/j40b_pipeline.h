@@ -155,24 +155,37 @@ public:
                 n_lf += im.nlf; n_hf += im.ng;
             } else {
                 im.err_off = wk_alloc(4 * (p.pg_sec.size() + 2));
+                // coded channel list of the global image: palette (meta) channels first, each with its own size
                 int nch = d.num_channels;
-                for (int c = 0; c < nch; ++c) im.plane[c] = wk_alloc(2 * (size_t) d.width * d.height);
-                im.nmod = p.pg_sec.size() + (p.num_gm_channels > 0 ? 1 : 0);
+                for (int c = 0; c < nch; ++c) im.plane[c] = wk_alloc(2 * (size_t) std::max(1, p.gmod.ch[c].w) * std::max(1, p.gmod.ch[c].h));
+                const bool has_global = p.num_gm_channels > 0; // work item 0 = the channels coded in LfGlobal
+                im.nmod = p.pg_sec.size() + (has_global ? 1 : 0);
                 auto spec_lz = [&](uint32_t off) { return off && ((const DCodeSpec *) (p.arena.bytes.data() + off))->lz77_enabled; };
                 const bool wp_g = d.global_tree_uses_wp != 0, lz_g = spec_lz(d.global_spec_off);
                 int gsize = 1 << d.group_size_shift;
                 im.mod.resize(im.nmod);
                 for (size_t g = 0; g < im.nmod; ++g) {
                     ModBuf &mb = im.mod[g];
-                    bool global = p.num_gm_channels > 0;
-                    int gw = global ? d.width : std::min(d.width, ((int) (g % (size_t) d.gcolumns) + 1) * gsize) - (int) (g % (size_t) d.gcolumns) * gsize;
-                    int gh = global ? d.height : std::min(d.height, ((int) (g / (size_t) d.gcolumns) + 1) * gsize) - (int) (g / (size_t) d.gcolumns) * gsize;
+                    const bool global = has_global && g == 0;
+                    const size_t pg = g - (has_global ? 1 : 0);
+                    int gw, gh;
+                    size_t syms = 0;
+                    if (global) {
+                        gw = gh = 1;
+                        for (int c = 0; c < p.num_gm_channels; ++c) {
+                            gw = std::max(gw, p.gmod.ch[c].w); gh = std::max(gh, p.gmod.ch[c].h);
+                            syms += (size_t) p.gmod.ch[c].w * p.gmod.ch[c].h;
+                        }
+                    } else {
+                        gw = std::min(d.width, ((int) (pg % (size_t) d.gcolumns) + 1) * gsize) - (int) (pg % (size_t) d.gcolumns) * gsize;
+                        gh = std::min(d.height, ((int) (pg / (size_t) d.gcolumns) + 1) * gsize) - (int) (pg / (size_t) d.gcolumns) * gsize;
+                        syms = (size_t) (nch - p.num_gm_channels) * gw * gh;
+                    }
                     mb.gw = gw; mb.gh = gh;
-                    const FramePlan::LocalHeader *lh = global ? &p.gmod_local : (g < p.pg_local.size() ? &p.pg_local[g] : nullptr);
+                    const FramePlan::LocalHeader *lh = global ? &p.gmod_local : (pg < p.pg_local.size() ? &p.pg_local[pg] : nullptr);
                     const bool local = lh && lh->present;
                     const bool wp = local ? lh->uses_wp != 0 : wp_g, lz = local ? spec_lz(lh->spec_off) : lz_g;
                     mb.wp = wp ? wk_alloc(4 * 2 * 5 * (size_t) gw) : (size_t) -1;
-                    size_t syms = (size_t) nch * gw * gh;
                     uint32_t capl = 1;
                     while (capl < syms && capl < (1u << 20)) capl <<= 1;
                     mb.lz_mask = capl - 1;
@@ -321,31 +334,43 @@ public:
                 rw->any_err = derr + im.nmod; // summary word written by nobody: per-section words are checked on the host
                 rw->rgba = dwork + im.rgba_off; rw->rgba_stride = results[k].stride;
                 int gsize = 1 << d.group_size_shift;
+                const bool has_global = p.num_gm_channels > 0;
                 for (size_t g = 0; g < im.nmod; ++g) {
                     ModWork &w = mw[g];
                     const ModBuf &mb = im.mod[g];
                     memset(&w, 0, sizeof(w));
                     w.f = dframe; w.arena = darena; w.cs = dcs;
-                    bool global = p.num_gm_channels > 0;
-                    const SectionRef &s = global ? p.gmod_sec : p.pg_sec[g];
+                    const bool global = has_global && g == 0;
+                    const size_t pg = g - (has_global ? 1 : 0);
+                    const SectionRef &s = global ? p.gmod_sec : p.pg_sec[pg];
                     w.sec_off = (uint32_t) s.off; w.sec_size = s.size; w.sec_start_bit = s.start_bit;
-                    w.sidx = global ? 0 : (int32_t) (1 + 3 * d.num_lf_groups + 17 + (int64_t) g);
+                    w.sidx = global ? 0 : (int32_t) (1 + 3 * d.num_lf_groups + 17 + (int64_t) pg);
                     w.header_parsed = global ? 1 : 0;
                     w.is_global = global ? 1 : 0;
+                    w.check_end = global && p.single_section ? 1 : 0;
                     w.tree_off = d.global_tree_off; w.spec_off = d.global_spec_off; w.tree_uses_wp = d.global_tree_uses_wp;
-                    const FramePlan::LocalHeader *lh = global ? &p.gmod_local : (g < p.pg_local.size() ? &p.pg_local[g] : nullptr);
+                    const FramePlan::LocalHeader *lh = global ? &p.gmod_local : (pg < p.pg_local.size() ? &p.pg_local[pg] : nullptr);
                     if (lh && lh->present) {
                         w.preset_err = lh->host_err;
                         w.tree_off = lh->tree_off; w.spec_off = lh->spec_off; w.tree_uses_wp = lh->uses_wp;
                         if (!global) { w.header_parsed = 1; w.sec_start_bit = lh->start_bit; w.m = lh->hdr; }
                     }
-                    int gx = global ? 0 : (int) (g % (size_t) d.gcolumns) * gsize, gy = global ? 0 : (int) (g / (size_t) d.gcolumns) * gsize;
-                    if (global) w.m = p.gmod;
-                    w.m.num_channels = d.num_channels;
-                    for (int c = 0; c < d.num_channels; ++c) {
-                        w.m.ch[c].px = (int16_t *) (dwork + im.plane[c]) + (size_t) gy * d.width + gx;
-                        w.m.ch[c].stride = d.width; w.m.ch[c].w = mb.gw; w.m.ch[c].h = mb.gh;
-                        w.m.ch[c].hshift = w.m.ch[c].vshift = 0;
+                    if (global) {
+                        // the channels coded with the global image: all of them (single group) or the palettes
+                        w.m = p.gmod;
+                        w.m.num_channels = p.num_gm_channels;
+                        for (int c = 0; c < p.num_gm_channels; ++c) {
+                            w.m.ch[c].px = (int16_t *) (dwork + im.plane[c]);
+                            w.m.ch[c].stride = p.gmod.ch[c].w;
+                        }
+                    } else {
+                        const int gx = (int) (pg % (size_t) d.gcolumns) * gsize, gy = (int) (pg / (size_t) d.gcolumns) * gsize;
+                        w.m.num_channels = d.num_channels - p.num_gm_channels;
+                        for (int c = 0; c < w.m.num_channels; ++c) {
+                            w.m.ch[c].px = (int16_t *) (dwork + im.plane[p.num_gm_channels + c]) + (size_t) gy * d.width + gx;
+                            w.m.ch[c].stride = d.width; w.m.ch[c].w = mb.gw; w.m.ch[c].h = mb.gh;
+                            w.m.ch[c].hshift = w.m.ch[c].vshift = 0;
+                        }
                     }
                     w.wp_scratch = mb.wp == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.wp);
                     w.lz_window = mb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.lz);
@@ -413,9 +438,9 @@ public:
                 for (size_t i = 0; i < im.nlf; ++i) if (e[i] && p.lfg_sec[i].rank < best_rank) { best = e[i]; best_rank = p.lfg_sec[i].rank; }
                 for (size_t g = 0; g < im.ng; ++g) if (e[im.nlf + g] && p.pg_sec[g].rank < best_rank) { best = e[im.nlf + g]; best_rank = p.pg_sec[g].rank; }
             } else {
-                bool global = p.num_gm_channels > 0;
+                const bool has_global = p.num_gm_channels > 0;
                 for (size_t g = 0; g < im.nmod; ++g) {
-                    int64_t rank = global ? -2 : p.pg_sec[g].rank;
+                    int64_t rank = has_global && g == 0 ? -2 : p.pg_sec[g - (has_global ? 1 : 0)].rank;
                     if (e[g] && rank < best_rank) { best = e[g]; best_rank = rank; }
                 }
             }

@@ -84,6 +84,8 @@ struct DFrame {
     int32_t num_channels, num_gm_channels, alpha_channel; // alpha_channel < 0: opaque
     int32_t nb_global_transforms;
     ModTransform global_tr[MOD_MAX_TRANSFORMS];
+    int32_t nb_meta_channels;  // palette channels in front of the coded channel list (modular frames)
+    int32_t num_out_channels;  // channels after the inverse global transforms (3 colours + extra channels)
     WPParams global_wp;
 };
 

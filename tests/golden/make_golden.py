@@ -30,6 +30,7 @@ CASES = {
     "vardct_alpha_extra_channel_264x264": lambda: streamgen.vardct(264, 264, seed=9, mix=1, tree=1, alpha=1),
     "modular_rgb_rct_300x200": lambda: streamgen.modular(300, 200, seed=7),
     "modular_local_trees_300x280": lambda: streamgen.modular(300, 280, seed=10, local_tree=1),
+    "modular_palette_300x280": lambda: streamgen.modular(300, 280, seed=11, palette=1),
     "modular_alpha_wp_ans": lambda: streamgen.modular(130, 70, seed=8, alpha=1, tree=2, ans=1, lz77=0),
 }
 

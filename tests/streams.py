@@ -56,6 +56,12 @@ MODULAR_CASES = [
     ("local_tree_odd_groups", 600, 400, 6, dict(local_tree=1)),
     ("local_tree_all_groups_wp_ans", 600, 400, 6, dict(local_tree=2, ans=1, lz77=0, tree=2, alpha=1)),
     ("local_tree_single_group", 200, 100, 6, dict(local_tree=1, ans=1)),
+    # palette transform (j40.h:3762-3792, 4402-4490): table coded with the global image, index channel per group,
+    # implicit entries (index < 0, index >= nb_colours) in a few rows
+    ("palette_single_group", 200, 100, 7, dict(palette=1)),
+    ("palette_groups_prefix_lz77", 600, 400, 7, dict(palette=1)),
+    ("palette_alpha_wp_ans", 600, 400, 7, dict(palette=1, alpha=1, ans=1, lz77=0, tree=2)),
+    ("palette_local_trees_shift7", 300, 300, 7, dict(palette=1, group_shift=7, local_tree=1)),
 ]
 
 

@@ -21,6 +21,8 @@ struct ModularParams {
     bool container = false;
     int smooth = 1;          // 0 = raw synthetic photo, 1 = posterise a little so that runs exist
     int max_clusters = 8;
+    int palette = 0;         // 1: RGB coded through a palette transform (colours posterised to <= 216), no RCT; a few rows
+                             // use the implicit entries (index < 0 and index >= nb_colours)
     int local_tree = 0;      // 1: odd pass groups (or the global image of a single-group frame) carry a tree and code
                              // spec of their own; 2: all of them do and the frame has no global tree at all
 };
@@ -37,6 +39,31 @@ public:
         // full-frame planes after the forward transform
         std::vector<std::vector<int32_t>> plane((size_t) nch, std::vector<int32_t>((size_t) W * (size_t) H));
         Rng rng(P.seed * 31 + 5);
+        Channel pal; // palette transform: meta channel nb_colours x 3 (j40.h:3762-3792)
+        if (P.palette) {
+            nch = P.alpha ? 2 : 1;
+            plane.assign((size_t) nch, std::vector<int32_t>((size_t) W * (size_t) H));
+            std::map<uint32_t, int> index;
+            std::vector<uint32_t> colours;
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+                size_t o = (size_t) y * (size_t) W + (size_t) x;
+                uint32_t key = 0;
+                for (int c = 0; c < 3; ++c) key = key << 8 | (uint32_t) (im.px[o * 3 + (size_t) c] * 5 / 255 * 51);
+                auto it = index.find(key);
+                if (it == index.end()) { it = index.insert({key, (int) colours.size()}).first; colours.push_back(key); }
+                plane[0][o] = it->second;
+                if (P.alpha) plane[1][o] = ((x / 37 + y / 53) % 5 == 0) ? 128 + ((x + y) & 63) : 255;
+            }
+            int K = (int) colours.size();
+            if (H > 24) for (int x = 0; x < W; ++x) for (int r = 0; r < 4; ++r) {
+                plane[0][(size_t) (8 + r) * (size_t) W + (size_t) x] = K + (x % 64);        // 4x4x4 cube
+                plane[0][(size_t) (12 + r) * (size_t) W + (size_t) x] = K + 64 + (x % 125); // 5x5x5 cube
+                plane[0][(size_t) (16 + r) * (size_t) W + (size_t) x] = -1 - (x % 143);     // hard-coded deltas
+            }
+            pal.w = K; pal.h = 3; pal.vshift = -1;
+            pal.px.resize((size_t) K * 3);
+            for (int c = 0; c < 3; ++c) for (int k = 0; k < K; ++k) pal.px[(size_t) c * (size_t) K + (size_t) k] = (int32_t) (colours[(size_t) k] >> (8 * (2 - c)) & 255);
+        } else
         for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
             size_t o = (size_t) y * (size_t) W + (size_t) x;
             int v[3];
@@ -75,6 +102,7 @@ public:
                 }
             }
             int64_t sidx = single ? 0 : 1 + 3 * (int64_t) num_lfg + 17 + g;
+            if (single && P.palette) ch.insert(ch.begin(), pal);
             mt.run(ch, sidx, ts[(size_t) g]);
             if (P.local_tree) group_channels[(size_t) g] = ch;
             stats.lf_symbols += (int64_t) ts[(size_t) g].size();
@@ -86,10 +114,17 @@ public:
         eo.max_clusters = P.max_clusters;
         eo.lz77 = P.lz77;
         if (eo.lz77) for (int g = 0; g < num_groups; ++g) lz77_rle(ts[(size_t) g], eo.min_length, gwidth[(size_t) g], 4);
+        TokStream global_ts; // multi-group frames: the palette is coded with the global image in LfGlobal
+        if (P.palette && !single) {
+            std::vector<Channel> gch{pal};
+            mt.run(gch, 0, global_ts);
+            if (eo.lz77) lz77_rle(global_ts, eo.min_length, pal.w, 4);
+        }
         CodeSpec spec;
         {
             std::vector<const TokStream *> all;
             for (auto &s : ts) all.push_back(&s);
+            all.push_back(&global_ts);
             spec.build(tree.num_leaves, eo, all);
         }
         stats.coef_clusters = spec.nclusters;
@@ -110,7 +145,8 @@ public:
             spec.write(lfglobal);
         }
         ModularHeaderOpts gh;
-        if (P.rct_type >= 0) gh.rcts.push_back({0, P.rct_type});
+        if (P.palette) gh.palettes.push_back({0, 3, pal.w, 0, 0});
+        else if (P.rct_type >= 0) gh.rcts.push_back({0, P.rct_type});
         gh.use_global_tree = !(single ? is_local(0) : !have_global_tree);
         write_modular_header_prefix(lfglobal, gh);
         if (!gh.use_global_tree) { // the same tree, but stored with the sub-bitstream (j40.h:3827-3835)
@@ -120,8 +156,7 @@ public:
         if (single) {
             spec.encode(lfglobal, ts[0]);
         } else {
-            TokStream empty;
-            spec.encode(lfglobal, empty); // an ANS stream still carries its final state
+            spec.encode(lfglobal, global_ts); // (an empty ANS stream still carries its final state)
         }
 
         BitWriter out;

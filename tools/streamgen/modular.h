@@ -316,6 +316,8 @@ struct ModularHeaderOpts {
     bool use_global_tree = true;
     WPParams wp;
     std::vector<std::pair<int, int>> rcts; // (begin_c, type)
+    struct Pal { int begin_c, num_c, nb_colours, nb_deltas, d_pred; };
+    std::vector<Pal> palettes;             // written before the RCTs
 };
 
 inline void write_modular_header_prefix(BitWriter &bw, const ModularHeaderOpts &h) {
@@ -328,7 +330,15 @@ inline void write_modular_header_prefix(BitWriter &bw, const ModularHeaderOpts &
         for (int i = 0; i < 5; ++i) bw.put((uint64_t) h.wp.p3[i], 5);
         for (int i = 0; i < 4; ++i) bw.put((uint64_t) h.wp.w[i], 4);
     }
-    bw.u32((uint32_t) h.rcts.size(), 0, 0, 1, 0, 2, 4, 18, 8);
+    bw.u32((uint32_t) (h.rcts.size() + h.palettes.size()), 0, 0, 1, 0, 2, 4, 18, 8);
+    for (auto &pl : h.palettes) {
+        bw.put(1, 2); // palette
+        bw.u32((uint32_t) pl.begin_c, 0, 3, 8, 6, 72, 10, 1096, 13);
+        bw.u32((uint32_t) pl.num_c, 1, 0, 3, 0, 4, 0, 1, 13);
+        bw.u32((uint32_t) pl.nb_colours, 0, 8, 256, 10, 1280, 12, 5376, 16);
+        bw.u32((uint32_t) pl.nb_deltas, 0, 0, 1, 8, 257, 10, 1281, 16);
+        bw.put((uint64_t) pl.d_pred, 4);
+    }
     for (auto &r : h.rcts) {
         bw.put(0, 2); // RCT
         bw.u32((uint32_t) r.first, 0, 3, 8, 6, 72, 10, 1096, 13);
