@@ -1053,6 +1053,35 @@ struct Parser {
         }
     }
 
+    // Decodes channels [0, count) of a modular image on the host, where a sub-bitstream sits in the middle of what
+    // the host has to read anyway: the extra channels of a single-section VarDCT frame (between LfGlobal and
+    // HfGlobal) and RAW dequantisation matrices (inside HfGlobal). Runs the device's own channel decoder
+    // (modular_channel_t is __host__ __device__); a few thousand to 65536 samples per channel.
+    void host_modular_channels(ModImage &m, int count, const FramePlan::LocalHeader &lh, int32_t sidx, std::vector<std::vector<int16_t>> &planes) {
+        const DFrame &d = plan.df;
+        HostCode hc;
+        hc.begin(arena, lh.present ? lh.spec_off : d.global_spec_off);
+        const DTreeNode *tree = (const DTreeNode *) (arena.bytes.data() + (lh.present ? lh.tree_off : d.global_tree_off));
+        const bool uses_wp = (lh.present ? lh.uses_wp : d.global_tree_uses_wp) != 0;
+        planes.assign((size_t) m.num_channels, std::vector<int16_t>());
+        int maxw = 1;
+        for (int c = 0; c < m.num_channels; ++c) {
+            planes[(size_t) c].assign((size_t) std::max(1, m.ch[c].w) * (size_t) std::max(1, m.ch[c].h), 0);
+            m.ch[c].px = planes[(size_t) c].data();
+            m.ch[c].stride = m.ch[c].w;
+            maxw = std::max(maxw, m.ch[c].w);
+        }
+        std::vector<int32_t> wp_scratch(uses_wp ? (size_t) maxw * 10 : 1);
+        for (int c = 0; c < count && !err; ++c) {
+            if (m.ch[c].w <= 0 || m.ch[c].h <= 0) continue;
+            if (uses_wp) modular_channel_t<true>(br, hc.es, hc.cc, hc.cs, tree, wp_scratch.data(), h_div24_table.v, m, c, sidx);
+            else modular_channel_t<false>(br, hc.es, hc.cc, hc.cs, tree, wp_scratch.data(), h_div24_table.v, m, c, sidx);
+            if (hc.es.err) err = hc.es.err;
+            else if (overrun()) err = E_SHRT;
+        }
+        hfinish(hc);
+    }
+
     void lf_global() { // j40.h:6257-6340
         ImageInfo &im = plan.im;
         FrameInfo &f = plan.fh;
@@ -1135,7 +1164,34 @@ struct Parser {
     void read_dq_matrix(int idx, int rows, int columns) {
         int mode = (int) u(3);
         if (mode == 0) return;
-        if (mode == 7) FAIL(E_TODO); // RAW matrices are a modular sub-image inside HfGlobal: not supported yet
+        if (mode == 7) { // RAW: a 3-channel modular image of columns x rows weights over a common denominator (j40.h:4705-4743)
+            const float denom = f16();
+            if (err) return;
+            CHECK(!(denom == 0.0f), E4("dqm0")); // j40__surely_nonzero
+            const float inv_denom = 1.0f / denom;
+            ModImage m;
+            memset(&m, 0, sizeof(m));
+            m.num_channels = 3;
+            for (int c = 0; c < 3; ++c) { m.ch[c].w = columns; m.ch[c].h = rows; m.ch[c].stride = columns; }
+            FramePlan::LocalHeader lh;
+            host_modular_header(m, lh);
+            if (err) return;
+            std::vector<std::vector<int16_t>> planes;
+            host_modular_channels(m, 3, lh, (int32_t) (1 + 3 * plan.fh.num_lf_groups + idx), planes);
+            if (err) return;
+            for (int t = m.nb_transforms - 1; t >= 0; --t) {
+                ModImage one = m;
+                one.nb_transforms = 1;
+                one.tr[0] = m.tr[t];
+                inverse_transforms(one, 0, 1);
+            }
+            std::vector<float> mat((size_t) rows * columns * 3);
+            for (int c = 0; c < 3; ++c) for (int i = 0; i < rows * columns; ++i) mat[(size_t) i * 3 + (size_t) c] = (float) planes[(size_t) c][(size_t) i] * inv_denom;
+            uint32_t off = arena.alloc(mat.size() * 4, 16);
+            memcpy(arena.at<uint8_t>(off), mat.data(), mat.size() * 4);
+            plan.custom_dq_off[idx] = off;
+            return;
+        }
         static const int8_t HOW[7][4] = {{0, 0, 0, 0}, {1, 3, 3, 0}, {1, 6, 6, 0}, {1, 2, 2, 1}, {1, 1, 0, 1}, {1, 9, 6, 2}, {1, 0, 0, 1}};
         int nparams = HOW[mode][1], nscaled = HOW[mode][2], ndct = HOW[mode][3];
         if (HOW[mode][0]) CHECK(rows == 8 && columns == 8, E4("dqm?"));
@@ -1651,7 +1707,16 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
     } else {
         // single section: LfGlobal, HfGlobal, LfGroup, PassGroup back to back
         if (!f.is_modular) {
-            if (plan.gmod_has_stream) return plan.err = E_TODO; // extra channels in a single-group VarDCT frame
+            if (plan.gmod_has_stream) {
+                // extra channels of a single-group VarDCT frame: coded right here, between LfGlobal and HfGlobal;
+                // the reference decodes and then discards them (j40.h:7869-7870)
+                if (plan.gmod.nb_transforms != 0) return plan.err = E_TODO;
+                std::vector<std::vector<int16_t>> scratch;
+                ModImage m = plan.gmod;
+                q.host_modular_channels(m, plan.num_gm_channels, plan.gmod_local, 0, scratch);
+                if (q.err) return plan.err = q.err;
+                plan.gmod_has_stream = false;
+            }
             q.hf_global();
             if (!q.err) q.check_overrun();
             if (q.err) return plan.err = q.err;

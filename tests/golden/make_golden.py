@@ -28,6 +28,7 @@ CASES = {
     "vardct_container_jxlp_lz77": lambda: streamgen.vardct(96, 80, seed=5, mix=1, container=1, jxlp=1, lz77=1),
     "vardct_permuted_orders_presets": lambda: streamgen.vardct(300, 280, seed=6, mix=1, permuted=1, orders=0x1f, presets=2, block_ctx=1),
     "vardct_alpha_extra_channel_264x264": lambda: streamgen.vardct(264, 264, seed=9, mix=1, tree=1, alpha=1),
+    "vardct_raw_dq_alpha_136x120": lambda: streamgen.vardct(136, 120, seed=12, mix=1, tree=1, raw_dq=0x11, alpha=1),
     "modular_rgb_rct_300x200": lambda: streamgen.modular(300, 200, seed=7),
     "modular_local_trees_300x280": lambda: streamgen.modular(300, 280, seed=10, local_tree=1),
     "modular_palette_300x280": lambda: streamgen.modular(300, 280, seed=11, palette=1),

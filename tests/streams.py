@@ -33,6 +33,13 @@ VARDCT_CASES = [
     # decodes and then discards it: A = 255)
     ("alpha_extra_channel_ans", 520, 392, 22, dict(mix=1, tree=1, alpha=1)),
     ("alpha_extra_channel_prefix", 300, 520, 23, dict(mix=1, tree=2, alpha=1, ans=0)),
+    # ... in a single-group frame: coded between LfGlobal and HfGlobal, decoded (and dropped) by the host
+    ("alpha_single_group", 200, 100, 24, dict(mix=1, tree=1, alpha=1)),
+    ("alpha_single_group_256_prefix", 256, 256, 25, dict(mix=1, tree=2, alpha=1, ans=0)),
+    # RAW dequantisation matrices (modular images inside HfGlobal, j40.h:4705-4743) for 8x8 and 16x16
+    ("raw_dq_8x8_single_group", 200, 136, 26, dict(mix=1, tree=1, raw_dq=1)),
+    ("raw_dq_8x8_16x16", 520, 392, 27, dict(mix=1, tree=1, raw_dq=0x11)),
+    ("raw_dq_prefix_alpha", 300, 200, 28, dict(mix=1, tree=2, raw_dq=0x11, ans=0, alpha=1)),
 ]
 
 MODULAR_CASES = [

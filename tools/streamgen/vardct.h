@@ -41,6 +41,7 @@ struct VarDCTParams {
     bool custom_cfl_base = false;
     bool smooth_lf = true;     // false sets skip_adapt_lf_smooth
     int extra_prec = 0;
+    int raw_dq = 0;            // bit i: dequantisation matrix i (only 0 = 8x8 and 4 = 16x16) is sent RAW, as a modular image
     bool alpha = false;        // 8-bit alpha extra channel, coded per pass group with the global tree (multi-group frames only)
     int tree_preset = 1;       // 0 single gradient leaf, 1 WP + property tree, 2 stress tree
     bool custom_block_ctx = false;
@@ -204,6 +205,16 @@ public:
         JG_CHECK(im.w == P.width && im.h == P.height);
         XYBImage xyb = rgb_to_xyb(im);
         setup_contexts();
+        for (int i = 0; i < 17; ++i) if ((P.raw_dq >> i) & 1) { // weights as the decoder will see them: integers over 2
+            raw_int[i].resize(T.dq[i].size());
+            raw_dq[i].resize(T.dq[i].size());
+            for (size_t k = 0; k < T.dq[i].size(); ++k) {
+                int32_t v = (int32_t) std::lround((double) T.dq[i][k] * 2.0);
+                v = std::min(32767, std::max(1, v));
+                raw_int[i][k] = v;
+                raw_dq[i][k] = (float) v / 2.0f;
+            }
+        }
         group_cols = (P.width + 255) / 256; group_rows = (P.height + 255) / 256;
         lfg_cols = (P.width + 2047) / 2048; lfg_rows = (P.height + 2047) / 2048;
         int num_groups = group_cols * group_rows, num_lfg = lfg_cols * lfg_rows;
@@ -245,9 +256,25 @@ public:
             stats.lf_symbols += (int64_t) lf_ts[(size_t) i].size() + (int64_t) meta_ts[(size_t) i].size();
         }
         // extra channel (alpha): one modular sub-stream per pass group, after the HF coefficients (j40.h:7024-7033)
+        for (int i = 0; i < 17; ++i) if ((P.raw_dq >> i) & 1) {
+            int rows = i == 0 ? 8 : 16, cols = rows;
+            JG_CHECK(i == 0 || i == 4);
+            std::vector<Channel> ch(3);
+            for (int c = 0; c < 3; ++c) {
+                ch[(size_t) c].w = cols; ch[(size_t) c].h = rows;
+                for (int k = 0; k < rows * cols; ++k) ch[(size_t) c].px.push_back(raw_int[i][(size_t) k * 3 + (size_t) c]);
+            }
+            mt.run(ch, 1 + 3 * num_lfg + i, raw_ts[i]);
+        }
         std::vector<TokStream> ec_ts;
-        if (P.alpha) {
-            JG_CHECK(num_groups > 1);
+        if (P.alpha && num_groups == 1) {
+            // single group: the channel fits a group and is coded with the global image in LfGlobal (j40.h:6327-6337)
+            std::vector<Channel> ch(1);
+            ch[0].w = P.width; ch[0].h = P.height;
+            for (int Y = 0; Y < P.height; ++Y) for (int X = 0; X < P.width; ++X) ch[0].px.push_back(((X / 37 + Y / 53) % 5 == 0) ? 200 + ((X >> 3) & 7) : 255);
+            mt.run(ch, 0, ec_global_ts);
+            stats.lf_symbols += (int64_t) ec_global_ts.size();
+        } else if (P.alpha) {
             ec_ts.resize((size_t) num_groups);
             for (int g = 0; g < num_groups; ++g) {
                 int grow = g / group_cols, gcol = g % group_cols;
@@ -273,6 +300,8 @@ public:
             for (auto &s : lf_ts) all.push_back(&s);
             for (auto &s : meta_ts) all.push_back(&s);
             for (auto &s : ec_ts) all.push_back(&s);
+            all.push_back(&ec_global_ts);
+            for (int i = 0; i < 17; ++i) all.push_back(&raw_ts[i]);
             mspec.build(tree.num_leaves, mo, all);
         }
 
@@ -300,6 +329,7 @@ public:
         BitWriter lfglobal;
         write_lf_global(lfglobal, tree, mspec, mo);
         BitWriter hfglobal;
+        mspec_ptr = &mspec;
         write_hf_global(hfglobal, num_groups, cspec);
         std::vector<BitWriter> lfsec((size_t) num_lfg), pgsec((size_t) num_groups);
         for (int i = 0; i < num_lfg; ++i) {
@@ -317,7 +347,7 @@ public:
             BitWriter &bw = pgsec[(size_t) g];
             bw.put((uint64_t) group_preset[(size_t) g], ceil_lg((uint32_t) P.num_hf_presets));
             cspec.encode(bw, hf_ts[(size_t) g]);
-            if (P.alpha) {
+            if (P.alpha && num_groups > 1) {
                 ModularHeaderOpts mh;
                 write_modular_header_prefix(bw, mh);
                 mspec.encode(bw, ec_ts[(size_t) g]);
@@ -585,7 +615,7 @@ private:
         static const float QBIAS[3] = {1.0f - 0.05465007330715401f, 1.0f - 0.07005449891748593f, 1.0f - 0.049935103337343655f};
         const DctSel &d = kDctSel[vb.dctsel];
         int R = 1 << d.log_rows, C = 1 << d.log_cols, size = R * C;
-        const std::vector<float> &dq = T.dq[d.param_idx];
+        const std::vector<float> &dq = raw_dq[d.param_idx].empty() ? T.dq[d.param_idx] : raw_dq[d.param_idx];
         JG_CHECK((int) dq.size() == size * 3);
         float mult[3];
         mult[1] = 65536.0f / (float) P.global_scale / (float) vb.hfmul;
@@ -819,6 +849,12 @@ public:
         return out;
     }
 
+    TokStream ec_global_ts; // alpha of a single-group frame
+    std::vector<float> raw_dq[17];   // weights actually in force where a matrix is sent RAW (multiples of 1/2)
+    std::vector<int32_t> raw_int[17];
+    TokStream raw_ts[17];
+    const CodeSpec *mspec_ptr = nullptr;
+
 private:
     void write_lf_global(BitWriter &bw, const MATree &tree, const CodeSpec &mspec, const EntropyOpts &mo) {
         bw.bit(1); // LF dequant defaults
@@ -865,8 +901,7 @@ private:
         if (P.alpha) {
             ModularHeaderOpts gh;
             write_modular_header_prefix(bw, gh);
-            TokStream empty;
-            mspec.encode(bw, empty); // an ANS stream still carries its final state
+            mspec.encode(bw, ec_global_ts); // (an empty ANS stream still carries its final state)
         }
     }
 
@@ -899,7 +934,19 @@ private:
     }
 
     void write_hf_global(BitWriter &bw, int num_groups, const CodeSpec &cspec) {
-        bw.bit(1); // default dequantisation matrices
+        if (!P.raw_dq) {
+            bw.bit(1); // default dequantisation matrices
+        } else {
+            bw.bit(0);
+            for (int i = 0; i < 17; ++i) {
+                if (!((P.raw_dq >> i) & 1)) { bw.put(0, 3); continue; } // library default
+                bw.put(7, 3); // RAW (j40.h:4705-4743)
+                bw.f16(2.0f); // denominator
+                ModularHeaderOpts mh;
+                write_modular_header_prefix(bw, mh);
+                mspec_ptr->encode(bw, raw_ts[i]);
+            }
+        }
         bw.put((uint64_t) (P.num_hf_presets - 1), ceil_lg((uint32_t) num_groups));
         // HfPass (one pass)
         int used = P.custom_orders & 0x1fff;
