@@ -518,7 +518,7 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
     val += mod_predict(PRED >= 0 ? PRED : leaf.predictor, pw, pn, pnw, pne, pnn, pww, pnee, USE_WP ? wp.pred[4] : 0, &bad);
     if (bad) es.set(br, E_PRED);
     if (es.err) return false; // uniform: every lane sees the same error
-    if (val < -32768 || val > 32767) { es.set(br, E_POVF); return false; }
+    if ((uint32_t) (val + 32768) > 65535u) { es.set(br, E_POVF); return false; }
     S.cur[x] = (int16_t) val;
     S.prev2 = S.prev;
     S.prev = val;
