@@ -152,6 +152,8 @@ def main():
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w, h = args.width, args.height

@@ -377,28 +377,36 @@ J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, const
     return true;
 }
 
-// `xs` = x relative to the start of the current segment of the row (refp holds one segment)
+// `xs` = x relative to the start of the current segment of the row (refp holds one segment).
+// INTERIOR: x >= 2, so the x == 0 special case of property 8 cannot apply. The sum is written as independent
+// pairs (integer addition wraps, so the grouping does not change the value) to keep the dependent chain short,
+// and the reference-property value is loaded unconditionally and selected (lanes differ in `refslot`; a branch
+// here would diverge on every sample).
+template <bool INTERIOR>
 J40B_HD J40B_INLINE bool simt_decision(const SimtLane &L, int32_t x, int32_t xs, int32_t y, int32_t pn, int32_t pw, int32_t pnw, int32_t pne,
                                        int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr, const int32_t *refp, int32_t cap) {
-    int32_t v = L.c[0] * pn + L.c[1] * pw + L.c[2] * pnw + L.c[3] * pne + L.c[4] * pnn + L.c[5] * pww + L.c[6] * pnww
-              + L.cx * x + L.cy * y + L.ce * maxerr;
-    if (L.refslot >= 0) v = refp[(size_t) L.refslot * cap + xs];
-    if ((L.flags & 2) && x == 0) v = pw;
+    const int32_t s0 = L.c[0] * pn + L.c[1] * pw, s1 = L.c[2] * pnw + L.c[3] * pne, s2 = L.c[4] * pnn + L.c[5] * pww;
+    const int32_t s3 = L.c[6] * pnww + L.cx * x, s4 = L.cy * y + L.ce * maxerr;
+    int32_t v = ((s0 + s1) + (s2 + s3)) + s4;
+    const int32_t rv = refp[(size_t) (L.refslot >= 0 ? L.refslot : 0) * cap + xs];
+    if (L.refslot >= 0) v = rv;
+    if (!INTERIOR && (L.flags & 2) && x == 0) v = pw;
     if (L.flags & 1) v = iabs(v);
     return (L.flags & 4) && v > L.thr;
 }
 
 // index (into ModSmem::leaves) of the leaf the current sample falls into
+template <bool INTERIOR>
 J40B_HD J40B_INLINE int32_t simt_tree_leaf(const SimtLane *tab, const SimtLane &mine, int32_t x, int32_t xs, int32_t y, int32_t pn, int32_t pw,
                                            int32_t pnw, int32_t pne, int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr,
                                            const int32_t *refp, int32_t cap) {
 #ifdef __CUDA_ARCH__
-    const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision(mine, x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
+    const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision<INTERIOR>(mine, x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
     const uint32_t hit = __ballot_sync(0xffffffffu, mine.leaf_node >= 0 && (dec & mine.care) == mine.want);
     return __ffs((int) hit) - 1;
 #else
     uint32_t dec = 0;
-    for (int j = 0; j < SIMT_LANES; ++j) dec |= (uint32_t) simt_decision(tab[j], x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap) << j;
+    for (int j = 0; j < SIMT_LANES; ++j) dec |= (uint32_t) simt_decision<INTERIOR>(tab[j], x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap) << j;
     for (int j = 0; j < SIMT_LANES; ++j) if (tab[j].leaf_node >= 0 && (dec & tab[j].care) == tab[j].want) return j;
     return -1;
 #endif
@@ -509,7 +517,7 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
         if (iabs(maxerr) < iabs(wp.te_ne)) maxerr = wp.te_ne;
     }
 
-    const int32_t li = simt_tree_leaf(S.tab, mine, x, x - S.seg0, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
+    const int32_t li = simt_tree_leaf<INTERIOR>(S.tab, mine, x, x - S.seg0, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
     const SimtLeaf leaf = S.leaves[li];
     int32_t val;
     if (MODE == 1 || !code_copy(cs, val)) val = code_cluster<false, MODE>(br, es, cc, cs, leaf.cl, S.dist_mult);
