@@ -27,6 +27,11 @@ if ROOT not in sys.path:
 STREAM_OPTS = dict(mix=1, tree=1, hfmul=10, hfmul_var=4)  # the "d1/e6-like" preset
 
 
+def workload_name(w, h, frames, distinct):
+    return (f"batch of {frames} independent {w}x{h} VarDCT frames per GPU ({distinct} distinct, cycled), "
+            f"tools/streamgen d1/e6-like preset {STREAM_OPTS}")
+
+
 def _gen_one(args):
     w, h, seed = args
     from tools import streamgen
@@ -105,8 +110,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "Mpixels/s decoded (4K VarDCT batch)", "value": mpix, "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w}x{h} VarDCT frames (tools/streamgen d1/e6-like preset), reference j40.h -O3 -ffp-contract=off",
-                   "frames_per_step": nproc, "processes": nproc},
+        "config": {"workload": workload_name(w, h, args.frames_per_gpu, args.distinct),
+                   "implementation": "reference j40.h (unmodified, -O3 -ffp-contract=off) on the host CPU, one process per frame",
+                   "frames_per_step": nproc, "processes": nproc,
+                   "sample": f"each step decodes {nproc} frames of the workload (one per process) instead of all {args.frames_per_gpu}"},
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": nproc, "kind": "reference",
                          "sample": f"{nproc} frames per step, one process per frame, {args.steps} steps"},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -357,8 +364,7 @@ def main():
         "metric": "Mpixels/s decoded (4K VarDCT batch)", "value": value, "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch of {F} independent {w}x{h} VarDCT frames per GPU ({args.distinct} distinct, cycled), "
-                               f"tools/streamgen d1/e6-like preset {STREAM_OPTS}",
+        "config": {"workload": workload_name(w, h, F, args.distinct),
                    "frames_per_gpu": F, "groups_per_gpu": F * ((w + 255) // 256) * ((h + 255) // 256),
                    "compressed_bytes_per_gpu": comp_bytes, "bits_per_pixel": 8.0 * comp_bytes / pixels,
                    "hf_symbols_per_pixel": sum(s["hf_symbols"] for s in stats) / (len(stats) * w * h),

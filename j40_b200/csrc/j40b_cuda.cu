@@ -20,7 +20,7 @@ static bool cuda_ok(cudaError_t e) { return e == cudaSuccess; }
 
 struct CudaBackend {
     int device = 0;
-    cudaStream_t stream = nullptr, stream_lo = nullptr;
+    cudaStream_t stream = nullptr;
     bool ok = false;
     int num_sms = 148;
     float *big_pool = nullptr;
@@ -38,11 +38,7 @@ struct CudaBackend {
         cudaDeviceProp prop;
         if (!cuda_ok(cudaGetDeviceProperties(&prop, dev))) return false;
         num_sms = prop.multiProcessorCount;
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        const char *pe = getenv("J40B_PRIO"); // 1: back kernels on a lowest-priority side stream
-        if (!cuda_ok(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, pe && atoi(pe) ? prio_hi : 0))) return false;
-        if (pe && atoi(pe) == 1 && !cuda_ok(cudaStreamCreateWithPriority(&stream_lo, cudaStreamNonBlocking, prio_lo))) return false;
+        if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
         if (!kl_init_lf() || !kl_init_back() || !kl_init_mod()) return false;
         ok = true;
@@ -54,7 +50,6 @@ struct CudaBackend {
         if (big_pool) cudaFree(big_pool);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
-        if (stream_lo) cudaStreamDestroy(stream_lo);
         ok = false;
     }
     void *dev_alloc(size_t n) { void *p = nullptr; cudaSetDevice(device); if (!cuda_ok(cudaMalloc(&p, n ? n : 1))) return nullptr; return p; }
@@ -101,19 +96,6 @@ struct CudaBackend {
         ++launches;
     }
     void launch_back(const BackWork *w, int n) {
-        cudaStream_t main_stream = stream;
-        if (stream_lo) { // the short-block throughput kernels yield block slots to the latency-bound serial decoders
-            cudaEventRecord(ev[7], stream);
-            cudaStreamWaitEvent(stream_lo, ev[7], 0);
-            stream = stream_lo;
-        }
-        launch_back_on(w, n);
-        if (stream_lo) {
-            stream = main_stream;
-            cudaStreamWaitEvent(stream, ev[4], 0);
-        }
-    }
-    void launch_back_on(const BackWork *w, int n) {
         kl_back_tile(n, stream, w);
         cudaEventRecord(ev[3], stream);
         ++launches;

@@ -33,10 +33,6 @@ __global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
 
 bool kl_init_lf() {
     const int lf_smem = (int) (SPEC_COPY_BYTES + 4 * warp_slice_bytes(LF_ROW_CAP));
-    if (const char *e = getenv("J40B_LF_CARVEOUT")) { // experiment: shared-memory carve-out (percent) while these kernels run
-        cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-        cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-    }
     return cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
            cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
 }
