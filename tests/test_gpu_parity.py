@@ -138,6 +138,35 @@ def test_batch_reuse_and_async_readback(oracle, gen):
         b.close()
 
 
+def test_phase_control_and_stage_timeline(oracle, gen):
+    """j40b_batch_after orders one batch behind a stage of another; j40b_batch_event_ms reports when the stages of
+    a decode ended relative to a mark (the diagnostics DESIGN.md's pipelining analysis is based on)"""
+    datas = [streams.make(gen, "vardct", 520, 392, 70 + i, dict(mix=1, tree=1)) for i in range(3)]
+    a, b = J.Batch(0), J.Batch(0)
+    for d in datas:
+        a.add(d)
+        b.add(d)
+    a.upload(); b.upload()
+    a.mark(0)
+    a.decode()
+    assert b.after(a, 2) == 0          # b starts only when a's decode has finished completely
+    b.decode()
+    a.join(b)
+    a.mark(1)
+    assert a.wait() == 0 and b.wait() == 0
+    total = a.mark_ms()
+    ev_a = [a.event_ms(a, i) for i in (0, 5, 6, 1, 2, 3, 4)]
+    ev_b = [b.event_ms(a, i) for i in (0, 5, 6, 1, 2, 3, 4)]
+    assert all(x >= 0 for x in ev_a + ev_b) and ev_a == sorted(ev_a) and ev_b == sorted(ev_b)
+    assert ev_b[1] >= ev_a[-1] - 1e-3 and ev_b[-1] <= total + 1e-3   # b's first kernel ended after a's last
+    km = a.kernel_ms()
+    assert abs(km["lf_group"] - (km["lf_image"] + km["lf_hfmeta"] + km["lf_llf"])) < 0.05
+    for i, d in enumerate(datas):
+        want, _, _, _ = oracle.decode(d)
+        assert np.array_equal(a.read_pixels(i), want) and np.array_equal(b.read_pixels(i), want)
+    a.close(); b.close()
+
+
 def test_sharded_decode_two_ranks_one_gpu(oracle, gen):
     """the sharding helper with the real GPU decoder: two 'ranks' (sequential here) cover the list once"""
     import hashlib

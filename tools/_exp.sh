@@ -1,16 +1,4 @@
-run() { # name, args
-  name=$1; shift
-  timeout 400 python bench.py "$@" > gpurun_out/x_$name.json 2> gpurun_out/x_$name.err
-  python - <<PY
-import json
-try:
-    d=json.loads([l for l in open("gpurun_out/x_$name.json") if l.startswith("{")][-1])
-    print("$name", "value %.0f ms/step %.1f e2e %.0f" % (d["value"], d["ms_per_step"], d["e2e"]["value"] if d["e2e"] else 0), d["e2e"]["includes"][-60:], d["device_bytes"])
-except Exception as e:
-    print("$name failed", e); print(open("gpurun_out/x_$name.err").read()[-800:])
-PY
-  grep "e2e host" gpurun_out/x_$name.err
-}
-export J40B_TIMELINE=1
-( time run sets2 --steps 24 --warmup 3 ) 2>&1 | grep -v "^$\|user\|sys"
-run sets2s6 --steps 24 --warmup 3 --streams 6
+timeout 800 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 400 python bench.py > gpurun_out/bench_v7.json 2> gpurun_out/bench_v7.err; tail -c 1500 gpurun_out/bench_v7.json; tail -2 gpurun_out/bench_v7.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v7_ref.json 2>> gpurun_out/bench_v7.err; cut -c1-300 gpurun_out/bench_v7_ref.json
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
