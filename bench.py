@@ -35,6 +35,25 @@ def workload_name(w, h, frames, distinct):
             f"tools/streamgen d1/e6-like preset {STREAM_OPTS}")
 
 
+def host_memory_budget():
+    """bytes of host memory available to this process tree: MemAvailable, capped by the cgroup limit if there is one"""
+    avail = 1 << 62
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit():
+                avail = min(avail, int(v))
+        except Exception:
+            pass
+    return avail
+
+
 def _gen_one(args):
     w, h, seed = args
     from tools import streamgen
@@ -269,7 +288,17 @@ def main():
         # phases, and a phase-staggered mix of LF / HF / tile kernels runs ~40 % slower than waves.
         W = len(batches)
         sets = max(1, args.e2e_sets)
-        objs = list(batches)
+        # every object in flight owns a pinned destination for its frames (2.1 GB at 64 x 4K): stay well inside the
+        # host memory this rank can count on (all ranks of the node allocate the same)
+        per_obj = F * h * b.info(0)[2]
+        budget = host_memory_budget() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        if sets * W * per_obj > 0.5 * budget:
+            sets = 1
+        if W * per_obj > 0.5 * budget:
+            W = max(2, int(0.5 * budget / per_obj))
+        if sets > 1 and (sets - 1) * W * b.stat(0) > 0.8 * torch.cuda.mem_get_info()[0]:
+            sets = 1  # not enough free HBM for a second group of batch objects
+        objs = list(batches[:W])
         for m in range(W, sets * W):
             bm = J.Batch(local_rank)
             objs.append(bm)
