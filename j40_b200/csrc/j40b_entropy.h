@@ -162,13 +162,11 @@ J40B_HD J40B_INLINE void ans_seed(BitReader &br, uint32_t &state) {
     state |= br.u(16) << 16;
 }
 
-template <bool INIT_CHECK = true>
-J40B_HD J40B_INLINE int32_t ans_symbol(BitReader &br, uint32_t &state, int log_bucket_size, const uint64_t *table) {
-    if (INIT_CHECK && state == 0) ans_seed(br, state);
+// the rANS step once the alias entry `e` of bucket (state & 0xfff) >> log_bucket_size is known
+J40B_HD J40B_INLINE int32_t ans_symbol_entry(BitReader &br, uint32_t &state, int log_bucket_size, uint64_t e) {
     uint32_t idx = state & 0xfff;
     uint32_t i = idx >> log_bucket_size;
     uint32_t p = idx & ((1u << log_bucket_size) - 1);
-    uint64_t e = table[i];
     uint32_t lo = (uint32_t) e, hi = (uint32_t) (e >> 32);
     bool own = p < (lo & 0xff);
     uint32_t sym = own ? i : ((lo >> 8) & 0xff);
@@ -177,6 +175,12 @@ J40B_HD J40B_INLINE int32_t ans_symbol(BitReader &br, uint32_t &state, int log_b
     state = d * (state >> 12) + off + p;
     if (state < (1u << 16)) state = (state << 16) | br.u(16);
     return (int32_t) sym;
+}
+
+template <bool INIT_CHECK = true>
+J40B_HD J40B_INLINE int32_t ans_symbol(BitReader &br, uint32_t &state, int log_bucket_size, const uint64_t *table) {
+    if (INIT_CHECK && state == 0) ans_seed(br, state);
+    return ans_symbol_entry(br, state, log_bucket_size, table[(state & 0xfff) >> log_bucket_size]);
 }
 
 J40B_HD J40B_INLINE int32_t prefix_symbol(BitReader &br, int root_bits, const uint32_t *table) {

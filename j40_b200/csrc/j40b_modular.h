@@ -429,6 +429,10 @@ struct WpSimt {
 struct SimtCtx {
     const SimtLane *tab; const SimtLeaf *leaves; const int32_t *refp; const int32_t *div24;
     int32_t cap, width, y, seg0, dist_mult, my_i;
+    // device, per lane: the alias table of "my" leaf's cluster (any valid table for lanes without a leaf), read one
+    // sample ahead of the tree decision; masks selecting this lane's weighted sub-predictor without branches
+    const uint64_t *my_table;
+    int32_t m0, m1, m2, m4;
     int16_t *cur; const int16_t *nrow, *nnrow;
     int32_t *err; const int32_t *nerr;
     int32_t prev, prev2, n_ww, n_w, n_c, n_e; // the two samples to the left; sliding window over the row above
@@ -474,6 +478,13 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
     const int32_t pnww = INTERIOR ? S.n_ww : (x > 1 && y > 0 ? S.n_ww : pww);
     WpSimt &wp = S.wp;
     int32_t maxerr = 0;
+#ifdef __CUDA_ARCH__
+    // MODE 1 (rANS, no LZ77): the bucket of the next symbol depends on the state alone, which cluster's table it
+    // is looked up in depends on the leaf. Every leaf lane fetches the entry of its own cluster now; the load
+    // completes under the predictor and tree arithmetic, and the lane of the chosen leaf hands it over by shuffle.
+    uint64_t e_mine = 0;
+    if (MODE == 1) e_mine = S.my_table[(cs.ans_state & 0xfff) >> cc.log_bucket];
+#endif
     if (USE_WP) {
         // j40.h:4011-4072
         const WPParams &wpp = S.wpp;
@@ -520,6 +531,14 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
     const int32_t li = simt_tree_leaf<INTERIOR>(S.tab, mine, x, x - S.seg0, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
     const SimtLeaf leaf = S.leaves[li];
     int32_t val;
+#ifdef __CUDA_ARCH__
+    if (MODE == 1) {
+        const uint32_t elo = __shfl_sync(0xffffffffu, (uint32_t) e_mine, li), ehi = __shfl_sync(0xffffffffu, (uint32_t) (e_mine >> 32), li);
+        val = ans_symbol_entry(br, cs.ans_state, cc.log_bucket, (uint64_t) ehi << 32 | elo);
+        val = hybrid_int(br, es, val, leaf.cl.cfg);
+        if (es.err) val = 0;
+    } else
+#endif
     if (MODE == 1 || !code_copy(cs, val)) val = code_cluster<false, MODE>(br, es, cc, cs, leaf.cl, S.dist_mult);
     val = unpack_signed(val) * leaf.multiplier + leaf.offset;
     bool bad = false;
@@ -537,8 +556,16 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
         const int32_t te = wp.pred[4] - v8;
         for (int k = 0; k < WP_NL; ++k) {
             const int i = WP_NL == 1 ? S.my_i : k;
+#ifdef __CUDA_ARCH__
+            // this lane's sub-predictor by masks (lane constants) instead of a three-way branch on the lane index
+            const int32_t p3 = wp.pred[3];
+            const int32_t psel = p3 ^ ((wp.pred[0] ^ p3) & S.m0) ^ ((wp.pred[1] ^ p3) & S.m1) ^ ((wp.pred[2] ^ p3) & S.m2);
+            const int32_t esub = (iabs(psel - v8) + 3) >> 3;
+            const int32_t e = (esub & ~S.m4) | (te & S.m4);
+#else
             const int32_t psel = i == 0 ? wp.pred[0] : i == 1 ? wp.pred[1] : i == 2 ? wp.pred[2] : wp.pred[3];
             const int32_t e = i < 4 ? (iabs(psel - v8) + 3) >> 3 : te;
+#endif
             S.err[(size_t) x * 5 + i] = e;
             wp.e_ww[k] = wp.e_w[k];
             wp.e_w[k] = e;
@@ -575,6 +602,8 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
     S.tab = ms.tab; S.leaves = ms.leaves; S.refp = ms.refp; S.div24 = div24;
     S.cap = cap; S.width = width; S.dist_mult = m.dist_mult;
     S.my_i = lane < 4 ? lane : 4; // this lane's weighted-predictor index (device)
+    S.m0 = -(int32_t) (S.my_i == 0); S.m1 = -(int32_t) (S.my_i == 1); S.m2 = -(int32_t) (S.my_i == 2); S.m4 = -(int32_t) (S.my_i == 4);
+    S.my_table = (const uint64_t *) (cc.arena + ms.leaves[mine.leaf_node >= 0 ? (lane & (SIMT_LANES - 1)) : 0].cl.table_off);
     S.wpp = m.wp;
     WpSimt &wp = S.wp;
     // the first call below always reads a symbol (or continues an LZ77 copy that an earlier channel began):
@@ -693,7 +722,7 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
         }
         ms.info[0] = uses_wp;
         ms.info[1] = nslots;
-        ms.info[2] = simt ? 1 + variant : 0;
+        ms.info[2] = simt ? 1 + variant + (!cc.prefix && !cc.lz77 ? 8 : 0) : 0; // bit 3: rANS without LZ77 (MODE 1)
         ms.info[3] = n;
     }
     sync();
@@ -702,14 +731,21 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
     if (ms.info[2]) {
         int32_t refprops[SIMT_REF_SLOTS];
         for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
-        const int variant = ms.info[2] - 1, ns = ms.info[1];
-        if (c.w > ms.cap) { // wide channels: generic variants only
-            if (uses_wp) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        const int variant = ((ms.info[2] & 7) - 1), ns = ms.info[1];
+        const bool mode1 = (ms.info[2] & 8) != 0;
+        if (c.w > ms.cap) { // wide channels: no predictor specialisation
+            if (mode1) {
+                if (uses_wp) modular_channel_simt<true, -1, 1, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+                else modular_channel_simt<false, -1, 1, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+            }
+            else if (uses_wp) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
             else modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         }
         else if (variant == 2) modular_channel_simt<true, 6, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else if (variant == 1 && uses_wp) modular_channel_simt<true, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else if (variant == 1) modular_channel_simt<false, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (mode1 && uses_wp) modular_channel_simt<true, -1, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else if (mode1) modular_channel_simt<false, -1, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else if (uses_wp) modular_channel_simt<true, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else modular_channel_simt<false, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else {
