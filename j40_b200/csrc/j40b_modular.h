@@ -722,7 +722,7 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
         }
         ms.info[0] = uses_wp;
         ms.info[1] = nslots;
-        ms.info[2] = simt ? 1 + variant + (!cc.prefix && !cc.lz77 ? 8 : 0) : 0; // bit 3: rANS without LZ77 (MODE 1)
+        ms.info[2] = simt ? 1 + variant : 0;
         ms.info[3] = n;
     }
     sync();
@@ -731,21 +731,17 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
     if (ms.info[2]) {
         int32_t refprops[SIMT_REF_SLOTS];
         for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
-        const int variant = ((ms.info[2] & 7) - 1), ns = ms.info[1];
-        const bool mode1 = (ms.info[2] & 8) != 0;
-        if (c.w > ms.cap) { // wide channels: no predictor specialisation
-            if (mode1) {
-                if (uses_wp) modular_channel_simt<true, -1, 1, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-                else modular_channel_simt<false, -1, 1, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-            }
-            else if (uses_wp) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        const int variant = ms.info[2] - 1, ns = ms.info[1];
+        // (specialising the generic-predictor variants for rANS without LZ77 as well was measured: the extra loop
+        // bodies push the kernel to 254 registers, or to spills under a register cap, and the LF image kernel went
+        // from 70 to 91 ms)
+        if (c.w > ms.cap) { // wide channels: generic variants only
+            if (uses_wp) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
             else modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         }
         else if (variant == 2) modular_channel_simt<true, 6, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else if (variant == 1 && uses_wp) modular_channel_simt<true, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else if (variant == 1) modular_channel_simt<false, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (mode1 && uses_wp) modular_channel_simt<true, -1, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (mode1) modular_channel_simt<false, -1, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else if (uses_wp) modular_channel_simt<true, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
         else modular_channel_simt<false, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else {
