@@ -10,6 +10,7 @@
 #include "j40b_host.h"
 #include <memory>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -146,6 +147,7 @@ public:
                     gb.gh = std::min(d.height, (grow + 1) * 256) - grow * 256;
                     size_t full = (size_t) 3 * 64 * ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8);
                     size_t cap = full_token_cap ? full : std::min(full, (size_t) p.pg_sec[g].size * 3 + 256);
+                    if (!full_token_cap && token_squeeze) cap = std::min<size_t>(cap, 64); // tests: force the overflow + retry path
                     gb.tok_first = tok_total; gb.tok_cap = cap;
                     tok_total += cap;
                     gb.lz = lz_coef ? wk_alloc(4u << 18) : (size_t) -1;
@@ -500,6 +502,7 @@ private:
     uint8_t *dev = nullptr, *staging = nullptr;
     size_t upload_bytes = 0, work_bytes = 0, dev_cap = 0, staging_cap = 0;
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, num_lf = 0, num_hf = 0;
+    bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry
     size_t max_global_blob = 0, max_coeff_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
 };
 

@@ -138,6 +138,24 @@ def test_batch_reuse_and_async_readback(oracle, gen):
         b.close()
 
 
+def test_token_arena_overflow_is_retried(oracle, gen, monkeypatch):
+    """the per-group token arena is sized from the section's byte count; a group with more non-zero coefficients
+    than that estimate reports the internal code `tokv` and the batch is decoded again with worst-case capacity.
+    J40B_TEST_TOKEN_SQUEEZE shrinks the first estimate to 64 tokens so that every group takes that path."""
+    monkeypatch.setenv("J40B_TEST_TOKEN_SQUEEZE", "1")
+    datas = [streams.make(gen, "vardct", 520, 392, 80 + i, dict(mix=1, tree=1)) for i in range(2)]
+    b = J.Batch(0)
+    for d in datas:
+        b.add(d)
+    b.upload()
+    b.decode()
+    assert b.wait() == 0
+    for i, d in enumerate(datas):
+        want, _, _, _ = oracle.decode(d)
+        assert b.error(i) == "" and np.array_equal(b.read_pixels(i), want)
+    b.close()
+
+
 def test_phase_control_and_stage_timeline(oracle, gen):
     """j40b_batch_after orders one batch behind a stage of another; j40b_batch_event_ms reports when the stages of
     a decode ended relative to a mark (the diagnostics DESIGN.md's pipelining analysis is based on)"""

@@ -92,3 +92,11 @@ def test_error_codes_on_corrupt_streams_newer_features(oracle, emu, gen):
                 mismatches += 1
     assert mismatches <= total // 10, (mismatches, total)
     assert unnoticed <= 6, unnoticed
+
+
+def test_token_arena_overflow_is_retried(oracle, emu, gen, monkeypatch):
+    """J40B_TEST_TOKEN_SQUEEZE shrinks the first token-arena estimate to 64 tokens per group: every group reports the
+    internal code `tokv` and the decode is repeated with worst-case capacity (same logic as j40b_batch_wait)"""
+    monkeypatch.setenv("J40B_TEST_TOKEN_SQUEEZE", "1")
+    _cmp(oracle, emu, streams.make(gen, "vardct", 520, 392, 81, dict(mix=1, tree=1)))
+    _cmp(oracle, emu, streams.make(gen, "vardct", 64, 64, 82, dict(mix=1, tree=1, ans=0)))
