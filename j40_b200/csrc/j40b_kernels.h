@@ -17,10 +17,11 @@ enum { SPEC_COPY_BYTES = 40 * 1024 };
 // wide; modular groups at most 1024 pixels
 enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
 
-// Serial modular decoders (LF image, HF metadata, modular groups): one *warp* per work item. Lane 0 runs
-// the decoder; the other lanes keep its per-sample working set (sample rows, weighted-predictor error rows,
-// reference-channel rows) in shared memory. The CTA's warps share one staged copy of the code spec (work
-// lists are ordered image by image, so they nearly always belong to the same image).
+// Serial modular decoders (LF image, HF metadata, modular groups): one *warp* per work item, SIMT-uniform: all
+// lanes run the same sample; lane j evaluates decision node j and leaf j of the compiled MA tree (two ballots pick
+// the leaf), lanes 0..3 the weighted predictor's sub-predictors, every leaf lane pre-fetches its cluster's alias
+// entry. The warp's working set (sample rows, weighted-predictor error rows, reference-channel property rows, the
+// compiled tree) lives in its slice of shared memory; the CTA's warps can share one staged copy of the code spec.
 #if defined(__CUDACC__)
 struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
 #endif
