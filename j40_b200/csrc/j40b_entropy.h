@@ -98,12 +98,15 @@ struct BitReader {
         int n = (int) ((8 - (bits_consumed() & 7)) & 7);
         return u(n) == 0;
     }
-    // end-of-section check (j40__no_more_bytes, j40.h:2011): 0 or an error code
+    // end of a single-section frame (j40__end_of_frame, j40.h:7884-7893): 0 or an error code. Note the reference's
+    // naming: a frame that ends *before* its advertised size is "shrt" there (the bytes up to the advertised end
+    // would have to be skipped), and one that runs past its size into trailing data is "excs"; running past the
+    // end of the file is "shrt" from the bit reader itself, which is all a section-bounded reader can see.
     J40B_HD uint32_t finish() {
         if (overrun()) return E_SHRT;
         if (!zero_pad_to_byte()) return E_PAD0;
         if (overrun()) return E_SHRT;
-        if (bits_consumed() != (uint64_t) size * 8) return E_EXCS;
+        if (bits_consumed() != (uint64_t) size * 8) return E_SHRT;
         return 0;
     }
     // U32 field coding (j40.h:1934)
