@@ -1544,7 +1544,13 @@ static uint32_t linearise(const uint8_t *data, size_t size, FramePlan &plan) {
     size_t pos = 32;
     bool seen_jxll = false, seen_jxli = false, seen_jxlc = false, seen_jxlp = false, no_more = false;
     while (pos < size) {
-        if (size - pos < 8) return no_more ? 0u : (uint32_t) E_SHRT;
+        if (size - pos < 8) {
+            // a truncated box header. Before the codestream is complete it is a short file. Behind the last
+            // codestream box the reference only ever sees it if it lies in the first 64 KiB of the file, which its
+            // first buffer fill scans box by box (j40.h:1676); later refills stay inside the codestream box.
+            if (!no_more || pos < 65536) return E_SHRT;
+            break;
+        }
         uint32_t size32 = be32(data + pos), type = be32(data + pos + 4);
         size_t hdr = 8;
         uint64_t payload;
