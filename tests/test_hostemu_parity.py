@@ -100,3 +100,15 @@ def test_token_arena_overflow_is_retried(oracle, emu, gen, monkeypatch):
     monkeypatch.setenv("J40B_TEST_TOKEN_SQUEEZE", "1")
     _cmp(oracle, emu, streams.make(gen, "vardct", 520, 392, 81, dict(mix=1, tree=1)))
     _cmp(oracle, emu, streams.make(gen, "vardct", 64, 64, 82, dict(mix=1, tree=1, ans=0)))
+
+
+def test_trailing_bytes_behind_the_container(oracle, emu, gen):
+    """a truncated box header behind the codestream box: the reference reports `shrt` only if it lies within the
+    first 64 KiB of the file (its first buffer fill); complete trailing boxes are ignored either way"""
+    small = streams.make(gen, "modular", 300, 100, 305, dict(tree=0, lz77=0, alpha=1, container=1))
+    large = streams.make(gen, "modular", 300, 136, 305, dict(tree=0, lz77=0, alpha=1, container=1))
+    assert len(small) < 65536 < len(large)
+    for data in (small, large):
+        for tail in (b"\x07", b"\x00\x00\x00", b"\x00\x00\x00\x10abcd1234", b"\x00\x00\x00\x10abcd12345678"):
+            _cmp(oracle, emu, data + tail)
+    assert oracle.decode(small + b"\x07")[1] == "shrt" and oracle.decode(large + b"\x07")[1] == ""
