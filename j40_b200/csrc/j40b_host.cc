@@ -1546,9 +1546,11 @@ static uint32_t linearise(const uint8_t *data, size_t size, FramePlan &plan) {
     while (pos < size) {
         if (size - pos < 8) {
             // a truncated box header. Before the codestream is complete it is a short file. Behind the last
-            // codestream box the reference only ever sees it if it lies in the first 64 KiB of the file, which its
-            // first buffer fill scans box by box (j40.h:1676); later refills stay inside the codestream box.
+            // codestream box the reference sees it if it lies in the first 64 KiB of the file, which its first
+            // buffer fill scans box by box (j40.h:1676), or when it reads a single-section frame through to its
+            // end; a multi-section frame is left by a seek and later refills stay inside the codestream box.
             if (!no_more || pos < 65536) return E_SHRT;
+            plan.trailing_partial_box = true; // a single-section frame still runs into it at its end (see collect_errors)
             break;
         }
         uint32_t size32 = be32(data + pos), type = be32(data + pos + 4);

@@ -57,6 +57,7 @@ struct FramePlan {
     DFrame df;          // table offsets refer to `arena`; pointer-typed members are filled by the executor
     Arena arena;        // per-image tables (code specs, tree, block context map, custom dq / orders)
     bool single_section = false;
+    bool trailing_partial_box = false; // container: a truncated box header follows the last codestream box (beyond 64 KiB)
     std::vector<SectionRef> lfg_sec, pg_sec; // per LF group / per group (one pass)
     uint64_t end_codeoff = 0;
     // custom (non-library) tables: 0 = use the process-wide default tables

@@ -453,6 +453,7 @@ public:
                 if (p.single_section) {
                     if (p.cs_size > p.end_codeoff) best = E_EXCS;
                     else if (p.cs_size < p.end_codeoff) best = E_SHRT;
+                    else if (p.trailing_partial_box) best = E_SHRT; // read through to the end of the box, then the next header
                 } else if (p.cs_size > p.end_codeoff && p.end_codeoff < 65536) best = E_EXCS;
             }
             results[k].err = best;

@@ -112,3 +112,9 @@ def test_trailing_bytes_behind_the_container(oracle, emu, gen):
         for tail in (b"\x07", b"\x00\x00\x00", b"\x00\x00\x00\x10abcd1234", b"\x00\x00\x00\x10abcd12345678"):
             _cmp(oracle, emu, data + tail)
     assert oracle.decode(small + b"\x07")[1] == "shrt" and oracle.decode(large + b"\x07")[1] == ""
+    # ... but a single-section frame is read through to the end of its box and then runs into the broken header
+    single = streams.make(gen, "modular", 200, 300, 746, dict(tree=1, lz77=1, alpha=1, group_shift=9, container=1))
+    assert len(single) > 65536
+    for tail in (b"\x07", b"\x00" * 5, b"\x00\x00\x00\x10abcd1234"):
+        _cmp(oracle, emu, single + tail)
+    assert oracle.decode(single + b"\x07")[1] == "shrt"
