@@ -147,8 +147,8 @@ J40B_HD inline void lf_decode1_body(const LfWork &w, WarpScratch &ws, const ModS
     if (lane == 0) {
         g.extra_prec = extra_prec;
         g.mid_bit = br.bits_consumed();
-        g.nb_tr1 = m.nb_transforms;
-        for (int t = 0; t < m.nb_transforms; ++t) g.tr1[t] = m.tr[t];
+        g.nb_tr1 = imin(m.nb_transforms, MOD_MAX_TRANSFORMS);
+        for (int t = 0; t < g.nb_tr1; ++t) g.tr1[t] = m.tr[t];
         if (es.err) *w.err = es.err;
     }
 }

@@ -769,7 +769,7 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
     for (int i = 0; i < 5; ++i) m.wp.p3[i] = default_wp ? (int8_t) (7 * (i < 3)) : (int8_t) br.u(5);
     for (int i = 0; i < 4; ++i) m.wp.w[i] = default_wp ? (int8_t) (12 + (i < 1)) : (int8_t) br.u(4);
     m.nb_transforms = (int32_t) br.u32(0, 0, 1, 0, 2, 4, 18, 8);
-    if (m.nb_transforms > MOD_MAX_TRANSFORMS) { es.set(br, E_XLIM); return; }
+    if (m.nb_transforms > MOD_MAX_TRANSFORMS) { m.nb_transforms = 0; es.set(br, E_XLIM); return; } // (callers copy tr[0..nb_transforms))
     for (int i = 0; i < m.nb_transforms; ++i) {
         uint32_t id = br.u(2);
         m.tr[i].kind = 0; m.tr[i].num_c = m.tr[i].nb_colours = m.tr[i].nb_deltas = m.tr[i].d_pred = 0;

@@ -118,3 +118,13 @@ def test_trailing_bytes_behind_the_container(oracle, emu, gen):
     for tail in (b"\x07", b"\x00" * 5, b"\x00\x00\x00\x10abcd1234"):
         _cmp(oracle, emu, single + tail)
     assert oracle.decode(single + b"\x07")[1] == "shrt"
+
+
+def test_too_many_transforms_is_an_error_not_an_overflow(oracle, emu):
+    """regression (found by the ASan/UBSan corruption sweep): an LF-group modular header announcing more than eight
+    transforms used to be copied into the eight-entry list of the LF group before the error was looked at"""
+    import os
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bad_too_many_transforms.jxl"), "rb").read()
+    a, ea, _, _ = oracle.decode(data)
+    b, eb, _ = emu.decode(data)
+    assert ea == eb == "xlim" and a is None and b is None
