@@ -1207,7 +1207,14 @@ struct Parser {
         check_overrun();
         if (err) return;
         std::vector<float> mat = compute_dq(idx, mode, n, m, params.data());
-        if (mat.empty()) FAIL(E4("band"));
+        if (mat.empty()) {
+            // the reference computes the weights later (j40__load_dq_matrix via j40__prepare_dq_matrices, after the LF
+            // groups) and therefore reports anything else wrong with the rest of HfGlobal first: keep parsing and
+            // raise "band" at the end of the host parse if nothing else failed. (It also computes them only for
+            // transforms the frame uses; an invalid but unused matrix still fails here -- DESIGN.md §8.)
+            if (!plan.deferred_err) plan.deferred_err = E4("band");
+            return;
+        }
         uint32_t off = arena.alloc(mat.size() * 4, 16);
         memcpy(arena.at<uint8_t>(off), mat.data(), mat.size() * 4);
         plan.custom_dq_off[idx] = off;
@@ -1773,6 +1780,7 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
     d.nb_global_transforms = plan.gmod.nb_transforms;
     for (int i = 0; i < plan.gmod.nb_transforms; ++i) d.global_tr[i] = plan.gmod.tr[i];
     d.global_wp = plan.gmod.wp;
+    if (plan.deferred_err) return plan.err = plan.deferred_err;
     return 0;
 }
 

@@ -47,6 +47,7 @@ struct FrameInfo {
 
 struct FramePlan {
     uint32_t err = 0;
+    uint32_t deferred_err = 0; // a host-side error the reference would only raise after everything else in the host's part
     // linearised codestream (points into the caller's buffer for bare codestreams)
     const uint8_t *cs = nullptr;
     size_t cs_size = 0;
