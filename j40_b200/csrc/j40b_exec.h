@@ -392,7 +392,7 @@ J40B_HD J40B_INLINE int16_t palette_value(const ModTransform &t, const int16_t *
         if (i < 3) {
             idx = (int16_t) (~idx % 143);
             val = (int16_t) palette_delta(idx, i);
-            if (bpp > 8) val = (int16_t) (val << (imin(bpp, 24) - 8));
+            if (bpp > 8) val = (int16_t) (val * (1 << (imin(bpp, 24) - 8))); // (the reference shifts; same bits, defined for negatives)
         } else {
             val = 0;
         }
