@@ -78,8 +78,9 @@ struct TileVb {
     uint16_t log_off;    // the same without the bank skew: position in the tile's raster order of 64-float chunks
     uint8_t dctsel, log_rows, log_cols, param_idx;
     uint8_t cx, cy;      // top-left cell inside the tile
-    uint8_t special;
+    uint8_t special, order_idx;
     uint8_t mlog;        // log2 of the swizzled layout's row length (longer side); 0 = plain layout (special 8x8)
+    uint8_t pad_[3];
     float m[3];          // dequantisation multipliers mult[c] of j40__dequant_hf
     uint32_t first[3];   // first token of channel c (X, Y, B) in the image's token array
     uint16_t cnt[3];     // number of tokens of channel c
@@ -87,7 +88,7 @@ struct TileVb {
 
 struct TileShared {
     unsigned long long *phase; // diagnostic builds: global per-phase cycle counters
-    int32_t nvb;
+    int32_t nvb, nchunks;
     TileVb vb[64];
     int32_t cell_voff[64];  // per cell: varblock index if the cell is a top-left handled here, else -1
     uint32_t cell_first[64][3]; // per cell: first token / token count per channel of the varblock starting there
@@ -177,8 +178,10 @@ J40B_HD J40B_INLINE void tile_pass(float *coef, const TileShared &ts, int pass, 
 // tile (tx, ty) of group w.grp; coef = 3 * TILE_CH floats of shared memory
 template <class Sync>
 J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coef, TileShared &ts, int tid, int nth, Sync sync) {
-    if (*w.lf_err || *w.hf_err) return;
+    if (*w.lf_err) return;
     const DFrame &f = *w.f;
+    const int npass = f.num_passes;
+    for (int p = 0; p < npass; ++p) if (w.hf_err[(size_t) p * w.hf_err_stride]) return;
     const DLfGroup &g = *w.g;
     const DGroup &grp = *w.grp;
     const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
@@ -231,9 +234,10 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const float gs = J40B_FDIV(65536.0f, (float) f.global_scale);
         for (int c = tid; c < 64; c += nth) {
             if (c == 63) {
-                int n = 0, tt = 0;
-                for (int k = 0; k < 64; ++k) if (ts.cell_voff[k] >= 0) { ++n; tt += ts.cell_cnt[k][0] + ts.cell_cnt[k][1] + ts.cell_cnt[k][2]; }
+                int n = 0, tt = 0, nch = 0;
+                for (int k = 0; k < 64; ++k) if (ts.cell_voff[k] >= 0) { ++n; nch += ts.cell_size64[k]; tt += ts.cell_cnt[k][0] + ts.cell_cnt[k][1] + ts.cell_cnt[k][2]; }
                 ts.nvb = n;
+                ts.nchunks = nch;
                 ts.tstart[n] = (uint16_t) tt;
             }
             const int32_t voff = ts.cell_voff[c];
@@ -253,6 +257,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             t.dctsel = vb.dctsel; t.log_rows = (uint8_t) d.log_rows; t.log_cols = (uint8_t) d.log_columns; t.param_idx = (uint8_t) d.param_idx;
             t.cx = (uint8_t) (c & 7); t.cy = (uint8_t) (c >> 3);
             t.special = is_special_8x8(vb.dctsel) ? 1 : 0;
+            t.order_idx = (uint8_t) d.order_idx;
             t.mlog = t.special ? 0 : (uint8_t) (d.log_rows > d.log_columns ? d.log_rows : d.log_columns);
             t.m[1] = J40B_FMUL(gs, vb.hfmul_inv);
             t.m[0] = J40B_FMUL(t.m[1], f.x_qm_mult);
@@ -281,7 +286,28 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     // buffer thus receives at most two addends on top of the initial +0, its own coefficient and the luma
     // term; float addition is commutative and 0 + a is exact, so adding them in either order (shared-memory
     // atomics, which keep denormals) gives the reference's x + y * kx bit for bit.
-    {
+    for (int pass = 0; pass < npass; ++pass) {
+        if (pass > 0) {
+            // the token ranges of this pass (pass 0's were fetched in phase 0), then their prefix sums
+            sync();
+            for (int c = tid; c < 64; c += nth) {
+                const int32_t vo = ts.cell_voff[c];
+                if (vo < 0) continue;
+                TileVb &t = ts.vb[ts.cover[c]];
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t *slot = g.vb_tok + (((size_t) pass * 3 + k) * n8 + vo) * 2;
+                    t.first[k] = slot[0];
+                    t.cnt[k] = (uint16_t) slot[1];
+                }
+            }
+            sync();
+            for (int v = tid; v <= nvb; v += nth) {
+                int tt = 0;
+                for (int k = 0; k < v; ++k) tt += ts.vb[k].cnt[0] + ts.vb[k].cnt[1] + ts.vb[k].cnt[2];
+                ts.tstart[v] = (uint16_t) tt;
+            }
+            sync();
+        }
         const float qbn = f.quant_bias_num;
         const float kx_hf = ts.kx_hf, kb_hf = ts.kb_hf;
         const int total = ts.tstart[nvb];
@@ -294,10 +320,16 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             int c = 1;
             if (j >= (int) t.cnt[1]) { j -= t.cnt[1]; c = 0; if (j >= (int) t.cnt[0]) { j -= t.cnt[0]; c = 2; } }
             const DToken tk = w.tokens[t.first[c] + (uint32_t) j];
+            const int32_t pos = f.order[pass][t.order_idx][c][tk.pos]; // the token carries the scan index
+            const int p = t.chunk_off + tile_swz(pos, t.mlog);
             float q = (float) tk.val;
+            if (npass > 1) {
+                // several passes: their values add up first (j40.h:6989; integers, exact in any order); dequantised below
+                tile_add(c == 0 ? &coefx[p] : c == 1 ? &coefy[p] : &coefb[p], q);
+                continue;
+            }
             q = (-1.0f <= q && q <= 1.0f) ? J40B_FMUL(q, f.quant_bias[c]) : J40B_FSUB(q, J40B_FDIV(qbn, q));
-            q = J40B_FMUL(q, J40B_FDIV(t.m[c], f.dq[t.param_idx][(size_t) tk.pos * 3 + c]));
-            const int p = t.chunk_off + tile_swz(tk.pos, t.mlog);
+            q = J40B_FMUL(q, J40B_FDIV(t.m[c], f.dq[t.param_idx][(size_t) pos * 3 + c]));
             if (c == 1) {
                 coefy[p] = q;
                 tile_add(&coefx[p], J40B_FMUL(q, kx_hf));
@@ -306,6 +338,28 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
                 tile_add(c == 0 ? &coefx[p] : &coefb[p], q);
             }
         }
+    }
+    if (npass > 1) {
+        // dense form of j40__dequant_hf and the chroma-from-luma step over the tile's coefficients (the LLF corner is
+        // still zero here and stays zero: 0 * bias * weight)
+        sync();
+        const float qbn = f.quant_bias_num;
+        const float kx_hf = ts.kx_hf, kb_hf = ts.kb_hf;
+        for (int e = tid; e < ts.nchunks * 64; e += nth) {
+            const TileVb &t = ts.vb[ts.chunk_vb[e >> 6]];
+            const int i = e - (int) t.log_off;
+            const int p = t.chunk_off + tile_swz(i, t.mlog);
+            const float *dq = f.dq[t.param_idx] + (size_t) i * 3;
+            float q[3] = {coefx[p], coefy[p], coefb[p]};
+            for (int c = 0; c < 3; ++c) {
+                q[c] = (-1.0f <= q[c] && q[c] <= 1.0f) ? J40B_FMUL(q[c], f.quant_bias[c]) : J40B_FSUB(q[c], J40B_FDIV(qbn, q[c]));
+                q[c] = J40B_FMUL(q[c], J40B_FDIV(t.m[c], dq[c]));
+            }
+            coefy[p] = q[1];
+            coefx[p] = J40B_FADD(q[0], J40B_FMUL(q[1], kx_hf));
+            coefb[p] = J40B_FADD(q[2], J40B_FMUL(q[1], kb_hf));
+        }
+        sync();
     }
     J40B_PHASE(2);
     // (no barrier: the LLF corner below is disjoint from every token position -- the coefficient scan starts

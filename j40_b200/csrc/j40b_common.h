@@ -97,6 +97,7 @@ struct DCodeSpec {
     uint32_t cluster_map_off; // uint8_t[num_dist]
     uint32_t clusters_off;    // DCluster[num_clusters]
     uint32_t blob_lo, blob_hi; // arena byte range holding everything this spec points to (and the spec)
+    uint32_t ans_tables_off;   // ANS: the clusters' alias tables, contiguous in cluster order (cluster k at + (k << log_alpha_size) entries)
 };
 
 // ANS alias entry: one 64-bit word per bucket (see j40b_entropy.h)

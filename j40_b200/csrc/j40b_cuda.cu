@@ -11,6 +11,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
+#include <memory>
+#include <vector>
 
 using namespace j40b;
 
@@ -54,9 +56,20 @@ struct CudaBackend {
     }
     void *dev_alloc(size_t n) { void *p = nullptr; cudaSetDevice(device); if (!cuda_ok(cudaMalloc(&p, n ? n : 1))) return nullptr; return p; }
     void dev_free(void *p) { cudaSetDevice(device); cudaFree(p); }
-    void *host_alloc(size_t n) { void *p = nullptr; if (!cuda_ok(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault))) return malloc(n ? n : 1); pinned = true; return p; }
-    void host_free(void *p) { if (pinned) cudaFreeHost(p); else free(p); }
-    bool pinned = false;
+    // staging memory: pinned if the driver grants it, plain otherwise (the kind is remembered per pointer)
+    void *host_alloc(size_t n) {
+        void *p = nullptr;
+        if (cuda_ok(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault))) return p;
+        cudaGetLastError();
+        p = malloc(n ? n : 1);
+        if (p) unpinned.push_back(p);
+        return p;
+    }
+    void host_free(void *p) {
+        for (size_t i = 0; i < unpinned.size(); ++i) if (unpinned[i] == p) { unpinned.erase(unpinned.begin() + (long) i); free(p); return; }
+        cudaFreeHost(p);
+    }
+    std::vector<void *> unpinned;
     void h2d(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream); }
     void d2h(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); }
     void d2h_async(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); }
@@ -82,7 +95,9 @@ struct CudaBackend {
         cudaEventRecord(ev[1], stream);
         launches += 4;
     }
-    void launch_hf(const HfWork *w, int n, size_t spec_bytes) {
+    void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t spec_bytes) {
+        kl_hf_prep(ngroups, stream, pw);
+        ++launches;
         const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
         // lanes per warp: aim at ~4 warps per SM before filling warps completely. Measured at 8640 groups: 8 lanes
         // is the latency optimum of one batch alone (26 ms against 34 ms at 16 lanes), 16 lanes the throughput
@@ -239,7 +254,7 @@ static void gather_times(j40b_batch *b) {
     for (float &k : be.kernel_ms) k = 0;
     // events are only recorded when the corresponding kernels were launched in this decode
     bool vardct = false;
-    for (auto &p : b->batch->plans) if (!p->err && !p->df.is_modular) vardct = true;
+    for (auto &p : b->batch->plans) if (!p->err && !p->df.is_modular && !p->lfg_sec.empty() && !p->pg_sec.empty()) vardct = true;
     if (be.mod_marked) cudaEventElapsedTime(&be.kernel_ms[4], be.ev[8], be.ev[9]); // k_modular + k_render of all modular images
     be.mod_marked = false;
     if (vardct) {
@@ -266,10 +281,13 @@ EXPORT int j40b_batch_wait(j40b_batch *b) {
     if (retry && !b->batch->full_token_cap) {
         b->batch->full_token_cap = true;
         if (b->batch->upload()) {
+            cudaEventRecord(b->t0, b->be.stream);
             b->batch->execute();
+            cudaEventRecord(b->t1, b->be.stream);
             if (b->read_dst) b->batch->download_all_async(b->read_dst, b->read_pitch);
         }
         b->batch->collect_errors();
+        gather_times(b); // describe the decode that produced the result, not the aborted first attempt
     }
     int failed = 0;
     for (auto &r : b->batch->results) failed += r.err != 0;
@@ -571,28 +589,31 @@ EXPORT j40_err j40_output_format(j40_image *image, int32_t channel, int32_t form
     return 0;
 }
 
-static std::mutex g_api_mutex; // one shared backend per device for the single-image API
+// The single-image API shares one lazily created batch object (stream, events, device block, pinned staging) per
+// process: creating and destroying those per image costs tens of milliseconds. Handles stay independent; decodes
+// of different handles are serialised by the mutex (the reference has no threading at all, j40.h:8034).
+static std::mutex g_api_mutex;
 static j40b_batch *g_api_ctx = nullptr;
-static bool g_api_failed = false;
+static int g_api_dev = -1;
 
 static j40_err advance(j40__inner *inner) {
     if (inner->advanced) return 0;
-    { // header-level errors do not need a GPU to be diagnosed
-        FramePlan probe;
-        uint32_t e = parse_frame(inner->data, inner->size, probe);
-        if (e) return e;
-    }
+    // header-level errors do not need a GPU to be diagnosed; the plan is handed to the batch as parsed
+    std::unique_ptr<FramePlan> plan(new FramePlan);
+    if (uint32_t e = parse_frame(inner->data, inner->size, *plan)) return e;
     std::lock_guard<std::mutex> lock(g_api_mutex);
     int dev = 0;
     if (const char *e = getenv("J40B_DEVICE")) dev = atoi(e);
-    j40b_batch *b = j40b_batch_create(dev);
+    if (g_api_ctx && g_api_dev != dev) { j40b_batch_destroy(g_api_ctx); g_api_ctx = nullptr; }
+    if (!g_api_ctx) { g_api_ctx = j40b_batch_create(dev); g_api_dev = dev; }
+    j40b_batch *b = g_api_ctx;
     if (!b) return ERR4("!gpu");
+    j40b_batch_reset(b);
+    b->batch->plans.push_back(std::move(plan));
+    b->inputs.push_back({inner->data, inner->size});
+    const int idx = 0;
     j40_err err = 0;
-    int idx = j40b_batch_add(b, inner->data, inner->size);
-    err = j40b_batch_error(b, idx);
-    if (!err) {
-        if (j40b_batch_upload(b) != 0) err = ERR4("!gpu");
-    }
+    if (j40b_batch_upload(b) != 0) err = j40b_batch_error(b, idx) ? j40b_batch_error(b, idx) : ERR4("!gpu");
     if (!err) {
         j40b_batch_decode(b);
         j40b_batch_wait(b);
@@ -603,15 +624,14 @@ static j40_err advance(j40__inner *inner) {
         size_t total = (size_t) inner->stride * (size_t) inner->height;
         void *p = nullptr;
         if (cuda_ok(cudaHostAlloc(&p, total ? total : 1, cudaHostAllocDefault))) inner->pixels_pinned = true;
-        else p = malloc(total ? total : 1);
+        else { cudaGetLastError(); p = malloc(total ? total : 1); }
         if (!p) err = ERR4("!mem");
         else {
             inner->pixels = (uint8_t *) p;
             if (j40b_batch_read_pixels(b, idx, p) != 0) err = ERR4("!gpu");
         }
     }
-    j40b_batch_destroy(b);
-    (void) g_api_ctx; (void) g_api_failed;
+    j40b_batch_reset(b); // drops the borrowed input pointers; allocations stay for the next image
     if (!err) inner->advanced = 1;
     return err;
 }

@@ -12,7 +12,7 @@
 //   back_generic persistent blocks   varblocks larger than 64x64 / straddling tiles
 // Modular frame: modular (warp per group) -> render (thread per pixel).
 #pragma once
-#include "j40b_vardct.h"
+#include "j40b_hf.h"
 
 namespace j40b {
 
@@ -26,12 +26,13 @@ struct LfWork {
     float *llf_scratch;     // [2048] for LF patches larger than 8x8 cells, or null
 };
 
-struct HfWork {
+struct HfWork { // one per (pass, group)
     const DFrame *f;
     const uint8_t *arena;
     const uint8_t *cs;
     DLfGroup *g;
-    DGroup *grp;
+    DGroup *grp;            // this pass's record of the group
+    const DGroup *geo;      // pass 0's record (varblock list)
     DToken *tokens;         // image token array
     const uint32_t *lf_err; // error word of the LF group this group depends on
     uint32_t *err;
@@ -43,7 +44,8 @@ struct BackWork {
     const DLfGroup *g;
     const DGroup *grp;
     const DToken *tokens;
-    const uint32_t *lf_err, *hf_err;
+    const uint32_t *lf_err, *hf_err; // hf_err[pass * hf_err_stride]: the group's pass sections
+    int32_t hf_err_stride;
     uint8_t *rgba;
     int32_t rgba_stride;
     float *big_scratch;     // [4 * 65536] for varblocks larger than 64x64, or null
@@ -260,44 +262,80 @@ J40B_HD inline void lf_llf_body(const LfWork &w, int tid, int nth, Sync sync) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One group per *thread*: the lanes of a warp decode several groups side by side (the decoder is a state
-// machine with one symbol read per iteration, so the lanes reconverge at every read). `spec_copy` is an
-// optional shared-memory copy of the coefficient code spec of image `copy_arena` (null = none).
-J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, const uint8_t *copy_arena, const uint16_t *ctx_lut) {
-    if (*w.lf_err) return;
+// One (pass, group) section per *thread*: the lanes of a warp decode 32 sections side by side in a warp-uniform
+// two-phase loop (see j40b_hf.h). `spec_copy` is an optional shared-memory copy of the coefficient code spec of
+// (image `copy_arena`, pass `copy_pass`); lanes of other images / passes read their tables from global memory.
+// `active`: this lane has a work item. AnyFn(bool) -> bool: warp-wide "any" (identity with a single lane).
+template <int MODE>
+J40B_HD J40B_INLINE void hf_lane_init(HfLane<MODE> &L, const HfWork &w, const uint8_t *spec_copy, const uint8_t *copy_arena, int copy_pass,
+                                     const uint16_t *ctx_lut) {
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
     DGroup &grp = *w.grp;
-    int8_t *nonzeros = grp.nonzeros;
-    BitReader br;
-    ErrSlot es;
-    es.err = 0;
-    uint64_t start_bit = grp.sec_start_bit == ~0ull ? g.end_bit : grp.sec_start_bit;
-    br.init(w.cs + grp.sec_off, grp.sec_size, start_bit);
-    CodeCtx cc;
-    init_code_ctx(cc, w.arena, f.coeff_spec_off, spec_copy, copy_arena);
-    CodeState cs;
-    cs.init(grp.lz_window, (1u << 18) - 1);
-    int32_t preset = (int32_t) br.u(ceil_lg32((uint32_t) f.num_hf_presets));
-    int32_t ctxoff = 495 * f.nb_block_ctx * preset;
-    if (preset >= f.num_hf_presets) {
-        // contexts beyond the code spec: the reference reads out of bounds here; treat as corrupt
-        es.set(br, E_COEF);
-    } else {
-        if (!cc.prefix && !cc.lz77) {
-            // every group reads at least one symbol (its first varblock's non-zero count): seed the rANS state
-            // now, so that the symbol loop need not test for it
-            ans_seed(br, cs.ans_state);
-            hf_coeffs_tokens<1>(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros, ctx_lut);
-        } else {
-            hf_coeffs_tokens<0>(br, es, cc, cs, f, w.arena, g, grp, ctxoff, w.tokens, nonzeros, ctx_lut);
-        }
+    L.es.err = 0;
+    L.done = false;
+    const uint64_t start_bit = grp.sec_start_bit == ~0ull ? g.end_bit : grp.sec_start_bit;
+    L.br.init(w.cs + grp.sec_off, grp.sec_size, start_bit);
+    init_code_ctx(L.cc, w.arena, f.coeff_spec_off[grp.pass], grp.pass == copy_pass ? spec_copy : nullptr, copy_arena);
+    L.cs.init(grp.lz_window, (1u << 18) - 1);
+    L.ans_tables = (const uint64_t *) (L.cc.arena + L.cc.spec->ans_tables_off);
+    L.las = L.cc.spec->log_alpha_size;
+    L.ctx_lut = ctx_lut;
+    L.vbs = w.geo->vbs;
+    L.nvb = w.geo->nvb;
+    L.tokens = w.tokens;
+    L.n8 = g.width8 * g.height8;
+    L.vb_tok = g.vb_tok + (size_t) grp.pass * 6 * (size_t) L.n8;
+    L.colbuf = grp.nonzeros;
+    L.nb_block_ctx = f.nb_block_ctx;
+    L.tok = grp.tok_first;
+    L.tok_end = grp.tok_first + grp.tok_cap;
+    L.first_tok = L.tok;
+    L.vb_i = -1; L.c_yxb = 2; L.nz = 0; L.i = 0; L.prev = 0; L.cctx = 0; L.c = 0;
+    L.rec_voff_cell = L.rec_bctx = 0; L.log_first = L.log_w8 = 0;
+    const int32_t preset = (int32_t) L.br.u(ceil_lg32((uint32_t) f.num_hf_presets));
+    L.ctxoff = 495 * f.nb_block_ctx * preset;
+    // contexts beyond the code spec: the reference reads out of bounds here; treat as corrupt
+    if (preset >= f.num_hf_presets) L.fail(E_COEF);
+    // MODE 1: every group reads at least one symbol (its first varblock's non-zero count): seed the rANS state now,
+    // so that the symbol loop need not test for it
+    else if (MODE == 1) ans_seed(L.br, L.cs.ans_state);
+}
+
+template <int MODE>
+J40B_HD J40B_INLINE void hf_lane_finish(HfLane<MODE> &L, const HfWork &w) {
+    DGroup &grp = *w.grp;
+    grp.tok_used = L.tok - grp.tok_first;
+    if (!L.es.err) finish_code(L.br, L.es, L.cc, L.cs);
+    if (!L.es.err) {
+        if (grp.sec_start_bit == ~0ull) { uint32_t e = L.br.finish(); if (e) L.es.set_raw(e); } // single-section frame: real check
+        else if (L.br.overrun()) L.es.set_raw(E_SHRT); // see lf_decode2_body
     }
-    if (!es.err) {
-        if (grp.sec_start_bit == ~0ull) { uint32_t e = br.finish(); if (e) es.set_raw(e); } // single-section frame: real check
-        else if (br.overrun()) es.set_raw(E_SHRT); // see lf_decode2_body
+    if (L.es.err) *w.err = L.es.err;
+}
+
+template <int MODE, class AnyFn, class Sync>
+J40B_HD inline void hf_lanes_run(const HfWork *w, bool active, const uint8_t *spec_copy, const uint8_t *copy_arena, int copy_pass,
+                                 const uint16_t *ctx_lut, AnyFn any, Sync sync) {
+    HfLane<MODE> L;
+    L.done = true;
+    if (active) hf_lane_init(L, *w, spec_copy, copy_arena, copy_pass, ctx_lut);
+    for (;;) {
+        if (!any(!L.done)) break;
+        sync();
+        // phase R: lanes whose channel is exhausted (or that have not started) open the next one
+        if (!L.done && L.nz == 0) { do L.next_channel(); while (!L.done && L.nz == 0); }
+        sync();
+        // phase C: one coefficient symbol per lane
+        if (!L.done) L.coefficient();
     }
-    if (es.err) *w.err = es.err;
+    if (active) hf_lane_finish(L, *w);
+}
+
+// whether the section of work item `w` can take the MODE 1 path (the lanes of a warp must agree: the caller votes)
+J40B_HD J40B_INLINE bool hf_is_plain_ans(const HfWork &w) {
+    const DCodeSpec *spec = (const DCodeSpec *) (w.arena + w.f->coeff_spec_off[w.grp->pass]);
+    return !spec->use_prefix_code && !spec->lz77_enabled;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -305,7 +343,8 @@ J40B_HD inline void hf_group_body(const HfWork &w, const uint8_t *spec_copy, con
 // with all threads and buffers in w.big_scratch (4 * 65536 floats of global memory)
 template <class Sync>
 J40B_HD inline void back_generic_body(const BackWork &w, int tid, int nth, Sync sync) {
-    if (*w.lf_err || *w.hf_err) return;
+    if (*w.lf_err) return;
+    for (int p = 0; p < w.f->num_passes; ++p) if (w.hf_err[(size_t) p * w.hf_err_stride]) return;
     if (!w.g->has_big) return;
     const DFrame &f = *w.f;
     const DLfGroup &g = *w.g;

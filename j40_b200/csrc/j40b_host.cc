@@ -502,6 +502,9 @@ struct Parser {
                 if (err) return 0;
                 if (overrun()) FAILV(E_SHRT, 0);
                 c.table_off = build_alias_table(D, spec.log_alpha_size);
+                // the tables of a spec follow each other in the arena (8-byte entries, 8-byte aligned allocations)
+                if (&c == &clusters[0]) spec.ans_tables_off = c.table_off;
+                if (c.table_off != spec.ans_tables_off + (uint32_t) ((&c - &clusters[0]) << (spec.log_alpha_size + 3))) { fprintf(stderr, "j40_b200: alias tables not contiguous\n"); abort(); }
             }
         }
         if (overrun()) FAILV(E_SHRT, 0);
@@ -992,22 +995,24 @@ struct Parser {
         lf_global_off = sec[0].off; lf_global_size = sec[0].size;
         size_t nlf = (size_t) f.num_lf_groups, ng = (size_t) f.num_groups;
         hf_global_off = sec[1 + nlf].off; hf_global_size = sec[1 + nlf].size;
-        CHECK(f.num_passes == 1, E_TODO); // multi-pass frames: not on the device path yet
         plan.lfg_sec.resize(nlf);
-        plan.pg_sec.resize(ng);
+        CHECK(f.num_passes == 1 || !f.is_modular, E_TODO); // every pass of a modular frame re-codes the same channels (j40.h:7022): not built
+        const size_t npg = ng * (size_t) f.num_passes; // pass groups: index pass * ng + group (j40.h:5555-5561)
+        plan.pg_sec.resize(npg);
         for (size_t i = 0; i < nlf; ++i) { plan.lfg_sec[i].off = sec[1 + i].off; plan.lfg_sec[i].size = sec[1 + i].size; }
-        for (size_t i = 0; i < ng; ++i) { plan.pg_sec[i].off = sec[2 + nlf + i].off; plan.pg_sec[i].size = sec[2 + nlf + i].size; }
+        for (size_t i = 0; i < npg; ++i) { plan.pg_sec[i].off = sec[2 + nlf + i].off; plan.pg_sec[i].size = sec[2 + nlf + i].size; }
         // decoding order of the reference: by codestream offset, except that a group stored before
         // its LF group is decoded right after that LF group
         struct Item { uint64_t off; int kind; size_t idx; };
         std::vector<Item> main_list;
         std::vector<std::vector<Item>> reloc(nlf);
         for (size_t i = 0; i < nlf; ++i) main_list.push_back({plan.lfg_sec[i].off, 0, i});
-        for (size_t g = 0; g < ng; ++g) {
+        for (size_t pg = 0; pg < npg; ++pg) {
+            size_t g = pg % ng;
             size_t grow = g / (size_t) f.gcolumns, gcol = g % (size_t) f.gcolumns;
             size_t gg = (grow / 8) * (size_t) f.ggcolumns + gcol / 8;
-            if (plan.pg_sec[g].off > plan.lfg_sec[gg].off) main_list.push_back({plan.pg_sec[g].off, 1, g});
-            else reloc[gg].push_back({plan.pg_sec[g].off, 1, g});
+            if (plan.pg_sec[pg].off > plan.lfg_sec[gg].off) main_list.push_back({plan.pg_sec[pg].off, 1, pg});
+            else reloc[gg].push_back({plan.pg_sec[pg].off, 1, pg});
         }
         auto by_off = [](const Item &a, const Item &b) { return a.off < b.off; };
         std::stable_sort(main_list.begin(), main_list.end(), by_off);
@@ -1236,36 +1241,41 @@ struct Parser {
         d.num_hf_presets = (int32_t) u(ceil_lg32((uint32_t) f.num_groups)) + 1;
         check_overrun();
         if (err) return;
-        // HfPass (single pass)
-        int32_t used_orders = (int32_t) u32(0x5f, 0, 0x13, 0, 0, 0, 0, 13);
-        if (used_orders > 0) {
-            uint32_t spec = read_code_spec(8);
-            if (err) return;
-            HostCode h;
-            h.begin(arena, spec);
-            const GlobalTables &gt = GlobalTables::get();
-            for (int j = 0; j < 13; ++j) if (used_orders >> j & 1) {
-                int32_t size = 1 << (ORDER_LOG[j][0] + ORDER_LOG[j][1]);
-                for (int c = 0; c < 3; ++c) {
-                    std::vector<int32_t> lehmer;
-                    read_permutation(h, size, size / 64, lehmer);
-                    if (err) return;
-                    if (lehmer.empty()) continue;
-                    std::vector<int32_t> order = gt.order[j];
-                    apply_permutation(order.data() + size / 64, lehmer);
-                    // (the arena may grow here; `h` holds pointers into it, so allocate afterwards)
-                    pending_orders.push_back({j, c, std::move(order)});
+        // HfPass, once per pass: custom coefficient orders, then the pass's coefficient code spec
+        d.num_passes = f.num_passes;
+        for (int pass = 0; pass < f.num_passes; ++pass) {
+            int32_t used_orders = (int32_t) u32(0x5f, 0, 0x13, 0, 0, 0, 0, 13);
+            if (used_orders > 0) {
+                uint32_t spec = read_code_spec(8);
+                if (err) return;
+                HostCode h;
+                h.begin(arena, spec);
+                const GlobalTables &gt = GlobalTables::get();
+                pending_orders.clear();
+                for (int j = 0; j < 13; ++j) if (used_orders >> j & 1) {
+                    int32_t size = 1 << (ORDER_LOG[j][0] + ORDER_LOG[j][1]);
+                    for (int c = 0; c < 3; ++c) {
+                        std::vector<int32_t> lehmer;
+                        read_permutation(h, size, size / 64, lehmer);
+                        if (err) return;
+                        if (lehmer.empty()) continue;
+                        std::vector<int32_t> order = gt.order[j];
+                        apply_permutation(order.data() + size / 64, lehmer);
+                        // (the arena may grow here; `h` holds pointers into it, so allocate afterwards)
+                        pending_orders.push_back({j, c, std::move(order)});
+                    }
+                }
+                hfinish(h);
+                if (err) return;
+                for (auto &po : pending_orders) {
+                    uint32_t off = arena.alloc(po.order.size() * 4, 16);
+                    memcpy(arena.at<uint8_t>(off), po.order.data(), po.order.size() * 4);
+                    plan.custom_order_off[pass][po.j][po.c] = off;
                 }
             }
-            hfinish(h);
+            d.coeff_spec_off[pass] = read_code_spec(495 * d.nb_block_ctx * d.num_hf_presets);
             if (err) return;
-            for (auto &po : pending_orders) {
-                uint32_t off = arena.alloc(po.order.size() * 4, 16);
-                memcpy(arena.at<uint8_t>(off), po.order.data(), po.order.size() * 4);
-                plan.custom_order_off[po.j][po.c] = off;
-            }
         }
-        d.coeff_spec_off = read_code_spec(495 * d.nb_block_ctx * d.num_hf_presets);
     }
     struct PendingOrder { int j, c; std::vector<int32_t> order; };
     std::vector<PendingOrder> pending_orders;
@@ -1578,18 +1588,21 @@ static uint32_t linearise(const uint8_t *data, size_t size, FramePlan &plan) {
         }
         size_t body = pos + hdr;
         size_t avail = (size_t) std::min<uint64_t>(payload, size - body);
-        bool codestream_box = false;
+        bool codestream_box = false, stop = false;
         size_t skip = 0;
         switch (type) {
-        case 0x6a786c6c: if (seen_jxll) return no_more ? 0u : E4("box?"); seen_jxll = true; break;
-        case 0x6a786c69: if (seen_jxli) return no_more ? 0u : E4("box?"); seen_jxli = true; break;
+        // A misplaced box behind the last codestream box is seen by the reference like a truncated header there: if it
+        // lies in the first 64 KiB of the file (first buffer fill, j40.h:1676) or when a single-section frame is read
+        // through to its end (collect_errors); a multi-section frame is left by a seek and never gets that far.
+#define J40B_DUP_BOX() do { if (!no_more || pos < 65536) return E4("box?"); plan.trailing_box_err = E4("box?"); stop = true; } while (0)
+        case 0x6a786c6c: if (seen_jxll) J40B_DUP_BOX(); seen_jxll = true; break;
+        case 0x6a786c69: if (seen_jxli) J40B_DUP_BOX(); seen_jxli = true; break;
         case 0x6a786c63:
-            if (no_more || seen_jxlp || seen_jxlc) return no_more ? 0u : E4("box?");
+            if (no_more || seen_jxlp || seen_jxlc) { J40B_DUP_BOX(); break; }
             seen_jxlc = true; no_more = true; codestream_box = true;
             break;
         case 0x6a786c70:
-            if (no_more) return 0;
-            if (seen_jxlc) return E4("box?");
+            if (no_more || seen_jxlc) { J40B_DUP_BOX(); break; }
             seen_jxlp = true; codestream_box = true;
             if (payload < 4) return E4("jxlp");
             if (avail < 4) return E_SHRT;
@@ -1608,6 +1621,7 @@ static uint32_t linearise(const uint8_t *data, size_t size, FramePlan &plan) {
             break;
         default: break;
         }
+        if (stop) break;
         if (codestream_box) plan.cs_owned.insert(plan.cs_owned.end(), data + body + skip, data + body + avail);
         if (to_eof) break;
         if (payload > size - body) break; // truncated box: whatever was there has been taken

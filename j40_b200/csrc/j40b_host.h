@@ -58,12 +58,13 @@ struct FramePlan {
     DFrame df;          // table offsets refer to `arena`; pointer-typed members are filled by the executor
     Arena arena;        // per-image tables (code specs, tree, block context map, custom dq / orders)
     bool single_section = false;
+    uint32_t trailing_box_err = 0;     // container: a misplaced box follows the last codestream box beyond 64 KiB (`box?`); single-section frames run into it
     bool trailing_partial_box = false; // container: a truncated box header follows the last codestream box (beyond 64 KiB)
-    std::vector<SectionRef> lfg_sec, pg_sec; // per LF group / per group (one pass)
+    std::vector<SectionRef> lfg_sec, pg_sec; // per LF group / per (pass, group): index pass * num_groups + group
     uint64_t end_codeoff = 0;
     // custom (non-library) tables: 0 = use the process-wide default tables
     uint32_t custom_dq_off[17] = {0};
-    uint32_t custom_order_off[13][3] = {{0}};
+    uint32_t custom_order_off[MAX_PASSES][13][3] = {{{0}}};
     // modular frames: global image
     ModImage gmod;               // channel geometry (px pointers are assigned by the executor)
     SectionRef gmod_sec;         // where the globally-coded channels start (inside LfGlobal)

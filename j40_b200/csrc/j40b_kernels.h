@@ -55,6 +55,7 @@ bool kl_init_mod();
 void kl_lf_decode(int stage, int blocks, int threads, size_t smem, cudaStream_t stream, const LfWork *w, int n, int cap, int spec_cap);
 void kl_lf_post(int n, cudaStream_t stream, const LfWork *w);
 void kl_lf_llf(int n, cudaStream_t stream, const LfWork *w);
+void kl_hf_prep(int n, cudaStream_t stream, const HfPrepWork *w);
 void kl_hf_group(int blocks, size_t smem, cudaStream_t stream, const HfWork *w, int n, int lanes, int spec_cap);
 void kl_back_tile(int n, cudaStream_t stream, const BackWork *w);
 void kl_back_generic(int blocks, cudaStream_t stream, const BackWork *w, int n, float *pool);

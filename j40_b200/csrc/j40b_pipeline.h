@@ -67,7 +67,7 @@ public:
     int host_threads = 0; // for upload()'s copies into the staging buffer
 
     // forgets the images but keeps the device / pinned allocations for the next upload()
-    void reset() { plans.clear(); results.clear(); img.clear(); num_lf = num_hf = 0; }
+    void reset() { plans.clear(); results.clear(); img.clear(); num_lf = num_hf = num_grp = 0; }
 
     // ---- step 2: lay out + upload (asynchronous on the backend's stream). Returns false when out of memory.
     bool upload() {
@@ -85,7 +85,7 @@ public:
         size_t gt_lut = up_alloc(SRGB_LUT_BYTES);
         size_t work = 0;                    // device-only area cursor (follows the upload blob)
         auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
-        size_t n_lf = 0, n_hf = 0, n_mod = 0;
+        size_t n_lf = 0, n_hf = 0, n_grp = 0, n_mod = 0;
         max_global_blob = max_coeff_blob = 0;
         for (size_t k = 0; k < n; ++k) {
             FramePlan &p = *plans[k];
@@ -105,16 +105,20 @@ public:
                     const DCodeSpec *gs = (const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off);
                     max_global_blob = std::max(max_global_blob, (size_t) (gs->blob_hi - gs->blob_lo));
                 }
-                const DCodeSpec *cs_ = (const DCodeSpec *) (p.arena.bytes.data() + d.coeff_spec_off);
-                max_coeff_blob = std::max(max_coeff_blob, (size_t) (cs_->blob_hi - cs_->blob_lo));
-                im.nlf = p.lfg_sec.size(); im.ng = p.pg_sec.size();
+                bool lz_coef = false;
+                for (int ps = 0; ps < d.num_passes; ++ps) {
+                    const DCodeSpec *cs_ = (const DCodeSpec *) (p.arena.bytes.data() + d.coeff_spec_off[ps]);
+                    max_coeff_blob = std::max(max_coeff_blob, (size_t) (cs_->blob_hi - cs_->blob_lo));
+                    lz_coef = lz_coef || cs_->lz77_enabled;
+                }
+                const size_t npass = (size_t) d.num_passes;
+                im.nlf = p.lfg_sec.size(); im.npg = p.pg_sec.size(); im.ng = im.npg / npass;
                 im.lfg_off = up_alloc(sizeof(DLfGroup) * im.nlf);
-                im.grp_off = up_alloc(sizeof(DGroup) * im.ng);
-                im.err_off = wk_alloc(4 * (im.nlf + im.ng + 1));
+                im.grp_off = up_alloc(sizeof(DGroup) * im.npg);
+                im.err_off = wk_alloc(4 * (im.nlf + im.npg + 1));
                 im.lf.resize(im.nlf);
                 bool wp = d.global_tree_uses_wp != 0;
                 bool lz_mod = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
-                bool lz_coef = ((const DCodeSpec *) (p.arena.bytes.data() + d.coeff_spec_off))->lz77_enabled;
                 for (size_t i = 0; i < im.nlf; ++i) {
                     LfBuf &b = im.lf[i];
                     int ggx = (int) (i % (size_t) d.ggcolumns), ggy = (int) (i / (size_t) d.ggcolumns);
@@ -135,26 +139,28 @@ public:
                     b.llf = wk_alloc(4 * 3 * n8);
                     b.wp = wp ? wk_alloc(4 * 2 * 5 * std::max<size_t>(cap, (size_t) b.w8)) : (size_t) -1;
                     b.lz = lz_mod ? wk_alloc(4u << 18) : (size_t) -1;
-                    b.vb_tok = wk_alloc(4 * 2 * 3 * n8);
+                    b.vb_tok = wk_alloc(4 * 2 * 3 * n8 * npass);
                     b.llf_scratch = wk_alloc(4 * 2048);
                 }
-                im.grp.resize(im.ng);
+                im.grp.resize(im.npg);
                 size_t tok_total = 0;
-                for (size_t g = 0; g < im.ng; ++g) {
-                    GrpBuf &gb = im.grp[g];
+                for (size_t pg = 0; pg < im.npg; ++pg) {
+                    GrpBuf &gb = im.grp[pg];
+                    const size_t g = pg % im.ng;
                     int grow = (int) (g / (size_t) d.gcolumns), gcol = (int) (g % (size_t) d.gcolumns);
                     gb.gw = std::min(d.width, (gcol + 1) * 256) - gcol * 256;
                     gb.gh = std::min(d.height, (grow + 1) * 256) - grow * 256;
                     size_t full = (size_t) 3 * 64 * ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8);
-                    size_t cap = full_token_cap ? full : std::min(full, (size_t) p.pg_sec[g].size * 3 + 256);
+                    size_t cap = full_token_cap ? full : std::min(full, (size_t) p.pg_sec[pg].size * 3 + 256);
                     if (!full_token_cap && token_squeeze) cap = std::min<size_t>(cap, 64); // tests: force the overflow + retry path
                     gb.tok_first = tok_total; gb.tok_cap = cap;
                     tok_total += cap;
                     gb.lz = lz_coef ? wk_alloc(4u << 18) : (size_t) -1;
-                    gb.nonzeros = wk_alloc(3 * 1024);
+                    gb.nonzeros = wk_alloc(3 * 32);
+                    gb.vbs = pg < im.ng ? wk_alloc(sizeof(HfVb) * (size_t) ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8)) : im.grp[g].vbs;
                 }
                 im.tok_off = wk_alloc(sizeof(DToken) * std::max<size_t>(tok_total, 1));
-                n_lf += im.nlf; n_hf += im.ng;
+                n_lf += im.nlf; n_hf += im.npg; n_grp += im.ng;
             } else {
                 im.err_off = wk_alloc(4 * (p.pg_sec.size() + 2));
                 // coded channel list of the global image: palette (meta) channels first, each with its own size
@@ -200,8 +206,9 @@ public:
         }
         lfw_off = up_alloc(sizeof(LfWork) * std::max<size_t>(n_lf, 1));
         hfw_off = up_alloc(sizeof(HfWork) * std::max<size_t>(n_hf, 1));
-        bkw_off = up_alloc(sizeof(BackWork) * std::max<size_t>(n_hf, 1));
-        num_lf = n_lf; num_hf = n_hf;
+        bkw_off = up_alloc(sizeof(BackWork) * std::max<size_t>(n_grp, 1));
+        ppw_off = up_alloc(sizeof(HfPrepWork) * std::max<size_t>(n_grp, 1));
+        num_lf = n_lf; num_hf = n_hf; num_grp = n_grp;
         upload_bytes = align_up(up, 256);
         work_bytes = align_up(work, 256);
         if (upload_bytes + work_bytes > dev_cap) {
@@ -218,7 +225,7 @@ public:
             release();
             for (size_t k = 0; k < n; ++k) if (!results[k].err) results[k].err = E_MEM;
             for (size_t k = 0; k < n; ++k) if (!plans[k]->err) plans[k]->err = E_MEM;
-            num_lf = num_hf = 0;
+            num_lf = num_hf = num_grp = 0;
             return false;
         }
         // zero everything but the codestream / arena payloads (those are overwritten below, in parallel)
@@ -248,7 +255,8 @@ public:
         LfWork *lfw = (LfWork *) (staging + lfw_off);
         HfWork *hfw = (HfWork *) (staging + hfw_off);
         BackWork *bkw = (BackWork *) (staging + bkw_off);
-        size_t ilf = 0, ihf = 0;
+        HfPrepWork *ppw = (HfPrepWork *) (staging + ppw_off);
+        size_t ilf = 0, ihf = 0, igrp = 0;
         std::vector<std::pair<int64_t, LfWork>> lf_sorted; // (cells, item)
         for (size_t k = 0; k < n; ++k) {
             FramePlan &p = *plans[k];
@@ -261,8 +269,8 @@ public:
             for (int i = 0; i < 17; ++i) {
                 d.dq[i] = (const float *) (p.custom_dq_off[i] ? dev + im.arena_off + p.custom_dq_off[i] : dev + gt_dq[i]);
             }
-            for (int i = 0; i < 13; ++i) for (int c = 0; c < 3; ++c) {
-                d.order[i][c] = (const int32_t *) (p.custom_order_off[i][c] ? dev + im.arena_off + p.custom_order_off[i][c] : dev + gt_order[i]);
+            for (int ps = 0; ps < MAX_PASSES; ++ps) for (int i = 0; i < 13; ++i) for (int c = 0; c < 3; ++c) {
+                d.order[ps][i][c] = (const int32_t *) (p.custom_order_off[ps][i][c] ? dev + im.arena_off + p.custom_order_off[ps][i][c] : dev + gt_order[i]);
             }
             d.srgb_thr = (const float *) (dev + gt_thr);
             d.srgb_lut = dev + gt_lut;
@@ -296,36 +304,46 @@ public:
                     w.llf_scratch = (float *) (dwork + b.llf_scratch);
                     lf_sorted.emplace_back((int64_t) b.w8 * b.h8, w);
                 }
-                for (size_t gi = 0; gi < im.ng; ++gi) {
-                    const GrpBuf &gb = im.grp[gi];
-                    DGroup &g = gr[gi];
+                for (size_t pg = 0; pg < im.npg; ++pg) {
+                    const GrpBuf &gb = im.grp[pg];
+                    DGroup &g = gr[pg];
+                    const size_t gi = pg % im.ng;
                     int grow = (int) (gi / (size_t) d.gcolumns), gcol = (int) (gi % (size_t) d.gcolumns);
                     g.idx = (int32_t) gi;
+                    g.pass = (int32_t) (pg / im.ng);
                     g.lfg = (grow / 8) * d.ggcolumns + gcol / 8;
                     g.gx8 = (gcol % 8) * 32; g.gy8 = (grow % 8) * 32;
                     g.gw = gb.gw; g.gh = gb.gh;
-                    g.sec_off = (uint32_t) p.pg_sec[gi].off; g.sec_size = p.pg_sec[gi].size; g.sec_start_bit = p.pg_sec[gi].start_bit;
+                    g.sec_off = (uint32_t) p.pg_sec[pg].off; g.sec_size = p.pg_sec[pg].size; g.sec_start_bit = p.pg_sec[pg].start_bit;
                     g.tok_first = (uint32_t) gb.tok_first; g.tok_cap = (uint32_t) gb.tok_cap;
                     g.lz_window = gb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + gb.lz);
-                    g.nonzeros = (int8_t *) (dwork + gb.nonzeros);
+                    g.nonzeros = dwork + gb.nonzeros;
                     g.tok_used = 0;
-                    HfWork &w = hfw[ihf];
+                    g.vbs = (HfVb *) (dwork + gb.vbs);
+                    g.nvb = 0;
+                    HfWork &w = hfw[ihf++];
                     w.f = dframe; w.arena = darena; w.cs = dcs;
                     w.g = (DLfGroup *) (dev + im.lfg_off) + g.lfg;
-                    w.grp = (DGroup *) (dev + im.grp_off) + gi;
+                    w.grp = (DGroup *) (dev + im.grp_off) + pg;
+                    w.geo = (DGroup *) (dev + im.grp_off) + gi;
                     w.tokens = dtok;
                     w.lf_err = derr + g.lfg;
-                    w.err = derr + im.nlf + gi;
-                    BackWork &bw = bkw[ihf++];
+                    w.err = derr + im.nlf + pg;
+                    if (pg >= im.ng) continue;
+                    BackWork &bw = bkw[igrp];
                     bw.f = dframe; bw.arena = darena; bw.g = w.g; bw.grp = w.grp; bw.tokens = dtok;
-                    bw.lf_err = w.lf_err; bw.hf_err = w.err;
+                    bw.lf_err = w.lf_err; bw.hf_err = w.err; bw.hf_err_stride = (int32_t) im.ng;
                     bw.rgba = dwork + im.rgba_off; bw.rgba_stride = results[k].stride;
                     bw.big_scratch = nullptr;
+                    HfPrepWork &pw = ppw[igrp++];
+                    pw.f = dframe; pw.arena = darena; pw.g = w.g; pw.grp = w.grp; pw.lf_err = w.lf_err;
                 }
                 // pass groups of one image, longest section first: the lanes of a warp (one group each) then
                 // carry similar amounts of work, and the long ones start first
+                // (pass by pass: the lanes of a block share one staged code spec)
                 std::stable_sort(hfw + ihf_image, hfw + ihf, [&](const HfWork &a, const HfWork &b2) {
-                    return gr[a.grp - (DGroup *) (dev + im.grp_off)].sec_size > gr[b2.grp - (DGroup *) (dev + im.grp_off)].sec_size;
+                    const DGroup &ga = gr[a.grp - (DGroup *) (dev + im.grp_off)], &gb2 = gr[b2.grp - (DGroup *) (dev + im.grp_off)];
+                    return ga.pass != gb2.pass ? ga.pass < gb2.pass : ga.sec_size > gb2.sec_size;
                 });
             } else {
                 ModWork *mw = (ModWork *) (staging + im.mod_off);
@@ -397,13 +415,13 @@ public:
             FramePlan &p = *plans[k];
             Img &im = img[k];
             if (p.err) continue;
-            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.ng + 1;
+            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.npg + 1;
             be.dev_memset(dwork + im.err_off, 0, 4 * nerr);
-            if (!p.df.is_modular) for (const LfBuf &b : im.lf) be.dev_memset(dwork + b.vb_tok, 0, 4 * 2 * 3 * (size_t) b.w8 * b.h8);
+            if (!p.df.is_modular) for (const LfBuf &b : im.lf) be.dev_memset(dwork + b.vb_tok, 0, 4 * 2 * 3 * (size_t) b.w8 * b.h8 * (size_t) p.df.num_passes);
         }
         if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob);
-        if (num_hf) be.launch_hf((const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
-        if (num_hf) be.launch_back((const BackWork *) (dev + bkw_off), (int) num_hf);
+        if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
+        if (num_grp) be.launch_back((const BackWork *) (dev + bkw_off), (int) num_grp);
         bool any_mod = false;
         for (size_t k = 0; k < plans.size(); ++k) {
             FramePlan &p = *plans[k];
@@ -431,14 +449,14 @@ public:
             FramePlan &p = *plans[k];
             Img &im = img[k];
             if (p.err) continue;
-            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.ng + 1;
+            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.npg + 1;
             std::vector<uint32_t> e(nerr);
             be.d2h(e.data(), dwork + im.err_off, 4 * nerr);
             uint32_t best = 0;
             int64_t best_rank = INT64_MAX;
             if (!p.df.is_modular) {
                 for (size_t i = 0; i < im.nlf; ++i) if (e[i] && p.lfg_sec[i].rank < best_rank) { best = e[i]; best_rank = p.lfg_sec[i].rank; }
-                for (size_t g = 0; g < im.ng; ++g) if (e[im.nlf + g] && p.pg_sec[g].rank < best_rank) { best = e[im.nlf + g]; best_rank = p.pg_sec[g].rank; }
+                for (size_t g = 0; g < im.npg; ++g) if (e[im.nlf + g] && p.pg_sec[g].rank < best_rank) { best = e[im.nlf + g]; best_rank = p.pg_sec[g].rank; }
             } else {
                 const bool has_global = p.num_gm_channels > 0;
                 for (size_t g = 0; g < im.nmod; ++g) {
@@ -453,6 +471,7 @@ public:
                 if (p.single_section) {
                     if (p.cs_size > p.end_codeoff) best = E_EXCS;
                     else if (p.cs_size < p.end_codeoff) best = E_SHRT;
+                    else if (p.trailing_box_err) best = p.trailing_box_err;
                     else if (p.trailing_partial_box) best = E_SHRT; // read through to the end of the box, then the next header
                 } else if (p.cs_size > p.end_codeoff && p.end_codeoff < 65536) best = E_EXCS;
             }
@@ -489,12 +508,12 @@ public:
 
 private:
     struct LfBuf { int left, top, w, h, w8, h8, w64, h64; size_t lfq, lfdeq, lf, lfidx, xfromy, bfromy, blockinfo, sharp, blocks, varblocks, llf, wp, lz, vb_tok, llf_scratch; };
-    struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz, nonzeros; };
+    struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz, nonzeros, vbs; };
     struct ModBuf { int gw, gh; size_t wp, lz; uint32_t lz_mask; };
     struct Img {
         size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;
         size_t rgba_off = 0, err_off = 0, tok_off = 0, plane[MOD_MAX_CH] = {0};
-        size_t nlf = 0, ng = 0, nmod = 0;
+        size_t nlf = 0, ng = 0, npg = 0, nmod = 0; // LF groups, groups, (pass, group) sections, modular sub-bitstreams
         std::vector<LfBuf> lf;
         std::vector<GrpBuf> grp;
         std::vector<ModBuf> mod;
@@ -502,7 +521,7 @@ private:
     std::vector<Img> img;
     uint8_t *dev = nullptr, *staging = nullptr;
     size_t upload_bytes = 0, work_bytes = 0, dev_cap = 0, staging_cap = 0;
-    size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, num_lf = 0, num_hf = 0;
+    size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, ppw_off = 0, num_lf = 0, num_hf = 0, num_grp = 0;
     bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry
     size_t max_global_blob = 0, max_coeff_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
 };

@@ -1,7 +1,7 @@
 // j40-b200: VarDCT group decoding -- device functions (also compiled for the CPU kernel-logic tests).
 //
 // Replaces, per SURVEY.md §8(a):
-//   a6  j40__hf_coeffs                       j40.h:6888-7004  -> hf_coeffs_tokens()
+//   a6  j40__hf_coeffs                       j40.h:6888-7004  -> j40b_hf.h
 //   a10 j40__lf_quant / j40__smooth_lf       j40.h:6492-6583  -> lf_dequant(), lf_smooth()
 //   a11 j40__hf_metadata (+LLF forward DCT)  j40.h:6585-6720, 5944 -> place_varblocks(), llf_from_lf()
 //   a12 j40__dequant_hf                      j40.h:7053-7097  -> inside varblock_to_pixels()
@@ -55,6 +55,8 @@ struct NoSync { J40B_HD void operator()() const {} };
 // ---------------------------------------------------------------------------------------------
 // frame-level constants the kernels need (one per image, in device memory)
 
+enum { MAX_PASSES = 11 }; // j40.h:5259: 1, 2, 3 or 4 + u(3)
+
 struct DFrame {
     int32_t width, height;
     int32_t is_modular, xyb_encoded, bpp;
@@ -73,10 +75,11 @@ struct DFrame {
     uint32_t block_ctx_map_off;      // uint8_t[block_ctx_size]
     uint32_t global_tree_off;        // DTreeNode[]
     uint32_t global_spec_off;        // DCodeSpec (0 = none)
-    uint32_t coeff_spec_off;         // DCodeSpec for pass 0
+    int32_t num_passes;
+    uint32_t coeff_spec_off[MAX_PASSES]; // DCodeSpec per pass
     // device pointers, filled in by the executor (shared library tables or per-image custom ones)
     const float *dq[17];             // float[n][3] per parameter set
-    const int32_t *order[13][3];     // int32_t[size] per order and channel
+    const int32_t *order[MAX_PASSES][13][3]; // int32_t[size] per pass, order and channel
     const float *srgb_thr;           // float[255]: smallest v whose 8-bit output is >= k+1
     const uint8_t *srgb_lut;         // uint8[SRGB_LUT_N + 1]: number of thresholds <= b / SRGB_LUT_N
     int32_t global_tree_uses_wp, have_global_tree;
@@ -117,7 +120,7 @@ struct DLfGroup {
     int32_t nb_varblocks; // written by the kernel
     int32_t has_big;      // written by the kernel: some varblock is larger than 64x64
     uint64_t end_bit;     // written by the kernel (single-section frames continue from here)
-    uint32_t *vb_tok;     // [3][h8*w8][2] {first token, count}, written by the pass-group kernel
+    uint32_t *vb_tok;     // [num_passes][3][h8*w8][2] {first token, count}, written by the pass-group kernel (zeroed before)
     // hand-over between the LF kernels (decode LF image -> post-process -> decode HF metadata -> LLF)
     uint64_t mid_bit;     // bit position after the LF image
     int32_t extra_prec;
@@ -125,18 +128,23 @@ struct DLfGroup {
     ModTransform tr1[MOD_MAX_TRANSFORMS], tr2[MOD_MAX_TRANSFORMS];
 };
 
-struct DToken { uint32_t pos; int32_t val; };
+struct DToken { uint32_t pos; int32_t val; }; // pos = index in the scan order (the back-end applies the order table)
 
+struct HfVb;
+// one record per (pass, group); the records of pass p follow those of pass p - 1 (num_groups apart)
 struct DGroup {
     int32_t idx, lfg;            // group index, LF group index
     int32_t gx8, gy8;            // cell offset inside the LF group
     int32_t gw, gh;              // pixel size
+    int32_t pass;
     uint32_t sec_off, sec_size;
     uint64_t sec_start_bit;
     uint32_t tok_first, tok_cap; // slice of the image's token array
     int32_t *lz_window;          // or null
-    int8_t *nonzeros;            // [3 * 1024] scratch of the coefficient decoder
+    uint8_t *nonzeros;           // [3 * 32] scratch of the coefficient decoder (see HfLane::colbuf)
     uint32_t tok_used;           // written by the kernel
+    HfVb *vbs;                   // the group's varblocks in decoding order (shared by the passes; written by hf_prep)
+    int32_t nvb;                 // written by hf_prep (pass 0's record only)
 };
 
 // =============================================================================================
@@ -722,126 +730,6 @@ J40B_HD inline void llf_from_lf(const DLfGroup &g, const DVarblock &vb, float *s
 }
 
 // =============================================================================================
-// PassGroup: HF coefficient decoding into per-varblock token lists (serial; j40.h:6888-7004)
-
-// CoeffFreqContext / CoeffNumNonzeroContext of the format, pre-multiplied by 2 (j40.h:6935-6947)
-J40B_HD J40B_INLINE int coeff_freq_ctx2(int k) { // k in [1, 64)
-    return k < 16 ? 2 * (k - 1) : k < 32 ? 30 + 2 * ((k - 16) >> 1) : 46 + 2 * ((k - 32) >> 2);
-}
-J40B_HD J40B_INLINE int coeff_nnz_ctx2(int q) { // q in [0, 64)
-    return q < 2 ? 0 : q == 2 ? 62 : q < 5 ? 124 : q < 9 ? 186 : q < 13 ? 246 : q < 21 ? 304 : q < 33 ? 360 : 412;
-}
-
-// Written as a state machine with exactly one symbol read per loop iteration: several groups can then be
-// decoded by the lanes of one warp (one group per lane) and stay convergent at the symbol read, whatever
-// their position inside a block is. `nonzeros`: [gh8*gw8][3] bytes of per-group scratch. `ctx_lut`: optional
-// 128-entry table (shared memory on the device): [q] = coeff_nnz_ctx2(q), [64 + k] = coeff_freq_ctx2(k).
-// MODE 1: the code spec is rANS without LZ77 and the caller has seeded the state (see code_cluster).
-template <int MODE>
-J40B_HD inline void hf_coeffs_tokens(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
-                                     const DFrame &f, const uint8_t *arena, const DLfGroup &g, DGroup &grp,
-                                     int32_t ctxoff, DToken *tokens /* image token array */, int8_t *nonzeros,
-                                     const uint16_t *ctx_lut) {
-    const int gw8 = ceil_div(grp.gw, 8), gh8 = ceil_div(grp.gh, 8);
-    const int nb_block_ctx = f.nb_block_ctx, qf_count = f.nb_qf_thr + 1;
-    const int lfidx_size = (f.nb_lf_thr[0] + 1) * (f.nb_lf_thr[1] + 1) * (f.nb_lf_thr[2] + 1);
-    const int bctxc = 13 * qf_count * lfidx_size;
-    const uint8_t *block_ctx_map = arena + f.block_ctx_map_off;
-    const int n8 = g.width8 * g.height8, w8 = g.width8;
-    const int32_t *blocks = g.blocks + grp.gy8 * w8 + grp.gx8;
-    const uint8_t *lfidx_map = g.lfidx + grp.gy8 * w8 + grp.gx8;
-    const DVarblock *varblocks = g.varblocks;
-    uint32_t *vb_tok = g.vb_tok;
-    uint32_t tok = grp.tok_first;
-    const uint32_t tok_end = grp.tok_first + grp.tok_cap;
-    // scan position and per-block / per-channel state
-    int x8 = -1, y8 = 0, cell = -1; // current varblock's top-left cell inside the group (cell = y8 * gw8 + x8)
-    int c_yxb = 2;            // channel being decoded, in Y, X, B order
-    int nz = 0;               // non-zero coefficients still to come in this channel
-    int i = 0, size = 0, log_first = 0, prev = 0, cctx = 0, c = 0, bctx0 = 0, order_idx = 0, log_rows = 0, log_columns = 0;
-    int32_t voff = 0;
-    uint32_t first_tok = 0;
-    const int32_t *order = 0;
-    for (;;) {
-        int ctx;
-        const bool reading_nnz = nz == 0;
-        if (reading_nnz) {
-            // next channel, or the next varblock in raster order of top-left cells
-            if (++c_yxb == 3) {
-                c_yxb = 0;
-                int32_t b = 0;
-                for (;;) {
-                    ++cell;
-                    if (++x8 == gw8) { x8 = 0; ++y8; }
-                    if (y8 >= gh8) break;
-                    b = blocks[y8 * w8 + x8];
-                    if ((b >> 20) >= 2) break;
-                }
-                if (y8 >= gh8) break; // group finished
-                voff = b & 0xfffff;
-                DctSelectInfo d = dct_select_info((b >> 20) - 2);
-                log_rows = d.log_rows; log_columns = d.log_columns; order_idx = d.order_idx;
-                size = 1 << (log_rows + log_columns);
-                log_first = log_rows + log_columns - 6;
-                bctx0 = (order_idx * qf_count + varblocks[voff].qfidx) * lfidx_size + lfidx_map[y8 * w8 + x8];
-            }
-            c = c_yxb == 0 ? 1 : c_yxb == 1 ? 0 : 2;
-            order = f.order[order_idx][c];
-            const int bctx = block_ctx_map[bctx0 + bctxc * c_yxb];
-            int pred = x8 > 0 ? (y8 > 0 ? (nonzeros[(cell - 1) * 3 + c] + nonzeros[(cell - gw8) * 3 + c] + 1) >> 1
-                                         : nonzeros[(cell - 1) * 3 + c])
-                              : (y8 > 0 ? nonzeros[(cell - gw8) * 3 + c] : 32);
-            ctx = ctxoff + bctx + (pred < 8 ? pred : 4 + pred / 2) * nb_block_ctx;
-            cctx = ctxoff + 458 * bctx + 37 * nb_block_ctx;
-        } else {
-            const int q = (nz + (1 << log_first) - 1) >> log_first, k = i >> log_first;
-            ctx = cctx + prev + (ctx_lut ? (int) ctx_lut[q] + (int) ctx_lut[64 + k] : coeff_nnz_ctx2(q) + coeff_freq_ctx2(k));
-        }
-        // ---- the one symbol read of this iteration
-        int32_t v;
-        if (MODE == 1) v = code_cluster<false, 1>(br, es, cc, cs, cc.clusters[cc.cluster_map[ctx]], 0);
-        else v = code(br, es, cc, cs, ctx, 0);
-        if (es.err) return;
-        if (reading_nnz) {
-            nz = v;
-            if (!(nz <= (63 << log_first))) { es.set(br, E_COEF); return; }
-            const int8_t qnz = (int8_t) ((nz + (1 << log_first) - 1) >> log_first);
-            if (log_first == 0) {
-                nonzeros[cell * 3 + c] = qnz;
-            } else {
-                for (int a = 0; a < (1 << (log_rows - 3)); ++a) for (int bb = 0; bb < (1 << (log_columns - 3)); ++bb) {
-                    nonzeros[(cell + a * gw8 + bb) * 3 + c] = qnz;
-                }
-            }
-            prev = nz <= (size >> 4);
-            i = 1 << log_first;
-            first_tok = tok;
-            if (nz == 0) {
-                vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
-                vb_tok[((size_t) c * n8 + voff) * 2 + 1] = 0;
-            }
-        } else {
-            if (v) {
-                if (tok >= tok_end) { es.set_raw(E_TOKV); return; }
-                DToken t;
-                t.pos = (uint32_t) order[i];
-                t.val = unpack_signed(v);
-                tokens[tok++] = t;
-            }
-            prev = v != 0;
-            nz -= prev;
-            ++i;
-            if (nz == 0) {
-                vb_tok[((size_t) c * n8 + voff) * 2 + 0] = first_tok;
-                vb_tok[((size_t) c * n8 + voff) * 2 + 1] = tok - first_tok;
-            } else if (i >= size) { es.set(br, E_COEF); return; }
-        }
-    }
-    grp.tok_used = tok - grp.tok_first;
-    finish_code(br, es, cc, cs);
-}
-
-// =============================================================================================
 // back half: tokens -> coefficients -> samples -> RGBA8 for one varblock
 
 // smallest index k in [0, 255] such that thr[k] > v, i.e. the number of thresholds <= v
@@ -881,15 +769,21 @@ J40B_HD inline void varblock_to_pixels(const DFrame &f, const uint8_t *arena, co
     // 1. zero + scatter the decoded (quantised) coefficients
     for (int c = 0; c < 3; ++c) for (int i = tid; i < size; i += nth) coef[c][i] = 0.0f;
     sync();
-    for (int c = 0; c < 3; ++c) {
-        uint32_t first = g.vb_tok[((size_t) c * n8 + voff) * 2 + 0], cnt = g.vb_tok[((size_t) c * n8 + voff) * 2 + 1];
-        // positions within one varblock-channel are distinct (a scan order is a permutation)
-        for (uint32_t k = tid; k < cnt; k += nth) {
-            DToken t = tokens[first + k];
-            coef[c][t.pos] = J40B_FADD(coef[c][t.pos], (float) t.val);
+    for (int pass = 0; pass < f.num_passes; ++pass) {
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t *slot = g.vb_tok + (((size_t) pass * 3 + c) * n8 + voff) * 2;
+            const uint32_t first = slot[0], cnt = slot[1];
+            const int32_t *order = f.order[pass][d.order_idx][c];
+            // positions within one varblock-channel and pass are distinct (a scan order is a permutation); the
+            // passes add up (j40.h:6989): integer-valued floats, exact in any order
+            for (uint32_t k = tid; k < cnt; k += nth) {
+                DToken t = tokens[first + k];
+                const int32_t pos = order[t.pos];
+                coef[c][pos] = J40B_FADD(coef[c][pos], (float) t.val);
+            }
         }
+        sync();
     }
-    sync();
     // 2. dequantise (j40.h:7078-7094)
     const float *dq = f.dq[d.param_idx];
     float mult[3];

@@ -18,8 +18,10 @@ __global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap, int spe
     modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
 }
 
-__global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height) {
-    int x = (int) (blockIdx.x * blockDim.x + threadIdx.x), y = (int) blockIdx.y;
+// rows go over grid.x together with the column blocks (grid.y is capped at 65535, frames may be 2^18 rows tall)
+__global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height, int xblocks) {
+    const int y = (int) (blockIdx.x / (unsigned) xblocks), xb = (int) (blockIdx.x % (unsigned) xblocks);
+    const int x = xb * (int) blockDim.x + (int) threadIdx.x;
     if (x < width && y < height) render_px(*w, x, y);
 }
 
@@ -31,8 +33,9 @@ void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap) {
     k_modular<<<n, 32, (size_t) spec_cap + warp_slice_bytes(cap), stream>>>(w, cap, spec_cap);
 }
 void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height) {
-    dim3 grid((unsigned) ((width + 255) / 256), (unsigned) height);
-    k_render<<<grid, 256, 0, stream>>>(w, width, height);
+    if (width <= 0 || height <= 0) return;
+    const int xblocks = (width + 255) / 256;
+    k_render<<<(unsigned) xblocks * (unsigned) height, 256, 0, stream>>>(w, width, height, xblocks);
 }
 
 } // namespace j40b

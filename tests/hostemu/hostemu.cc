@@ -48,14 +48,20 @@ struct HostEmuBackend {
             lf_llf_body(w[i], 0, 1, NoSync());
         }
     }
-    void launch_hf(const HfWork *w, int n, size_t) {
+    void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t) {
+        for (int i = 0; i < ngroups; ++i) hf_prep_body(pw[i], 0, 1, NoSync());
         std::vector<uint8_t> copy(40 * 1024);
+        auto any = [](bool p) { return p; };
         for (int i = 0; i < n; ++i) {
+            if (*w[i].lf_err) continue;
             // like the device kernel: every other "warp" gets a staged copy of the code spec tables
-            bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->coeff_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
+            const int pass = w[i].grp->pass;
+            bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->coeff_spec_off[pass], copy.data(), (uint32_t) copy.size(), 0, 1);
             uint16_t lut[128];
             for (int k = 0; k < 64; ++k) { lut[k] = (uint16_t) coeff_nnz_ctx2(k); lut[64 + k] = (uint16_t) (k ? coeff_freq_ctx2(k) : 0); }
-            hf_group_body(w[i], staged ? copy.data() : nullptr, w[i].arena, (i & 2) ? lut : nullptr);
+            const uint8_t *sc = staged ? copy.data() : nullptr;
+            if (hf_is_plain_ans(w[i])) hf_lanes_run<1>(&w[i], true, sc, w[i].arena, pass, (i & 2) ? lut : nullptr, any, NoSync());
+            else hf_lanes_run<0>(&w[i], true, sc, w[i].arena, pass, (i & 2) ? lut : nullptr, any, NoSync());
         }
     }
     void launch_back(const BackWork *w, int n) {

@@ -40,6 +40,15 @@ VARDCT_CASES = [
     ("raw_dq_8x8_single_group", 200, 136, 26, dict(mix=1, tree=1, raw_dq=1)),
     ("raw_dq_8x8_16x16", 520, 392, 27, dict(mix=1, tree=1, raw_dq=0x11)),
     ("raw_dq_prefix_alpha", 300, 200, 28, dict(mix=1, tree=2, raw_dq=0x11, ans=0, alpha=1)),
+    # more than one pass (j40.h:6844-6866, 7847-7854): per-pass orders and code specs, coefficients added up
+    ("passes2", 520, 392, 33, dict(mix=1, tree=1, passes=2)),
+    ("passes3_custom_orders", 520, 392, 34, dict(mix=1, tree=1, passes=3, orders=0x1f)),
+    ("passes4_prefix", 520, 392, 35, dict(mix=1, tree=1, passes=4, ans=0)),
+    ("passes2_presets_block_ctx", 520, 392, 36, dict(mix=1, tree=1, passes=2, presets=2, block_ctx=1)),
+    ("passes3_permuted_toc", 520, 392, 37, dict(mix=1, tree=1, passes=3, permuted=1)),
+    ("passes5_lz77", 300, 264, 38, dict(mix=1, tree=1, passes=5, lz77=1)),
+    ("passes2_dct128", 512, 512, 39, dict(force=21, hfmul=12, tree=1, passes=2)),
+    ("passes2_all_transforms", 520, 392, 40, dict(mix=2, tree=2, passes=2)),
 ]
 
 MODULAR_CASES = [

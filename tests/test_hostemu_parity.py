@@ -128,3 +128,45 @@ def test_too_many_transforms_is_an_error_not_an_overflow(oracle, emu):
     a, ea, _, _ = oracle.decode(data)
     b, eb, _ = emu.decode(data)
     assert ea == eb == "xlim" and a is None and b is None
+
+
+def _boxes(data):
+    """splits a container file into (type, payload) after the 32 bytes of signature + ftyp"""
+    out, pos = [], 32
+    while pos < len(data):
+        size = int.from_bytes(data[pos:pos + 4], "big")
+        typ = data[pos + 4:pos + 8]
+        end = len(data) if size == 0 else pos + size
+        out.append((typ, data[pos + 8:end]))
+        pos = end
+    return out
+
+
+def _box(typ, payload):
+    return (8 + len(payload)).to_bytes(4, "big") + typ + payload
+
+
+def test_duplicate_boxes_behind_the_codestream(oracle, emu, gen):
+    """a second jxll / jxlc / jxlp box behind the last codestream box is `box?` in the reference (advisor finding,
+    round 1) when the reference gets to see its header: within the first 64 KiB of the file, or behind a single-section
+    frame of any size (read through to its end); a large multi-section frame is left by a seek and decodes"""
+    for opts, w, h, want in ((dict(tree=0, lz77=0, container=1), 120, 90, "box?"), (dict(container=1), 600, 400, ""),
+                             (dict(container=1, group_shift=9), 200, 300, "box?")):
+        data = streams.make(gen, "modular", w, h, 11, opts)
+        head, boxes = data[:32], _boxes(data)
+        cs = [b for b in boxes if b[0] == b"jxlc"]
+        assert len(cs) == 1
+        jxlc = _box(b"jxlc", cs[0][1])
+        jxll = _box(b"jxll", b"\x05")
+        free = _box(b"free", b"\0" * 70000)
+        half = len(cs[0][1]) // 2
+        jxlp0 = _box(b"jxlp", b"\x80\0\0\0" + cs[0][1][:half])
+        jxlp1 = _box(b"jxlp", b"\0\0\0\x01" + cs[0][1][half:])  # clear top bit: the reference's "last" (App. B quirk)
+        variants = [head + jxlc + jxll + jxll, head + jxll + jxlc + jxll, head + jxlc + jxlc,
+                    head + jxlp0 + jxlp1 + jxlp1, head + free + jxlc + jxll + jxll, head + jxlc + free + jxlc,
+                    head + jxll + jxlc + free + jxll, head + jxlp0 + jxlp1 + jxlc, head + jxlc + jxlp1]
+        for v in variants:
+            assert oracle.decode(v)[1] == want
+            _cmp(oracle, emu, v)
+        _cmp(oracle, emu, head + jxll + jxlc)
+        _cmp(oracle, emu, head + jxlp0 + jxlp1)

@@ -54,6 +54,10 @@ struct VarDCTParams {
     bool lz77_coeffs = false;  // enable LZ77 in the coefficient stream (rare in practice)
     float quant_deadzone = 0.55f;
     int force_dctsel = -1;     // >= 0: use this transform wherever it fits (coverage tests)
+    int passes = 1;            // > 1: the quantised coefficients are split over this many passes (the decoder adds them up);
+                               // pass p has its own code spec and, with custom_orders, its own coefficient orders
+    float big_take = 0.75f;    // transform_mix 1: probability of taking a larger transform where the content allows it
+    float big_thr = 0.06f;     // transform_mix 1: activity threshold (scaled by 1/sqrt(cells)) below which it is allowed
 };
 
 struct GenStats {
@@ -306,9 +310,14 @@ public:
         }
 
         // ---- HF coefficient token streams
-        std::vector<TokStream> hf_ts((size_t) num_groups);
-        std::vector<std::vector<int32_t>> orders = make_orders();
-        for (int g = 0; g < num_groups; ++g) tokenize_group(g, orders, hf_ts[(size_t) g]);
+        JG_CHECK(P.passes >= 1 && P.passes <= 11 && (P.passes == 1 || num_groups > 1));
+        const int npass = P.passes;
+        std::vector<TokStream> hf_ts((size_t) num_groups * (size_t) npass); // [pass * num_groups + g]
+        std::vector<std::vector<std::vector<int32_t>>> orders_p((size_t) npass);
+        for (int ps = 0; ps < npass; ++ps) {
+            orders_p[(size_t) ps] = make_orders(ps);
+            for (int g = 0; g < num_groups; ++g) tokenize_group(g, orders_p[(size_t) ps], hf_ts[(size_t) ps * (size_t) num_groups + (size_t) g], ps);
+        }
         EntropyOpts co;
         co.use_prefix = !P.use_ans;
         co.log_alpha_size = P.lz77_coeffs ? 8 : P.log_alpha_size;
@@ -317,21 +326,21 @@ public:
         co.lz77 = P.lz77_coeffs;
         if (co.lz77) for (auto &s : hf_ts) lz77_rle(s, co.min_length, 0, 6);
         int num_coef_ctx = 495 * nb_block_ctx * P.num_hf_presets;
-        CodeSpec cspec;
-        {
+        std::vector<CodeSpec> cspecs((size_t) npass);
+        for (int ps = 0; ps < npass; ++ps) {
             std::vector<const TokStream *> all;
-            for (auto &s : hf_ts) { all.push_back(&s); stats.hf_symbols += (int64_t) s.size(); }
-            cspec.build(num_coef_ctx, co, all);
+            for (int g = 0; g < num_groups; ++g) { const TokStream &s = hf_ts[(size_t) ps * (size_t) num_groups + (size_t) g]; all.push_back(&s); stats.hf_symbols += (int64_t) s.size(); }
+            cspecs[(size_t) ps].build(num_coef_ctx, co, all);
         }
-        stats.coef_clusters = cspec.nclusters;
+        stats.coef_clusters = cspecs[0].nclusters;
 
         // ---- sections
         BitWriter lfglobal;
         write_lf_global(lfglobal, tree, mspec, mo);
         BitWriter hfglobal;
         mspec_ptr = &mspec;
-        write_hf_global(hfglobal, num_groups, cspec);
-        std::vector<BitWriter> lfsec((size_t) num_lfg), pgsec((size_t) num_groups);
+        write_hf_global(hfglobal, num_groups, cspecs, orders_p);
+        std::vector<BitWriter> lfsec((size_t) num_lfg), pgsec((size_t) num_groups * (size_t) npass);
         for (int i = 0; i < num_lfg; ++i) {
             BitWriter &bw = lfsec[(size_t) i];
             bw.put((uint64_t) P.extra_prec, 2);
@@ -343,10 +352,11 @@ public:
             write_modular_header_prefix(bw, mh);
             mspec.encode(bw, meta_ts[(size_t) i]);
         }
-        for (int g = 0; g < num_groups; ++g) {
-            BitWriter &bw = pgsec[(size_t) g];
+        for (int pg = 0; pg < num_groups * npass; ++pg) {
+            const int g = pg % num_groups;
+            BitWriter &bw = pgsec[(size_t) pg];
             bw.put((uint64_t) group_preset[(size_t) g], ceil_lg((uint32_t) P.num_hf_presets));
-            cspec.encode(bw, hf_ts[(size_t) g]);
+            cspecs[(size_t) (pg / num_groups)].encode(bw, hf_ts[(size_t) pg]);
             if (P.alpha && num_groups > 1) {
                 ModularHeaderOpts mh;
                 write_modular_header_prefix(bw, mh);
@@ -357,7 +367,7 @@ public:
         // ---- assemble the codestream
         BitWriter out;
         write_headers(out);
-        bool single = num_groups == 1; // one pass
+        bool single = num_groups == 1 && npass == 1;
         if (single) {
             // reference order for single-section frames: LfGlobal, HfGlobal, LfGroup, PassGroup (SURVEY B-12)
             BitWriter body;
@@ -595,8 +605,8 @@ private:
             }
             if (!free_) continue;
             // smoother content tolerates larger transforms
-            float thr = 0.06f / (float) std::sqrt((double) (r8 * c8));
-            double take = P.transform_mix == 2 ? 0.08 : 0.75;
+            float thr = P.big_thr / (float) std::sqrt((double) (r8 * c8));
+            double take = P.transform_mix == 2 ? 0.08 : (double) P.big_take;
             if ((P.transform_mix == 2 || amax < thr) && rng.uni() < take) return sel;
         }
         // 8x8 family
@@ -669,7 +679,7 @@ private:
     }
 
     // --------------------------------------------------------------------------------------
-    std::vector<std::vector<int32_t>> make_orders() {
+    std::vector<std::vector<int32_t>> make_orders(int pass = 0) {
         // orders[idx*3 + c]; custom ones are small perturbations of the natural order
         std::vector<std::vector<int32_t>> o(13 * 3);
         for (int i = 0; i < 13; ++i) for (int c = 0; c < 3; ++c) {
@@ -678,16 +688,30 @@ private:
                 std::vector<int32_t> &v = o[(size_t) i * 3 + (size_t) c];
                 int size = (int) v.size(), skip = size / 64;
                 int lim = std::min(size, skip + 200); // keep the Lehmer code short
-                Rng r2(P.seed * 131 + (uint64_t) (i * 3 + c));
+                Rng r2(P.seed * 131 + (uint64_t) (i * 3 + c) + (uint64_t) pass * 977);
                 for (int k = skip; k + 1 < lim; ++k) if (r2.uni() < 0.3) std::swap(v[(size_t) k], v[(size_t) k + 1 + (size_t) r2.below(std::min(3, lim - k - 1))]);
             }
         }
-        custom_order_cache = o;
         return o;
     }
-    std::vector<std::vector<int32_t>> custom_order_cache;
 
-    void tokenize_group(int gidx, const std::vector<std::vector<int32_t>> &orders, TokStream &ts) {
+    // the share of quantised coefficient v at scan index i that pass `pass` codes; the shares add up to v.
+    // Low frequencies go to the early passes, the rest is split by value so that positions meet in several passes.
+    int32_t pass_share(int32_t v, int i, int size, int pass) const {
+        const int n = P.passes;
+        if (n == 1) return v;
+        if (i < size / 8) { // low frequencies: passes 0 and 1 share the value
+            if (pass == 0) return v / 2;
+            if (pass == 1) return v - v / 2;
+            return 0;
+        }
+        // the rest: round-robin over the passes by position, except that every 5th goes to the last pass with an
+        // opposite-sign part in pass 0 (sums that cancel)
+        if (i % 5 == 0 && v != 0 && n > 1) return pass == n - 1 ? v + 1 : pass == 0 ? -1 : 0;
+        return pass == (i % n) ? v : 0;
+    }
+
+    void tokenize_group(int gidx, const std::vector<std::vector<int32_t>> &orders, TokStream &ts, int pass = 0) {
         static const int8_t FREQ_CTX[64] = {
             -1, 0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28,
             30, 30, 32, 32, 34, 34, 36, 36, 38, 38, 40, 40, 42, 42, 44, 44,
@@ -721,8 +745,15 @@ private:
             for (int cyxb = 0; cyxb < 3; ++cyxb) {
                 static const int YXB[3] = {1, 0, 2};
                 int c = YXB[cyxb];
-                const std::vector<int32_t> &q = vb.q[c];
                 const std::vector<int32_t> &order = orders[(size_t) d.order_idx * 3 + (size_t) c];
+                std::vector<int32_t> q = vb.q[c];
+                if (P.passes > 1) {
+                    // shares are assigned per *position* (the order tables differ between passes)
+                    const std::vector<int32_t> &nat = T.order[d.order_idx];
+                    std::vector<int32_t> share(q.size(), 0);
+                    for (int i = 1 << (log_size - 6); i < (1 << log_size); ++i) share[(size_t) nat[(size_t) i]] = pass_share(q[(size_t) nat[(size_t) i]], i, 1 << log_size, pass);
+                    q.swap(share);
+                }
                 int bctx = block_ctx_map[(size_t) (bctx0 + bctxc * cyxb)];
                 int pred = x8 > 0 ? (y8 > 0 ? (nonzeros[(size_t) (nzpos - 1) * 3 + (size_t) c] + nonzeros[(size_t) (nzpos - gw8) * 3 + (size_t) c] + 1) >> 1
                                             : nonzeros[(size_t) (nzpos - 1) * 3 + (size_t) c])
@@ -784,7 +815,12 @@ private:
         if (P.alpha) bw.put(0, 2); // ec upsampling
         bw.put((uint64_t) P.x_qm_scale, 3);
         bw.put((uint64_t) P.b_qm_scale, 3);
-        bw.u32(1, 1, 0, 2, 0, 3, 0, 4, 3); // num_passes
+        if (P.passes <= 3) bw.put((uint64_t) (P.passes - 1), 2); // num_passes: selectors 1, 2, 3
+        else { bw.put(3, 2); bw.put((uint64_t) (P.passes - 4), 3); }
+        if (P.passes > 1) {
+            bw.put(0, 2);   // num_ds = 0
+            for (int i = 0; i + 1 < P.passes; ++i) bw.put((uint64_t) (i & 3), 2); // shift[i]: parsed and ignored by j40
+        }
         bw.bit(0);          // have_crop
         bw.u32(0, 0, 0, 1, 0, 2, 0, 3, 2); // blend mode: replace
         if (P.alpha) bw.u32(0, 0, 0, 1, 0, 2, 0, 3, 2); // blend mode (alpha)
@@ -933,7 +969,7 @@ private:
         }
     }
 
-    void write_hf_global(BitWriter &bw, int num_groups, const CodeSpec &cspec) {
+    void write_hf_global(BitWriter &bw, int num_groups, const std::vector<CodeSpec> &cspecs, const std::vector<std::vector<std::vector<int32_t>>> &orders_p) {
         if (!P.raw_dq) {
             bw.bit(1); // default dequantisation matrices
         } else {
@@ -948,27 +984,29 @@ private:
             }
         }
         bw.put((uint64_t) (P.num_hf_presets - 1), ceil_lg((uint32_t) num_groups));
-        // HfPass (one pass)
-        int used = P.custom_orders & 0x1fff;
-        if (!used) bw.put(2, 2); // selector 2: used_orders = 0
-        else { bw.put(3, 2); bw.put((uint64_t) used, 13); }
-        if (used) {
-            TokStream ts;
-            for (int i = 0; i < 13; ++i) if ((used >> i) & 1) {
-                for (int c = 0; c < 3; ++c) lehmer_tokens(T.order[i], custom_order_cache[(size_t) i * 3 + (size_t) c], ts);
+        // HfPass, once per pass
+        for (size_t ps = 0; ps < cspecs.size(); ++ps) {
+            int used = P.custom_orders & 0x1fff;
+            if (!used) bw.put(2, 2); // selector 2: used_orders = 0
+            else { bw.put(3, 2); bw.put((uint64_t) used, 13); }
+            if (used) {
+                TokStream ts;
+                for (int i = 0; i < 13; ++i) if ((used >> i) & 1) {
+                    for (int c = 0; c < 3; ++c) lehmer_tokens(T.order[i], orders_p[ps][(size_t) i * 3 + (size_t) c], ts);
+                }
+                EntropyOpts po;
+                po.use_prefix = !P.use_ans;
+                po.log_alpha_size = 8;
+                po.cfg = {4, 1, 0};
+                po.max_clusters = 4;
+                CodeSpec pspec;
+                std::vector<const TokStream *> v{&ts};
+                pspec.build(8, po, v);
+                pspec.write(bw);
+                pspec.encode(bw, ts);
             }
-            EntropyOpts po;
-            po.use_prefix = !P.use_ans;
-            po.log_alpha_size = 8;
-            po.cfg = {4, 1, 0};
-            po.max_clusters = 4;
-            CodeSpec ps;
-            std::vector<const TokStream *> v{&ts};
-            ps.build(8, po, v);
-            ps.write(bw);
-            ps.encode(bw, ts);
+            cspecs[ps].write(bw);
         }
-        cspec.write(bw);
     }
 
     // Lehmer code of `target` relative to `natural` for positions >= size/64 (j40.h:5428-5475)
