@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the JPEG XL group-decode hot path on B200 (BASELINE.json metric: Mpixels/s decoded,
-4K VarDCT batch), with roofline, CPU baseline and end-to-end numbers.
+4K VarDCT batch), with roofline, CPU baseline, end-to-end and single-image latency numbers.
 
-  python bench.py --gpus 1 --steps 5 --warmup 3                    # our CUDA path
+  python bench.py --gpus 1 --steps 5 --warmup 3                    # our CUDA path, BASELINE config 3/5 (4K VarDCT)
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU, batch-sharded
   python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # the reference j40.h on the host CPU cores
+  python bench.py --workload c2 | c4                               # 1920x1080 VarDCT / 8192x8192 lossless modular
+  python bench.py --scaling strong --total-frames 256              # C5 as written: one fixed batch of 256 distinct frames
 
-A "step" is one decode of this rank's batch of synthetic 4K VarDCT frames ("d1/e6-like" streams from
-tools/streamgen; no JPEG XL encoder exists offline). Frames are independent, so ranks share nothing: no
-collective on the data path (weak scaling: the per-GPU batch is fixed).
+A "step" is one decode of this rank's batch of synthetic frames (streams from tools/streamgen; no JPEG XL encoder
+exists offline). Frames are independent, so ranks share nothing: no collective on the data path. Weak scaling keeps
+the per-GPU batch fixed; strong scaling shards one fixed list of frames with j40_b200.sharding.shard_indices.
 """
 import argparse
 import json
@@ -23,16 +25,37 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# a dozen batch objects (CUDA streams) are in flight at once: with the default of 8 hardware work queues, streams
+# many batch objects (CUDA streams) are in flight at once: with the default of 8 hardware work queues, streams
 # that share a queue serialise behind each other (measured: +4 % device-resident, +15 % end to end with 32)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-STREAM_OPTS = dict(mix=1, tree=1, hfmul=10, hfmul_var=4)  # the "d1/e6-like" preset
+# "d1": >= 1.5 bpp with an 8x8-majority transform histogram (measured 1.85 bpp, 65 % of the varblocks
+# in the 8x8 family, 0.36 non-zeros per pixel). "light": round 1's preset (0.9 bpp, large transforms), for history.
+PRESETS = {
+    "d1": dict(mix=1, tree=1, hfmul=18, hfmul_var=6, big_take=0.35, big_thr=0.03),
+    "light": dict(mix=1, tree=1, hfmul=10, hfmul_var=4),
+}
+WORKLOADS = {
+    # name: (kind, width, height, frames per GPU, distinct streams per rank, frames per batch object)
+    "c3": ("vardct", 3840, 2160, 64, 8, 64),
+    "c2": ("vardct", 1920, 1080, 256, 16, 256),
+    "c4": ("modular", 8192, 8192, 2, 1, 1),
+}
 
 
-def workload_name(w, h, frames, distinct):
-    return (f"batch of {frames} independent {w}x{h} VarDCT frames per GPU ({distinct} distinct, cycled), "
-            f"tools/streamgen d1/e6-like preset {STREAM_OPTS}")
+def stream_opts(args):
+    return dict(PRESETS[args.preset]) if WORKLOADS[args.workload][0] == "vardct" else {}
+
+
+def workload_name(args):
+    kind, w, h = WORKLOADS[args.workload][:3]
+    if kind == "modular":
+        what = "lossless modular frames (fjxl-shaped: prefix codes + LZ77, YCoCg, gradient-predictor MA tree, group shift 8)"
+    else:
+        what = f"VarDCT frames, tools/streamgen preset '{args.preset}' {PRESETS[args.preset]}"
+    if args.scaling == "strong":
+        return f"one batch of {args.total_frames} distinct {w}x{h} {what}, sharded over the GPUs"
+    return f"batch of {args.frames_per_gpu} independent {w}x{h} {what} per GPU ({args.distinct} distinct, cycled)"
 
 
 def host_memory_budget():
@@ -54,21 +77,29 @@ def host_memory_budget():
     return avail
 
 
-def _gen_one(args):
-    w, h, seed = args
+def _gen_one(a):
+    kind, w, h, seed, opts = a
     from tools import streamgen
-    data, st = streamgen.vardct(w, h, seed=seed, **STREAM_OPTS)
-    return data, st
+    if kind == "modular":
+        import numpy as np
+        # an 8192x8192 source tiled from a 2048x2048 synthetic photo (the generator's noise synthesis is the slow part)
+        t = min(2048, w, h)
+        rgb = None
+        if w % t == 0 and h % t == 0 and w > t:
+            rgb = np.tile(streamgen.synth(t, t, seed), (h // t, w // t, 1))
+        return streamgen.modular(w, h, seed=seed, rgb=rgb, **opts)
+    return streamgen.vardct(w, h, seed=seed, **opts)
 
 
-def make_streams(w, h, seeds):
+def make_streams(kind, w, h, seeds, opts, share=1):
     from tools import streamgen
-    streamgen._ensure_tables()  # oracle-derived tables, inherited by forked workers
-    procs = max(1, min(len(seeds), (os.cpu_count() or 2) - 1, 32))
-    if procs == 1:
-        return [_gen_one((w, h, s)) for s in seeds]
+    if kind == "vardct":
+        streamgen._ensure_tables()  # oracle-derived tables, inherited by forked workers
+    procs = max(1, min(len(seeds), ((os.cpu_count() or 2) - 1) // max(1, share), 32))
+    if procs == 1 or kind == "modular":  # (the modular writer is multi-threaded itself)
+        return [_gen_one((kind, w, h, s, opts)) for s in seeds]
     with mp.get_context("fork").Pool(procs) as pool:
-        return pool.map(_gen_one, [(w, h, s) for s in seeds])
+        return pool.map(_gen_one, [(kind, w, h, s, opts) for s in seeds])
 
 
 class ClockSampler(threading.Thread):
@@ -102,8 +133,8 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def _ref_worker(args):
-    data, reps = args
+def _ref_worker(a):
+    data, reps = a
     from oracle import ref
     good, secs = ref.time_decode(data, reps)
     return good, secs
@@ -113,10 +144,12 @@ def run_reference(args, rank, world):
     """The reference's own CPU implementation (oracle/_ref = unmodified j40.h) on all host cores."""
     if rank != 0:
         return
-    w, h = args.width, args.height
+    kind, w, h = WORKLOADS[args.workload][:3]
     cores = os.cpu_count() or 1
     nproc = max(1, min(cores, 64))
-    datas = [d for d, _ in make_streams(w, h, list(range(min(args.distinct, nproc))))]
+    if kind == "modular":
+        nproc = min(nproc, 4)  # ~3 GB of planes per 8192x8192 decode
+    datas = [d for d, _ in make_streams(kind, w, h, list(range(min(args.distinct, nproc))), stream_opts(args))]
     work = [(datas[i % len(datas)], 1) for i in range(nproc)]
     ctx = mp.get_context("fork")
     with ctx.Pool(nproc) as pool:
@@ -129,18 +162,70 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
     mpix = nproc * args.steps * w * h / dt / 1e6
     line = {
-        "impl": "reference", "metric": "Mpixels/s decoded (4K VarDCT batch)", "value": mpix, "unit": "Mpix/s",
+        "impl": "reference", "metric": metric_name(args), "value": mpix, "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(w, h, args.frames_per_gpu, args.distinct),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if kind == "vardct" else "i16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args),
                    "implementation": "reference j40.h (unmodified, -O3 -ffp-contract=off) on the host CPU, one process per frame",
                    "frames_per_step": nproc, "processes": nproc,
-                   "sample": f"each step decodes {nproc} frames of the workload (one per process) instead of all {args.frames_per_gpu}"},
+                   "sample": f"each step decodes {nproc} frames of the workload (one per process)"},
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": nproc, "kind": "reference",
                          "sample": f"{nproc} frames per step, one process per frame, {args.steps} steps"},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def metric_name(args):
+    return {"c3": "Mpixels/s decoded (4K VarDCT batch)", "c2": "Mpixels/s decoded (1080p VarDCT batch)",
+            "c4": "Mpixels/s decoded (8192x8192 lossless modular)"}[args.workload]
+
+
+def d2h_ceiling(torch, nbytes, reps, dist):
+    """what a bare device-to-pinned-host copy of one step's output achieves on this box, all ranks at once: the
+    ceiling of any end-to-end number that returns every decoded frame to the host"""
+    n = min(nbytes, 1 << 30)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dst = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del src, dst
+    return n * reps / float(t.item()) / 1e9  # GB/s per rank with all ranks copying
+
+
+def latency_section(J, ref, np, args):
+    """single-image latency through j40_from_memory ... j40_frame_pixels_u8x4 (what a dj40.c user sees), next to the
+    reference on one host core, for BASELINE configs C1-C3 (and C4 when it is the workload)"""
+    from tools import streamgen
+    cases = [("c1_256x256_vardct_dct8", "vardct", 256, 256, dict(mix=0, tree=0, cfl=0)),
+             ("c2_1920x1080_vardct", "vardct", 1920, 1080, PRESETS[args.preset]),
+             ("c3_3840x2160_vardct", "vardct", 3840, 2160, PRESETS[args.preset])]
+    if args.workload == "c4":
+        cases.append(("c4_8192x8192_modular", "modular", 8192, 8192, {}))
+    out = {}
+    for name, kind, w, h, opts in cases:
+        data, _ = _gen_one((kind, w, h, 1, dict(opts)))
+        want, e0, _, _ = ref.decode(data)
+        ms = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            got, err, _, _ = J.decode(data)
+            ms.append((time.perf_counter() - t0) * 1e3)
+            assert err == "" and np.array_equal(got, want), "single-image decode differs from the reference"
+        _, secs = ref.time_decode(data, 1 if kind == "modular" else 2)
+        out[name] = {"ours_ms": min(ms[1:]), "reference_ms": min(secs) * 1e3}
+    return out
 
 
 def main():
@@ -149,19 +234,24 @@ def main():
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=3840)
-    ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--frames-per-gpu", type=int, default=64)
-    ap.add_argument("--distinct", type=int, default=8, help="distinct streams per rank (cycled to fill the batch)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--preset", default="d1", choices=sorted(PRESETS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-frames", type=int, default=256, help="strong scaling: size of the fixed batch (distinct frames)")
+    ap.add_argument("--frames-per-gpu", type=int, default=0, help="weak scaling: frames per GPU and step (0 = the workload's default)")
+    ap.add_argument("--distinct", type=int, default=0, help="weak scaling: distinct streams per rank, cycled to fill the batch")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-latency", action="store_true")
     ap.add_argument("--streams", type=int, default=12, help="batch objects (CUDA streams) the timed steps are pipelined over")
     ap.add_argument("--e2e-sets", type=int, default=2, help="groups of `streams` batch objects the end-to-end loop alternates between")
-    ap.add_argument("--lag", type=int, default=0, help="step s starts its LF stage when step s-lag has finished its own "
-                    "(keeps the batches in flight out of phase); 0 = no phase control (default: measured best), -1 = streams/2")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    kind, w, h, F_default, distinct_default, obj_frames = WORKLOADS[args.workload]
+    args.frames_per_gpu = args.frames_per_gpu or F_default
+    args.distinct = args.distinct or distinct_default
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
 
@@ -172,6 +262,7 @@ def main():
     import numpy as np
     import torch
     import j40_b200 as J
+    from j40_b200.sharding import shard_indices
     from oracle import ref
 
     if not J.gpu_available():
@@ -185,62 +276,80 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    host_threads = max(1, min(16, (os.cpu_count() or 1) // local_world))  # parse threads of this rank
 
-    w, h = args.width, args.height
-    F = args.frames_per_gpu
-    gen = make_streams(w, h, [rank * args.distinct + i for i in range(args.distinct)])
-    datas = [g[0] for g in gen]
+    # ---- this rank's frames
+    opts = stream_opts(args)
+    if args.scaling == "strong":
+        mine = shard_indices(args.total_frames, rank, world)   # frame i of the fixed batch = seed i
+        gen = make_streams(kind, w, h, list(mine), opts, share=local_world)
+        datas = [g[0] for g in gen]
+        frames = datas
+    else:
+        gen = make_streams(kind, w, h, [rank * args.distinct + i for i in range(args.distinct)], opts, share=local_world)
+        datas = [g[0] for g in gen]
+        frames = [datas[i % len(datas)] for i in range(args.frames_per_gpu)]
     stats = [g[1] for g in gen]
-    frames = [datas[i % len(datas)] for i in range(F)]
+    F = len(frames)
     comp_bytes = sum(len(d) for d in frames)
     pixels = F * w * h
+    # a step = this rank's frames, in chunks of at most `obj_frames` frames per batch object
+    chunks = [frames[i:i + obj_frames] for i in range(0, F, obj_frames)]
+    C_ = len(chunks)
 
-    # ---- parity gate: no number counts unless the GPU output equals the reference's, byte for byte
-    want, e0, _, _ = ref.decode(datas[0])
-    assert e0 == "", "oracle rejected a bench stream"
+    # ---- parity gate: no number counts unless the GPU output of EVERY distinct frame equals the reference's
+    want = {}
+    for d in datas:
+        if d not in want:
+            px, e0, _, _ = ref.decode(d)
+            assert e0 == "", "oracle rejected a bench stream"
+            want[d] = px
+
+    def check_batch(bm, chunk):
+        seen = set()
+        for i, d in enumerate(chunk):
+            if d in seen:
+                continue
+            seen.add(d)
+            assert np.array_equal(bm.read_pixels(i), want[d]), "GPU output differs from the reference"
 
     # ---- device-resident throughput: inputs + tables already in HBM, kernels only
-    b = J.Batch(local_rank)
-    for d in frames:
-        b.add(d)
-    b.upload()
-    b.decode()
-    failed = b.wait()
-    assert failed == 0, [b.error(i) for i in range(F) if b.error(i)]
-    assert np.array_equal(b.read_pixels(0), want), "GPU output differs from the reference"
-    # serial pass (one batch, steps back to back): per-kernel device times for the roofline section
+    M = max(C_, (max(1, args.streams) // C_) * C_)   # batch objects in flight: whole steps
+    batches = []
+    for m in range(M):
+        bm = J.Batch(local_rank)
+        chunk = chunks[m % C_]
+        rot = (m // C_) % max(1, len(chunk))         # (another rotation of the same frames per object in flight)
+        chunk = chunk[rot:] + chunk[:rot]
+        bm.add_many(chunk, host_threads)
+        bm.upload()
+        bm.decode()
+        assert bm.wait() == 0, [bm.error(i) for i in range(len(chunk)) if bm.error(i)]
+        check_batch(bm, chunk)
+        batches.append(bm)
+    b = batches[0]
+    # serial pass (the first step's objects, one after the other): per-kernel device times for the roofline section
     step_ms, kernel_ms = [], []
     for it in range(args.warmup + 2):
-        b.decode()
-        b.wait()
+        tot, ks = 0.0, None
+        for bm in batches[:C_]:
+            bm.decode()
+            bm.wait()
+            tot += bm.last_decode_ms()
+            k = bm.kernel_ms()
+            ks = k if ks is None else {n: ks[n] + k[n] for n in k}
         if it >= args.warmup:
-            step_ms.append(b.last_decode_ms())
-            kernel_ms.append(b.kernel_ms())
+            step_ms.append(tot)
+            kernel_ms.append(ks)
     serial_ms = sum(step_ms) / len(step_ms)
-    dev_bytes = b.stat(0)
-    launches_per_step = b.stat(2)
-    # timed region: K steps pipelined over M batch objects (one CUDA stream each), so that the latency-bound
-    # LF-group kernel of one step overlaps the HF / back kernels of its neighbours. All K steps run inside the
+    dev_bytes = sum(bm.stat(0) for bm in batches)
+    launches_per_step = sum(bm.stat(2) for bm in batches[:C_])
+    # timed region: K steps pipelined over the M batch objects (one CUDA stream each), so that the latency-bound
+    # LF-group kernels of one step overlap the HF / back kernels of its neighbours. All K steps run inside the
     # region; device time is taken with CUDA events on stream 0 after joining every stream.
-    M = max(1, min(args.streams, args.steps))
-    lag = M // 2 if args.lag < 0 else min(args.lag, M - 1)
-
-    def submit_decode(s_):
-        # phase control: without it all batches in flight run their LF stages together, then their HF stages ...
-        if lag and s_ >= lag:
-            batches[s_ % M].after(batches[(s_ - lag) % M], 0)
-        batches[s_ % M].decode()
-
-    batches = [b]
-    for m in range(1, M):
-        bm = J.Batch(local_rank)
-        for i in range(F):
-            bm.add(frames[(i + m) % F])
-        bm.upload()
-        batches.append(bm)
     for _ in range(args.warmup):
-        for k in range(M):
-            submit_decode(k)
+        for bm in batches:
+            bm.decode()
         for bm in batches:
             assert bm.wait() == 0
     sampler = ClockSampler(local_rank)
@@ -250,30 +359,35 @@ def main():
     torch.cuda.synchronize()
     b.mark(0)
     for s_ in range(args.steps):
-        submit_decode(s_)
+        for c in range(C_):
+            batches[(s_ * C_ + c) % M].decode()
     for bm in batches[1:]:
         b.join(bm)
     b.mark(1)
+    stage_sum = {}
     for bm in batches:
         assert bm.wait() == 0
     torch.cuda.synchronize()
     total_ms = b.mark_ms()
+    for bm in batches[:min(M, args.steps * C_)]:      # stage times of the last decode of each object, as stretched by co-running
+        for n, v in bm.kernel_ms().items():
+            stage_sum[n] = stage_sum.get(n, 0.0) + v
     if os.environ.get("J40B_TIMELINE"):
-        # when each stage of the last decode on every batch object ended, relative to the start of the region
         for k, bm in enumerate(batches):
             print("timeline batch %d: " % k + " ".join("%s=%.1f" % (n, bm.event_ms(b, i)) for n, i in
                   [("lf0", 0), ("lfimg", 5), ("hfmeta", 6), ("lf", 1), ("hf", 2), ("tiles", 3), ("end", 4)]), file=sys.stderr)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     launches = launches_per_step * args.steps
-    for bm in batches[1:]:
-        dev_bytes += bm.stat(0)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, float(pixels)], dtype=torch.float64, device="cuda")
+    tmax = t.clone()
     if dist:
         dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * pixels * args.steps / (total_ms_max / 1e3) / 1e6
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total_ms_max = float(tmax[0].item())
+    job_pixels = float(t[1].item()) if dist else float(pixels)   # all ranks' pixels per step
+    value = job_pixels * args.steps / (total_ms_max / 1e3) / 1e6
 
     # ---- end to end through the C ABI with HOST buffers, every step: host parse of all frames + one H2D of
     # codestreams and tables + kernels + D2H of every decoded frame into pinned host memory. The batch objects
@@ -283,45 +397,39 @@ def main():
     if not args.skip_e2e:
         # Serving loop: `sets` groups of W batch objects. A group is submitted as one wave (all W decodes back to
         # back) and the next wave of the same group only after all of its D2H copies have landed; while one group
-        # copies out and is re-parsed / re-uploaded, the other one computes. Waves matter: resubmitting each
-        # object as soon as its own copy is done (the obvious rolling scheme) spreads the batches evenly over all
-        # phases, and a phase-staggered mix of LF / HF / tile kernels runs ~40 % slower than waves.
-        W = len(batches)
+        # copies out and is re-parsed / re-uploaded, the other one computes.
+        stride = b.info(0)[2]
+        pitch = h * stride
+        W = M
         sets = max(1, args.e2e_sets)
-        # every object in flight owns a pinned destination for its frames (2.1 GB at 64 x 4K): stay well inside the
-        # host memory this rank can count on (all ranks of the node allocate the same)
-        per_obj = F * h * b.info(0)[2]
-        budget = host_memory_budget() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        per_obj = max(len(c) for c in chunks) * pitch
+        budget = host_memory_budget() // local_world
         if sets * W * per_obj > 0.5 * budget:
             sets = 1
         if W * per_obj > 0.5 * budget:
-            W = max(2, int(0.5 * budget / per_obj))
-        if sets > 1 and (sets - 1) * W * b.stat(0) > 0.8 * torch.cuda.mem_get_info()[0]:
+            W = max(C_, int(0.5 * budget / per_obj) // C_ * C_)
+        if sets > 1 and (sets - 1) * W * max(bm.stat(0) for bm in batches) > 0.8 * torch.cuda.mem_get_info()[0]:
             sets = 1  # not enough free HBM for a second group of batch objects
+        ceiling = d2h_ceiling(torch, per_obj, 4, dist)
         objs = list(batches[:W])
         for m in range(W, sets * W):
-            bm = J.Batch(local_rank)
-            objs.append(bm)
+            objs.append(J.Batch(local_rank))
         E = len(objs)
-        pitch = h * b.info(0)[2]
-        host_out = [torch.empty((F, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(E)]
+        obj_chunk = [chunks[k % C_] for k in range(E)]
+        host_out = [torch.empty((len(obj_chunk[k]), pitch), dtype=torch.uint8, pin_memory=True) for k in range(E)]
         out_np = [t_.numpy() for t_ in host_out]
-
         host_t = [0.0] * 6
-        skip = os.environ.get("J40B_E2E_SKIP", "")  # diagnostics only ("d2h"): such a run is not an e2e number
 
         def submit(k):
             bm = objs[k]
-            t = [time.perf_counter()]
-            bm.reset(); t.append(time.perf_counter())
-            bm.add_many(frames); t.append(time.perf_counter())
-            bm.upload(); t.append(time.perf_counter())
-            bm.decode(); t.append(time.perf_counter())
-            if skip != "d2h":
-                bm.read_all_async(out_np[k])
-            t.append(time.perf_counter())
+            tt = [time.perf_counter()]
+            bm.reset(); tt.append(time.perf_counter())
+            bm.add_many(obj_chunk[k], host_threads); tt.append(time.perf_counter())
+            bm.upload(); tt.append(time.perf_counter())
+            bm.decode(); tt.append(time.perf_counter())
+            bm.read_all_async(out_np[k]); tt.append(time.perf_counter())
             for i in range(5):
-                host_t[i] += t[i + 1] - t[i]
+                host_t[i] += tt[i + 1] - tt[i]
 
         for k in range(E):          # warm-up (also pages the pinned buffers in)
             submit(k)
@@ -330,8 +438,8 @@ def main():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
-        n_waves = max(3 * sets, -(-args.steps // W))
-        n_e2e = n_waves * W
+        n_waves = max(3 * sets, -(-args.steps * C_ // W))
+        n_obj = n_waves * W
         host_t[:] = [0.0] * 6
         t0 = time.perf_counter()
         for wv in range(n_waves):
@@ -350,19 +458,41 @@ def main():
         if os.environ.get("J40B_TIMELINE"):
             print("e2e host seconds (whole run): reset %.3f add_many %.3f upload %.3f decode %.3f read_async %.3f wait %.3f of %.3f"
                   % (*host_t, dt), file=sys.stderr)
-        h2d = batches[0].stat(1)
-        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        e2e_pixels = sum(len(obj_chunk[(wv % sets) * W + j]) for wv in range(n_waves) for j in range(W)) * w * h
+        h2d = sum(bm.stat(1) for bm in objs[:C_])
+        te = torch.tensor([dt, float(e2e_pixels)], dtype=torch.float64, device="cuda")
+        tem = te.clone()
         if dist:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        stride = b.info(0)[2]
-        got = out_np[0][0].reshape(h, stride)[:, : w * 4].reshape(h, w, 4)
-        assert np.array_equal(got, want), "end-to-end output differs from the reference"
-        e2e = {"value": world * pixels * n_e2e / float(te.item()) / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(F * pitch), "steps": n_e2e,
+            dist.all_reduce(tem, op=dist.ReduceOp.MAX)
+            dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        # every distinct frame of every object, as it arrived in host memory
+        for k in range(E):
+            seen = set()
+            for i, d in enumerate(obj_chunk[k]):
+                if d in seen:
+                    continue
+                seen.add(d)
+                got = out_np[k][i].reshape(h, stride)[:, : w * 4].reshape(h, w, 4)
+                assert np.array_equal(got, want[d]), "end-to-end output differs from the reference"
+        e2e_value = (float(te[1].item()) if dist else float(e2e_pixels)) / float(tem[0].item()) / 1e6
+        d2h_step = F * pitch
+        e2e = {"value": e2e_value, "unit": "Mpix/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_step), "steps": n_obj // C_,
+               "d2h_gbs_per_gpu": e2e_value / world * 1e6 * (pitch / (w * h)) / 1e9,
+               "ceiling_gbs_per_gpu": ceiling,
+               "frac_of_ceiling": e2e_value / world * 1e6 * (pitch / (w * h)) / 1e9 / ceiling,
+               "ceiling": "bare cudaMemcpyAsync of one batch object's output into pinned host memory, all ranks at once",
+               "host_parse_threads": host_threads,
                "includes": "host parse + H2D + kernels + D2H of all frames into pinned host memory, "
-                           f"{n_waves} waves of {W} steps over {sets} groups of {W} reused batch objects"}
+                           f"{n_waves} waves of {W} batch objects over {sets} groups of {W} reused objects"}
         for bm in objs[W:]:
             bm.close()
+        del host_out, out_np
+
+    latency = None
+    if rank == 0 and not args.skip_latency:
+        latency = latency_section(J, ref, np, args)
+
     for bm in batches[1:]:
         bm.close()
     b.close()
@@ -385,46 +515,60 @@ def main():
     alg_bytes = comp_bytes + 4 * pixels
     ms_step = total_ms / args.steps
     kavg = {k: sum(x[k] for x in kernel_ms) / len(kernel_ms) for k in kernel_ms[0]}
-    names = {"lf_image": "k_lf_decode<1>", "lf_hfmeta": "k_lf_post+k_lf_decode<2>", "lf_llf": "k_lf_llf", "hf_group": "k_hf_group",
-             "back": "k_back_tile", "back_big": "k_back_generic", "modular": "k_modular", "render": "k_render"}
+    names = {"lf_image": "k_lf_decode<1>", "lf_hfmeta": "k_lf_post+k_lf_decode<2>", "lf_llf": "k_lf_llf", "hf_group": "k_hf_prep+k_hf_group",
+             "back": "k_back_tile", "back_big": "k_back_generic", "modular": "k_modular+k_render"}
     dominant = max(names, key=lambda k: kavg.get(k, 0.0))
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    traffic = traffic_total = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         ent = tr.get(names[dominant])
-        if ent:
+        if ent and ent.get("preset", args.preset) == args.preset:
             traffic = ent["dram_bytes_per_frame"] * F
+        tot = [v["dram_bytes_per_frame"] for v in tr.values() if isinstance(v, dict) and "dram_bytes_per_frame" in v]
+        if tot:
+            traffic_total = sum(tot) * F
     except Exception:
         pass
     achieved = alg_bytes / (kavg[dominant] / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_total": traffic_total,
                 "kernel": names[dominant], "kernel_ms": kavg[dominant],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "the path is bound by the serial entropy decoders' dependent-issue latency, not by HBM (SURVEY 8d)",
                 "all_kernel_ms": kavg, "serial_ms_per_step": serial_ms,
+                "stage_ms_in_region": {k: v / max(1, min(M, args.steps * C_)) * C_ for k, v in stage_sum.items()},
                 "step_achieved": alg_bytes / (ms_step / 1e3) / 1e9, "step_frac": alg_bytes / (ms_step / 1e3) / 1e9 / peak,
                 "back_tile_achieved": alg_bytes / (kavg["back"] / 1e3) / 1e9 if kavg.get("back") else None}
 
     # ---- CPU baseline: the reference itself, one thread, bounded sample of the same workload
-    reps = 6
+    reps = 6 if kind == "vardct" else 1
     good, secs = ref.time_decode(datas[0], reps)
     cpu = {"value": w * h / statistics.median(secs) / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "reference",
            "sample": f"{reps} decodes of one {w}x{h} bench frame through j40_from_memory..j40_frame_pixels_u8x4, median",
            "host_cores_available": os.cpu_count()}
 
+    npx = len(stats) * w * h
+    hist = [sum(s["transform_hist"][i] for s in stats) for i in range(27)]
     line = {
-        "metric": "Mpixels/s decoded (4K VarDCT batch)", "value": value, "unit": "Mpix/s", "n_gpus": world,
+        "metric": metric_name(args), "value": value, "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(w, h, F, args.distinct),
-                   "frames_per_gpu": F, "groups_per_gpu": F * ((w + 255) // 256) * ((h + 255) // 256),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if kind == "vardct" else "i16", "data": "synthetic",
+        "config": {"workload": workload_name(args), "preset": args.preset if kind == "vardct" else None,
+                   "frames_per_gpu": F, "batch_objects_per_step": C_,
+                   "groups_per_gpu": F * ((w + 255) // 256) * ((h + 255) // 256),
                    "compressed_bytes_per_gpu": comp_bytes, "bits_per_pixel": 8.0 * comp_bytes / pixels,
-                   "hf_symbols_per_pixel": sum(s["hf_symbols"] for s in stats) / (len(stats) * w * h),
+                   "hf_symbols_per_pixel": sum(s["hf_symbols"] for s in stats) / npx,
+                   "lf_symbols_per_pixel": sum(s["lf_symbols"] for s in stats) / npx,
+                   "nonzeros_per_pixel": sum(s["nonzeros"] for s in stats) / npx,
+                   "varblocks_per_frame": sum(s["num_varblocks"] for s in stats) / len(stats),
+                   "transform_hist": hist,
+                   "share_8x8_family": (sum(hist[i] for i in (0, 1, 2, 3, 12, 13, 14, 15, 16, 17)) / max(1, sum(hist))) if kind == "vardct" else None,
                    "l2": "inputs+outputs per step (%.1f GB) exceed L2" % ((comp_bytes + 4 * pixels) / 1e9),
-                   "pipelining": f"{args.steps} steps over {M} batch objects / CUDA streams, LF stage of step s gated on step s-{lag}",
+                   "pipelining": f"{args.steps} steps over {M} batch objects / CUDA streams, free-running",
+                   "parity_gate": "every distinct frame of every batch object compared with the reference before timing, and again as it arrives in host memory in the end-to-end loop",
                    "parallelism": f"batch-sharded x{world}, no collective"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency": latency, "gpu_launches": int(launches),
         "clocks": sampler.result(), "device_bytes": int(dev_bytes),
     }
     print(json.dumps(line))

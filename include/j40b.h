@@ -85,6 +85,13 @@ int j40b_batch_after(j40b_batch *b, j40b_batch *other, int stage);
  * 5 LF image decoded, 6 HF metadata decoded, 1 LF stage done, 2 HF done, 3 tiles done, 4 all done); -1 if unknown */
 float j40b_batch_event_ms(const j40b_batch *b, const j40b_batch *ref, int which);
 
+/* diagnostics: copies an intermediate array of LF group `lf_group` of VarDCT image `index` (after a decode) to dst, in
+ * the layout of the reference's j40__lf_group_st members (j40.h:6360-6391): what = 0 blocks, 1 varblocks, 2 lfindices,
+ * 3/4/5 llfcoeffs X/Y/B, 6/7/8 coeffs as decoded, 9/10 xfromy/bfromy, 11 sharpness, 12/13/14 coeffs after
+ * j40__dequant_hf, 15/16/17 LF planes after smoothing. Returns the bytes written (0: unavailable / cap too small).
+ * The parity tests compare these with the reference's own arrays (float intermediates within 1e-5). */
+size_t j40b_batch_debug_dump(j40b_batch *b, int index, int lf_group, int what, void *dst, size_t cap);
+
 /* 1 if a CUDA device is usable by this library, else 0 */
 int j40b_gpu_available(void);
 

@@ -85,11 +85,16 @@ struct CudaBackend {
         const int spec_cap = stage && spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
         const size_t smem = (size_t) spec_cap + (size_t) warps * warp_slice_bytes(cap);
         const int blocks = (n + warps - 1) / warps;
+        // Many streams: one per lane (throughput; no shared memory, 1/20 of the issue slots). Few streams (a single
+        // image has 1-4 LF groups): one per warp (latency). J40B_LF_MODE=lane|warp overrides.
+        bool lane_mode = n >= 64;
+        if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
         cudaEventRecord(ev[0], stream);
-        kl_lf_decode(1, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
+        if (lane_mode) kl_lf_lane(1, stream, w, n); else kl_lf_decode(1, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
         cudaEventRecord(ev[5], stream);
         kl_lf_post(n, stream, w);
-        kl_lf_decode(2, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
+        if (lane_mode) { kl_lf_lane(2, stream, w, n); kl_lf_place(n, stream, w); ++launches; }
+        else kl_lf_decode(2, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
         cudaEventRecord(ev[6], stream);
         kl_lf_llf(n, stream, w);
         cudaEventRecord(ev[1], stream);
@@ -126,6 +131,9 @@ struct CudaBackend {
     }
     // `spec_bytes`: the image's code-spec blob; `max_w`: its widest channel (sizes the shared-memory rows)
     void launch_mod(ModWork *w, int n, size_t spec_bytes, int max_w) {
+        bool lane_mode = n >= 64;
+        if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
+        if (lane_mode) { kl_mod_lane(n, stream, w); ++launches; return; }
         int cap = (max_w + 63) & ~63;
         if (cap > MOD_ROW_CAP || cap <= 0) cap = MOD_ROW_CAP;
         int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
@@ -137,6 +145,7 @@ struct CudaBackend {
         kl_modular(n, stream, w, cap, spec_cap);
         ++launches;
     }
+    void launch_dump(const DumpWork &w, int n) { kl_dump_coeffs(n, stream, w); ++launches; }
     void mark_modular(int which) { cudaEventRecord(ev[8 + which], stream); mod_marked = true; }
     void launch_render(const RenderWork *w, int width, int height) {
         kl_render(stream, w, width, height);
@@ -321,6 +330,12 @@ EXPORT int j40b_batch_read_pixels(j40b_batch *b, int i, void *dst) {
     cudaSetDevice(b->be.device);
     b->batch->download_pixels((size_t) i, (uint8_t *) dst);
     return 0;
+}
+EXPORT size_t j40b_batch_debug_dump(j40b_batch *b, int i, int lf_group, int what, void *dst, size_t cap) {
+    if (!b || !dst || !b->decoded || i < 0 || lf_group < 0) return 0;
+    cudaSetDevice(b->be.device);
+    b->be.sync();
+    return b->batch->debug_dump((size_t) i, (size_t) lf_group, what, dst, cap);
 }
 EXPORT float j40b_batch_last_decode_ms(const j40b_batch *b) { return b ? b->last_ms : 0.0f; }
 

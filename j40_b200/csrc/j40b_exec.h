@@ -13,6 +13,7 @@
 // Modular frame: modular (warp per group) -> render (thread per pixel).
 #pragma once
 #include "j40b_hf.h"
+#include "j40b_modlane.h"
 
 namespace j40b {
 
@@ -24,6 +25,7 @@ struct LfWork {
     DLfGroup *g;
     uint32_t *err;          // this section's error word
     float *llf_scratch;     // [2048] for LF patches larger than 8x8 cells, or null
+    ModLaneScratch *lane_scratch; // per-stream record of the lane-per-stream decoder
 };
 
 struct HfWork { // one per (pass, group)
@@ -51,6 +53,16 @@ struct BackWork {
     float *big_scratch;     // [4 * 65536] for varblocks larger than 64x64, or null
 };
 
+// diagnostics (j40b_batch_debug_dump): the dense coefficient planes of an LF group in the reference's layout
+// (gg->coeffs[c][coeffoff + pos], j40.h:6614), rebuilt from the token lists
+struct DumpWork {
+    const DFrame *f;
+    const DLfGroup *g;
+    const DToken *tokens;
+    float *out;       // [3][width8 * height8 * 64]
+    int32_t dequant;  // 0: the decoded integers (j40.h:6989); 1: after j40__dequant_hf (j40.h:7053-7097)
+};
+
 struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, or the global channels
     const DFrame *f;
     const uint8_t *arena;
@@ -69,6 +81,7 @@ struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, 
     int32_t *lz_window;     // or null
     uint32_t lz_mask;
     uint32_t *err;
+    ModLaneScratch *lane_scratch; // per-stream record of the lane-per-stream decoder
 };
 
 struct RenderWork { // modular frames: inverse global transforms + interleave to RGBA8
@@ -399,6 +412,218 @@ J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms,
         one.tr[0] = m.tr[t];
         inverse_transforms(one, lane, nlanes);
         sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lane-per-stream variants of the three serial decoders (j40b_modlane.h): every thread of a warp owns one work item.
+// `active`: this lane has one. `props`/`pstride`: the lane's 16 property slots. AnyFn / Sync as in hf_lanes_run.
+template <int MODE, class AnyFn, class Sync>
+J40B_HD J40B_INLINE void mod_lane_loop(ModLane<MODE> &L, AnyFn any, Sync sync) {
+    for (;;) {
+        if (!any(!L.done)) break;
+        sync();
+        if (!L.done && L.need_setup) L.setup();   // next channel: rare, lanes of one geometry get here together
+        sync();
+        if (!L.done) L.sample();
+    }
+}
+
+J40B_HD J40B_INLINE bool spec_is_plain_ans(const uint8_t *arena, uint32_t spec_off) {
+    if (!spec_off) return false;
+    const DCodeSpec *spec = (const DCodeSpec *) (arena + spec_off);
+    return !spec->use_prefix_code && !spec->lz77_enabled;
+}
+
+// LF group, stage 1: LfQuant, the 3-channel modular LF image (j40.h:6739-6757); same hand-over as lf_decode1_body
+template <int MODE, class AnyFn, class Sync>
+J40B_HD inline void lf_decode1_lanes(const LfWork *wp, bool active, const int32_t *div24, int32_t *props, int pstride, AnyFn any, Sync sync) {
+    ModLane<MODE> L;
+    L.done = true; L.need_setup = false; L.es.err = 0;
+    int32_t extra_prec = 0;
+    if (active) {
+        const LfWork &w = *wp;
+        const DFrame &f = *w.f;
+        DLfGroup &g = *w.g;
+        const int n8 = g.width8 * g.height8;
+        L.sc = w.lane_scratch; L.div24 = div24; L.props = props; L.pstride = pstride;
+        L.br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
+        extra_prec = (int32_t) L.br.u(2);
+        ModImage &m = L.sc->m;
+        m.num_channels = 3;
+        for (int c = 0; c < 3; ++c) {
+            m.ch[c].px = g.lfq + (size_t) c * n8;
+            m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
+            m.ch[c].hshift = m.ch[c].vshift = 0;
+        }
+        modular_header(L.br, L.es, f.have_global_tree != 0, m);
+        if (!L.es.err) L.begin(w.arena, f.global_spec_off, (const DTreeNode *) (w.arena + f.global_tree_off), f.global_tree_uses_wp, 1 + g.idx,
+                               g.wp_scratch, g.lz_window, (1u << 18) - 1);
+    }
+    mod_lane_loop(L, any, sync);
+    if (active) {
+        const LfWork &w = *wp;
+        DLfGroup &g = *w.g;
+        const ModImage &m = L.sc->m;
+        if (!L.es.err) finish_code(L.br, L.es, L.cc, L.cs);
+        g.extra_prec = extra_prec;
+        g.mid_bit = L.br.bits_consumed();
+        g.nb_tr1 = imin(m.nb_transforms, MOD_MAX_TRANSFORMS);
+        for (int t = 0; t < g.nb_tr1; ++t) g.tr1[t] = m.tr[t];
+        if (L.es.err) *w.err = L.es.err;
+    }
+}
+
+// the four channels of the HF metadata image (j40.h:6766-6772)
+J40B_HD J40B_INLINE void hf_meta_channels(const DLfGroup &g, int32_t nvb, ModImage &m) {
+    m.num_channels = 4;
+    m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
+    m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
+    m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
+    m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
+    for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
+}
+
+// LF group, stage 3a: entropy decode of the HF metadata image; transforms and varblock placement follow in lf_place_body
+template <int MODE, class AnyFn, class Sync>
+J40B_HD inline void lf_decode2_lanes(const LfWork *wp, bool active, const int32_t *div24, int32_t *props, int pstride, AnyFn any, Sync sync) {
+    ModLane<MODE> L;
+    L.done = true; L.need_setup = false; L.es.err = 0;
+    if (active) {
+        const LfWork &w = *wp;
+        const DFrame &f = *w.f;
+        DLfGroup &g = *w.g;
+        const int n8 = g.width8 * g.height8;
+        L.sc = w.lane_scratch; L.div24 = div24; L.props = props; L.pstride = pstride;
+        L.br.init(w.cs + g.sec_off, g.sec_size, g.mid_bit);
+        const int32_t nvb = (int32_t) L.br.u(ceil_lg32((uint32_t) n8)) + 1;
+        g.nb_varblocks = nvb;
+        ModImage &m = L.sc->m;
+        hf_meta_channels(g, nvb, m);
+        modular_header(L.br, L.es, f.have_global_tree != 0, m);
+        if (!L.es.err) L.begin(w.arena, f.global_spec_off, (const DTreeNode *) (w.arena + f.global_tree_off), f.global_tree_uses_wp,
+                               1 + 2 * f.num_lf_groups + g.idx, g.wp_scratch, g.lz_window, (1u << 18) - 1);
+    }
+    mod_lane_loop(L, any, sync);
+    if (active) {
+        const LfWork &w = *wp;
+        DLfGroup &g = *w.g;
+        const ModImage &m = L.sc->m;
+        if (!L.es.err) finish_code(L.br, L.es, L.cc, L.cs);
+        g.nb_tr2 = imin(m.nb_transforms, MOD_MAX_TRANSFORMS);
+        for (int t = 0; t < g.nb_tr2; ++t) g.tr2[t] = m.tr[t];
+        g.end_bit = L.br.bits_consumed();
+        g.meta_overrun = L.br.overrun() ? 1 : 0;
+        if (L.es.err) *w.err = L.es.err;
+    }
+}
+
+// LF group, stage 3b (one warp): inverse transforms of the HF metadata image, varblock placement (j40.h:6585-6720)
+template <class Sync>
+J40B_HD inline void lf_place_body(const LfWork &w, uint32_t *bitmap /* [height8 * 8] or null */, int lane, int nlanes, Sync sync) {
+    if (*w.err) return;
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    ErrSlot es;
+    es.err = 0;
+    BitReader br; // stands for the decode stage's reader where errors are classified: only "ran past the end" matters
+    br.base = nullptr; br.size = 0; br.buf = 0; br.nbits = 0; br.pos = g.meta_overrun ? 1u : 0u;
+    ModImage m;
+    hf_meta_channels(g, g.nb_varblocks, m);
+    m.nb_transforms = g.nb_tr2;
+    for (int t = 0; t < g.nb_tr2; ++t) m.tr[t] = g.tr2[t];
+    // (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide)
+    for (int t = m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = m;
+        one.nb_transforms = 1;
+        one.tr[0] = m.tr[t];
+        inverse_transforms(one, lane, nlanes);
+        sync();
+    }
+    if (bitmap) place_varblocks_warp(f, g, es, br, bitmap, lane, nlanes, sync);
+    else if (lane == 0) place_varblocks(f, g, es, br);
+    if (lane == 0) {
+        // multi-section frames: the reference drops pad0/excs found at a section's end; running short is still an error
+        if (!es.err && g.meta_overrun) es.set_raw(E_SHRT);
+        if (es.err) *w.err = es.err;
+    }
+}
+
+// one modular sub-bitstream per lane (same hand-over as modular_body)
+template <int MODE, class AnyFn, class Sync>
+J40B_HD inline void modular_lanes(ModWork *wp, bool active, const int32_t *div24, int32_t *props, int pstride, AnyFn any, Sync sync) {
+    ModLane<MODE> L;
+    L.done = true; L.need_setup = false; L.es.err = 0;
+    bool preset = false;
+    if (active) {
+        ModWork &w = *wp;
+        const DFrame &f = *w.f;
+        if (w.preset_err) { *w.err = w.preset_err; preset = true; }
+        else {
+            L.sc = w.lane_scratch; L.div24 = div24; L.props = props; L.pstride = pstride;
+            L.br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
+            L.sc->m = w.m;
+            if (!w.header_parsed) modular_header(L.br, L.es, f.have_global_tree != 0, L.sc->m);
+            if (!L.es.err) L.begin(w.arena, w.spec_off, (const DTreeNode *) (w.arena + w.tree_off), w.tree_uses_wp, w.sidx, w.wp_scratch, w.lz_window, w.lz_mask);
+        }
+    }
+    mod_lane_loop(L, any, sync);
+    if (active && !preset) {
+        ModWork &w = *wp;
+        const ModImage &m = L.sc->m;
+        if (!L.es.err) finish_code(L.br, L.es, L.cc, L.cs);
+        if (!L.es.err) {
+            if (w.check_end) { uint32_t e = L.br.finish(); if (e) L.es.set_raw(e); }
+            else if (L.br.overrun()) L.es.set_raw(E_SHRT);
+        }
+        if (L.es.err) *w.err = L.es.err;
+        else if (!w.is_global) { // global transforms are applied by the render step
+            for (int t = m.nb_transforms - 1; t >= 0; --t) {
+                ModImage one = m;
+                one.nb_transforms = 1;
+                one.tr[0] = m.tr[t];
+                inverse_transforms(one, 0, 1);
+            }
+        }
+    }
+}
+
+// diagnostics: varblock `voff` of w.g into the dense planes; same arithmetic as the tile back-end's scatter phase
+template <class Sync>
+J40B_HD inline void dump_coeffs_body(const DumpWork &w, int voff, int tid, int nth, Sync sync) {
+    const DFrame &f = *w.f;
+    const DLfGroup &g = *w.g;
+    if (voff >= g.nb_varblocks) return;
+    const DVarblock vb = g.varblocks[voff];
+    const DctSelectInfo d = dct_select_info(vb.dctsel);
+    const int size = 1 << (d.log_rows + d.log_columns);
+    const size_t n8 = (size_t) g.width8 * g.height8;
+    float *coef[3] = {w.out + vb.coeffoff, w.out + n8 * 64 + vb.coeffoff, w.out + 2 * n8 * 64 + vb.coeffoff};
+    for (int c = 0; c < 3; ++c) for (int i = tid; i < size; i += nth) coef[c][i] = 0.0f;
+    sync();
+    for (int pass = 0; pass < f.num_passes; ++pass) {
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t *slot = g.vb_tok + (((size_t) pass * 3 + c) * n8 + voff) * 2;
+            const int32_t *order = f.order[pass][d.order_idx][c];
+            for (uint32_t k = tid; k < slot[1]; k += nth) {
+                const DToken t = w.tokens[slot[0] + k];
+                const int32_t pos = order[t.pos];
+                coef[c][pos] = J40B_FADD(coef[c][pos], (float) t.val);
+            }
+        }
+        sync();
+    }
+    if (!w.dequant) return;
+    const float *dq = f.dq[d.param_idx];
+    float mult[3];
+    mult[1] = J40B_FMUL(J40B_FDIV(65536.0f, (float) f.global_scale), vb.hfmul_inv);
+    mult[0] = J40B_FMUL(mult[1], f.x_qm_mult);
+    mult[2] = J40B_FMUL(mult[1], f.b_qm_mult);
+    for (int c = 0; c < 3; ++c) for (int i = tid; i < size; i += nth) {
+        float v = coef[c][i];
+        if (-1.0f <= v && v <= 1.0f) v = J40B_FMUL(v, f.quant_bias[c]);
+        else v = J40B_FSUB(v, J40B_FDIV(f.quant_bias_num, v));
+        coef[c][i] = J40B_FMUL(v, J40B_FDIV(mult[c], dq[i * 3 + c]));
     }
 }
 

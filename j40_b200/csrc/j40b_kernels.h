@@ -48,11 +48,19 @@ __device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *
 #endif
 
 enum { HF_WARPS = 4 };
+// warps per block of the lane-per-stream kernels (k_lf_lane, k_mod_lane): one, so that a launch of a few hundred streams
+// spreads over as many SMs as it has warps (each warp is latency-bound and wants a scheduler and an L1 of its own)
+enum { LANE_WARPS = 1 };
+#if defined(__CUDACC__)
+struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };
+#endif
 
 bool kl_init_lf();   // raises the dynamic shared-memory limits of the kernels in that translation unit
 bool kl_init_back();
 bool kl_init_mod();
 void kl_lf_decode(int stage, int blocks, int threads, size_t smem, cudaStream_t stream, const LfWork *w, int n, int cap, int spec_cap);
+void kl_lf_lane(int stage, cudaStream_t stream, const LfWork *w, int n);
+void kl_lf_place(int n, cudaStream_t stream, const LfWork *w);
 void kl_lf_post(int n, cudaStream_t stream, const LfWork *w);
 void kl_lf_llf(int n, cudaStream_t stream, const LfWork *w);
 void kl_hf_prep(int n, cudaStream_t stream, const HfPrepWork *w);
@@ -60,7 +68,9 @@ void kl_hf_group(int blocks, size_t smem, cudaStream_t stream, const HfWork *w, 
 void kl_back_tile(int n, cudaStream_t stream, const BackWork *w);
 void kl_back_generic(int blocks, cudaStream_t stream, const BackWork *w, int n, float *pool);
 void kl_back_phase_dump(); // diagnostic builds (make PHASE_CLOCKS=1): prints and clears the tile kernel's phase counters
+void kl_dump_coeffs(int n, cudaStream_t stream, const DumpWork &w); // diagnostics
 void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap);
+void kl_mod_lane(int n, cudaStream_t stream, ModWork *w);
 void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height);
 
 } // namespace j40b

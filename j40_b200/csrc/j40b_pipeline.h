@@ -141,6 +141,7 @@ public:
                     b.lz = lz_mod ? wk_alloc(4u << 18) : (size_t) -1;
                     b.vb_tok = wk_alloc(4 * 2 * 3 * n8 * npass);
                     b.llf_scratch = wk_alloc(4 * 2048);
+                    b.lane = wk_alloc(sizeof(ModLaneScratch));
                 }
                 im.grp.resize(im.npg);
                 size_t tok_total = 0;
@@ -198,6 +199,7 @@ public:
                     while (capl < syms && capl < (1u << 20)) capl <<= 1;
                     mb.lz_mask = capl - 1;
                     mb.lz = lz ? wk_alloc(4 * (size_t) capl) : (size_t) -1;
+                    mb.lane = wk_alloc(sizeof(ModLaneScratch));
                 }
                 im.mod_off = up_alloc(sizeof(ModWork) * std::max<size_t>(im.nmod, 1));
                 im.render_off = up_alloc(sizeof(RenderWork));
@@ -302,6 +304,7 @@ public:
                     w.g = (DLfGroup *) (dev + im.lfg_off) + i;
                     w.err = derr + i;
                     w.llf_scratch = (float *) (dwork + b.llf_scratch);
+                    w.lane_scratch = (ModLaneScratch *) (dwork + b.lane);
                     lf_sorted.emplace_back((int64_t) b.w8 * b.h8, w);
                 }
                 for (size_t pg = 0; pg < im.npg; ++pg) {
@@ -396,6 +399,7 @@ public:
                     w.lz_window = mb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.lz);
                     w.lz_mask = mb.lz_mask;
                     w.err = derr + g;
+                    w.lane_scratch = (ModLaneScratch *) (dwork + mb.lane);
                 }
             }
         }
@@ -496,6 +500,59 @@ public:
         }
     }
 
+    // Diagnostics: an intermediate array of LF group `lfg` of (VarDCT) image k after a decode, in the layout of the
+    // reference's j40__lf_group_st members (the numbering follows oracle/ref_harness.c's ref_staged_lf_group_array):
+    //   0 blocks i32[h8][w8]; 1 varblocks {coeffoff | qfidx, bits of 1/HfMul} i32[nb][2]; 2 lfindices u8[h8][w8];
+    //   3/4/5 llfcoeffs f32[w8*h8] X/Y/B; 6/7/8 coeffs f32[w8*h8*64] as decoded; 9/10 xfromy/bfromy i16[h64][w64];
+    //   11 sharpness i16[h8][w8]; 12/13/14 coeffs after dequantisation; 15/16/17 the smoothed LF planes f32[h8][w8].
+    // Returns the number of bytes written, 0 if unavailable or `cap` is too small.
+    size_t debug_dump(size_t k, size_t lfg, int what, void *dst, size_t cap) {
+        if (!dev || k >= plans.size() || plans[k]->err || results[k].err || plans[k]->df.is_modular) return 0;
+        const Img &im = img[k];
+        if (lfg >= im.nlf) return 0;
+        const LfBuf &b = im.lf[lfg];
+        uint8_t *dwork = dev + upload_bytes;
+        const size_t n8 = (size_t) b.w8 * b.h8, n64 = (size_t) b.w64 * b.h64;
+        auto copy = [&](size_t off, size_t bytes) -> size_t { if (bytes > cap) return 0; be.d2h(dst, dwork + off, bytes); return bytes; };
+        switch (what) {
+        case 0: return copy(b.blocks, n8 * 4);
+        case 1: {
+            DLfGroup g;
+            be.d2h(&g, dev + im.lfg_off + lfg * sizeof(DLfGroup), sizeof(g));
+            std::vector<DVarblock> vb((size_t) std::max(0, g.nb_varblocks));
+            if (vb.size() * 8 > cap) return 0;
+            if (!vb.empty()) be.d2h(vb.data(), dwork + b.varblocks, vb.size() * sizeof(DVarblock));
+            int32_t *o = (int32_t *) dst;
+            for (size_t i = 0; i < vb.size(); ++i) { o[2 * i] = vb[i].coeffoff | vb[i].qfidx; memcpy(&o[2 * i + 1], &vb[i].hfmul_inv, 4); }
+            return vb.size() * 8;
+        }
+        case 2: return copy(b.lfidx, n8);
+        case 3: case 4: case 5: return copy(b.llf + (size_t) (what - 3) * n8 * 4, n8 * 4);
+        case 9: return copy(b.xfromy, n64 * 2);
+        case 10: return copy(b.bfromy, n64 * 2);
+        case 11: return copy(b.sharp, n8 * 2);
+        case 15: case 16: case 17: return copy(b.lf + (size_t) (what - 15) * n8 * 4, n8 * 4);
+        case 6: case 7: case 8: case 12: case 13: case 14: {
+            if (n8 * 64 * 4 > cap) return 0;
+            float *planes = (float *) be.dev_alloc(3 * n8 * 64 * 4);
+            if (!planes) return 0;
+            be.dev_memset(planes, 0, 3 * n8 * 64 * 4);
+            DumpWork w;
+            w.f = (const DFrame *) (dev + im.frame_off);
+            w.g = (const DLfGroup *) (dev + im.lfg_off) + lfg;
+            w.tokens = (const DToken *) (dwork + im.tok_off);
+            w.out = planes;
+            w.dequant = what >= 12 ? 1 : 0;
+            be.launch_dump(w, (int) n8);
+            const int c = what >= 12 ? what - 12 : what - 6;
+            be.d2h(dst, planes + (size_t) c * n8 * 64, n8 * 64 * 4);
+            be.dev_free(planes);
+            return n8 * 64 * 4;
+        }
+        default: return 0;
+        }
+    }
+
     void release() {
         if (dev) be.dev_free(dev);
         if (staging) be.host_free(staging);
@@ -507,9 +564,9 @@ public:
     size_t h2d_bytes() const { return upload_bytes; }
 
 private:
-    struct LfBuf { int left, top, w, h, w8, h8, w64, h64; size_t lfq, lfdeq, lf, lfidx, xfromy, bfromy, blockinfo, sharp, blocks, varblocks, llf, wp, lz, vb_tok, llf_scratch; };
+    struct LfBuf { int left, top, w, h, w8, h8, w64, h64; size_t lfq, lfdeq, lf, lfidx, xfromy, bfromy, blockinfo, sharp, blocks, varblocks, llf, wp, lz, vb_tok, llf_scratch, lane; };
     struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz, nonzeros, vbs; };
-    struct ModBuf { int gw, gh; size_t wp, lz; uint32_t lz_mask; };
+    struct ModBuf { int gw, gh; size_t wp, lz, lane; uint32_t lz_mask; };
     struct Img {
         size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;
         size_t rgba_off = 0, err_off = 0, tok_off = 0, plane[MOD_MAX_CH] = {0};

@@ -123,6 +123,7 @@ struct DLfGroup {
     uint32_t *vb_tok;     // [num_passes][3][h8*w8][2] {first token, count}, written by the pass-group kernel (zeroed before)
     // hand-over between the LF kernels (decode LF image -> post-process -> decode HF metadata -> LLF)
     uint64_t mid_bit;     // bit position after the LF image
+    int32_t meta_overrun; // the HF metadata decode ran past the end of the section (lane-per-stream path: read by lf_place_body)
     int32_t extra_prec;
     int32_t nb_tr1, nb_tr2;               // transforms of the LF image / of the HF metadata image
     ModTransform tr1[MOD_MAX_TRANSFORMS], tr2[MOD_MAX_TRANSFORMS];

@@ -43,6 +43,12 @@ __global__ void __launch_bounds__(256) k_back_generic(const BackWork *items, int
 }
 
 
+// diagnostics (j40b_batch_debug_dump): one block per varblock
+__global__ void __launch_bounds__(128) k_dump_coeffs(DumpWork w) {
+    dump_coeffs_body(w, (int) blockIdx.x, (int) threadIdx.x, (int) blockDim.x, BlockSync());
+}
+void kl_dump_coeffs(int n, cudaStream_t stream, const DumpWork &w) { if (n > 0) k_dump_coeffs<<<n, 128, 0, stream>>>(w); }
+
 bool kl_init_back() {
     return cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4) == cudaSuccess;
 }

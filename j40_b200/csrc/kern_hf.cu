@@ -9,8 +9,6 @@ __global__ void __launch_bounds__(128) k_hf_prep(const HfPrepWork *items, int n)
     if (i < n) hf_prep_body(items[i], (int) threadIdx.x & 31, 32, WarpSync());
 }
 
-struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); } };
-
 // HF coefficient entropy decode, SIMT: one warp per `lanes` consecutive (pass, group) sections, one section per lane,
 // in a warp-uniform two-phase loop (j40b_hf.h). The work list is ordered image by image and pass by pass, so a
 // block's lanes nearly always share one code spec (cluster map + alias tables / prefix LUTs), which is staged in

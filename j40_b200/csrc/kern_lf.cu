@@ -22,6 +22,35 @@ __global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, i
     else lf_decode2_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
 }
 
+// Lane-per-stream variant (j40b_modlane.h): every thread owns one LF group; 32 * LANE_WARPS work items per block.
+// Shared memory: the 64-entry divisor table and 16 property slots per thread.
+template <int STAGE>
+__global__ void __launch_bounds__(32 * LANE_WARPS, 1) k_lf_lane(const LfWork *items, int n) {
+    __shared__ int32_t div24[64];
+    __shared__ int32_t props[16 * 32 * LANE_WARPS];
+    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
+    __syncthreads();
+    const int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    const LfWork *w = &items[i < n ? i : n - 1];
+    const bool active = i < n && (STAGE == 1 || !*w->err);
+    // the fast path (rANS, no LZ77) is taken when every stream of the warp qualifies
+    const bool plain = __all_sync(0xffffffffu, !active || spec_is_plain_ans(w->arena, w->f->global_spec_off));
+    int32_t *my = props + threadIdx.x;
+    if (STAGE == 1) {
+        if (plain) lf_decode1_lanes<1>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
+        else lf_decode1_lanes<0>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
+    } else {
+        if (plain) lf_decode2_lanes<1>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
+        else lf_decode2_lanes<0>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
+    }
+}
+
+// inverse transforms of the HF metadata image + varblock placement behind k_lf_lane<2>: one warp per LF group
+__global__ void __launch_bounds__(32) k_lf_place(const LfWork *items) {
+    __shared__ uint32_t bitmap[256 * 8];
+    lf_place_body(items[blockIdx.x], bitmap, (int) threadIdx.x, 32, WarpSync());
+}
+
 __global__ void __launch_bounds__(256) k_lf_post(const LfWork *items) {
     lf_post_body(items[blockIdx.x], (int) threadIdx.x, (int) blockDim.x, BlockSync());
 }
@@ -40,6 +69,12 @@ void kl_lf_decode(int stage, int blocks, int threads, size_t smem, cudaStream_t 
     if (stage == 1) k_lf_decode<1><<<blocks, threads, smem, stream>>>(w, n, cap, spec_cap);
     else k_lf_decode<2><<<blocks, threads, smem, stream>>>(w, n, cap, spec_cap);
 }
+void kl_lf_lane(int stage, cudaStream_t stream, const LfWork *w, int n) {
+    const int per_block = 32 * LANE_WARPS, blocks = (n + per_block - 1) / per_block;
+    if (stage == 1) k_lf_lane<1><<<blocks, per_block, 0, stream>>>(w, n);
+    else k_lf_lane<2><<<blocks, per_block, 0, stream>>>(w, n);
+}
+void kl_lf_place(int n, cudaStream_t stream, const LfWork *w) { k_lf_place<<<n, 32, 0, stream>>>(w); }
 void kl_lf_post(int n, cudaStream_t stream, const LfWork *w) { k_lf_post<<<n, 256, 0, stream>>>(w); }
 void kl_lf_llf(int n, cudaStream_t stream, const LfWork *w) { k_lf_llf<<<n, 128, 0, stream>>>(w); }
 

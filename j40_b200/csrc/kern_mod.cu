@@ -18,6 +18,20 @@ __global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap, int spe
     modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
 }
 
+// Lane-per-stream variant (j40b_modlane.h): every thread owns one sub-bitstream
+__global__ void __launch_bounds__(32 * LANE_WARPS, 1) k_mod_lane(ModWork *items, int n) {
+    __shared__ int32_t div24[64];
+    __shared__ int32_t props[16 * 32 * LANE_WARPS];
+    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
+    __syncthreads();
+    const int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    ModWork *w = &items[i < n ? i : n - 1];
+    const bool active = i < n;
+    const bool plain = __all_sync(0xffffffffu, !active || spec_is_plain_ans(w->arena, w->spec_off));
+    if (plain) modular_lanes<1>(w, active, div24, props + threadIdx.x, 32 * LANE_WARPS, WarpAny(), WarpSync());
+    else modular_lanes<0>(w, active, div24, props + threadIdx.x, 32 * LANE_WARPS, WarpAny(), WarpSync());
+}
+
 // rows go over grid.x together with the column blocks (grid.y is capped at 65535, frames may be 2^18 rows tall)
 __global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, int height, int xblocks) {
     const int y = (int) (blockIdx.x / (unsigned) xblocks), xb = (int) (blockIdx.x % (unsigned) xblocks);
@@ -31,6 +45,10 @@ bool kl_init_mod() {
 }
 void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap) {
     k_modular<<<n, 32, (size_t) spec_cap + warp_slice_bytes(cap), stream>>>(w, cap, spec_cap);
+}
+void kl_mod_lane(int n, cudaStream_t stream, ModWork *w) {
+    const int per_block = 32 * LANE_WARPS;
+    k_mod_lane<<<(n + per_block - 1) / per_block, per_block, 0, stream>>>(w, n);
 }
 void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height) {
     if (width <= 0 || height <= 0) return;

@@ -26,6 +26,8 @@ def lib():
         L.hostemu_srgb_lut_lookup.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hostemu_inverse_transform.argtypes = [C.c_int, C.c_void_p]
         L.hostemu_forward_llf.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.hostemu_dump.restype = C.c_size_t
+        L.hostemu_dump.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         _LIB = L
     return _LIB
 
@@ -45,3 +47,8 @@ def decode(data: bytes):
         out = raw[:, : w.value * 4].reshape(h.value, w.value, 4).copy()
         L.hostemu_free(px)
     return out, err_str(err), stride.value
+
+
+def dump(data: bytes, lf_group: int, what: int, out):
+    """intermediate array `what` (include/j40b.h, j40b_batch_debug_dump) of an LF group into numpy array `out`"""
+    return int(lib().hostemu_dump(data, len(data), lf_group, what, out.ctypes.data, out.nbytes))

@@ -36,9 +36,28 @@ struct HostEmuBackend {
     };
     // HOSTEMU_ROW_CAP overrides the row-path width limit (0 = always take the plain path)
     static int row_cap(int dflt) { const char *e = getenv("HOSTEMU_ROW_CAP"); return e ? atoi(e) : dflt; }
+    // HOSTEMU_LANE=1: the lane-per-stream decoders (j40b_modlane.h) instead of the warp-per-stream ones
+    static bool lane_mode() { const char *e = getenv("HOSTEMU_LANE"); return e && atoi(e) != 0; }
     void launch_lf(const LfWork *w, int n, size_t) {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(256));
+        if (lane_mode()) {
+            int32_t props[16];
+            std::vector<uint32_t> bitmap(256 * 8);
+            auto any = [](bool p) { return p; };
+            for (int i = 0; i < n; ++i) {
+                if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode1_lanes<1>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                else lf_decode1_lanes<0>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                lf_post_body(w[i], 0, 1, NoSync());
+                if (!*w[i].err) {
+                    if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode2_lanes<1>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                    else lf_decode2_lanes<0>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                }
+                lf_place_body(w[i], (i & 1) ? bitmap.data() : nullptr, 0, 1, NoSync());
+                lf_llf_body(w[i], 0, 1, NoSync());
+            }
+            return;
+        }
         for (int i = 0; i < n; ++i) {
             bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->global_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
             const uint8_t *sc = staged ? copy.data() : nullptr;
@@ -76,11 +95,21 @@ struct HostEmuBackend {
     void launch_mod(ModWork *w, int n, size_t, int) {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(1024));
+        if (lane_mode()) {
+            int32_t props[16];
+            auto any = [](bool p) { return p; };
+            for (int i = 0; i < n; ++i) {
+                if (spec_is_plain_ans(w[i].arena, w[i].spec_off)) modular_lanes<1>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                else modular_lanes<0>(&w[i], true, wm.div24, props, 1, any, NoSync());
+            }
+            return;
+        }
         for (int i = 0; i < n; ++i) {
             bool staged = !(i & 1) && stage_spec_blob(w[i].arena, w[i].spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
             modular_body(w[i], wm.ws, wm.ms, wm.div24, staged ? copy.data() : nullptr, w[i].arena, 0, 1, NoSync());
         }
     }
+    void launch_dump(const DumpWork &w, int n) { for (int v = 0; v < n; ++v) dump_coeffs_body(w, v, 0, 1, NoSync()); }
     void mark_modular(int) {}
     void launch_render(const RenderWork *w, int width, int height) {
         for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) render_px(*w, x, y);
@@ -117,6 +146,19 @@ __attribute__((visibility("default"))) uint32_t hostemu_decode(const uint8_t *da
 }
 
 __attribute__((visibility("default"))) void hostemu_free(void *p) { free(p); }
+
+// decodes one image and returns intermediate array `what` of LF group `lfg` (Batch::debug_dump); bytes written or 0
+__attribute__((visibility("default"))) size_t hostemu_dump(const uint8_t *data, size_t size, int lfg, int what, void *dst, size_t cap) {
+    HostEmuBackend be;
+    Batch<HostEmuBackend> b(be);
+    b.full_token_cap = true;
+    b.add(data, size);
+    if (b.plans[0]->err) return 0;
+    b.upload();
+    b.execute();
+    b.collect_errors();
+    return b.debug_dump(0, (size_t) lfg, what, dst, cap);
+}
 
 // table helpers exposed for unit tests
 __attribute__((visibility("default"))) int hostemu_dq_matrix(int idx, float *out, int cap) {

@@ -212,3 +212,98 @@ def test_reference_dj40_unchanged_writes_the_oracle_pixels(oracle, gen, tmp_path
     a, ea, _, _ = oracle.decode(data)
     got = np.array(Image.open(tmp_path / "a.png").convert("RGBA"))
     assert np.array_equal(got, a)
+
+
+@pytest.mark.parametrize("opts", [dict(mix=1, tree=1), dict(mix=2, tree=2, block_ctx=1, orders=0x1f), dict(mix=1, tree=1, passes=3, smooth=0, extra_prec=1)],
+                         ids=["e6like", "all_transforms_custom", "passes3_nosmooth"])
+def test_intermediate_arrays_match_the_reference(oracle, gen, opts):
+    """north_star: float intermediates within 1e-5 of the reference. j40b_batch_debug_dump returns the device's block
+    map, varblock records, LF indices, CfL maps, LLF coefficients and HF coefficients (as decoded and dequantised);
+    oracle.ref.Staged replays the reference up to the same points. Expected and asserted: bit-equal."""
+    from tests import intermediates
+    data, _ = gen.vardct(2100, 200, seed=50, hfmul=8, **opts)
+    b = J.Batch(0)
+    b.add(data)
+    b.upload()
+    b.decode()
+    assert b.wait() == 0
+    n = intermediates.check(oracle, data, lambda gg, what, out: b.debug_dump(0, gg, what, out))
+    assert n > 100000
+    b.close()
+
+
+def test_c4_8192_modular_bit_exact(oracle, gen):
+    """BASELINE.json configs[3]: 8192x8192 lossless modular (fjxl-shaped: prefix codes + LZ77, YCoCg, 1024 groups):
+    bit-exact against the reference and exact reconstruction of the source"""
+    import numpy as np
+    w = h = 8192
+    src = np.tile((gen.synth(2048, 2048, 9) >> 2) << 2, (4, 4, 1))
+    data, _ = gen.modular(w, h, seed=9, rgb=src)
+    px, err, _, _ = J.decode(data)
+    assert err == ""
+    assert np.array_equal(px[..., :3], src) and (px[..., 3] == 255).all()
+    a, ea, _, sa = oracle.decode(data)
+    assert ea == "" and np.array_equal(a, px)
+
+
+def test_tall_narrow_modular_frame(oracle, gen):
+    """more than 65535 rows (the render kernel's rows used to sit on grid.y; advisor finding, round 1)"""
+    data, _ = gen.modular(24, 70000, seed=3, tree=0, lz77=0)
+    _cmp(oracle, data)
+
+
+@pytest.mark.parametrize("case", [c for c in streams.VARDCT_CASES if c[0].startswith("passes")], ids=lambda c: c[0])
+def test_multi_pass_through_the_batch_api(oracle, gen, case):
+    """several images with different pass counts in one batch"""
+    _, w, h, seed, opts = case
+    datas = [streams.make(gen, "vardct", w, h, seed, opts), streams.make(gen, "vardct", 264, 200, seed, dict(mix=1, tree=1))]
+    b = J.Batch(0)
+    for d in datas:
+        b.add(d)
+    b.upload()
+    b.decode()
+    assert b.wait() == 0
+    for i, d in enumerate(datas):
+        a, ea, _, _ = oracle.decode(d)
+        assert np.array_equal(b.read_pixels(i), a)
+    b.close()
+
+
+_LANE_CASES = [("vardct",) + c for c in streams.VARDCT_CASES[::2]] + [("modular",) + c for c in streams.MODULAR_CASES[::2]]
+
+
+@pytest.mark.parametrize("case", _LANE_CASES, ids=[c[1] for c in _LANE_CASES])
+def test_lane_per_stream_decoders(oracle, gen, case, monkeypatch):
+    """the lane-per-stream serial decoders (k_lf_lane, k_lf_place, k_mod_lane; j40b_modlane.h), which the executor
+    picks by itself only for launches of 64 and more streams, forced on small images"""
+    monkeypatch.setenv("J40B_LF_MODE", "lane")
+    kind, _, w, h, seed, opts = case
+    _cmp(oracle, streams.make(gen, kind, w, h, seed, opts))
+
+
+def test_lane_mode_is_taken_by_large_batches_and_matches(oracle, gen):
+    """80 small VarDCT frames + 70 modular groups in one batch: both launches are large enough for the lane kernels"""
+    datas = [streams.make(gen, "vardct", 136 + 8 * (i % 5), 72 + 8 * (i % 3), 200 + i, dict(mix=1, tree=1)) for i in range(80)]
+    datas.append(streams.make(gen, "modular", 2300, 2000, 3, dict(tree=2, ans=1, lz77=0)))  # 72 groups
+    b = J.Batch(0)
+    b.add_many(datas)
+    b.upload()
+    b.decode()
+    assert b.wait() == 0
+    for i in list(range(0, 80, 7)) + [80]:
+        a, ea, _, _ = oracle.decode(datas[i])
+        assert ea == "" and np.array_equal(b.read_pixels(i), a), i
+    b.close()
+
+
+def test_error_codes_on_corrupt_streams_lane_mode(oracle, gen, monkeypatch):
+    monkeypatch.setenv("J40B_LF_MODE", "lane")
+    base = [streams.make(gen, "vardct", 264, 136, 3, dict(mix=1, tree=1)),
+            streams.make(gen, "modular", 300, 200, 5, dict())]
+    for bi, data in enumerate(base):
+        for name, bad in streams.corruptions(data, 50 + bi, 45):
+            a, ea, _, _ = oracle.decode(bad)
+            b, eb, _, _ = J.decode(bad)
+            assert (ea == "") == (eb == ""), (bi, name, ea, eb)
+            if ea == "":
+                assert np.array_equal(a, b), (bi, name)

@@ -170,3 +170,41 @@ def test_duplicate_boxes_behind_the_codestream(oracle, emu, gen):
             _cmp(oracle, emu, v)
         _cmp(oracle, emu, head + jxll + jxlc)
         _cmp(oracle, emu, head + jxlp0 + jxlp1)
+
+
+@pytest.mark.parametrize("opts", [dict(mix=1, tree=1), dict(mix=2, tree=2, block_ctx=1, orders=0x1f), dict(mix=1, tree=1, passes=3, smooth=0, extra_prec=1)],
+                         ids=["e6like", "all_transforms_custom", "passes3_nosmooth"])
+def test_intermediate_arrays_match_the_reference(oracle, emu, gen, opts):
+    """block map, varblocks, LF indices, CfL maps, LLF and HF coefficients (before and after dequantisation) of the
+    kernel bodies against the reference's own arrays (two LF groups: 2100 pixels wide)"""
+    from tests import intermediates
+    data, _ = gen.vardct(2100, 200, seed=50, hfmul=8, **opts)
+    n = intermediates.check(oracle, data, lambda gg, what, out: emu.dump(data, gg, what, out))
+    assert n > 100000
+
+
+_LANE_CASES = [("vardct",) + c for c in streams.VARDCT_CASES] + [("modular",) + c for c in streams.MODULAR_CASES]
+
+
+@pytest.mark.parametrize("case", _LANE_CASES, ids=[c[1] for c in _LANE_CASES])
+def test_lane_per_stream_decoders(oracle, emu, gen, case, monkeypatch):
+    """the lane-per-stream serial decoders (j40b_modlane.h: lf_decode1_lanes, lf_decode2_lanes + lf_place_body,
+    modular_lanes) run by the emulator instead of the warp-per-stream ones"""
+    monkeypatch.setenv("HOSTEMU_LANE", "1")
+    kind, _, w, h, seed, opts = case
+    _cmp(oracle, emu, streams.make(gen, kind, w, h, seed, opts))
+
+
+def test_error_codes_on_corrupt_streams_lane_mode(oracle, emu, gen, monkeypatch):
+    monkeypatch.setenv("HOSTEMU_LANE", "1")
+    base = [streams.make(gen, "vardct", 264, 136, 3, dict(mix=1, tree=1)),
+            streams.make(gen, "vardct", 64, 64, 4, dict(mix=1, tree=1, ans=0)),
+            streams.make(gen, "modular", 300, 200, 5, dict()),
+            streams.make(gen, "modular", 300, 280, 4, dict(local_tree=2, ans=1, lz77=0, tree=2))]
+    for bi, data in enumerate(base):
+        for name, bad in streams.corruptions(data, 70 + bi, 60):
+            a, ea, _, _ = oracle.decode(bad)
+            b, eb, _ = emu.decode(bad)
+            assert (ea == "") == (eb == ""), (bi, name, ea, eb)
+            if ea == "":
+                assert np.array_equal(a, b), (bi, name)

@@ -3,6 +3,10 @@
 // global MA tree, per-group modular sub-bitstreams, prefix codes + LZ77 run-lengths or ANS
 // (SURVEY.md §8d C4, App. E.2/E.3/E.6).
 #pragma once
+#include <atomic>
+#include <exception>
+#include <mutex>
+#include <thread>
 #include "modular.h"
 #include "synth.h"
 #include "vardct.h"
@@ -89,7 +93,8 @@ public:
         std::vector<TokStream> ts((size_t) num_groups);
         std::vector<int> gwidth((size_t) num_groups);
         std::vector<std::vector<Channel>> group_channels((size_t) (P.local_tree ? num_groups : 0));
-        for (int g = 0; g < num_groups; ++g) {
+        // groups are tokenised independently: on all cores for big frames (the 8192x8192 configuration has 1024)
+        auto tokenize = [&](int g, ModularTokenizer &tk) {
             int gx = (g % gcols) * gsize, gy = (g / gcols) * gsize;
             int gw = std::min(W, gx + gsize) - gx, gh = std::min(H, gy + gsize) - gy;
             gwidth[(size_t) g] = gw;
@@ -103,17 +108,18 @@ public:
             }
             int64_t sidx = single ? 0 : 1 + 3 * (int64_t) num_lfg + 17 + g;
             if (single && P.palette) ch.insert(ch.begin(), pal);
-            mt.run(ch, sidx, ts[(size_t) g]);
+            tk.run(ch, sidx, ts[(size_t) g]);
             if (P.local_tree) group_channels[(size_t) g] = ch;
-            stats.lf_symbols += (int64_t) ts[(size_t) g].size();
-        }
+        };
+        parallel_groups(num_groups, [&](int g) { ModularTokenizer tk(tree); tokenize(g, tk); });
+        for (int g = 0; g < num_groups; ++g) stats.lf_symbols += (int64_t) ts[(size_t) g].size();
         EntropyOpts eo;
         eo.use_prefix = !P.use_ans;
         eo.log_alpha_size = 8;
         eo.cfg = {4, 1, 0};
         eo.max_clusters = P.max_clusters;
         eo.lz77 = P.lz77;
-        if (eo.lz77) for (int g = 0; g < num_groups; ++g) lz77_rle(ts[(size_t) g], eo.min_length, gwidth[(size_t) g], 4);
+        if (eo.lz77) parallel_groups(num_groups, [&](int g) { lz77_rle(ts[(size_t) g], eo.min_length, gwidth[(size_t) g], 4); });
         TokStream global_ts; // multi-group frames: the palette is coded with the global image in LfGlobal
         if (P.palette && !single) {
             std::vector<Channel> gch{pal};
@@ -206,7 +212,7 @@ public:
         } else {
             std::vector<BitWriter> secs((size_t) (2 + num_lfg + num_groups));
             secs[0] = lfglobal;
-            for (int g = 0; g < num_groups; ++g) {
+            parallel_groups(num_groups, [&](int g) {
                 BitWriter &bw = secs[(size_t) (2 + num_lfg + g)];
                 ModularHeaderOpts mh;
                 if (is_local(g)) {
@@ -226,11 +232,11 @@ public:
                     write_tree(bw, lt, to);
                     ls.write(bw);
                     ls.encode(bw, lts);
-                    continue;
+                    return;
                 }
                 write_modular_header_prefix(bw, mh);
                 spec.encode(bw, ts[(size_t) g]);
-            }
+            });
             out.bit(0); out.pad();
             for (auto &s : secs) { s.pad(); out.u32((uint32_t) s.bytes.size(), 0, 10, 1024, 14, 17408, 22, 4211712, 30); }
             out.pad();
@@ -244,6 +250,20 @@ public:
     }
 
 private:
+    template <class F>
+    static void parallel_groups(int n, F fn) {
+        unsigned th = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        if (n < 64 || th <= 1) { for (int g = 0; g < n; ++g) fn(g); return; }
+        std::atomic<int> next(0);
+        std::vector<std::thread> pool;
+        std::exception_ptr err;
+        std::mutex mu;
+        auto work = [&] { try { for (int g; (g = next.fetch_add(1)) < n;) fn(g); } catch (...) { std::lock_guard<std::mutex> l(mu); err = std::current_exception(); } };
+        for (unsigned t = 1; t < th; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        if (err) std::rethrow_exception(err);
+    }
     static int fl_avg(int a, int b) { return (a + b) >> 1; }
 
     void forward_rct(int v[3]) const {
