@@ -407,6 +407,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     const float ob0 = f.opsin_bias[0], ob1 = f.opsin_bias[1], ob2 = f.opsin_bias[2], itscale = f.itscale;
     float om[9];
     for (int i = 0; i < 9; ++i) om[i] = f.opsin_inv_mat[i];
+    const float wrap_hi = f.srgb_wrap_hi;
     uint8_t *rgba = w.rgba;
     const size_t rgba_stride = (size_t) w.rgba_stride;
     for (int pix = tid; pix < 4096; pix += nth) {
@@ -429,7 +430,7 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float v = J40B_FADD(J40B_FADD(J40B_FMUL(l0, om[c * 3 + 0]), J40B_FMUL(l1, om[c * 3 + 1])), J40B_FMUL(l2, om[c * 3 + 2]));
-            out |= (uint32_t) srgb_u8_lut(ts.thr, ts.lut, v) << (8 * c);
+            out |= (uint32_t) (srgb_needs_wrap(v, wrap_hi) ? srgb_u8_wrapped(v, 8) : srgb_u8_lut(ts.thr, ts.lut, v)) << (8 * c);
         }
         *(uint32_t *) (rgba + (size_t) Y * rgba_stride + (size_t) X * 4) = out;
     }

@@ -75,6 +75,7 @@ struct CudaBackend {
     void d2h_async(void *d, const void *s, size_t n) { cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream); }
     void dev_memset(void *d, int v, size_t n) { cudaMemsetAsync(d, v, n, stream); }
     void sync() { cudaStreamSynchronize(stream); }
+    int lane_stride() const { return 32 * LANE_WARPS; } // work items per slot of the lane decoders' interleaved buffers
 
     // `spec_bytes`: largest code-spec blob among the batch's images (sizes the staging area)
     void launch_lf(const LfWork *w, int n, size_t spec_bytes) {

@@ -25,26 +25,34 @@ struct BitReader {
     int32_t nbits;
 
 #if defined(__CUDA_ARCH__)
-    // Device: aligned 32-bit loads. Bytes past the section end are whatever follows in the codestream
-    // buffer (the executor pads it); they are never *accepted*: any consumption past the end is an
-    // overrun, which is the only thing the error model looks at.
+    // Device: aligned 32-bit loads, one word ahead (`nxt` holds the word at `pos`, so that a refill never waits for
+    // memory: the load of the following word is issued when the current one is consumed). Bytes past the section end
+    // are whatever follows in the codestream buffer (the executor pads it by 16 bytes) up to 8 bytes behind the end
+    // and zeros from there on; they are never *accepted*: any consumption past the end is an overrun, which is the
+    // only thing the error model looks at. The clamp keeps a decoder that runs on after a truncated section (until
+    // its next overrun check) inside the buffer.
+    uint32_t nxt;
+    J40B_HD J40B_INLINE uint32_t load_word(uint32_t at) const {
+        return at < size + 8 ? *(const uint32_t *) (base + at) : 0u;
+    }
     J40B_HD void init(const uint8_t *b, uint32_t size_bytes, uint64_t start_bit = 0) {
         base = b;
         size = size_bytes;
         const uint8_t *p = b + (start_bit >> 3);
         uint32_t mis = (uint32_t) ((uintptr_t) p & 3);
-        const uint32_t *wp = (const uint32_t *) (p - mis);
+        const uint32_t *wp = (const uint32_t *) (p - mis); // (callers start inside the section or right behind it)
         buf = (uint64_t) (*wp >> (8 * mis));
         nbits = 32 - 8 * (int32_t) mis;
-        pos = (uint32_t) (start_bit >> 3) + 4 - mis;
+        pos = (uint32_t) (start_bit >> 3) + 4 - mis;       // base + pos is 4-byte aligned from here on
+        nxt = load_word(pos);
         int skip = (int) (start_bit & 7);
         if (skip) { buf >>= skip; nbits -= skip; }
     }
     J40B_HD J40B_INLINE void refill() { // precondition: nbits <= 32
-        uint32_t w = *(const uint32_t *) (base + pos);
-        buf |= (uint64_t) w << nbits;
+        buf |= (uint64_t) nxt << nbits;
         nbits += 32;
         pos += 4;
+        nxt = load_word(pos);
     }
     J40B_HD J40B_INLINE uint32_t u(int n) { // n in [0, 32]
         if (nbits < 32) refill();

@@ -26,6 +26,9 @@ struct LfWork {
     uint32_t *err;          // this section's error word
     float *llf_scratch;     // [2048] for LF patches larger than 8x8 cells, or null
     ModLaneScratch *lane_scratch; // per-stream record of the lane-per-stream decoder
+    int16_t *ring;          // this lane's slot of its warp's row ring (LaneEnv), or null
+    int32_t *wring;
+    int32_t ring_w, ring_lstride;
 };
 
 struct HfWork { // one per (pass, group)
@@ -82,6 +85,9 @@ struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, 
     uint32_t lz_mask;
     uint32_t *err;
     ModLaneScratch *lane_scratch; // per-stream record of the lane-per-stream decoder
+    int16_t *ring;          // this lane's slot of its warp's row ring (LaneEnv), or null
+    int32_t *wring;
+    int32_t ring_w, ring_lstride;
 };
 
 struct RenderWork { // modular frames: inverse global transforms + interleave to RGBA8
@@ -437,7 +443,7 @@ J40B_HD J40B_INLINE bool spec_is_plain_ans(const uint8_t *arena, uint32_t spec_o
 
 // LF group, stage 1: LfQuant, the 3-channel modular LF image (j40.h:6739-6757); same hand-over as lf_decode1_body
 template <int MODE, class AnyFn, class Sync>
-J40B_HD inline void lf_decode1_lanes(const LfWork *wp, bool active, const int32_t *div24, int32_t *props, int pstride, AnyFn any, Sync sync) {
+J40B_HD inline void lf_decode1_lanes(const LfWork *wp, bool active, LaneEnv env, AnyFn any, Sync sync) {
     ModLane<MODE> L;
     L.done = true; L.need_setup = false; L.es.err = 0;
     int32_t extra_prec = 0;
@@ -446,7 +452,8 @@ J40B_HD inline void lf_decode1_lanes(const LfWork *wp, bool active, const int32_
         const DFrame &f = *w.f;
         DLfGroup &g = *w.g;
         const int n8 = g.width8 * g.height8;
-        L.sc = w.lane_scratch; L.div24 = div24; L.props = props; L.pstride = pstride;
+        L.sc = w.lane_scratch; L.env = env;
+        L.env.ring = w.ring; L.env.wring = w.wring; L.env.ring_w = w.ring_w; // (env.lstride is the launch's: w.ring_lstride)
         L.br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
         extra_prec = (int32_t) L.br.u(2);
         ModImage &m = L.sc->m;
@@ -486,7 +493,7 @@ J40B_HD J40B_INLINE void hf_meta_channels(const DLfGroup &g, int32_t nvb, ModIma
 
 // LF group, stage 3a: entropy decode of the HF metadata image; transforms and varblock placement follow in lf_place_body
 template <int MODE, class AnyFn, class Sync>
-J40B_HD inline void lf_decode2_lanes(const LfWork *wp, bool active, const int32_t *div24, int32_t *props, int pstride, AnyFn any, Sync sync) {
+J40B_HD inline void lf_decode2_lanes(const LfWork *wp, bool active, LaneEnv env, AnyFn any, Sync sync) {
     ModLane<MODE> L;
     L.done = true; L.need_setup = false; L.es.err = 0;
     if (active) {
@@ -494,7 +501,8 @@ J40B_HD inline void lf_decode2_lanes(const LfWork *wp, bool active, const int32_
         const DFrame &f = *w.f;
         DLfGroup &g = *w.g;
         const int n8 = g.width8 * g.height8;
-        L.sc = w.lane_scratch; L.div24 = div24; L.props = props; L.pstride = pstride;
+        L.sc = w.lane_scratch; L.env = env;
+        L.env.ring = w.ring; L.env.wring = w.wring; L.env.ring_w = w.ring_w; // (env.lstride is the launch's: w.ring_lstride)
         L.br.init(w.cs + g.sec_off, g.sec_size, g.mid_bit);
         const int32_t nvb = (int32_t) L.br.u(ceil_lg32((uint32_t) n8)) + 1;
         g.nb_varblocks = nvb;
@@ -551,7 +559,7 @@ J40B_HD inline void lf_place_body(const LfWork &w, uint32_t *bitmap /* [height8 
 
 // one modular sub-bitstream per lane (same hand-over as modular_body)
 template <int MODE, class AnyFn, class Sync>
-J40B_HD inline void modular_lanes(ModWork *wp, bool active, const int32_t *div24, int32_t *props, int pstride, AnyFn any, Sync sync) {
+J40B_HD inline void modular_lanes(ModWork *wp, bool active, LaneEnv env, AnyFn any, Sync sync) {
     ModLane<MODE> L;
     L.done = true; L.need_setup = false; L.es.err = 0;
     bool preset = false;
@@ -560,7 +568,8 @@ J40B_HD inline void modular_lanes(ModWork *wp, bool active, const int32_t *div24
         const DFrame &f = *w.f;
         if (w.preset_err) { *w.err = w.preset_err; preset = true; }
         else {
-            L.sc = w.lane_scratch; L.div24 = div24; L.props = props; L.pstride = pstride;
+            L.sc = w.lane_scratch; L.env = env;
+        L.env.ring = w.ring; L.env.wring = w.wring; L.env.ring_w = w.ring_w; // (env.lstride is the launch's: w.ring_lstride)
             L.br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
             L.sc->m = w.m;
             if (!w.header_parsed) modular_header(L.br, L.es, f.have_global_tree != 0, L.sc->m);

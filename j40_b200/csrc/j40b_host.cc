@@ -1531,6 +1531,17 @@ const GlobalTables &GlobalTables::get() {
         static const int8_t ORDER_LOG[13][2] = {{3, 3}, {3, 3}, {4, 4}, {5, 5}, {3, 4}, {3, 5}, {4, 5}, {6, 6}, {5, 6}, {7, 7}, {6, 7}, {8, 8}, {7, 8}};
         for (int i = 0; i < 13; ++i) t->order[i] = compute_natural_order(ORDER_LOG[i][0], ORDER_LOG[i][1]);
         compute_srgb_thresholds(8, t->srgb_thr);
+        { // smallest float whose encoded value (255 * sRGB(v) + 0.5, the expression of j40.h:7233-7234) reaches 32768
+            uint32_t lo = 1, hi = 0x7f7fffffu;
+            while (lo < hi) {
+                uint32_t mid = lo + (hi - lo) / 2;
+                float fm;
+                memcpy(&fm, &mid, 4);
+                float s_ = (fm <= 0.0031308f ? 12.92f * fm : 1.055f * powf(fm, 1.0f / 2.4f) - 0.055f);
+                if (255.0f * s_ + 0.5f >= 32768.0f) hi = mid; else lo = mid + 1;
+            }
+            memcpy(&t->srgb_wrap_hi, &lo, 4);
+        }
         memset(t->srgb_lut, 0, sizeof(t->srgb_lut));
         for (int b = 0; b <= SRGB_LUT_N; ++b) {
             int n = 0;

@@ -201,10 +201,23 @@ public:
                     mb.lz = lz ? wk_alloc(4 * (size_t) capl) : (size_t) -1;
                     mb.lane = wk_alloc(sizeof(ModLaneScratch));
                 }
+                {   // row ring of the lane-per-stream decoder: as wide as the widest group, at most 1024
+                    int max_w = 1;
+                    for (const ModBuf &mb : im.mod) max_w = std::max(max_w, mb.gw);
+                    im.ring_w = max_w <= 1024 ? (size_t) ((max_w + 63) & ~63) : 0;
+                    const size_t LS = (size_t) be.lane_stride(), slots = (im.nmod + LS - 1) / LS;
+                    im.ring_off = im.ring_w ? wk_alloc(2 * slots * 3 * im.ring_w * LS) : 0;
+                    im.wring_off = im.ring_w ? wk_alloc(4 * slots * 2 * im.ring_w * 5 * LS) : 0;
+                }
                 im.mod_off = up_alloc(sizeof(ModWork) * std::max<size_t>(im.nmod, 1));
                 im.render_off = up_alloc(sizeof(RenderWork));
                 n_mod += im.nmod;
             }
+        }
+        {
+            const size_t LS = (size_t) be.lane_stride(), slots = (n_lf + LS - 1) / LS;
+            lf_ring_off = wk_alloc(2 * slots * 3 * LF_RING_W * LS);
+            lf_wring_off = wk_alloc(4 * slots * 2 * LF_RING_W * 5 * LS);
         }
         lfw_off = up_alloc(sizeof(LfWork) * std::max<size_t>(n_lf, 1));
         hfw_off = up_alloc(sizeof(HfWork) * std::max<size_t>(n_hf, 1));
@@ -276,6 +289,7 @@ public:
             }
             d.srgb_thr = (const float *) (dev + gt_thr);
             d.srgb_lut = dev + gt_lut;
+            d.srgb_wrap_hi = gt.srgb_wrap_hi;
             memcpy(staging + im.frame_off, &d, sizeof(d));
             const DFrame *dframe = (const DFrame *) (dev + im.frame_off);
             const uint8_t *darena = dev + im.arena_off, *dcs = dev + im.cs_off;
@@ -400,13 +414,26 @@ public:
                     w.lz_mask = mb.lz_mask;
                     w.err = derr + g;
                     w.lane_scratch = (ModLaneScratch *) (dwork + mb.lane);
+                    {
+                        const size_t LS = (size_t) be.lane_stride(), slot = g / LS, lane = g % LS;
+                        w.ring_w = (int32_t) im.ring_w; w.ring_lstride = (int32_t) LS;
+                        w.ring = im.ring_w ? (int16_t *) (dwork + im.ring_off) + slot * 3 * im.ring_w * LS + lane : nullptr;
+                        w.wring = im.ring_w ? (int32_t *) (dwork + im.wring_off) + slot * 2 * im.ring_w * 5 * LS + lane : nullptr;
+                    }
                 }
             }
         }
         // LF groups, largest first: a 4K frame has two big and two tiny LF groups; in image order the
         // one-warp blocks of the serial decoders land two big ones per SM on half of the SMs
         std::stable_sort(lf_sorted.begin(), lf_sorted.end(), [](const std::pair<int64_t, LfWork> &a, const std::pair<int64_t, LfWork> &b2) { return a.first > b2.first; });
-        for (size_t i = 0; i < lf_sorted.size(); ++i) lfw[i] = lf_sorted[i].second;
+        for (size_t i = 0; i < lf_sorted.size(); ++i) {
+            lfw[i] = lf_sorted[i].second;
+            // the lane-per-stream decoders' row ring: one per warp (LS consecutive items), lane-interleaved
+            const size_t LS = (size_t) be.lane_stride(), slot = i / LS, lane = i % LS;
+            lfw[i].ring_w = LF_RING_W; lfw[i].ring_lstride = (int32_t) LS;
+            lfw[i].ring = (int16_t *) (dwork + lf_ring_off) + slot * 3 * LF_RING_W * LS + lane;
+            lfw[i].wring = (int32_t *) (dwork + lf_wring_off) + slot * 2 * LF_RING_W * 5 * LS + lane;
+        }
         be.h2d(dev, staging, upload_bytes);
         return true;
     }
@@ -570,6 +597,7 @@ private:
     struct Img {
         size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;
         size_t rgba_off = 0, err_off = 0, tok_off = 0, plane[MOD_MAX_CH] = {0};
+        size_t ring_w = 0, ring_off = 0, wring_off = 0; // modular frames: the lane decoders' row ring
         size_t nlf = 0, ng = 0, npg = 0, nmod = 0; // LF groups, groups, (pass, group) sections, modular sub-bitstreams
         std::vector<LfBuf> lf;
         std::vector<GrpBuf> grp;
@@ -578,6 +606,8 @@ private:
     std::vector<Img> img;
     uint8_t *dev = nullptr, *staging = nullptr;
     size_t upload_bytes = 0, work_bytes = 0, dev_cap = 0, staging_cap = 0;
+    size_t lf_ring_off = 0, lf_wring_off = 0;
+    enum { LF_RING_W = 256 }; // LF groups are at most 256 cells wide
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, ppw_off = 0, num_lf = 0, num_hf = 0, num_grp = 0;
     bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry
     size_t max_global_blob = 0, max_coeff_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)

@@ -14,6 +14,7 @@
 // association); only data movement and the order of independent operations differ.
 #pragma once
 #include "j40b_modular.h"
+#include <math.h>
 #include "j40b_tables.inc"
 
 namespace j40b {
@@ -82,6 +83,7 @@ struct DFrame {
     const int32_t *order[MAX_PASSES][13][3]; // int32_t[size] per pass, order and channel
     const float *srgb_thr;           // float[255]: smallest v whose 8-bit output is >= k+1
     const uint8_t *srgb_lut;         // uint8[SRGB_LUT_N + 1]: number of thresholds <= b / SRGB_LUT_N
+    float srgb_wrap_hi;              // samples >= this wrap around in the reference's int16 cast (srgb_u8_wrapped)
     int32_t global_tree_uses_wp, have_global_tree;
     // modular frames
     int32_t num_channels, num_gm_channels, alpha_channel; // alpha_channel < 0: opaque
@@ -757,6 +759,35 @@ J40B_HD J40B_INLINE int srgb_u8_lut(const float *thr, const uint8_t *lut, float 
     return code;
 }
 
+// Samples outside the range the threshold table covers. The reference converts the sRGB-encoded value with an unchecked
+// `(int16_t)` cast (j40.h:7234): on x86-64 that is a truncating float -> int32 conversion (0x80000000 for NaN and for
+// values outside the int32 range) of which the low 16 bits are kept, so that huge samples wrap around before the render
+// step clamps them (j40.h:7950). `srgb_wrap_hi` (host, same libm as the table) is the smallest v whose encoded value
+// reaches 32768; on the negative side (the linear branch, exact arithmetic) the first wrap is near v = -9.947. powf of
+// the host's libm is replaced by a double-precision pow rounded to float on the device; an integer step of the
+// encoded value takes >= 480 float steps of v here, so a last-bit difference in powf almost never reaches the result.
+J40B_HD inline int srgb_u8_wrapped(float v, int bpp) {
+    float s;
+    if (v <= 0.0031308f) s = J40B_FMUL(12.92f, v);
+    else {
+#if defined(__CUDA_ARCH__)
+        const float p = (float) pow((double) v, (double) (1.0f / 2.4f));
+#else
+        const float p = powf(v, 1.0f / 2.4f);
+#endif
+        s = J40B_FSUB(J40B_FMUL(1.055f, p), 0.055f);
+    }
+    const float q = J40B_FADD(J40B_FMUL((float) ((1 << bpp) - 1), s), 0.5f);
+    int32_t t;
+    if (!(q >= -2147483648.0f && q < 2147483648.0f)) t = (int32_t) 0x80000000u; // cvttss2si's "integer indefinite"
+    else t = (int32_t) q;                                                        // truncation towards zero
+    const int32_t i16 = (int32_t) (int16_t) (uint16_t) ((uint32_t) t & 0xffffu);
+    const int32_t maxpixel = (1 << bpp) - 1, half = 1 << (bpp - 1);
+    const int32_t p8 = imin(imax(0, i16), maxpixel);
+    return (p8 * 255 + half) / maxpixel;
+}
+J40B_HD J40B_INLINE bool srgb_needs_wrap(float v, float wrap_hi) { return v >= wrap_hi || v < -9.9f; }
+
 // Working buffers: coef[3] (X, Y, B) each `size` floats, scratch `size` floats; `size` = R*C.
 // Executed by `nth` cooperating threads (a warp or a block) separated by `sync`.
 template <class Sync>
@@ -849,7 +880,7 @@ J40B_HD inline void varblock_to_pixels(const DFrame &f, const uint8_t *arena, co
         for (int c = 0; c < 3; ++c) {
             float v = J40B_FADD(J40B_FADD(J40B_FMUL(lin[0], f.opsin_inv_mat[c * 3 + 0]), J40B_FMUL(lin[1], f.opsin_inv_mat[c * 3 + 1])),
                                 J40B_FMUL(lin[2], f.opsin_inv_mat[c * 3 + 2]));
-            out[c] = (uint8_t) srgb_u8_from_linear(thr, v);
+            out[c] = (uint8_t) (srgb_needs_wrap(v, f.srgb_wrap_hi) ? srgb_u8_wrapped(v, 8) : srgb_u8_from_linear(thr, v));
         }
         out[3] = 255;
         o[0] = out[0]; o[1] = out[1]; o[2] = out[2]; o[3] = out[3];

@@ -23,25 +23,40 @@ __global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, i
 }
 
 // Lane-per-stream variant (j40b_modlane.h): every thread owns one LF group; 32 * LANE_WARPS work items per block.
-// Shared memory: the 64-entry divisor table and 16 property slots per thread.
+// Shared memory (lane-interleaved): the 64-entry divisor table, 16 property slots and the compiled tree of the current
+// channel (LANE_NODE_CAP nodes) per thread.
+struct LaneSmem {
+    int32_t div24[64];
+    int32_t props[16 * 32 * LANE_WARPS];
+    int32_t nodes[LANE_NODE_CAP * 4 * 32 * LANE_WARPS];
+};
+__device__ inline LaneEnv lane_env(LaneSmem &sm) {
+    LaneEnv env;
+    env.div24 = sm.div24;
+    env.props = sm.props + threadIdx.x;
+    env.nodes = sm.nodes + threadIdx.x;
+    env.ring = nullptr; env.wring = nullptr; env.ring_w = 0;
+    env.lstride = 32 * LANE_WARPS;
+    return env;
+}
+
 template <int STAGE>
 __global__ void __launch_bounds__(32 * LANE_WARPS, 1) k_lf_lane(const LfWork *items, int n) {
-    __shared__ int32_t div24[64];
-    __shared__ int32_t props[16 * 32 * LANE_WARPS];
-    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
+    __shared__ LaneSmem sm;
+    fill_div24(sm.div24, (int) threadIdx.x, (int) blockDim.x);
     __syncthreads();
     const int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
     const LfWork *w = &items[i < n ? i : n - 1];
     const bool active = i < n && (STAGE == 1 || !*w->err);
     // the fast path (rANS, no LZ77) is taken when every stream of the warp qualifies
     const bool plain = __all_sync(0xffffffffu, !active || spec_is_plain_ans(w->arena, w->f->global_spec_off));
-    int32_t *my = props + threadIdx.x;
+    const LaneEnv env = lane_env(sm);
     if (STAGE == 1) {
-        if (plain) lf_decode1_lanes<1>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
-        else lf_decode1_lanes<0>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
+        if (plain) lf_decode1_lanes<1>(w, active, env, WarpAny(), WarpSync());
+        else lf_decode1_lanes<0>(w, active, env, WarpAny(), WarpSync());
     } else {
-        if (plain) lf_decode2_lanes<1>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
-        else lf_decode2_lanes<0>(w, active, div24, my, 32 * LANE_WARPS, WarpAny(), WarpSync());
+        if (plain) lf_decode2_lanes<1>(w, active, env, WarpAny(), WarpSync());
+        else lf_decode2_lanes<0>(w, active, env, WarpAny(), WarpSync());
     }
 }
 

@@ -18,18 +18,22 @@ __global__ void __launch_bounds__(32) k_modular(ModWork *items, int cap, int spe
     modular_body(w, *ws, ms, div24, staged ? smem : nullptr, w.arena, (int) threadIdx.x, 32, WarpSync());
 }
 
-// Lane-per-stream variant (j40b_modlane.h): every thread owns one sub-bitstream
+// Lane-per-stream variant (j40b_modlane.h): every thread owns one sub-bitstream (shared memory as in k_lf_lane)
 __global__ void __launch_bounds__(32 * LANE_WARPS, 1) k_mod_lane(ModWork *items, int n) {
     __shared__ int32_t div24[64];
     __shared__ int32_t props[16 * 32 * LANE_WARPS];
+    __shared__ int32_t nodes[LANE_NODE_CAP * 4 * 32 * LANE_WARPS];
     fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
     __syncthreads();
     const int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
     ModWork *w = &items[i < n ? i : n - 1];
     const bool active = i < n;
     const bool plain = __all_sync(0xffffffffu, !active || spec_is_plain_ans(w->arena, w->spec_off));
-    if (plain) modular_lanes<1>(w, active, div24, props + threadIdx.x, 32 * LANE_WARPS, WarpAny(), WarpSync());
-    else modular_lanes<0>(w, active, div24, props + threadIdx.x, 32 * LANE_WARPS, WarpAny(), WarpSync());
+    LaneEnv env;
+    env.div24 = div24; env.props = props + threadIdx.x; env.nodes = nodes + threadIdx.x;
+    env.ring = nullptr; env.wring = nullptr; env.ring_w = 0; env.lstride = 32 * LANE_WARPS;
+    if (plain) modular_lanes<1>(w, active, env, WarpAny(), WarpSync());
+    else modular_lanes<0>(w, active, env, WarpAny(), WarpSync());
 }
 
 // rows go over grid.x together with the column blocks (grid.y is capped at 65535, frames may be 2^18 rows tall)

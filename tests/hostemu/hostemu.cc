@@ -20,6 +20,7 @@ struct HostEmuBackend {
     void d2h_async(void *d, const void *s, size_t n) { memcpy(d, s, n); }
     void dev_memset(void *d, int v, size_t n) { memset(d, v, n); }
     void sync() {}
+    int lane_stride() const { return 1; } // work items per slot of the lane decoders' interleaved buffers
     // shared memory of one warp of the serial decoders
     struct WarpMem {
         WarpScratch ws;
@@ -42,16 +43,21 @@ struct HostEmuBackend {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(256));
         if (lane_mode()) {
-            int32_t props[16];
+            int32_t props[16], nodes[LANE_NODE_CAP * 4];
             std::vector<uint32_t> bitmap(256 * 8);
             auto any = [](bool p) { return p; };
             for (int i = 0; i < n; ++i) {
-                if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode1_lanes<1>(&w[i], true, wm.div24, props, 1, any, NoSync());
-                else lf_decode1_lanes<0>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                LaneEnv env;
+                env.div24 = wm.div24; env.props = props; env.nodes = (i & 2) ? nodes : nullptr; env.lstride = 1;
+                env.ring = nullptr; env.wring = nullptr; env.ring_w = 0;
+                LfWork ww = w[i];
+                if (i & 1) ww.ring = nullptr; // every other stream without the row ring (the path of channels wider than it)
+                if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode1_lanes<1>(&ww, true, env, any, NoSync());
+                else lf_decode1_lanes<0>(&ww, true, env, any, NoSync());
                 lf_post_body(w[i], 0, 1, NoSync());
                 if (!*w[i].err) {
-                    if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode2_lanes<1>(&w[i], true, wm.div24, props, 1, any, NoSync());
-                    else lf_decode2_lanes<0>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                    if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode2_lanes<1>(&ww, true, env, any, NoSync());
+                    else lf_decode2_lanes<0>(&ww, true, env, any, NoSync());
                 }
                 lf_place_body(w[i], (i & 1) ? bitmap.data() : nullptr, 0, 1, NoSync());
                 lf_llf_body(w[i], 0, 1, NoSync());
@@ -96,11 +102,16 @@ struct HostEmuBackend {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(1024));
         if (lane_mode()) {
-            int32_t props[16];
+            int32_t props[16], nodes[LANE_NODE_CAP * 4];
             auto any = [](bool p) { return p; };
             for (int i = 0; i < n; ++i) {
-                if (spec_is_plain_ans(w[i].arena, w[i].spec_off)) modular_lanes<1>(&w[i], true, wm.div24, props, 1, any, NoSync());
-                else modular_lanes<0>(&w[i], true, wm.div24, props, 1, any, NoSync());
+                LaneEnv env;
+                env.div24 = wm.div24; env.props = props; env.nodes = (i & 1) ? nodes : nullptr; env.lstride = 1;
+                env.ring = nullptr; env.wring = nullptr; env.ring_w = 0;
+                ModWork ww = w[i];
+                if (i & 2) ww.ring = nullptr;
+                if (spec_is_plain_ans(w[i].arena, w[i].spec_off)) modular_lanes<1>(&ww, true, env, any, NoSync());
+                else modular_lanes<0>(&ww, true, env, any, NoSync());
             }
             return;
         }

@@ -51,6 +51,14 @@ VARDCT_CASES = [
     ("passes2_all_transforms", 520, 392, 40, dict(mix=2, tree=2, passes=2)),
 ]
 
+# samples far outside [0, 1]: a RAW dequantisation matrix whose written denominator is `raw_dq_lie` times the one the
+# writer quantised with. The reference's unchecked (int16_t) cast wraps such samples around (j40.h:7234).
+WRAP_CASES = [
+    ("int16_wrap_x8", 136, 72, 5, dict(mix=0, tree=1, raw_dq=1, raw_dq_lie=8, hfmul=4)),
+    ("int16_wrap_x512", 136, 72, 5, dict(mix=0, tree=1, raw_dq=1, raw_dq_lie=512, hfmul=4)),
+    ("int16_wrap_x16384_mixed", 264, 136, 6, dict(mix=1, tree=1, raw_dq=0x11, raw_dq_lie=16384, hfmul=4)),
+]
+
 MODULAR_CASES = [
     ("fjxl_like_prefix_lz77", 600, 400, 2, dict()),
     ("ans_no_lz77", 600, 400, 2, dict(ans=1, lz77=0)),

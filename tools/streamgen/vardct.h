@@ -54,6 +54,8 @@ struct VarDCTParams {
     bool lz77_coeffs = false;  // enable LZ77 in the coefficient stream (rare in practice)
     float quant_deadzone = 0.55f;
     int force_dctsel = -1;     // >= 0: use this transform wherever it fits (coverage tests)
+    float raw_dq_lie = 1.0f;   // RAW matrices: the denominator written is this many times the one used for quantising, so that the
+                               // decoder's coefficients come out that much larger (out-of-range samples; tests of the int16 wrap, j40.h:7234)
     int passes = 1;            // > 1: the quantised coefficients are split over this many passes (the decoder adds them up);
                                // pass p has its own code spec and, with custom_orders, its own coefficient orders
     float big_take = 0.75f;    // transform_mix 1: probability of taking a larger transform where the content allows it
@@ -977,7 +979,7 @@ private:
             for (int i = 0; i < 17; ++i) {
                 if (!((P.raw_dq >> i) & 1)) { bw.put(0, 3); continue; } // library default
                 bw.put(7, 3); // RAW (j40.h:4705-4743)
-                bw.f16(2.0f); // denominator
+                bw.f16(2.0f * P.raw_dq_lie); // denominator
                 ModularHeaderOpts mh;
                 write_modular_header_prefix(bw, mh);
                 mspec_ptr->encode(bw, raw_ts[i]);
