@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--skip-latency", action="store_true")
     ap.add_argument("--streams", type=int, default=12, help="batch objects (CUDA streams) the timed steps are pipelined over")
     ap.add_argument("--e2e-sets", type=int, default=2, help="groups of `streams` batch objects the end-to-end loop alternates between")
+    ap.add_argument("--e2e-mode", default="waves", choices=["waves", "rolling"], help="waves: a group of objects is resubmitted when all of it has "
+                    "landed in host memory; rolling: every object is resubmitted as soon as its own frames have landed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -419,6 +421,7 @@ def main():
         host_out = [torch.empty((len(obj_chunk[k]), pitch), dtype=torch.uint8, pin_memory=True) for k in range(E)]
         out_np = [t_.numpy() for t_ in host_out]
         host_t = [0.0] * 6
+        skip = os.environ.get("J40B_E2E_SKIP", "")  # diagnostics only ("d2h"): such a run is not an end-to-end number
 
         def submit(k):
             bm = objs[k]
@@ -427,7 +430,9 @@ def main():
             bm.add_many(obj_chunk[k], host_threads); tt.append(time.perf_counter())
             bm.upload(); tt.append(time.perf_counter())
             bm.decode(); tt.append(time.perf_counter())
-            bm.read_all_async(out_np[k]); tt.append(time.perf_counter())
+            if skip != "d2h":
+                bm.read_all_async(out_np[k])
+            tt.append(time.perf_counter())
             for i in range(5):
                 host_t[i] += tt[i + 1] - tt[i]
 
@@ -444,6 +449,14 @@ def main():
         t0 = time.perf_counter()
         for wv in range(n_waves):
             ids = range((wv % sets) * W, (wv % sets) * W + W)
+            if args.e2e_mode == "rolling":
+                for k in ids:
+                    if wv >= sets:
+                        tw = time.perf_counter()
+                        assert objs[k].wait() == 0  # this object's previous decode, including its D2H
+                        host_t[5] += time.perf_counter() - tw
+                    submit(k)
+                continue
             if wv >= sets:
                 tw = time.perf_counter()
                 for k in ids:
@@ -466,7 +479,7 @@ def main():
             dist.all_reduce(tem, op=dist.ReduceOp.MAX)
             dist.all_reduce(te, op=dist.ReduceOp.SUM)
         # every distinct frame of every object, as it arrived in host memory
-        for k in range(E):
+        for k in range(E if skip != "d2h" else 0):
             seen = set()
             for i, d in enumerate(obj_chunk[k]):
                 if d in seen:
@@ -484,7 +497,7 @@ def main():
                "ceiling": "bare cudaMemcpyAsync of one batch object's output into pinned host memory, all ranks at once",
                "host_parse_threads": host_threads,
                "includes": "host parse + H2D + kernels + D2H of all frames into pinned host memory, "
-                           f"{n_waves} waves of {W} batch objects over {sets} groups of {W} reused objects"}
+                           f"{n_waves} waves of {W} batch objects over {sets} groups of {W} reused objects, {args.e2e_mode}"}
         for bm in objs[W:]:
             bm.close()
         del host_out, out_np

@@ -9,10 +9,12 @@
 #define J40B_HD __host__ __device__
 #define J40B_D __device__
 #define J40B_INLINE __forceinline__
+#define J40B_NOINLINE __noinline__
 #else
 #define J40B_HD
 #define J40B_D
 #define J40B_INLINE inline
+#define J40B_NOINLINE
 #endif
 
 // float arithmetic must round once per operation, in the written order:
@@ -58,7 +60,12 @@ enum : uint32_t {
     E_TOKV = J40B_4CC('t', 'o', 'k', 'v'), // internal: token arena too small, host retries larger
 };
 
-J40B_HD J40B_INLINE int32_t unpack_signed(int32_t x) { return (x & 1) ? -(x / 2 + 1) : x / 2; }
+// j40__unpack_signed: (x & 1) ? -(x / 2 + 1) : x / 2 with C's truncating division, also for negative x (a hybrid integer
+// that overflowed): x / 2 == (x + (x < 0)) >> 1 and -(q + 1) == ~q
+J40B_HD J40B_INLINE int32_t unpack_signed(int32_t x) {
+    const int32_t q = (x + (int32_t) ((uint32_t) x >> 31)) >> 1;
+    return (x & 1) ? ~q : q;
+}
 J40B_HD J40B_INLINE int32_t ceil_div(int32_t x, int32_t y) { return (x + y - 1) / y; }
 J40B_HD J40B_INLINE int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
 J40B_HD J40B_INLINE int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }

@@ -86,9 +86,11 @@ struct CudaBackend {
         const int spec_cap = stage && spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
         const size_t smem = (size_t) spec_cap + (size_t) warps * warp_slice_bytes(cap);
         const int blocks = (n + warps - 1) / warps;
-        // Many streams: one per lane (throughput; no shared memory, 1/20 of the issue slots). Few streams (a single
-        // image has 1-4 LF groups): one per warp (latency). J40B_LF_MODE=lane|warp overrides.
-        bool lane_mode = n >= 64;
+        // One stream per warp (SIMT-uniform decoder, j40b_modular.h) or, with J40B_LF_MODE=lane, one per lane
+        // (j40b_modlane.h): 1/20 of the issue slots and no shared memory, but 6-7 times the latency per stream (measured:
+        // LF image of 64 4K frames 70 ms against 490 ms), which a pipeline can only hide with more batches in flight than
+        // fit the device memory at 6 GB per batch of 64 4K frames. The default stays the warp decoder.
+        bool lane_mode = false;
         if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
         cudaEventRecord(ev[0], stream);
         if (lane_mode) kl_lf_lane(1, stream, w, n); else kl_lf_decode(1, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
@@ -105,10 +107,10 @@ struct CudaBackend {
         kl_hf_prep(ngroups, stream, pw);
         ++launches;
         const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
-        // lanes per warp: aim at ~4 warps per SM before filling warps completely. Measured at 8640 groups: 8 lanes
-        // is the latency optimum of one batch alone (26 ms against 34 ms at 16 lanes), 16 lanes the throughput
-        // optimum with a dozen batches in flight (fewer resident blocks per group decoded)
-        int lanes = (n + num_sms * 4 - 1) / (num_sms * 4);
+        // sections per warp (one per lane): full warps as soon as that still leaves two warps per SM -- a warp of 32 lanes
+        // costs the same issue slots per iteration as one of 8 -- and fewer lanes per warp for small launches (a single
+        // 4K image has 135 sections), where latency is what counts
+        int lanes = (n + num_sms * 2 - 1) / (num_sms * 2);
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
         const int per_block = HF_WARPS * lanes;
@@ -132,7 +134,7 @@ struct CudaBackend {
     }
     // `spec_bytes`: the image's code-spec blob; `max_w`: its widest channel (sizes the shared-memory rows)
     void launch_mod(ModWork *w, int n, size_t spec_bytes, int max_w) {
-        bool lane_mode = n >= 64;
+        bool lane_mode = false; // (see launch_lf; 8192x8192 lossless: 183 ms per frame against 1019 ms)
         if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
         if (lane_mode) { kl_mod_lane(n, stream, w); ++launches; return; }
         int cap = (max_w + 63) & ~63;

@@ -100,7 +100,9 @@ struct BitReader {
 #endif
     J40B_HD J40B_INLINE void skip(int n) { buf >>= n; nbits -= n; }
     J40B_HD J40B_INLINE uint64_t bits_consumed() const { return (uint64_t) pos * 8 - (uint64_t) nbits; }
-    J40B_HD J40B_INLINE bool overrun() const { return bits_consumed() > (uint64_t) size * 8; }
+    // consumed more bits than the section has: 8 * pos - nbits > 8 * size, i.e. pos - size > floor(nbits / 8) (nbits >= 0;
+    // pos and size are below 2^31, so the difference fits 32 bits)
+    J40B_HD J40B_INLINE bool overrun() const { return (int32_t) (pos - size) > (nbits >> 3); }
     // j40__zero_pad_to_byte: returns false if a padding bit is set
     J40B_HD bool zero_pad_to_byte() {
         int n = (int) ((8 - (bits_consumed() & 7)) & 7);

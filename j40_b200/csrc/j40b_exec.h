@@ -88,6 +88,10 @@ struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, 
     int16_t *ring;          // this lane's slot of its warp's row ring (LaneEnv), or null
     int32_t *wring;
     int32_t ring_w, ring_lstride;
+    // extra channels of a VarDCT pass group (j40.h:7024-7033): the sub-bitstream starts where the coefficient decoder of
+    // the same section stopped, and only if that one succeeded (both report through the section's error word)
+    const uint64_t *start_bit_src; // or null: sec_start_bit
+    const uint32_t *skip_if;       // or null
 };
 
 struct RenderWork { // modular frames: inverse global transforms + interleave to RGBA8
@@ -243,8 +247,8 @@ J40B_HD inline void lf_decode2_body(const LfWork &w, WarpScratch &ws, const ModS
         inverse_transforms(one, lane, nlanes);
         sync();
     }
-    // the weighted predictor's shared-memory rows are free now: 8 words per row of cells serve as the
-    // occupancy bitmap of the placement (needs 256 * 8 words)
+    // the weighted predictor's shared-memory row and the reference-property rows behind it are free now: 8 words per
+    // row of cells serve as the occupancy bitmap of the placement (needs 256 * 8 words of the 256 * 9 there)
     if (ms.rows && ms.cap >= 256) place_varblocks_warp(f, g, es, br, (uint32_t *) ms.wp, lane, nlanes, sync);
     else if (lane == 0) place_varblocks(f, g, es, br);
     if (lane == 0) {
@@ -326,6 +330,7 @@ J40B_HD J40B_INLINE void hf_lane_finish(HfLane<MODE> &L, const HfWork &w) {
     DGroup &grp = *w.grp;
     grp.tok_used = L.tok - grp.tok_first;
     if (!L.es.err) finish_code(L.br, L.es, L.cc, L.cs);
+    grp.end_bit = L.br.bits_consumed(); // where the section's extra-channel sub-bitstream starts, if it has one
     if (!L.es.err) {
         if (grp.sec_start_bit == ~0ull) { uint32_t e = L.br.finish(); if (e) L.es.set_raw(e); } // single-section frame: real check
         else if (L.br.overrun()) L.es.set_raw(E_SHRT); // see lf_decode2_body
@@ -388,12 +393,13 @@ J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms,
                                  const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
     const DFrame &f = *w.f;
     if (w.preset_err) { if (lane == 0) *w.err = w.preset_err; return; }
+    if (w.skip_if && *w.skip_if) return;
     BitReader br;
     ErrSlot es;
     CodeCtx cc;
     CodeState cs;
     es.err = 0;
-    br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
+    br.init(w.cs + w.sec_off, w.sec_size, w.start_bit_src ? *w.start_bit_src : w.sec_start_bit);
     init_code_ctx(cc, w.arena, w.spec_off, spec_copy, copy_arena);
     cs.init(w.lz_window, w.lz_mask);
     const DTreeNode *tree = (const DTreeNode *) (w.arena + w.tree_off);
@@ -567,10 +573,11 @@ J40B_HD inline void modular_lanes(ModWork *wp, bool active, LaneEnv env, AnyFn a
         ModWork &w = *wp;
         const DFrame &f = *w.f;
         if (w.preset_err) { *w.err = w.preset_err; preset = true; }
+        else if (w.skip_if && *w.skip_if) preset = true;
         else {
             L.sc = w.lane_scratch; L.env = env;
         L.env.ring = w.ring; L.env.wring = w.wring; L.env.ring_w = w.ring_w; // (env.lstride is the launch's: w.ring_lstride)
-            L.br.init(w.cs + w.sec_off, w.sec_size, w.sec_start_bit);
+            L.br.init(w.cs + w.sec_off, w.sec_size, w.start_bit_src ? *w.start_bit_src : w.sec_start_bit);
             L.sc->m = w.m;
             if (!w.header_parsed) modular_header(L.br, L.es, f.have_global_tree != 0, L.sc->m);
             if (!L.es.err) L.begin(w.arena, w.spec_off, (const DTreeNode *) (w.arena + w.tree_off), w.tree_uses_wp, w.sidx, w.wp_scratch, w.lz_window, w.lz_mask);

@@ -28,7 +28,7 @@ struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
 
 __host__ __device__ inline size_t warp_slice_bytes(int cap) {
     size_t n = sizeof(WarpScratch) + (sizeof(SimtLane) + sizeof(SimtLeaf)) * SIMT_LANES;
-    n += (size_t) cap * (3 * 2 + 2 * 5 * 4 + SIMT_REF_SLOTS * 4);
+    n += (size_t) cap * (3 * 2 + 5 * 4 + SIMT_REF_SLOTS * 4);
     return (n + 15) & ~(size_t) 15;
 }
 
@@ -39,7 +39,7 @@ __device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *
     ms.leaves = (SimtLeaf *) (base + sizeof(WarpScratch));
     ms.tab = (SimtLane *) (ms.leaves + SIMT_LANES);
     ms.wp = (int32_t *) (ms.tab + SIMT_LANES);
-    ms.refp = ms.wp + (size_t) cap * 10;
+    ms.refp = ms.wp + (size_t) cap * 5;
     ms.rows = cap ? (int16_t *) (ms.refp + (size_t) cap * SIMT_REF_SLOTS) : nullptr;
     ms.info = ws->info;
     ms.cap = cap;

@@ -298,7 +298,7 @@ struct alignas(16) SimtLeaf { // leaf j with its context already resolved to a c
 
 struct ModSmem {
     int16_t *rows;   // [3][cap]  ring of the last three sample rows (null: no SIMT path)
-    int32_t *wp;     // [2][cap][5] weighted predictor error rows
+    int32_t *wp;     // [cap][5] weighted predictor error row (updated in place, see modular_channel_simt); refp follows
     int32_t *refp;   // [SIMT_REF_SLOTS][cap] reference-channel property values of the current row
     SimtLane *tab;   // [SIMT_LANES]
     SimtLeaf *leaves; // [SIMT_LANES]
@@ -627,8 +627,10 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
             S.cur = ms.rows + (size_t) (y % 3) * cap;
             S.nrow = ms.rows + (size_t) ((y + 2) % 3) * cap;
             S.nnrow = ms.rows + (size_t) ((y + 1) % 3) * cap;
-            S.err = ms.wp + (size_t) ((y & 1) ? width : 0) * 5;
-            S.nerr = ms.wp + (size_t) ((y & 1) ? 0 : width) * 5;
+            // one row serves as both the previous and the current row: sample x writes its errors at x and has read
+            // the previous row's up to x + 2 by then (halves the weighted predictor's shared memory)
+            S.err = ms.wp;
+            S.nerr = ms.wp;
         }
         for (int32_t seg0 = 0; seg0 < width; seg0 += cap) {
             const int32_t seg1 = seg0 + cap < width ? seg0 + cap : width;

@@ -86,7 +86,7 @@ public:
         size_t work = 0;                    // device-only area cursor (follows the upload blob)
         auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
         size_t n_lf = 0, n_hf = 0, n_grp = 0, n_mod = 0;
-        max_global_blob = max_coeff_blob = 0;
+        max_global_blob = max_coeff_blob = max_ec_blob = 0;
         for (size_t k = 0; k < n; ++k) {
             FramePlan &p = *plans[k];
             Img &im = img[k];
@@ -161,6 +161,37 @@ public:
                     gb.vbs = pg < im.ng ? wk_alloc(sizeof(HfVb) * (size_t) ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8)) : im.grp[g].vbs;
                 }
                 im.tok_off = wk_alloc(sizeof(DToken) * std::max<size_t>(tok_total, 1));
+                // extra channels (alpha ...) of a multi-section frame: coded per pass group behind the coefficients; the
+                // reference decodes them and then drops the planes (j40.h:7024-7033, 7869-7870). Decoded here into scratch
+                // planes for the sake of the errors that decoding can raise.
+                im.nec = p.gmod.num_channels > 0 && !p.single_section ? im.npg : 0;
+                if (im.nec) {
+                    im.ec.resize(im.nec);
+                    const int nch = p.gmod.num_channels - p.num_gm_channels;
+                    const bool lz_g = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
+                    int max_w = 1;
+                    for (size_t pg = 0; pg < im.nec; ++pg) {
+                        ModBuf &mb = im.ec[pg];
+                        mb.gw = im.grp[pg].gw; mb.gh = im.grp[pg].gh;
+                        max_w = std::max(max_w, mb.gw);
+                        mb.wp = wp ? wk_alloc(4 * 2 * 5 * (size_t) mb.gw) : (size_t) -1;
+                        uint32_t capl = 1;
+                        while (capl < (size_t) nch * mb.gw * mb.gh && capl < (1u << 20)) capl <<= 1;
+                        mb.lz_mask = capl - 1;
+                        mb.lz = lz_g ? wk_alloc(4 * (size_t) capl) : (size_t) -1;
+                        mb.lane = wk_alloc(sizeof(ModLaneScratch));
+                        mb.planes = wk_alloc(2 * (size_t) std::max(1, nch) * mb.gw * mb.gh);
+                    }
+                    im.ring_w = (size_t) ((max_w + 63) & ~63);
+                    const size_t LS = (size_t) be.lane_stride(), slots = (im.nec + LS - 1) / LS;
+                    im.ring_off = wk_alloc(2 * slots * 3 * im.ring_w * LS);
+                    im.wring_off = wk_alloc(4 * slots * 2 * im.ring_w * 5 * LS);
+                    im.mod_off = up_alloc(sizeof(ModWork) * im.nec);
+                    if (d.global_spec_off) {
+                        const DCodeSpec *gs = (const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off);
+                        max_ec_blob = std::max(max_ec_blob, (size_t) (gs->blob_hi - gs->blob_lo));
+                    }
+                }
                 n_lf += im.nlf; n_hf += im.npg; n_grp += im.ng;
             } else {
                 im.err_off = wk_alloc(4 * (p.pg_sec.size() + 2));
@@ -362,6 +393,36 @@ public:
                     const DGroup &ga = gr[a.grp - (DGroup *) (dev + im.grp_off)], &gb2 = gr[b2.grp - (DGroup *) (dev + im.grp_off)];
                     return ga.pass != gb2.pass ? ga.pass < gb2.pass : ga.sec_size > gb2.sec_size;
                 });
+                if (im.nec) {
+                    ModWork *mw = (ModWork *) (staging + im.mod_off);
+                    const int nch = p.gmod.num_channels - p.num_gm_channels;
+                    for (size_t pg = 0; pg < im.nec; ++pg) {
+                        ModWork &w = mw[pg];
+                        const ModBuf &mb = im.ec[pg];
+                        memset(&w, 0, sizeof(w));
+                        w.f = dframe; w.arena = darena; w.cs = dcs;
+                        w.sec_off = (uint32_t) p.pg_sec[pg].off; w.sec_size = p.pg_sec[pg].size;
+                        w.start_bit_src = &((DGroup *) (dev + im.grp_off) + pg)->end_bit;
+                        w.skip_if = derr + im.nlf + pg;
+                        w.err = derr + im.nlf + pg;
+                        // stream index of a pass group (j40.h:7012): behind LfGlobal, three per LF group, 17 matrices
+                        w.sidx = (int32_t) (1 + 3 * d.num_lf_groups + 17 + (int64_t) pg);
+                        w.tree_off = d.global_tree_off; w.spec_off = d.global_spec_off; w.tree_uses_wp = d.global_tree_uses_wp;
+                        w.m.num_channels = nch;
+                        for (int c = 0; c < nch; ++c) {
+                            w.m.ch[c].px = (int16_t *) (dwork + mb.planes) + (size_t) c * mb.gw * mb.gh;
+                            w.m.ch[c].stride = mb.gw; w.m.ch[c].w = mb.gw; w.m.ch[c].h = mb.gh;
+                        }
+                        w.wp_scratch = mb.wp == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.wp);
+                        w.lz_window = mb.lz == (size_t) -1 ? nullptr : (int32_t *) (dwork + mb.lz);
+                        w.lz_mask = mb.lz_mask;
+                        w.lane_scratch = (ModLaneScratch *) (dwork + mb.lane);
+                        const size_t LS = (size_t) be.lane_stride(), slot = pg / LS, lane = pg % LS;
+                        w.ring_w = (int32_t) im.ring_w; w.ring_lstride = (int32_t) LS;
+                        w.ring = (int16_t *) (dwork + im.ring_off) + slot * 3 * im.ring_w * LS + lane;
+                        w.wring = (int32_t *) (dwork + im.wring_off) + slot * 2 * im.ring_w * 5 * LS + lane;
+                    }
+                }
             } else {
                 ModWork *mw = (ModWork *) (staging + im.mod_off);
                 RenderWork *rw = (RenderWork *) (staging + im.render_off);
@@ -452,6 +513,13 @@ public:
         }
         if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob);
         if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
+        for (size_t k = 0; k < plans.size(); ++k) { // extra channels behind the coefficients (errors only; planes are scratch)
+            const Img &im = img[k];
+            if (plans[k]->err || !im.nec) continue;
+            int max_w = 0;
+            for (const ModBuf &mb : im.ec) max_w = std::max(max_w, mb.gw);
+            be.launch_mod((ModWork *) (dev + im.mod_off), (int) im.nec, max_ec_blob ? max_ec_blob : (size_t) -1, max_w);
+        }
         if (num_grp) be.launch_back((const BackWork *) (dev + bkw_off), (int) num_grp);
         bool any_mod = false;
         for (size_t k = 0; k < plans.size(); ++k) {
@@ -593,15 +661,15 @@ public:
 private:
     struct LfBuf { int left, top, w, h, w8, h8, w64, h64; size_t lfq, lfdeq, lf, lfidx, xfromy, bfromy, blockinfo, sharp, blocks, varblocks, llf, wp, lz, vb_tok, llf_scratch, lane; };
     struct GrpBuf { int gw, gh; size_t tok_first, tok_cap, lz, nonzeros, vbs; };
-    struct ModBuf { int gw, gh; size_t wp, lz, lane; uint32_t lz_mask; };
+    struct ModBuf { int gw, gh; size_t wp, lz, lane, planes; uint32_t lz_mask; };
     struct Img {
         size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;
         size_t rgba_off = 0, err_off = 0, tok_off = 0, plane[MOD_MAX_CH] = {0};
         size_t ring_w = 0, ring_off = 0, wring_off = 0; // modular frames: the lane decoders' row ring
-        size_t nlf = 0, ng = 0, npg = 0, nmod = 0; // LF groups, groups, (pass, group) sections, modular sub-bitstreams
+        size_t nlf = 0, ng = 0, npg = 0, nmod = 0, nec = 0; // LF groups, groups, (pass, group) sections, modular sub-bitstreams
         std::vector<LfBuf> lf;
         std::vector<GrpBuf> grp;
-        std::vector<ModBuf> mod;
+        std::vector<ModBuf> mod, ec; // modular frames: sub-bitstreams; VarDCT frames: extra channels per pass group
     };
     std::vector<Img> img;
     uint8_t *dev = nullptr, *staging = nullptr;
@@ -610,7 +678,7 @@ private:
     enum { LF_RING_W = 256 }; // LF groups are at most 256 cells wide
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, ppw_off = 0, num_lf = 0, num_hf = 0, num_grp = 0;
     bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry
-    size_t max_global_blob = 0, max_coeff_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
+    size_t max_global_blob = 0, max_coeff_blob = 0, max_ec_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
 };
 
 } // namespace j40b

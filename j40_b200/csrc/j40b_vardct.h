@@ -148,6 +148,7 @@ struct DGroup {
     uint32_t tok_used;           // written by the kernel
     HfVb *vbs;                   // the group's varblocks in decoding order (shared by the passes; written by hf_prep)
     int32_t nvb;                 // written by hf_prep (pass 0's record only)
+    uint64_t end_bit;            // written by the kernel: bit position behind the coefficients
 };
 
 // =============================================================================================

@@ -24,14 +24,14 @@ struct HostEmuBackend {
     // shared memory of one warp of the serial decoders
     struct WarpMem {
         WarpScratch ws;
-        std::vector<int32_t> wp, refp;
+        std::vector<int32_t> wp; // error row [cap][5] followed by the reference-property rows, as in carve_warp_slice
         std::vector<int16_t> rows;
         SimtLane tab[SIMT_LANES];
         SimtLeaf leaves[SIMT_LANES];
         int32_t div24[64];
         ModSmem ms;
-        explicit WarpMem(int cap) : wp((size_t) cap * 10 + 1), refp((size_t) cap * SIMT_REF_SLOTS + 1), rows((size_t) cap * 3 + 1) {
-            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = refp.data(); ms.tab = tab; ms.leaves = leaves; ms.info = ws.info; ms.cap = cap;
+        explicit WarpMem(int cap) : wp((size_t) cap * (5 + SIMT_REF_SLOTS) + 1), rows((size_t) cap * 3 + 1) {
+            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = wp.data() + (size_t) cap * 5; ms.tab = tab; ms.leaves = leaves; ms.info = ws.info; ms.cap = cap;
             fill_div24(div24, 0, 1);
         }
     };

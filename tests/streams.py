@@ -89,6 +89,15 @@ MODULAR_CASES = [
 ]
 
 
+# Error-code differences on corrupt input that are known and documented ("not built"): (reference, ours).
+# Everything else must agree exactly.
+ALLOWED_CODE_MISMATCHES = {
+    # a bit flip turns the LF group's modular header into one with a tree of its own: the reference reads the (garbage)
+    # tree and fails there; this decoder does not parse trees inside LF-group sections of VarDCT frames and says TODO
+    ("ans?", "TODO"),
+}
+
+
 def force_cases():
     return [(f"force_dctsel_{sel}", 512, 512, 3, dict(force=sel, hfmul=12, tree=1)) for sel in range(27)]
 

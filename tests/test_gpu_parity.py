@@ -106,9 +106,9 @@ def test_error_codes_on_corrupt_streams(oracle, gen):
             assert (ea == "") == (eb == ""), (bi, name, ea, eb)
             if ea == "":
                 assert np.array_equal(a, b), (bi, name)
-            elif ea != eb:
+            elif ea != eb and (ea, eb) not in streams.ALLOWED_CODE_MISMATCHES:
                 mismatches += 1
-    assert mismatches <= total // 10, (mismatches, total)
+    assert mismatches == 0, (mismatches, total)
 
 
 def test_batch_reuse_and_async_readback(oracle, gen):
@@ -281,8 +281,10 @@ def test_lane_per_stream_decoders(oracle, gen, case, monkeypatch):
     _cmp(oracle, streams.make(gen, kind, w, h, seed, opts))
 
 
-def test_lane_mode_is_taken_by_large_batches_and_matches(oracle, gen):
-    """80 small VarDCT frames + 70 modular groups in one batch: both launches are large enough for the lane kernels"""
+def test_lane_mode_large_batch_matches(oracle, gen, monkeypatch):
+    """80 small VarDCT frames + a modular frame of 72 groups in one batch through the lane kernels (full warps, lanes of
+    different geometry side by side)"""
+    monkeypatch.setenv("J40B_LF_MODE", "lane")
     datas = [streams.make(gen, "vardct", 136 + 8 * (i % 5), 72 + 8 * (i % 3), 200 + i, dict(mix=1, tree=1)) for i in range(80)]
     datas.append(streams.make(gen, "modular", 2300, 2000, 3, dict(tree=2, ans=1, lz77=0)))  # 72 groups
     b = J.Batch(0)
