@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--skip-latency", action="store_true")
     ap.add_argument("--streams", type=int, default=12, help="batch objects (CUDA streams) the timed steps are pipelined over")
     ap.add_argument("--e2e-sets", type=int, default=2, help="groups of `streams` batch objects the end-to-end loop alternates between")
-    ap.add_argument("--e2e-mode", default="waves", choices=["waves", "rolling"], help="waves: a group of objects is resubmitted when all of it has "
+    ap.add_argument("--e2e-mode", default="rolling", choices=["waves", "rolling"], help="waves: a group of objects is resubmitted when all of it has "
                     "landed in host memory; rolling: every object is resubmitted as soon as its own frames have landed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -58,6 +58,7 @@ enum : uint32_t {
     E_TODO = J40B_4CC('T', 'O', 'D', 'O'),
     E_MEM = J40B_4CC('!', 'm', 'e', 'm'),
     E_TOKV = J40B_4CC('t', 'o', 'k', 'v'), // internal: token arena too small, host retries larger
+    E_LTRE = J40B_4CC('l', 't', 'r', 'e'), // internal: an LF-group sub-bitstream has a tree of its own; the host reads it, then retries
 };
 
 // j40__unpack_signed: (x & 1) ? -(x / 2 + 1) : x / 2 with C's truncating division, also for negative x (a hybrid integer

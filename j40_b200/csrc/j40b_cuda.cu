@@ -287,11 +287,17 @@ EXPORT int j40b_batch_wait(j40b_batch *b) {
     cudaError_t ce = cudaGetLastError();
     gather_times(b);
     if (getenv("J40B_PHASE_DUMP")) kl_back_phase_dump();
-    // a token arena that turned out too small is an internal condition: redo with worst-case capacity
-    bool retry = false;
-    for (auto &r : b->batch->results) if (r.err == E_TOKV) retry = true;
-    if (retry && !b->batch->full_token_cap) {
-        b->batch->full_token_cap = true;
+    // internal conditions: a token arena that turned out too small (redo with worst-case capacity), LF-group
+    // sub-bitstreams with trees of their own (the host reads them where the device found them; at most one round per
+    // stage of an LF group)
+    for (int round = 0; round < 6; ++round) {
+        bool retry = false;
+        for (auto &r : b->batch->results) if (r.err == E_TOKV && !b->batch->full_token_cap) retry = true;
+        if (retry) b->batch->full_token_cap = true;
+        bool ltre = false;
+        for (auto &r : b->batch->results) if (r.err == E_LTRE) ltre = true;
+        if (ltre && b->batch->resolve_local_trees()) retry = true;
+        if (!retry) break;
         if (b->batch->upload()) {
             cudaEventRecord(b->t0, b->be.stream);
             b->batch->execute();

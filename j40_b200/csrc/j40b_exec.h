@@ -17,6 +17,16 @@
 
 namespace j40b {
 
+// a modular header with a tree of its own inside an LF-group section (j40.h:3827-3835), as the host read it
+struct LfLocal {
+    int32_t present;
+    uint32_t host_err;      // the header / tree / code spec is broken: reported when the decoder gets there
+    uint32_t tree_off, spec_off;
+    int32_t uses_wp;
+    uint64_t start_bit;     // first bit of the channel data
+    ModImage hdr;           // weighted-predictor parameters, transforms, dist_mult (channel geometry is the decoder's)
+};
+
 // one work item per LF group / group; all pointers are device pointers
 struct LfWork {
     const DFrame *f;
@@ -29,6 +39,7 @@ struct LfWork {
     int16_t *ring;          // this lane's slot of its warp's row ring (LaneEnv), or null
     int32_t *wring;
     int32_t ring_w, ring_lstride;
+    LfLocal local[2];       // LF image / HF metadata: local trees (filled in by the host after an E_LTRE round)
 };
 
 struct HfWork { // one per (pass, group)
@@ -136,6 +147,54 @@ J40B_HD inline void init_code_ctx(CodeCtx &cc, const uint8_t *arena, uint32_t sp
     else cc.init(arena, spec_off);
 }
 
+// the four channels of the HF metadata image (j40.h:6766-6772)
+J40B_HD J40B_INLINE void hf_meta_channels(const DLfGroup &g, int32_t nvb, ModImage &m) {
+    m.num_channels = 4;
+    m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
+    m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
+    m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
+    m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
+    for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
+}
+
+// The modular header of stage `stage` (0 LF image, 1 HF metadata) of an LF group; `m` holds the channel geometry.
+// A header naming a tree of its own cannot be finished here (trees and code specs are parsed by the host): the
+// first time round the decoder records where the header starts and reports the internal code E_LTRE; the host reads
+// header, tree and code spec there (Batch::resolve_local_trees) and the batch is decoded again with w.local[stage].
+// Returns false if the stage cannot go on (es.err is set).
+J40B_HD inline bool lf_stage_header(BitReader &br, ErrSlot &es, const LfWork &w, int stage, ModImage &m, const DTreeNode *&tree,
+                                    uint32_t &spec_off, int32_t &uses_wp, bool writer) {
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    const LfLocal &lo = w.local[stage];
+    tree = (const DTreeNode *) (w.arena + f.global_tree_off);
+    spec_off = f.global_spec_off;
+    uses_wp = f.global_tree_uses_wp;
+    if (lo.present) {
+        if (lo.host_err) { es.set_raw(lo.host_err); return false; }
+        m.wp = lo.hdr.wp;
+        m.nb_transforms = lo.hdr.nb_transforms;
+        for (int t = 0; t < MOD_MAX_TRANSFORMS; ++t) m.tr[t] = lo.hdr.tr[t];
+        m.dist_mult = lo.hdr.dist_mult;
+        m.nb_meta_channels = 0;
+        br.init(w.cs + g.sec_off, g.sec_size, lo.start_bit);
+        tree = (const DTreeNode *) (w.arena + lo.tree_off);
+        spec_off = lo.spec_off;
+        uses_wp = lo.uses_wp;
+        return true;
+    }
+    const uint64_t at = br.bits_consumed();
+    int local = 0;
+    modular_header(br, es, f.have_global_tree != 0, m, &local);
+    if (es.err) return false;
+    if (local) {
+        if (writer) { g.ltree_bit = at; g.ltree_stage = stage; }
+        es.set_raw(E_LTRE);
+        return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // LF group, stage 1 (one warp): LfQuant, the 3-channel modular LF image (j40.h:6739-6757)
 template <class Sync>
@@ -150,9 +209,7 @@ J40B_HD inline void lf_decode1_body(const LfWork &w, WarpScratch &ws, const ModS
     CodeState cs;
     es.err = 0;
     br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
-    init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
     cs.init(g.lz_window, (1u << 18) - 1);
-    const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
     // every lane runs the decoder on identical state (see modular_channel_warp); identical values are written
     // to the shared ModImage by all of them
     ModImage &m = ws.m;
@@ -163,10 +220,14 @@ J40B_HD inline void lf_decode1_body(const LfWork &w, WarpScratch &ws, const ModS
         m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
         m.ch[c].hshift = m.ch[c].vshift = 0;
     }
-    modular_header(br, es, f.have_global_tree != 0, m);
+    const DTreeNode *tree;
+    uint32_t spec_off;
+    int32_t uses_wp;
+    const bool go = lf_stage_header(br, es, w, 0, m, tree, spec_off, uses_wp, lane == 0);
+    init_code_ctx(cc, w.arena, spec_off, spec_off == f.global_spec_off ? spec_copy : nullptr, copy_arena);
     sync();
-    for (int c = 0; c < 3 && !es.err; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, 1 + g.idx, lane, nlanes, sync);
+    for (int c = 0; c < 3 && go && !es.err; ++c) {
+        modular_channel_warp(br, es, cc, cs, tree, uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, 1 + g.idx, lane, nlanes, sync);
     }
     if (!es.err) finish_code(br, es, cc, cs);
     if (lane == 0) {
@@ -218,22 +279,19 @@ J40B_HD inline void lf_decode2_body(const LfWork &w, WarpScratch &ws, const ModS
     CodeState cs;
     es.err = 0;
     br.init(w.cs + g.sec_off, g.sec_size, g.mid_bit);
-    init_code_ctx(cc, w.arena, f.global_spec_off, spec_copy, copy_arena);
     cs.init(g.lz_window, (1u << 18) - 1);
-    const DTreeNode *tree = (const DTreeNode *) (w.arena + f.global_tree_off);
     ModImage &m = ws.m;
     const int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
     if (lane == 0) g.nb_varblocks = nvb;
-    m.num_channels = 4;
-    m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
-    m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
-    m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
-    m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
-    for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
-    modular_header(br, es, f.have_global_tree != 0, m);
+    hf_meta_channels(g, nvb, m);
+    const DTreeNode *tree;
+    uint32_t spec_off;
+    int32_t uses_wp;
+    const bool go = lf_stage_header(br, es, w, 1, m, tree, spec_off, uses_wp, lane == 0);
+    init_code_ctx(cc, w.arena, spec_off, spec_off == f.global_spec_off ? spec_copy : nullptr, copy_arena);
     sync();
-    for (int c = 0; c < 4 && !es.err; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, f.global_tree_uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c,
+    for (int c = 0; c < 4 && go && !es.err; ++c) {
+        modular_channel_warp(br, es, cc, cs, tree, uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c,
                              1 + 2 * f.num_lf_groups + g.idx, lane, nlanes, sync);
     }
     if (!es.err) finish_code(br, es, cc, cs);
@@ -441,6 +499,11 @@ J40B_HD J40B_INLINE void mod_lane_loop(ModLane<MODE> &L, AnyFn any, Sync sync) {
     }
 }
 
+// code spec of stage `stage` of an LF group: the global one, or the local one once the host has read it
+J40B_HD J40B_INLINE uint32_t lf_stage_spec_off(const LfWork &w, int stage) {
+    return w.local[stage].present && !w.local[stage].host_err ? w.local[stage].spec_off : w.f->global_spec_off;
+}
+
 J40B_HD J40B_INLINE bool spec_is_plain_ans(const uint8_t *arena, uint32_t spec_off) {
     if (!spec_off) return false;
     const DCodeSpec *spec = (const DCodeSpec *) (arena + spec_off);
@@ -469,9 +532,11 @@ J40B_HD inline void lf_decode1_lanes(const LfWork *wp, bool active, LaneEnv env,
             m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
             m.ch[c].hshift = m.ch[c].vshift = 0;
         }
-        modular_header(L.br, L.es, f.have_global_tree != 0, m);
-        if (!L.es.err) L.begin(w.arena, f.global_spec_off, (const DTreeNode *) (w.arena + f.global_tree_off), f.global_tree_uses_wp, 1 + g.idx,
-                               g.wp_scratch, g.lz_window, (1u << 18) - 1);
+        const DTreeNode *tree;
+        uint32_t spec_off;
+        int32_t uses_wp;
+        if (lf_stage_header(L.br, L.es, w, 0, m, tree, spec_off, uses_wp, true))
+            L.begin(w.arena, spec_off, tree, uses_wp, 1 + g.idx, g.wp_scratch, g.lz_window, (1u << 18) - 1);
     }
     mod_lane_loop(L, any, sync);
     if (active) {
@@ -485,16 +550,6 @@ J40B_HD inline void lf_decode1_lanes(const LfWork *wp, bool active, LaneEnv env,
         for (int t = 0; t < g.nb_tr1; ++t) g.tr1[t] = m.tr[t];
         if (L.es.err) *w.err = L.es.err;
     }
-}
-
-// the four channels of the HF metadata image (j40.h:6766-6772)
-J40B_HD J40B_INLINE void hf_meta_channels(const DLfGroup &g, int32_t nvb, ModImage &m) {
-    m.num_channels = 4;
-    m.ch[0].px = g.xfromy; m.ch[0].w = g.width64; m.ch[0].h = g.height64; m.ch[0].stride = g.width64;
-    m.ch[1].px = g.bfromy; m.ch[1].w = g.width64; m.ch[1].h = g.height64; m.ch[1].stride = g.width64;
-    m.ch[2].px = g.blockinfo; m.ch[2].w = nvb; m.ch[2].h = 2; m.ch[2].stride = nvb;
-    m.ch[3].px = g.sharpness; m.ch[3].w = g.width8; m.ch[3].h = g.height8; m.ch[3].stride = g.width8;
-    for (int c = 0; c < 4; ++c) m.ch[c].hshift = m.ch[c].vshift = 0;
 }
 
 // LF group, stage 3a: entropy decode of the HF metadata image; transforms and varblock placement follow in lf_place_body
@@ -514,9 +569,11 @@ J40B_HD inline void lf_decode2_lanes(const LfWork *wp, bool active, LaneEnv env,
         g.nb_varblocks = nvb;
         ModImage &m = L.sc->m;
         hf_meta_channels(g, nvb, m);
-        modular_header(L.br, L.es, f.have_global_tree != 0, m);
-        if (!L.es.err) L.begin(w.arena, f.global_spec_off, (const DTreeNode *) (w.arena + f.global_tree_off), f.global_tree_uses_wp,
-                               1 + 2 * f.num_lf_groups + g.idx, g.wp_scratch, g.lz_window, (1u << 18) - 1);
+        const DTreeNode *tree;
+        uint32_t spec_off;
+        int32_t uses_wp;
+        if (lf_stage_header(L.br, L.es, w, 1, m, tree, spec_off, uses_wp, true))
+            L.begin(w.arena, spec_off, tree, uses_wp, 1 + 2 * f.num_lf_groups + g.idx, g.wp_scratch, g.lz_window, (1u << 18) - 1);
     }
     mod_lane_loop(L, any, sync);
     if (active) {

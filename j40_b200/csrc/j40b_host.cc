@@ -1646,6 +1646,35 @@ static uint32_t linearise(const uint8_t *data, size_t size, FramePlan &plan) {
 
 // ---------------------------------------------------------------------------------------------
 
+void parse_lf_group_local_tree(FramePlan &plan, size_t lfg, int stage, uint64_t start_bit, int32_t nb_varblocks) {
+    const FrameInfo &f = plan.fh;
+    if (plan.lfg_local.empty()) plan.lfg_local.resize(2 * plan.lfg_sec.size());
+    FramePlan::LocalHeader &lh = plan.lfg_local[2 * lfg + (size_t) stage];
+    const SectionRef &s = plan.lfg_sec[lfg];
+    const int ggx = (int) (lfg % (size_t) f.ggcolumns), ggy = (int) (lfg / (size_t) f.ggcolumns);
+    const int w = std::min(2048, f.width - ggx * 2048), h = std::min(2048, f.height - ggy * 2048);
+    const int w8 = ceil_div(w, 8), h8 = ceil_div(h, 8), w64 = ceil_div(w, 64), h64 = ceil_div(h, 64);
+    ModImage m;
+    memset(&m, 0, sizeof(m));
+    if (stage == 0) {
+        m.num_channels = 3;
+        for (int c = 0; c < 3; ++c) { m.ch[c].w = w8; m.ch[c].h = h8; m.ch[c].stride = w8; }
+    } else {
+        m.num_channels = 4;
+        m.ch[0].w = m.ch[1].w = w64; m.ch[0].h = m.ch[1].h = h64;
+        m.ch[2].w = nb_varblocks; m.ch[2].h = 2;
+        m.ch[3].w = w8; m.ch[3].h = h8;
+        for (int c = 0; c < 4; ++c) m.ch[c].stride = m.ch[c].w;
+    }
+    Parser h_(plan);
+    h_.br.init(plan.cs + s.off, s.size, start_bit);
+    h_.host_modular_header(m, lh);
+    if (!h_.err) h_.check_overrun();
+    lh.present = true;
+    if (h_.err) { lh.host_err = h_.err; return; }
+    lh.start_bit = h_.br.bits_consumed();
+}
+
 uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
     memset(&plan.df, 0, sizeof(plan.df));
     plan.err = linearise(data, size, plan);

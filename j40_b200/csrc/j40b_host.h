@@ -81,6 +81,7 @@ struct FramePlan {
         uint64_t start_bit = 0;  // first bit of the channel data, relative to the section start
         uint32_t host_err = 0;   // the header failed to parse: reported through the section's error slot
     };
+    std::vector<LocalHeader> lfg_local;  // VarDCT frames: [2 * LF group + stage] once Batch::resolve_local_trees has read them (else empty)
     LocalHeader gmod_local;              // the global image's
     std::vector<LocalHeader> pg_local;   // per pass group of a modular frame (empty: none is local)
 };
@@ -97,6 +98,10 @@ struct GlobalTables {
 
 // Parses `data` up to and including HfGlobal. Returns 0 or a four-character error code.
 uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan);
+
+// Reads the modular header, MA tree and code spec that start `start_bit` bits into LF-group section `lfg` of a VarDCT
+// frame (stage 0: the LF image, 1: the HF metadata image with `nb_varblocks` varblocks) into plan.lfg_local.
+void parse_lf_group_local_tree(FramePlan &plan, size_t lfg, int stage, uint64_t start_bit, int32_t nb_varblocks);
 
 // helpers shared with tests
 std::vector<float> compute_dq_matrix_default(int idx);

@@ -118,6 +118,7 @@ public:
                 im.err_off = wk_alloc(4 * (im.nlf + im.npg + 1));
                 im.lf.resize(im.nlf);
                 bool wp = d.global_tree_uses_wp != 0;
+                for (const FramePlan::LocalHeader &lh : p.lfg_local) wp = wp || (lh.present && lh.uses_wp);
                 bool lz_mod = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
                 for (size_t i = 0; i < im.nlf; ++i) {
                     LfBuf &b = im.lf[i];
@@ -350,6 +351,14 @@ public:
                     w.err = derr + i;
                     w.llf_scratch = (float *) (dwork + b.llf_scratch);
                     w.lane_scratch = (ModLaneScratch *) (dwork + b.lane);
+                    for (int st = 0; st < 2; ++st) {
+                        LfLocal &lo = w.local[st];
+                        memset(&lo, 0, sizeof(lo));
+                        if (p.lfg_local.empty() || !p.lfg_local[2 * i + (size_t) st].present) continue;
+                        const FramePlan::LocalHeader &lh = p.lfg_local[2 * i + (size_t) st];
+                        lo.present = 1; lo.host_err = lh.host_err; lo.tree_off = lh.tree_off; lo.spec_off = lh.spec_off;
+                        lo.uses_wp = lh.uses_wp; lo.start_bit = lh.start_bit; lo.hdr = lh.hdr;
+                    }
                     lf_sorted.emplace_back((int64_t) b.w8 * b.h8, w);
                 }
                 for (size_t pg = 0; pg < im.npg; ++pg) {
@@ -576,6 +585,31 @@ public:
             }
             results[k].err = best;
         }
+    }
+
+    // E_LTRE round: LF groups whose sub-bitstream names a tree of its own reported where its header starts; the host
+    // reads header, tree and code spec there. Returns true if anything was read (upload + execute again).
+    bool resolve_local_trees() {
+        if (!dev) return false;
+        bool any = false;
+        uint8_t *dwork = dev + upload_bytes;
+        for (size_t k = 0; k < plans.size(); ++k) {
+            FramePlan &p = *plans[k];
+            const Img &im = img[k];
+            if (p.err || p.df.is_modular || results[k].err != E_LTRE) continue;
+            std::vector<uint32_t> e(im.nlf);
+            be.d2h(e.data(), dwork + im.err_off, 4 * im.nlf);
+            for (size_t i = 0; i < im.nlf; ++i) {
+                if (e[i] != E_LTRE) continue;
+                DLfGroup g;
+                be.d2h(&g, dev + im.lfg_off + i * sizeof(DLfGroup), sizeof(g));
+                if (g.ltree_stage < 0 || g.ltree_stage > 1) continue;
+                if (!p.lfg_local.empty() && p.lfg_local[2 * i + (size_t) g.ltree_stage].present) continue; // (cannot happen twice)
+                parse_lf_group_local_tree(p, i, g.ltree_stage, g.ltree_bit, g.nb_varblocks);
+                any = true;
+            }
+        }
+        return any;
     }
 
     void download_pixels(size_t k, uint8_t *dst) {

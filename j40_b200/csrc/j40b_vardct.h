@@ -125,6 +125,8 @@ struct DLfGroup {
     uint32_t *vb_tok;     // [num_passes][3][h8*w8][2] {first token, count}, written by the pass-group kernel (zeroed before)
     // hand-over between the LF kernels (decode LF image -> post-process -> decode HF metadata -> LLF)
     uint64_t mid_bit;     // bit position after the LF image
+    uint64_t ltree_bit;   // E_LTRE: where the modular header that names a local tree starts (bits from the section start)
+    int32_t ltree_stage;  // E_LTRE: 0 = LF image, 1 = HF metadata
     int32_t meta_overrun; // the HF metadata decode ran past the end of the section (lane-per-stream path: read by lf_place_body)
     int32_t extra_prec;
     int32_t nb_tr1, nb_tr2;               // transforms of the LF image / of the HF metadata image

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32 * LANE_WARPS, 1) k_lf_lane(const LfWork *it
     const LfWork *w = &items[i < n ? i : n - 1];
     const bool active = i < n && (STAGE == 1 || !*w->err);
     // the fast path (rANS, no LZ77) is taken when every stream of the warp qualifies
-    const bool plain = __all_sync(0xffffffffu, !active || spec_is_plain_ans(w->arena, w->f->global_spec_off));
+    const bool plain = __all_sync(0xffffffffu, !active || spec_is_plain_ans(w->arena, lf_stage_spec_off(*w, STAGE - 1)));
     const LaneEnv env = lane_env(sm);
     if (STAGE == 1) {
         if (plain) lf_decode1_lanes<1>(w, active, env, WarpAny(), WarpSync());

@@ -52,11 +52,11 @@ struct HostEmuBackend {
                 env.ring = nullptr; env.wring = nullptr; env.ring_w = 0;
                 LfWork ww = w[i];
                 if (i & 1) ww.ring = nullptr; // every other stream without the row ring (the path of channels wider than it)
-                if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode1_lanes<1>(&ww, true, env, any, NoSync());
+                if (spec_is_plain_ans(w[i].arena, lf_stage_spec_off(w[i], 0))) lf_decode1_lanes<1>(&ww, true, env, any, NoSync());
                 else lf_decode1_lanes<0>(&ww, true, env, any, NoSync());
                 lf_post_body(w[i], 0, 1, NoSync());
                 if (!*w[i].err) {
-                    if (spec_is_plain_ans(w[i].arena, w[i].f->global_spec_off)) lf_decode2_lanes<1>(&ww, true, env, any, NoSync());
+                    if (spec_is_plain_ans(w[i].arena, lf_stage_spec_off(w[i], 1))) lf_decode2_lanes<1>(&ww, true, env, any, NoSync());
                     else lf_decode2_lanes<0>(&ww, true, env, any, NoSync());
                 }
                 lf_place_body(w[i], (i & 1) ? bitmap.data() : nullptr, 0, 1, NoSync());
@@ -135,16 +135,17 @@ __attribute__((visibility("default"))) uint32_t hostemu_decode(const uint8_t *da
     *out = nullptr;
     *w = *h = *stride = 0;
     uint32_t err = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        Batch<HostEmuBackend> b(be);
-        b.full_token_cap = attempt == 1;
-        b.add(data, size);
-        if (b.plans[0]->err) return b.plans[0]->err;
+    Batch<HostEmuBackend> b(be);
+    b.add(data, size);
+    if (b.plans[0]->err) return b.plans[0]->err;
+    for (int attempt = 0; attempt < 6; ++attempt) {
         b.upload();
         b.execute();
         b.collect_errors();
         err = b.results[0].err;
-        if (err == E_TOKV && attempt == 0) continue;
+        // internal conditions, handled like j40b_batch_wait does: a token arena that was too small, local MA trees
+        if (err == E_TOKV && !b.full_token_cap) { b.full_token_cap = true; continue; }
+        if (err == E_LTRE && b.resolve_local_trees()) continue;
         if (!err) {
             const ImageResult &r = b.results[0];
             *out = (uint8_t *) malloc((size_t) r.stride * (size_t) r.height);

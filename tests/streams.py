@@ -49,6 +49,12 @@ VARDCT_CASES = [
     ("passes5_lz77", 300, 264, 38, dict(mix=1, tree=1, passes=5, lz77=1)),
     ("passes2_dct128", 512, 512, 39, dict(force=21, hfmul=12, tree=1, passes=2)),
     ("passes2_all_transforms", 520, 392, 40, dict(mix=2, tree=2, passes=2)),
+    # LF-group sub-bitstreams with MA trees of their own (j40.h:3827-3835 reached from 6722-6783): the device reports where
+    # the header starts, the host reads header + tree + code spec there, the batch is decoded again (E_LTRE round)
+    ("lf_local_tree_lf_image", 520, 392, 41, dict(mix=1, tree=1, lf_local_tree=1)),
+    ("lf_local_tree_hf_meta_prefix", 520, 392, 42, dict(mix=1, tree=1, lf_local_tree=2, ans=0)),
+    ("lf_local_tree_both_two_lf_groups", 2100, 300, 43, dict(mix=1, tree=2, lf_local_tree=7, hfmul=6)),
+    ("lf_local_tree_single_group", 200, 100, 44, dict(mix=1, tree=1, lf_local_tree=3, lz77=1)),
 ]
 
 # samples far outside [0, 1]: a RAW dequantisation matrix whose written denominator is `raw_dq_lie` times the one the
@@ -90,12 +96,9 @@ MODULAR_CASES = [
 
 
 # Error-code differences on corrupt input that are known and documented ("not built"): (reference, ours).
-# Everything else must agree exactly.
-ALLOWED_CODE_MISMATCHES = {
-    # a bit flip turns the LF group's modular header into one with a tree of its own: the reference reads the (garbage)
-    # tree and fails there; this decoder does not parse trees inside LF-group sections of VarDCT frames and says TODO
-    ("ans?", "TODO"),
-}
+# Everything else must agree exactly. (Round 1 tolerated 10 % mismatches; the last known class -- a bit flip that turns
+# an LF group's modular header into one with a tree of its own -- went away with the E_LTRE round.)
+ALLOWED_CODE_MISMATCHES = set()
 
 
 def force_cases():

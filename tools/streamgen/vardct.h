@@ -54,6 +54,8 @@ struct VarDCTParams {
     bool lz77_coeffs = false;  // enable LZ77 in the coefficient stream (rare in practice)
     float quant_deadzone = 0.55f;
     int force_dctsel = -1;     // >= 0: use this transform wherever it fits (coverage tests)
+    int lf_local_tree = 0;     // bit 0: the LF image of every LF group, bit 1: its HF metadata image is coded with a tree of its
+                               // own (a copy of the global one, stored with the sub-bitstream, j40.h:3827-3835); bit 2: odd LF groups only
     float raw_dq_lie = 1.0f;   // RAW matrices: the denominator written is this many times the one used for quantising, so that the
                                // decoder's coefficients come out that much larger (out-of-range samples; tests of the int16 wrap, j40.h:7234)
     int passes = 1;            // > 1: the quantised coefficients are split over this many passes (the decoder adds them up);
@@ -346,12 +348,22 @@ public:
         for (int i = 0; i < num_lfg; ++i) {
             BitWriter &bw = lfsec[(size_t) i];
             bw.put((uint64_t) P.extra_prec, 2);
-            ModularHeaderOpts mh;
-            write_modular_header_prefix(bw, mh);
+            EntropyOpts lto; // as in write_lf_global
+            lto.use_prefix = !P.use_ans;
+            lto.log_alpha_size = 8;
+            lto.cfg = {4, 1, 0};
+            lto.max_clusters = 6;
+            const bool here = !(P.lf_local_tree & 4) || (i & 1);
+            ModularHeaderOpts mh, mh1, mh2;
+            mh1.use_global_tree = !(here && (P.lf_local_tree & 1));
+            mh2.use_global_tree = !(here && (P.lf_local_tree & 2));
+            write_modular_header_prefix(bw, mh1);
+            if (!mh1.use_global_tree) { write_tree(bw, tree, lto); mspec.write(bw); }
             mspec.encode(bw, lf_ts[(size_t) i]);
             int nvb = (int) lfgs[(size_t) i].vbs.size();
             bw.put((uint64_t) (nvb - 1), ceil_lg((uint32_t) (lfgs[(size_t) i].w8 * lfgs[(size_t) i].h8)));
-            write_modular_header_prefix(bw, mh);
+            write_modular_header_prefix(bw, mh2);
+            if (!mh2.use_global_tree) { write_tree(bw, tree, lto); mspec.write(bw); }
             mspec.encode(bw, meta_ts[(size_t) i]);
         }
         for (int pg = 0; pg < num_groups * npass; ++pg) {
