@@ -150,6 +150,7 @@ struct CudaBackend {
     }
     void launch_dump(const DumpWork &w, int n) { kl_dump_coeffs(n, stream, w); ++launches; }
     void mark_modular(int which) { cudaEventRecord(ev[8 + which], stream); mod_marked = true; }
+    void launch_palette_delta(const RenderWork *w, int num_c) { kl_palette_delta(stream, w, num_c); ++launches; }
     void launch_render(const RenderWork *w, int width, int height) {
         kl_render(stream, w, width, height);
         ++launches;

@@ -108,6 +108,9 @@ struct ModWork { // one modular sub-bitstream: a pass group of a modular frame, 
 struct RenderWork { // modular frames: inverse global transforms + interleave to RGBA8
     const DFrame *f;
     int16_t *plane[MOD_MAX_CH]; // full-frame planes, stride = width
+    // a delta palette (the last transform of the list) is undone ahead of the render step by palette_delta_body:
+    int16_t *dplane[MOD_MAX_CH]; // its num_c restored channels (null: the frame has none)
+    int32_t *dwp[MOD_MAX_CH];    // weighted-predictor error rows [2][width][5] per restored channel (d_pred == 6)
     const uint32_t *any_err;    // non-zero: skip
     uint8_t *rgba;
     int32_t rgba_stride;
@@ -748,6 +751,49 @@ J40B_HD J40B_INLINE int16_t palette_value(const ModTransform &t, const int16_t *
     return val;
 }
 
+// Inverse of a palette transform with delta entries (j40__inverse_palette with use_pred, j40.h:4416-4480): restored
+// channel `i`, a serial scan in raster order -- entries below nb_deltas are added to a prediction from the restored
+// neighbours. One thread per restored channel. (A rare feature: not worth a wavefront.)
+J40B_HD inline void palette_delta_body(const RenderWork &w, int i, const int32_t *div24) {
+    const DFrame &f = *w.f;
+    const ModTransform &tr = f.global_tr[f.nb_global_transforms - 1];
+    if (i >= tr.num_c) return;
+    const int32_t width = f.width, height = f.height;
+    const int16_t *table = w.plane[0], *index = w.plane[tr.begin_c + 1];
+    int16_t *out = w.dplane[i];
+    const bool use_wp = tr.d_pred == 6;
+    WPState wp;
+    wp.errors = w.dwp[i];
+    wp.width = width;
+    for (int k = 0; k < 5; ++k) wp.pred[k] = 0;
+    wp.trueerrw = wp.trueerrn = wp.trueerrnw = wp.trueerrne = 0;
+    if (use_wp) for (int32_t k = 0; k < width * 10; ++k) wp.errors[k] = 0;
+    for (int32_t y = 0; y < height; ++y) {
+        int16_t *row = out + (size_t) y * (size_t) width;
+        for (int32_t x = 0; x < width; ++x) {
+            const int32_t idx = index[(size_t) y * (size_t) width + x];
+            const bool is_delta = idx < tr.nb_deltas;
+            int32_t val = palette_value(tr, table, idx, i, f.bpp);
+            // neighbours of the restored channel (j40.h:3965-4009)
+            const int16_t *p = row + x;
+            const int32_t pw = x > 0 ? p[-1] : y > 0 ? p[-width] : 0;
+            const int32_t pn = y > 0 ? p[-width] : pw;
+            const int32_t pnw = x > 0 && y > 0 ? p[-1 - width] : pw;
+            const int32_t pne = x + 1 < width && y > 0 ? p[1 - width] : pn;
+            const int32_t pnn = y > 1 ? p[-2 * width] : pn;
+            const int32_t pnee = x + 2 < width && y > 0 ? p[2 - width] : pne;
+            const int32_t pww = x > 1 ? p[-2] : pw;
+            if (use_wp) wp_before_predict(wp, f.global_wp, div24, x, y, pw, pn, pnw, pne, pnn);
+            if (is_delta) {
+                bool bad = false;
+                val = (int16_t) (val + mod_predict(tr.d_pred, pw, pn, pnw, pne, pnn, pww, pnee, wp.pred[4], &bad));
+            }
+            if (use_wp) wp_after_predict(wp, x, y, val);
+            row[x] = (int16_t) val;
+        }
+    }
+}
+
 J40B_HD inline void render_px(const RenderWork &w, int x, int y) {
     const DFrame &f = *w.f;
     int16_t v[MOD_MAX_CH + 4];
@@ -768,7 +814,7 @@ J40B_HD inline void render_px(const RenderWork &w, int x, int y) {
             const int32_t idx = v[first];
             for (int k = n - 1; k > first; --k) v[k + (last - first)] = v[k]; // channels behind the index channel
             n += last - first;
-            for (int i = 0; i < tr.num_c; ++i) v[first + i] = palette_value(tr, table, idx, i, f.bpp);
+            for (int i = 0; i < tr.num_c; ++i) v[first + i] = tr.nb_deltas > 0 ? w.dplane[i][o] : palette_value(tr, table, idx, i, f.bpp);
             for (int k = 0; k + 1 < n; ++k) v[k] = v[k + 1]; // drop the palette channel itself
             --n; --meta;
         }

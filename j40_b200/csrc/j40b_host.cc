@@ -1831,6 +1831,9 @@ uint32_t parse_frame(const uint8_t *data, size_t size, FramePlan &plan) {
             if (plan.num_gm_channels != 0 || plan.gmod.nb_transforms != 0) return plan.err = E_TODO;
         }
     }
+    // a palette with delta entries is undone by a scan kernel ahead of the per-pixel render step: only where that is the
+    // first thing to undo, i.e. the last transform of the list
+    for (int i = 0; i + 1 < plan.gmod.nb_transforms; ++i) if (plan.gmod.tr[i].kind == 1 && plan.gmod.tr[i].nb_deltas > 0) return plan.err = E_TODO;
     d.nb_global_transforms = plan.gmod.nb_transforms;
     for (int i = 0; i < plan.gmod.nb_transforms; ++i) d.global_tr[i] = plan.gmod.tr[i];
     d.global_wp = plan.gmod.wp;

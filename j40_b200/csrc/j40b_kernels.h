@@ -71,6 +71,7 @@ void kl_back_phase_dump(); // diagnostic builds (make PHASE_CLOCKS=1): prints an
 void kl_dump_coeffs(int n, cudaStream_t stream, const DumpWork &w); // diagnostics
 void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap);
 void kl_mod_lane(int n, cudaStream_t stream, ModWork *w);
+void kl_palette_delta(cudaStream_t stream, const RenderWork *w, int num_c);
 void kl_render(cudaStream_t stream, const RenderWork *w, int width, int height);
 
 } // namespace j40b

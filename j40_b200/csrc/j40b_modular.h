@@ -813,8 +813,9 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
                 const ModChannel &a = m.ch[t.begin_c], &b = m.ch[k];
                 if (a.w != b.w || a.h != b.h || a.hshift != b.hshift || a.vshift != b.vshift) { es.set(br, J40B_4CC('p', 'a', 'l', 'd')); return; }
             }
-            // delta palettes predict from the restored neighbours (a serial scan per channel): not built
-            if (!allow_palette || t.nb_deltas > 0 || m.num_channels + 2 - t.num_c > MOD_MAX_CH) { es.set(br, E_TODO); return; }
+            // (delta palettes, nb_deltas > 0, predict from the restored neighbours: the executor undoes them with a scan
+            // kernel ahead of the render step, and only as the last transform of the list; the host checks that)
+            if (!allow_palette || m.num_channels + 2 - t.num_c > MOD_MAX_CH) { es.set(br, E_TODO); return; }
             const ModChannel input = m.ch[t.begin_c];
             ModChannel list[MOD_MAX_CH + 1];
             int n = 0;

@@ -243,6 +243,15 @@ public:
                 }
                 im.mod_off = up_alloc(sizeof(ModWork) * std::max<size_t>(im.nmod, 1));
                 im.render_off = up_alloc(sizeof(RenderWork));
+                im.ndelta = 0;
+                if (p.gmod.nb_transforms > 0 && p.gmod.tr[p.gmod.nb_transforms - 1].kind == 1 && p.gmod.tr[p.gmod.nb_transforms - 1].nb_deltas > 0) {
+                    const ModTransform &t = p.gmod.tr[p.gmod.nb_transforms - 1];
+                    im.ndelta = t.num_c;
+                    for (int c = 0; c < t.num_c && c < MOD_MAX_CH; ++c) {
+                        im.dplane[c] = wk_alloc(2 * (size_t) d.width * d.height);
+                        im.dwp[c] = t.d_pred == 6 ? wk_alloc(4 * 2 * 5 * (size_t) d.width) : (size_t) -1;
+                    }
+                }
                 n_mod += im.nmod;
             }
         }
@@ -438,6 +447,10 @@ public:
                 memset(rw, 0, sizeof(*rw));
                 rw->f = dframe;
                 for (int c = 0; c < d.num_channels; ++c) rw->plane[c] = (int16_t *) (dwork + im.plane[c]);
+                for (int c = 0; c < im.ndelta && c < MOD_MAX_CH; ++c) {
+                    rw->dplane[c] = (int16_t *) (dwork + im.dplane[c]);
+                    rw->dwp[c] = im.dwp[c] == (size_t) -1 ? nullptr : (int32_t *) (dwork + im.dwp[c]);
+                }
                 rw->any_err = derr + im.nmod; // summary word written by nobody: per-section words are checked on the host
                 rw->rgba = dwork + im.rgba_off; rw->rgba_stride = results[k].stride;
                 int gsize = 1 << d.group_size_shift;
@@ -543,6 +556,7 @@ public:
                 if (p.gmod_local.present || !p.pg_local.empty()) gs = nullptr; // local code specs: no common blob to stage
                 be.launch_mod((ModWork *) (dev + im.mod_off), (int) im.nmod, gs ? (size_t) (gs->blob_hi - gs->blob_lo) : (size_t) -1, max_w);
             }
+            if (im.ndelta) be.launch_palette_delta((const RenderWork *) (dev + im.render_off), im.ndelta);
             be.launch_render((const RenderWork *) (dev + im.render_off), p.df.width, p.df.height);
         }
         if (any_mod) be.mark_modular(1);
@@ -699,6 +713,8 @@ private:
     struct Img {
         size_t frame_off = 0, arena_off = 0, cs_off = 0, lfg_off = 0, grp_off = 0, mod_off = 0, render_off = 0;
         size_t rgba_off = 0, err_off = 0, tok_off = 0, plane[MOD_MAX_CH] = {0};
+        size_t dplane[MOD_MAX_CH] = {0}, dwp[MOD_MAX_CH] = {0}; // delta palette: restored channels, WP rows
+        int ndelta = 0;
         size_t ring_w = 0, ring_off = 0, wring_off = 0; // modular frames: the lane decoders' row ring
         size_t nlf = 0, ng = 0, npg = 0, nmod = 0, nec = 0; // LF groups, groups, (pass, group) sections, modular sub-bitstreams
         std::vector<LfBuf> lf;

@@ -43,6 +43,15 @@ __global__ void __launch_bounds__(256) k_render(const RenderWork *w, int width, 
     if (x < width && y < height) render_px(*w, x, y);
 }
 
+// delta palettes (palette_delta_body): one thread per restored channel
+__global__ void __launch_bounds__(32) k_palette_delta(const RenderWork *w, int num_c) {
+    __shared__ int32_t div24[64];
+    fill_div24(div24, (int) threadIdx.x, 32);
+    __syncwarp();
+    if ((int) threadIdx.x < num_c) palette_delta_body(*w, (int) threadIdx.x, div24);
+}
+void kl_palette_delta(cudaStream_t stream, const RenderWork *w, int num_c) { k_palette_delta<<<1, 32, 0, stream>>>(w, num_c); }
+
 bool kl_init_mod() {
     const int mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
     return cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem) == cudaSuccess;

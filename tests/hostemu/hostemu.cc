@@ -122,6 +122,7 @@ struct HostEmuBackend {
     }
     void launch_dump(const DumpWork &w, int n) { for (int v = 0; v < n; ++v) dump_coeffs_body(w, v, 0, 1, NoSync()); }
     void mark_modular(int) {}
+    void launch_palette_delta(const RenderWork *w, int num_c) { for (int i = 0; i < num_c; ++i) palette_delta_body(*w, i, h_div24_table.v); }
     void launch_render(const RenderWork *w, int width, int height) {
         for (int y = 0; y < height; ++y) for (int x = 0; x < width; ++x) render_px(*w, x, y);
     }

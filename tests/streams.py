@@ -92,6 +92,13 @@ MODULAR_CASES = [
     ("palette_groups_prefix_lz77", 600, 400, 7, dict(palette=1)),
     ("palette_alpha_wp_ans", 600, 400, 7, dict(palette=1, alpha=1, ans=1, lz77=0, tree=2)),
     ("palette_local_trees_shift7", 300, 300, 7, dict(palette=1, group_shift=7, local_tree=1)),
+    # delta palettes (nb_deltas > 0, j40.h:4416-4480): entries below nb_deltas are added to a prediction from the restored
+    # neighbours -- gradient, weighted predictor, the 7-tap predictor 13, select
+    ("palette_delta_gradient", 600, 400, 7, dict(palette=1, pal_deltas=3, pal_pred=5)),
+    ("palette_delta_wp_single_group", 200, 100, 7, dict(palette=1, pal_deltas=40, pal_pred=6)),
+    ("palette_delta_wp_groups", 600, 400, 7, dict(palette=1, pal_deltas=40, pal_pred=6, ans=1, lz77=0)),
+    ("palette_delta_pred13_alpha", 600, 400, 7, dict(palette=1, pal_deltas=200, pal_pred=13, alpha=1)),
+    ("palette_delta_all_select_shift7", 300, 300, 7, dict(palette=1, pal_deltas=1000, pal_pred=4, group_shift=7, local_tree=1)),
 ]
 
 

@@ -67,6 +67,9 @@ def test_error_codes_on_corrupt_streams_newer_features(oracle, emu, gen):
     base = {
         "palette": streams.make(gen, "modular", 300, 280, 3, dict(palette=1)),
         "palette_single_alpha": streams.make(gen, "modular", 120, 90, 3, dict(palette=1, alpha=1)),
+        "palette_delta_wp": streams.make(gen, "modular", 300, 280, 3, dict(palette=1, pal_deltas=20, pal_pred=6)),
+        "vardct_lf_local_trees": streams.make(gen, "vardct", 264, 136, 8, dict(mix=1, tree=1, lf_local_tree=3)),
+        "vardct_passes3": streams.make(gen, "vardct", 300, 264, 9, dict(mix=1, tree=1, passes=3)),
         "local_tree": streams.make(gen, "modular", 300, 280, 4, dict(local_tree=1)),
         "local_tree_all_ans": streams.make(gen, "modular", 300, 280, 4, dict(local_tree=2, ans=1, lz77=0, tree=2)),
         "raw_dq": streams.make(gen, "vardct", 264, 136, 5, dict(mix=1, tree=1, raw_dq=0x11)),

@@ -79,7 +79,7 @@ __attribute__((visibility("default"))) int jxlgen_modular(const char *params, co
         ModularParams p;
         GETI(width, "width"); GETI(height, "height"); GETI(seed, "seed"); GETI(group_shift, "group_shift");
         GETI(rct_type, "rct"); GETI(tree_preset, "tree"); GETI(use_ans, "ans"); GETI(lz77, "lz77"); GETI(alpha, "alpha");
-        GETI(container, "container"); GETI(smooth, "smooth"); GETI(max_clusters, "clusters"); GETI(local_tree, "local_tree"); GETI(palette, "palette");
+        GETI(container, "container"); GETI(smooth, "smooth"); GETI(max_clusters, "clusters"); GETI(local_tree, "local_tree"); GETI(palette, "palette"); GETI(pal_deltas, "pal_deltas"); GETI(pal_pred, "pal_pred");
         ImageRGB8 im;
         if (rgb) { im.w = p.width; im.h = p.height; im.px.assign(rgb, rgb + (size_t) p.width * (size_t) p.height * 3); }
         else im = synth_photo(p.width, p.height, p.seed);

@@ -27,6 +27,8 @@ struct ModularParams {
     int max_clusters = 8;
     int palette = 0;         // 1: RGB coded through a palette transform (colours posterised to <= 216), no RCT; a few rows
                              // use the implicit entries (index < 0 and index >= nb_colours)
+    int pal_deltas = 0;      // palette: nb_deltas (indices below it are deltas on top of predictor `pal_pred`, j40.h:4402-4490)
+    int pal_pred = 5;
     int local_tree = 0;      // 1: odd pass groups (or the global image of a single-group frame) carry a tree and code
                              // spec of their own; 2: all of them do and the frame has no global tree at all
 };
@@ -151,7 +153,7 @@ public:
             spec.write(lfglobal);
         }
         ModularHeaderOpts gh;
-        if (P.palette) gh.palettes.push_back({0, 3, pal.w, 0, 0});
+        if (P.palette) gh.palettes.push_back({0, 3, pal.w, P.pal_deltas, P.pal_pred});
         else if (P.rct_type >= 0) gh.rcts.push_back({0, P.rct_type});
         gh.use_global_tree = !(single ? is_local(0) : !have_global_tree);
         write_modular_header_prefix(lfglobal, gh);
