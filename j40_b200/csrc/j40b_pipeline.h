@@ -85,6 +85,10 @@ public:
         size_t gt_lut = up_alloc(SRGB_LUT_BYTES);
         size_t work = 0;                    // device-only area cursor (follows the upload blob)
         auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
+        // everything execute() has to zero before a decode (error words, token ranges) sits in one region, cleared by
+        // a single memset per decode instead of one per LF group (hundreds of tiny stream operations per batch)
+        size_t zero = 0;
+        auto zk_alloc = [&](size_t bytes) { size_t o = align_up(zero, 256); zero = o + bytes; return o; };
         size_t n_lf = 0, n_hf = 0, n_grp = 0, n_mod = 0;
         max_global_blob = max_coeff_blob = max_ec_blob = 0;
         for (size_t k = 0; k < n; ++k) {
@@ -115,11 +119,13 @@ public:
                 im.nlf = p.lfg_sec.size(); im.npg = p.pg_sec.size(); im.ng = im.npg / npass;
                 im.lfg_off = up_alloc(sizeof(DLfGroup) * im.nlf);
                 im.grp_off = up_alloc(sizeof(DGroup) * im.npg);
-                im.err_off = wk_alloc(4 * (im.nlf + im.npg + 1));
+                im.err_off = zk_alloc(4 * (im.nlf + im.npg + 1));
                 im.lf.resize(im.nlf);
                 bool wp = d.global_tree_uses_wp != 0;
                 for (const FramePlan::LocalHeader &lh : p.lfg_local) wp = wp || (lh.present && lh.uses_wp);
                 bool lz_mod = d.global_spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + d.global_spec_off))->lz77_enabled;
+                for (const FramePlan::LocalHeader &lh : p.lfg_local) // (trees local to LF-group sections bring their own code specs)
+                    if (lh.present && !lh.host_err && lh.spec_off && ((const DCodeSpec *) (p.arena.bytes.data() + lh.spec_off))->lz77_enabled) lz_mod = true;
                 for (size_t i = 0; i < im.nlf; ++i) {
                     LfBuf &b = im.lf[i];
                     int ggx = (int) (i % (size_t) d.ggcolumns), ggy = (int) (i / (size_t) d.ggcolumns);
@@ -140,7 +146,7 @@ public:
                     b.llf = wk_alloc(4 * 3 * n8);
                     b.wp = wp ? wk_alloc(4 * 2 * 5 * std::max<size_t>(cap, (size_t) b.w8)) : (size_t) -1;
                     b.lz = lz_mod ? wk_alloc(4u << 18) : (size_t) -1;
-                    b.vb_tok = wk_alloc(4 * 2 * 3 * n8 * npass);
+                    b.vb_tok = zk_alloc(4 * 2 * 3 * n8 * npass);
                     b.llf_scratch = wk_alloc(4 * 2048);
                     b.lane = wk_alloc(sizeof(ModLaneScratch));
                 }
@@ -195,7 +201,7 @@ public:
                 }
                 n_lf += im.nlf; n_hf += im.npg; n_grp += im.ng;
             } else {
-                im.err_off = wk_alloc(4 * (p.pg_sec.size() + 2));
+                im.err_off = zk_alloc(4 * (p.pg_sec.size() + 2));
                 // coded channel list of the global image: palette (meta) channels first, each with its own size
                 int nch = d.num_channels;
                 for (int c = 0; c < nch; ++c) im.plane[c] = wk_alloc(2 * (size_t) std::max(1, p.gmod.ch[c].w) * std::max(1, p.gmod.ch[c].h));
@@ -254,6 +260,13 @@ public:
                 }
                 n_mod += im.nmod;
             }
+        }
+        zero_off = wk_alloc(zero);
+        zero_bytes = zero;
+        for (size_t k = 0; k < n; ++k) {
+            if (plans[k]->err) continue;
+            img[k].err_off += zero_off;
+            for (LfBuf &b : img[k].lf) b.vb_tok += zero_off;
         }
         {
             const size_t LS = (size_t) be.lane_stride(), slots = (n_lf + LS - 1) / LS;
@@ -525,14 +538,7 @@ public:
     void execute() {
         if (!dev) return;
         uint8_t *dwork = dev + upload_bytes;
-        for (size_t k = 0; k < plans.size(); ++k) {
-            FramePlan &p = *plans[k];
-            Img &im = img[k];
-            if (p.err) continue;
-            size_t nerr = p.df.is_modular ? im.nmod + 2 : im.nlf + im.npg + 1;
-            be.dev_memset(dwork + im.err_off, 0, 4 * nerr);
-            if (!p.df.is_modular) for (const LfBuf &b : im.lf) be.dev_memset(dwork + b.vb_tok, 0, 4 * 2 * 3 * (size_t) b.w8 * b.h8 * (size_t) p.df.num_passes);
-        }
+        if (zero_bytes) be.dev_memset(dwork + zero_off, 0, zero_bytes);
         if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob);
         if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
         for (size_t k = 0; k < plans.size(); ++k) { // extra channels behind the coefficients (errors only; planes are scratch)
@@ -724,7 +730,7 @@ private:
     std::vector<Img> img;
     uint8_t *dev = nullptr, *staging = nullptr;
     size_t upload_bytes = 0, work_bytes = 0, dev_cap = 0, staging_cap = 0;
-    size_t lf_ring_off = 0, lf_wring_off = 0;
+    size_t lf_ring_off = 0, lf_wring_off = 0, zero_off = 0, zero_bytes = 0;
     enum { LF_RING_W = 256 }; // LF groups are at most 256 cells wide
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, ppw_off = 0, num_lf = 0, num_hf = 0, num_grp = 0;
     bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry

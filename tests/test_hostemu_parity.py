@@ -215,3 +215,13 @@ def test_out_of_range_samples_wrap_like_the_reference(oracle, emu, gen, case):
     a, ea, _, _ = oracle.decode(data)
     assert ea == "" and len(np.unique(a[..., :3])) > 2
     _cmp(oracle, emu, data)
+
+
+def test_local_tree_with_lz77_needs_a_window(oracle, emu):
+    """regression (found by the round-2 ASan/UBSan sweep): a corrupt LF-group header naming a tree of its own whose code
+    spec enables LZ77 while the global one does not -- the LZ77 window is sized from the local specs as well"""
+    import os
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bad_local_tree_lz77.jxl"), "rb").read()
+    a, ea, _, _ = oracle.decode(data)
+    b, eb, _ = emu.decode(data)
+    assert ea == eb != "" and a is None and b is None

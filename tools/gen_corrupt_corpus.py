@@ -10,13 +10,16 @@ while n < int(sys.argv[2]):
     w=rnd.choice([8,64,100,200,257,300]); h=rnd.choice([8,64,120,136,264])
     if kind=="vardct":
         kw=dict(mix=rnd.choice([0,1,2]),tree=rnd.choice([0,1,2]),ans=rnd.choice([0,1]),alpha=rnd.choice([0,0,1]),raw_dq=rnd.choice([0,0,0x11]),
-                container=rnd.choice([0,1]),lz77=rnd.choice([0,0,1]),orders=rnd.choice([0,0x1f]),block_ctx=0,seed=rnd.randrange(1000))
+                container=rnd.choice([0,1]),lz77=rnd.choice([0,0,1]),orders=rnd.choice([0,0x1f]),block_ctx=0,seed=rnd.randrange(1000),
+                passes=rnd.choice([1,1,2,3]),lf_local_tree=rnd.choice([0,0,1,2,3,7]))
+        if w <= 256 and h <= 256: kw["passes"]=1
         if kw["container"]: kw["jxlp"]=rnd.choice([0,1])
         try: data=streamgen.vardct(w,h,**kw)[0]
         except Exception: continue
     else:
         kw=dict(tree=rnd.choice([0,1,2]),ans=rnd.choice([0,1]),lz77=rnd.choice([0,1]),alpha=rnd.choice([0,1]),palette=rnd.choice([0,0,1]),local_tree=rnd.choice([0,1,2]),
                 group_shift=rnd.choice([7,8,9]),seed=rnd.randrange(1000),container=rnd.choice([0,1]))
+        if kw["palette"]: kw["pal_deltas"]=rnd.choice([0,3,50]); kw["pal_pred"]=rnd.choice([1,4,5,6,13])
         if kw["palette"] and kw["tree"]==2: kw["tree"]=1
         try: data=streamgen.modular(w,h,**kw)[0]
         except Exception: continue
