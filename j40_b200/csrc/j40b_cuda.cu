@@ -22,7 +22,8 @@ static bool cuda_ok(cudaError_t e) { return e == cudaSuccess; }
 
 struct CudaBackend {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr; // side: highest priority, for the short generic back-end kernel
+    cudaEvent_t ev_side[2] = {nullptr, nullptr};
     bool ok = false;
     int num_sms = 148;
     float *big_pool = nullptr;
@@ -41,6 +42,12 @@ struct CudaBackend {
         if (!cuda_ok(cudaGetDeviceProperties(&prop, dev))) return false;
         num_sms = prop.multiProcessorCount;
         if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
+        {
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            if (!cuda_ok(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, greatest))) { side = nullptr; cudaGetLastError(); }
+            for (auto &e : ev_side) if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return false;
+        }
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
         if (!kl_init_lf() || !kl_init_back() || !kl_init_mod()) return false;
         ok = true;
@@ -52,6 +59,8 @@ struct CudaBackend {
         if (big_pool) cudaFree(big_pool);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (side) cudaStreamDestroy(side);
+        for (auto &e : ev_side) if (e) cudaEventDestroy(e);
         ok = false;
     }
     void *dev_alloc(size_t n) { void *p = nullptr; cudaSetDevice(device); if (!cuda_ok(cudaMalloc(&p, n ? n : 1))) return nullptr; return p; }
@@ -77,31 +86,23 @@ struct CudaBackend {
     void sync() { cudaStreamSynchronize(stream); }
     int lane_stride() const { return 32 * LANE_WARPS; } // work items per slot of the lane decoders' interleaved buffers
 
-    // `spec_bytes`: largest code-spec blob among the batch's images (sizes the staging area)
-    void launch_lf(const LfWork *w, int n, size_t spec_bytes) {
-        int warps = 1, cap = LF_ROW_CAP, stage = 0; // staging the spec costs 33 KB of shared memory per warp for ~2 % latency
-        if (const char *e = getenv("J40B_LF_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 4) warps = v; }
-        if (const char *e = getenv("J40B_LF_CAP")) { int v = atoi(e); if (v == 0 || v == LF_ROW_CAP) cap = v; }
-        if (const char *e = getenv("J40B_LF_STAGE")) stage = atoi(e);
-        const int spec_cap = stage && spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
-        const size_t smem = (size_t) spec_cap + (size_t) warps * warp_slice_bytes(cap);
-        const int blocks = (n + warps - 1) / warps;
-        // One stream per warp (SIMT-uniform decoder, j40b_modular.h) or, with J40B_LF_MODE=lane, one per lane
-        // (j40b_modlane.h): 1/20 of the issue slots and no shared memory, but 6-7 times the latency per stream (measured:
-        // LF image of 64 4K frames 70 ms against 490 ms), which a pipeline can only hide with more batches in flight than
-        // fit the device memory at 6 GB per batch of 64 4K frames. The default stays the warp decoder.
+    void launch_lf(const LfWork *w, int n, size_t) {
+        // One stream per warp (SIMT-uniform decoder, j40b_modular.h; per channel and decoder class, lf_chan_body) or,
+        // with J40B_LF_MODE=lane, one per lane (j40b_modlane.h): 1/20 of the issue slots and no shared memory, but 6-7
+        // times the latency per stream (measured: LF image of 64 4K frames 70 ms against 490 ms), which a pipeline can
+        // only hide with more batches in flight than fit the device memory at 6 GB per batch of 64 4K frames.
         bool lane_mode = false;
         if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
         cudaEventRecord(ev[0], stream);
-        if (lane_mode) kl_lf_lane(1, stream, w, n); else kl_lf_decode(1, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
+        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP); launches += 12; }
         cudaEventRecord(ev[5], stream);
         kl_lf_post(n, stream, w);
-        if (lane_mode) { kl_lf_lane(2, stream, w, n); kl_lf_place(n, stream, w); ++launches; }
-        else kl_lf_decode(2, blocks, 32 * warps, smem, stream, w, n, cap, spec_cap);
+        if (lane_mode) { kl_lf_lane(2, stream, w, n); kl_lf_place(n, stream, w); launches += 2; }
+        else { kl_lf_stage(1, stream, w, n, LF_ROW_CAP); launches += 16; }
         cudaEventRecord(ev[6], stream);
         kl_lf_llf(n, stream, w);
         cudaEventRecord(ev[1], stream);
-        launches += 4;
+        launches += 2;
     }
     void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t spec_bytes) {
         kl_hf_prep(ngroups, stream, pw);
@@ -119,17 +120,25 @@ struct CudaBackend {
         ++launches;
     }
     void launch_back(const BackWork *w, int n) {
-        kl_back_tile(n, stream, w);
-        cudaEventRecord(ev[3], stream);
-        ++launches;
         if (!big_pool) {
             big_blocks = num_sms;
             if (!cuda_ok(cudaMalloc(&big_pool, (size_t) big_blocks * 4 * 65536 * sizeof(float)))) { big_pool = nullptr; big_blocks = 0; }
         }
-        if (big_pool) {
-            kl_back_generic(big_blocks < n ? big_blocks : n, stream, w, n, big_pool);
+        // The generic path (varblocks the tile kernel leaves out) next to the tile kernel, on a side stream of the highest
+        // priority: it usually has nothing to do and ends in microseconds, but behind the tile kernel on a saturated GPU
+        // its 148 blocks waited for slots for as long as a whole tile stage (83 ms measured with 12 batches in flight).
+        if (big_pool && side) {
+            cudaEventRecord(ev_side[0], stream);
+            cudaStreamWaitEvent(side, ev_side[0], 0);
+            kl_back_generic(big_blocks < n ? big_blocks : n, side, w, n, big_pool);
+            cudaEventRecord(ev_side[1], side);
             ++launches;
         }
+        kl_back_tile(n, stream, w);
+        cudaEventRecord(ev[3], stream);
+        ++launches;
+        if (big_pool && side) cudaStreamWaitEvent(stream, ev_side[1], 0);
+        else if (big_pool) { kl_back_generic(big_blocks < n ? big_blocks : n, stream, w, n, big_pool); ++launches; }
         cudaEventRecord(ev[4], stream);
     }
     // `spec_bytes`: the image's code-spec blob; `max_w`: its widest channel (sizes the shared-memory rows)

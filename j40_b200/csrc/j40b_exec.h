@@ -123,8 +123,9 @@ namespace j40b {
 enum { PTREE_CAP = 192 };
 
 // per-warp scratch of the serial decoders (shared memory on the device)
+// (the pruned tree of the current channel lives in the stream's global scratch record, ModLaneScratch::ptree: it is
+// only read when the channel is set up, or walked through L1 by the fallback decoder)
 struct alignas(16) WarpScratch {
-    DTreeNode ptree[PTREE_CAP];
     ModImage m;
     int32_t info[8];
 };
@@ -199,45 +200,113 @@ J40B_HD inline bool lf_stage_header(BitReader &br, ErrSlot &es, const LfWork &w,
 }
 
 // ---------------------------------------------------------------------------------------------
-// LF group, stage 1 (one warp): LfQuant, the 3-channel modular LF image (j40.h:6739-6757)
-template <class Sync>
-J40B_HD inline void lf_decode1_body(const LfWork &w, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
-                                    const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
+// The two serial stages of an LF group, one *channel* and one decoder class per kernel (modular_channel_prep / _run in
+// j40b_modular.h): stage 0 = the LF image (3 channels, j40.h:6739-6757), stage 1 = the HF metadata image (4 channels)
+// followed by the varblock placement (j40.h:6766-6777, 6585-6720). For every channel the executor launches the four
+// class kernels one after the other; each LF group is decoded by the one whose class its channel has and left alone by
+// the others. Between kernels the decoder state travels through the LF group record (bit position, rANS state, LZ77
+// counters) and the modular image header through the group's scratch record. Why: a kernel holding every variant
+// needs 168 / 236 registers per thread, the class kernels 64 ... 128, and the register file the long-lived serial
+// warps occupy is what keeps tile and coefficient blocks of other batches off the SMs ("what bounds a step").
+template <int K, class Sync>
+J40B_HD inline void lf_chan_body(const LfWork &w, int stage, int c, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
+                                 int lane, int nlanes, Sync sync) {
+    if (*w.err) return;
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
     const int n8 = g.width8 * g.height8;
+    const int nch = stage == 0 ? 3 : 4;
+    const int32_t sidx = stage == 0 ? 1 + g.idx : 1 + 2 * f.num_lf_groups + g.idx;
     BitReader br;
     ErrSlot es;
     CodeCtx cc;
     CodeState cs;
     es.err = 0;
-    br.init(w.cs + g.sec_off, g.sec_size, g.sec_start_bit);
     cs.init(g.lz_window, (1u << 18) - 1);
-    // every lane runs the decoder on identical state (see modular_channel_warp); identical values are written
-    // to the shared ModImage by all of them
-    ModImage &m = ws.m;
-    const int32_t extra_prec = (int32_t) br.u(2);
-    m.num_channels = 3;
-    for (int c = 0; c < 3; ++c) {
-        m.ch[c].px = g.lfq + (size_t) c * n8;
-        m.ch[c].stride = g.width8; m.ch[c].w = g.width8; m.ch[c].h = g.height8;
-        m.ch[c].hshift = m.ch[c].vshift = 0;
-    }
+    ModImage &m = ws.m; // (every lane runs on identical state and writes identical values to the shared image header)
     const DTreeNode *tree;
     uint32_t spec_off;
     int32_t uses_wp;
-    const bool go = lf_stage_header(br, es, w, 0, m, tree, spec_off, uses_wp, lane == 0);
-    init_code_ctx(cc, w.arena, spec_off, spec_off == f.global_spec_off ? spec_copy : nullptr, copy_arena);
-    sync();
-    for (int c = 0; c < 3 && go && !es.err; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, 1 + g.idx, lane, nlanes, sync);
+    bool go = true;
+    if (c == 0) {
+        // the stage's prologue; every class kernel of channel 0 runs it (same bits, same values)
+        br.init(w.cs + g.sec_off, g.sec_size, stage == 0 ? g.sec_start_bit : g.mid_bit);
+        if (stage == 0) {
+            const int32_t extra_prec = (int32_t) br.u(2);
+            if (lane == 0) g.extra_prec = extra_prec;
+            m.num_channels = 3;
+            for (int k = 0; k < 3; ++k) {
+                m.ch[k].px = g.lfq + (size_t) k * n8;
+                m.ch[k].stride = g.width8; m.ch[k].w = g.width8; m.ch[k].h = g.height8;
+                m.ch[k].hshift = m.ch[k].vshift = 0;
+            }
+        } else {
+            const int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
+            if (lane == 0) g.nb_varblocks = nvb;
+            hf_meta_channels(g, nvb, m);
+        }
+        go = lf_stage_header(br, es, w, stage, m, tree, spec_off, uses_wp, lane == 0);
+        sync();
+        if (go && lane == 0) w.lane_scratch->m = m;
+    } else {
+        m = w.lane_scratch->m;
+        const LfLocal &lo = w.local[stage];
+        const bool local = lo.present && !lo.host_err;
+        tree = (const DTreeNode *) (w.arena + (local ? lo.tree_off : f.global_tree_off));
+        spec_off = local ? lo.spec_off : f.global_spec_off;
+        uses_wp = local ? lo.uses_wp : f.global_tree_uses_wp;
+        br.init(w.cs + g.sec_off, g.sec_size, g.chan_bit);
+        cs.ans_state = g.chan_ans;
+        cs.num_to_copy = g.chan_copy[0]; cs.copy_pos = g.chan_copy[1]; cs.num_decoded = g.chan_copy[2];
     }
+    cc.init(w.arena, spec_off);
+    sync();
+    if (go && !es.err) {
+        const int cls = modular_channel_prep(cc, tree, uses_wp != 0, g.wp_scratch, w.lane_scratch->ptree, PTREE_CAP, ms, m, c, sidx, lane, sync);
+        if (cls != K && !(cls == MC_NONE && K == MC_REST)) return; // another class kernel's channel
+        modular_channel_run<K>(cls, br, es, cc, cs, tree, g.wp_scratch, div24, w.lane_scratch->ptree, ms, m, c, sidx, lane, nlanes, sync);
+    }
+    if (!es.err && c + 1 < nch) {
+        if (lane == 0) {
+            g.chan_bit = br.bits_consumed();
+            g.chan_ans = cs.ans_state;
+            g.chan_copy[0] = cs.num_to_copy; g.chan_copy[1] = cs.copy_pos; g.chan_copy[2] = cs.num_decoded;
+        }
+        return;
+    }
+    // ---- the stage's epilogue (last channel, or an error)
     if (!es.err) finish_code(br, es, cc, cs);
+    if (stage == 0) {
+        if (lane == 0) {
+            g.mid_bit = br.bits_consumed();
+            g.nb_tr1 = imin(m.nb_transforms, MOD_MAX_TRANSFORMS);
+            for (int t = 0; t < g.nb_tr1; ++t) g.tr1[t] = m.tr[t];
+            if (es.err) *w.err = es.err;
+        }
+        return;
+    }
+    if (es.err) { if (lane == 0) *w.err = es.err; return; }
+    sync();
+    // inverse transforms (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide)
+    for (int t = m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = m;
+        one.nb_transforms = 1;
+        one.tr[0] = m.tr[t];
+        inverse_transforms(one, lane, nlanes);
+        sync();
+    }
+    // the weighted predictor's shared-memory row and the reference-property rows behind it are free now: 8 words per
+    // row of cells serve as the occupancy bitmap of the placement (256 * 8 words; error row 256 * 5, property rows 256 * 2,
+    // sample rows 256 * 1.5 words follow each other in the warp's slice, see carve_warp_slice)
+    if (ms.rows && ms.cap >= 256) place_varblocks_warp(f, g, es, br, (uint32_t *) ms.wp, lane, nlanes, sync);
+    else if (lane == 0) place_varblocks(f, g, es, br);
     if (lane == 0) {
-        g.extra_prec = extra_prec;
-        g.mid_bit = br.bits_consumed();
-        g.nb_tr1 = imin(m.nb_transforms, MOD_MAX_TRANSFORMS);
-        for (int t = 0; t < g.nb_tr1; ++t) g.tr1[t] = m.tr[t];
+        if (!es.err) {
+            // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
+            // on the per-section state and never copied back, j40.h:7791-7798); running short is still an error
+            if (br.overrun()) es.set_raw(E_SHRT);
+            g.end_bit = br.bits_consumed();
+        }
         if (es.err) *w.err = es.err;
     }
 }
@@ -266,61 +335,6 @@ J40B_HD inline void lf_post_body(const LfWork &w, int tid, int nth, Sync sync) {
     lf_dequant(f, g, g.extra_prec, tid, nth);
     sync();
     if (!f.skip_adapt_lf_smooth) lf_smooth(f, g, tid, nth);
-}
-
-// LF group, stage 3 (one warp): HF metadata image + varblock placement (j40.h:6766-6777, 6585-6720)
-template <class Sync>
-J40B_HD inline void lf_decode2_body(const LfWork &w, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
-                                    const uint8_t *spec_copy, const uint8_t *copy_arena, int lane, int nlanes, Sync sync) {
-    if (*w.err) return;
-    const DFrame &f = *w.f;
-    DLfGroup &g = *w.g;
-    const int n8 = g.width8 * g.height8;
-    BitReader br;
-    ErrSlot es;
-    CodeCtx cc;
-    CodeState cs;
-    es.err = 0;
-    br.init(w.cs + g.sec_off, g.sec_size, g.mid_bit);
-    cs.init(g.lz_window, (1u << 18) - 1);
-    ModImage &m = ws.m;
-    const int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
-    if (lane == 0) g.nb_varblocks = nvb;
-    hf_meta_channels(g, nvb, m);
-    const DTreeNode *tree;
-    uint32_t spec_off;
-    int32_t uses_wp;
-    const bool go = lf_stage_header(br, es, w, 1, m, tree, spec_off, uses_wp, lane == 0);
-    init_code_ctx(cc, w.arena, spec_off, spec_off == f.global_spec_off ? spec_copy : nullptr, copy_arena);
-    sync();
-    for (int c = 0; c < 4 && go && !es.err; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, uses_wp != 0, g.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c,
-                             1 + 2 * f.num_lf_groups + g.idx, lane, nlanes, sync);
-    }
-    if (!es.err) finish_code(br, es, cc, cs);
-    if (es.err) { if (lane == 0) *w.err = es.err; return; }
-    sync();
-    // inverse transforms (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide)
-    for (int t = m.nb_transforms - 1; t >= 0; --t) {
-        ModImage one = m;
-        one.nb_transforms = 1;
-        one.tr[0] = m.tr[t];
-        inverse_transforms(one, lane, nlanes);
-        sync();
-    }
-    // the weighted predictor's shared-memory row and the reference-property rows behind it are free now: 8 words per
-    // row of cells serve as the occupancy bitmap of the placement (needs 256 * 8 words of the 256 * 9 there)
-    if (ms.rows && ms.cap >= 256) place_varblocks_warp(f, g, es, br, (uint32_t *) ms.wp, lane, nlanes, sync);
-    else if (lane == 0) place_varblocks(f, g, es, br);
-    if (lane == 0) {
-        if (!es.err) {
-            // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
-            // on the per-section state and never copied back, j40.h:7791-7798); running short is still an error
-            if (br.overrun()) es.set_raw(E_SHRT);
-            g.end_bit = br.bits_consumed();
-        }
-        if (es.err) *w.err = es.err;
-    }
 }
 
 // LF group, stage 4 (one block): LLF coefficients of every varblock (j40.h:6669-6683)
@@ -405,14 +419,20 @@ J40B_HD inline void hf_lanes_run(const HfWork *w, bool active, const uint8_t *sp
     HfLane<MODE> L;
     L.done = true;
     if (active) hf_lane_init(L, *w, spec_copy, copy_arena, copy_pass, ctx_lut);
-    for (;;) {
+    for (uint32_t iter = 0;; ++iter) {
         if (!any(!L.done)) break;
         sync();
-        // phase R: lanes whose channel is exhausted (or that have not started) open the next one
-        if (!L.done && L.nz == 0) { do L.next_channel(); while (!L.done && L.nz == 0); }
-        sync();
+        // phase R: lanes whose channel is exhausted (or that have not started) open the next one. With 32 lanes some
+        // lane needs it in every other iteration, and it costs more than a coefficient step, so it is batched: every
+        // fourth iteration, or at once when no lane has a coefficient to read; a lane waits 1.5 iterations on average
+        // per channel (2 % more iterations) and phase R runs half as often.
+        const bool want = !L.done && L.nz == 0;
+        if ((iter & 3) == 0 || !any(!L.done && L.nz != 0)) {
+            if (want) { do L.next_channel(); while (!L.done && L.nz == 0); }
+            sync();
+        }
         // phase C: one coefficient symbol per lane
-        if (!L.done) L.coefficient();
+        if (!L.done && L.nz != 0) L.coefficient();
     }
     if (active) hf_lane_finish(L, *w);
 }
@@ -469,7 +489,7 @@ J40B_HD inline void modular_body(ModWork &w, WarpScratch &ws, const ModSmem &ms,
     if (!w.header_parsed) modular_header(br, es, f.have_global_tree != 0, m);
     sync();
     for (int c = 0; c < m.num_channels && !es.err; ++c) {
-        modular_channel_warp(br, es, cc, cs, tree, w.tree_uses_wp != 0, w.wp_scratch, div24, ws.ptree, PTREE_CAP, ms, m, c, w.sidx, lane, nlanes, sync);
+        modular_channel_warp(br, es, cc, cs, tree, w.tree_uses_wp != 0, w.wp_scratch, div24, w.lane_scratch->ptree, PTREE_CAP, ms, m, c, w.sidx, lane, nlanes, sync);
     }
     if (!es.err) finish_code(br, es, cc, cs);
     if (!es.err) {

@@ -279,7 +279,7 @@ J40B_HD inline void modular_channel(BitReader &br, ErrSlot &es, const CodeCtx &c
 //     finished channels only) and the sample rows / error rows live in shared memory.
 // On the CPU (kernel-logic tests) the same code runs with one "lane" and loops over the lane-indexed parts.
 // Same integer arithmetic as modular_channel_t (j40.h:3965-4229).
-enum { SIMT_LANES = 32, SIMT_REF_SLOTS = 4 };
+enum { SIMT_LANES = 32, SIMT_REF_SLOTS = 2 }; // (trees with more distinct reference properties are walked instead)
 
 struct SimtLane {       // lane j: decision node j and leaf j of the compiled (pruned) tree
     int32_t c[7];       // coefficients of pn, pw, pnw, pne, pnn, pww, pnww
@@ -692,16 +692,24 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
     sync();
 }
 
-// Entry point for a warp; every lane calls it with identical arguments and identical decoder state, and leaves
-// it with identical state. Chooses between the SIMT path above and walking the tree (wide channels, trees that
-// do not compile); the latter is executed redundantly by all lanes so that their state stays in step.
+// One channel of a sub-bitstream, warp-cooperative, in two steps so that kernels can be specialised by decoder variant
+// (a kernel that holds all variants needs the registers of the greediest one plus what the allocator loses on the
+// dispatch: 168 / 236 registers for the LF-group kernels, against 64 ... 124 for a single variant):
+//   modular_channel_prep   lane 0 prunes the tree for (channel, stream) and compiles it; returns the class of decoder
+//                          the channel needs (uniform across the lanes)
+//   modular_channel_run<K> runs it if the class is K (K = MC_ANY: whatever it is)
+// Classes: MC_WP  weighted predictor in every leaf, rANS without LZ77, rows in shared memory (the LF image's luma)
+//          MC_GRAD gradient predictor in every leaf, no weighted-predictor property, same coding (its chroma, typically)
+//          MC_WIDE wider than the shared-memory rows, no weighted predictor (the block-info channel of the HF metadata)
+//          MC_REST everything else (generic predictors, prefix codes, LZ77, trees that do not compile)
+enum { MC_NONE = 0, MC_WP = 1, MC_GRAD = 2, MC_WIDE = 3, MC_REST = 4, MC_ANY = 5 };
+
 template <class Sync>
-J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
-                                         const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch, const int32_t *div24,
-                                         DTreeNode *ptree, int ptree_cap, const ModSmem &ms,
-                                         const ModImage &m, int32_t cidx, int32_t sidx, int lane, int nlanes, Sync sync) {
+J40B_HD inline int modular_channel_prep(const CodeCtx &cc, const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch,
+                                        DTreeNode *ptree, int ptree_cap, const ModSmem &ms,
+                                        const ModImage &m, int32_t cidx, int32_t sidx, int lane, Sync sync) {
     const ModChannel &c = m.ch[cidx];
-    if (c.w <= 0 || c.h <= 0) return;
+    if (c.w <= 0 || c.h <= 0) return MC_NONE;
     sync(); // the previous channel's readers of ptree / tab are done
     if (lane == 0) {
         bool uses_wp = tree_uses_wp;
@@ -729,29 +737,60 @@ J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeC
     }
     sync();
     const bool uses_wp = ms.info[0] != 0;
+    if (!ms.info[2]) return MC_REST;
+    const int variant = ms.info[2] - 1;
+    if (c.w > ms.cap) return uses_wp ? MC_REST : MC_WIDE;
+    if (variant == 2) return MC_WP;
+    if (variant == 1 && !uses_wp) return MC_GRAD;
+    return MC_REST;
+}
+
+// `cls`: what modular_channel_prep returned. Does nothing unless K is that class (or MC_ANY).
+template <int K, class Sync>
+J40B_HD inline void modular_channel_run(int cls, BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                        const DTreeNode *tree, int32_t *wp_scratch, const int32_t *div24,
+                                        const DTreeNode *ptree, const ModSmem &ms,
+                                        const ModImage &m, int32_t cidx, int32_t sidx, int lane, int nlanes, Sync sync) {
+    if (cls == MC_NONE || (K != MC_ANY && K != cls)) return;
+    const ModChannel &c = m.ch[cidx];
+    const bool uses_wp = ms.info[0] != 0;
     const int n = ms.info[3];
-    if (ms.info[2]) {
-        int32_t refprops[SIMT_REF_SLOTS];
-        for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
-        const int variant = ms.info[2] - 1, ns = ms.info[1];
-        // (specialising the generic-predictor variants for rANS without LZ77 as well was measured: the extra loop
-        // bodies push the kernel to 254 registers, or to spills under a register cap, and the LF image kernel went
-        // from 70 to 91 ms)
-        if (c.w > ms.cap) { // wide channels: generic variants only
-            if (uses_wp) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-            else modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+    int32_t refprops[SIMT_REF_SLOTS];
+    for (int k = 0; k < SIMT_REF_SLOTS; ++k) refprops[k] = ms.info[4 + k];
+    const int ns = ms.info[1];
+    if ((K == MC_WP || K == MC_ANY) && cls == MC_WP) {
+        modular_channel_simt<true, 6, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+    } else if ((K == MC_GRAD || K == MC_ANY) && cls == MC_GRAD) {
+        modular_channel_simt<false, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+    } else if ((K == MC_WIDE || K == MC_ANY) && cls == MC_WIDE) {
+        modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+    } else if ((K == MC_REST || K == MC_ANY) && cls == MC_REST) {
+        if (ms.info[2]) {
+            const int variant = ms.info[2] - 1;
+            // (specialising the generic-predictor variants for rANS without LZ77 as well was measured: no gain)
+            if (c.w > ms.cap) modular_channel_simt<true, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+            else if (variant == 1) modular_channel_simt<true, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+            else if (uses_wp) modular_channel_simt<true, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+            else modular_channel_simt<false, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        } else {
+            // trees that do not compile: walked, redundantly by all lanes so that their state stays in step
+            const DTreeNode *t = n > 0 ? ptree : tree;
+            if (uses_wp) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
+            else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
+            sync();
         }
-        else if (variant == 2) modular_channel_simt<true, 6, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (variant == 1 && uses_wp) modular_channel_simt<true, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (variant == 1) modular_channel_simt<false, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else if (uses_wp) modular_channel_simt<true, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-        else modular_channel_simt<false, -1, 0, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
-    } else {
-        const DTreeNode *t = n > 0 ? ptree : tree;
-        if (uses_wp) modular_channel_t<true>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
-        else modular_channel_t<false>(br, es, cc, cs, t, wp_scratch, div24, m, cidx, sidx);
-        sync();
     }
+}
+
+// Entry point for a warp that takes whatever the channel needs; every lane calls it with identical arguments and
+// identical decoder state, and leaves it with identical state.
+template <class Sync>
+J40B_HD inline void modular_channel_warp(BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs,
+                                         const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch, const int32_t *div24,
+                                         DTreeNode *ptree, int ptree_cap, const ModSmem &ms,
+                                         const ModImage &m, int32_t cidx, int32_t sidx, int lane, int nlanes, Sync sync) {
+    const int cls = modular_channel_prep(cc, tree, tree_uses_wp, wp_scratch, ptree, ptree_cap, ms, m, cidx, sidx, lane, sync);
+    modular_channel_run<MC_ANY>(cls, br, es, cc, cs, tree, wp_scratch, div24, ptree, ms, m, cidx, sidx, lane, nlanes, sync);
 }
 
 // ModularHeader as far as the device understands it (RCT transforms only). Mirrors the checks of

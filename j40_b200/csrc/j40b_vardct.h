@@ -125,6 +125,10 @@ struct DLfGroup {
     uint32_t *vb_tok;     // [num_passes][3][h8*w8][2] {first token, count}, written by the pass-group kernel (zeroed before)
     // hand-over between the LF kernels (decode LF image -> post-process -> decode HF metadata -> LLF)
     uint64_t mid_bit;     // bit position after the LF image
+    // hand-over between the per-channel kernels of a stage (lf_chan_body): where the next channel starts
+    uint64_t chan_bit;
+    uint32_t chan_ans;
+    int32_t chan_copy[3]; // LZ77: num_to_copy, copy_pos, num_decoded
     uint64_t ltree_bit;   // E_LTRE: where the modular header that names a local tree starts (bits from the section start)
     int32_t ltree_stage;  // E_LTRE: 0 = LF image, 1 = HF metadata
     int32_t meta_overrun; // the HF metadata decode ran past the end of the section (lane-per-stream path: read by lf_place_body)

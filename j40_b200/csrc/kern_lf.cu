@@ -4,22 +4,17 @@
 
 namespace j40b {
 
-// `spec_cap`: bytes of dynamic shared memory reserved for the staged code spec (0 = read the tables through L1)
-template <int STAGE>
-__global__ void __launch_bounds__(128) k_lf_decode(const LfWork *items, int n, int cap, int spec_cap) {
+// One channel of one serial stage of the LF groups, one decoder class per kernel (lf_chan_body in j40b_exec.h): one warp
+// per LF group; `cap`: width of the shared-memory rows. The work list is ordered largest group first.
+template <int K>
+__global__ void __launch_bounds__(32) k_lf_chan(const LfWork *items, int stage, int c, int cap) {
     __shared__ int32_t div24[64];
     extern __shared__ __align__(16) uint8_t smem[];
-    const int warps = (int) blockDim.x >> 5, warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
-    const LfWork &w0 = items[(int) blockIdx.x * warps];
-    const bool staged = spec_cap > 0 && stage_spec_blob(w0.arena, w0.f->global_spec_off, smem, (uint32_t) spec_cap, (int) threadIdx.x, (int) blockDim.x);
-    fill_div24(div24, (int) threadIdx.x, (int) blockDim.x);
-    __syncthreads();
-    const int i = (int) blockIdx.x * warps + warp;
-    if (i >= n) return;
+    fill_div24(div24, (int) threadIdx.x, 32);
+    __syncwarp();
     WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem + spec_cap + (size_t) warp * warp_slice_bytes(cap), cap, ws);
-    if (STAGE == 1) lf_decode1_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
-    else lf_decode2_body(items[i], *ws, ms, div24, staged ? smem : nullptr, w0.arena, lane, 32, WarpSync());
+    ModSmem ms = carve_warp_slice(smem, cap, ws);
+    lf_chan_body<K>(items[blockIdx.x], stage, c, *ws, ms, div24, (int) threadIdx.x, 32, WarpSync());
 }
 
 // Lane-per-stream variant (j40b_modlane.h): every thread owns one LF group; 32 * LANE_WARPS work items per block.
@@ -76,13 +71,21 @@ __global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
 
 
 bool kl_init_lf() {
-    const int lf_smem = (int) (SPEC_COPY_BYTES + 4 * warp_slice_bytes(LF_ROW_CAP));
-    return cudaFuncSetAttribute(k_lf_decode<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
-           cudaFuncSetAttribute(k_lf_decode<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
+    const int lf_smem = (int) warp_slice_bytes(LF_ROW_CAP);
+    return cudaFuncSetAttribute(k_lf_chan<MC_WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_lf_chan<MC_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_lf_chan<MC_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_lf_chan<MC_REST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
 }
-void kl_lf_decode(int stage, int blocks, int threads, size_t smem, cudaStream_t stream, const LfWork *w, int n, int cap, int spec_cap) {
-    if (stage == 1) k_lf_decode<1><<<blocks, threads, smem, stream>>>(w, n, cap, spec_cap);
-    else k_lf_decode<2><<<blocks, threads, smem, stream>>>(w, n, cap, spec_cap);
+// all channels of a stage (0: LF image, 1: HF metadata + placement): per channel the four class kernels in a row
+void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap) {
+    const size_t smem = warp_slice_bytes(cap);
+    for (int c = 0; c < (stage == 0 ? 3 : 4); ++c) {
+        k_lf_chan<MC_WP><<<n, 32, smem, stream>>>(w, stage, c, cap);
+        k_lf_chan<MC_GRAD><<<n, 32, smem, stream>>>(w, stage, c, cap);
+        k_lf_chan<MC_WIDE><<<n, 32, smem, stream>>>(w, stage, c, cap);
+        k_lf_chan<MC_REST><<<n, 32, smem, stream>>>(w, stage, c, cap);
+    }
 }
 void kl_lf_lane(int stage, cudaStream_t stream, const LfWork *w, int n) {
     const int per_block = 32 * LANE_WARPS, blocks = (n + per_block - 1) / per_block;

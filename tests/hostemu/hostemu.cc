@@ -64,14 +64,19 @@ struct HostEmuBackend {
             }
             return;
         }
-        for (int i = 0; i < n; ++i) {
-            bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->global_spec_off, copy.data(), (uint32_t) copy.size(), 0, 1);
-            const uint8_t *sc = staged ? copy.data() : nullptr;
-            lf_decode1_body(w[i], wm.ws, wm.ms, wm.div24, sc, w[i].arena, 0, 1, NoSync());
-            lf_post_body(w[i], 0, 1, NoSync());
-            lf_decode2_body(w[i], wm.ws, wm.ms, wm.div24, sc, w[i].arena, 0, 1, NoSync());
-            lf_llf_body(w[i], 0, 1, NoSync());
-        }
+        // like the device: per stage and channel the four class kernels in a row, every LF group in each
+        auto stage = [&](int st) {
+            for (int c = 0; c < (st == 0 ? 3 : 4); ++c) {
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_WP>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_GRAD>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_WIDE>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_REST>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
+            }
+        };
+        stage(0);
+        for (int i = 0; i < n; ++i) lf_post_body(w[i], 0, 1, NoSync());
+        stage(1);
+        for (int i = 0; i < n; ++i) lf_llf_body(w[i], 0, 1, NoSync());
     }
     void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t) {
         for (int i = 0; i < ngroups; ++i) hf_prep_body(pw[i], 0, 1, NoSync());
