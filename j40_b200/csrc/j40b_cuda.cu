@@ -107,7 +107,8 @@ struct CudaBackend {
     void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t spec_bytes) {
         kl_hf_prep(ngroups, stream, pw);
         ++launches;
-        const int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
+        int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
+        if (const char *e = getenv("J40B_HF_STAGE")) if (!atoi(e)) spec_cap = 0; // experiment: tables through L1, no shared memory
         // sections per warp (one per lane): full warps as soon as that still leaves two warps per SM -- a warp of 32 lanes
         // costs the same issue slots per iteration as one of 8 -- and fewer lanes per warp for small launches (a single
         // 4K image has 135 sections), where latency is what counts
@@ -134,7 +135,15 @@ struct CudaBackend {
             cudaEventRecord(ev_side[1], side);
             ++launches;
         }
-        kl_back_tile(n, stream, w);
+        // J40B_TILE_PRIO=1 (experiment): the tile kernel on the high-priority stream as well (short-lived blocks that
+        // finish a batch; they compete for slots with the long-lived serial decoders of the other batches in flight)
+        static const bool tile_prio = getenv("J40B_TILE_PRIO") && atoi(getenv("J40B_TILE_PRIO")) != 0;
+        if (tile_prio && big_pool && side) {
+            kl_back_tile(n, side, w);
+            cudaEventRecord(ev_side[1], side);
+        } else {
+            kl_back_tile(n, stream, w);
+        }
         cudaEventRecord(ev[3], stream);
         ++launches;
         if (big_pool && side) cudaStreamWaitEvent(stream, ev_side[1], 0);

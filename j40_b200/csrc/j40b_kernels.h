@@ -26,20 +26,21 @@ enum { LF_ROW_CAP = 256, MOD_ROW_CAP = 1024 };
 struct WarpSync { __device__ void operator()() const { __syncwarp(); } };
 #endif
 
-__host__ __device__ inline size_t warp_slice_bytes(int cap) {
+// `with_wp`: the slice has the weighted predictor's error row (decoder classes without it leave it out: 5 of 12.4 KB)
+__host__ __device__ inline size_t warp_slice_bytes(int cap, bool with_wp = true) {
     size_t n = sizeof(WarpScratch) + (sizeof(SimtLane) + sizeof(SimtLeaf)) * SIMT_LANES;
-    n += (size_t) cap * (3 * 2 + 5 * 4 + SIMT_REF_SLOTS * 4);
+    n += (size_t) cap * (3 * 2 + (with_wp ? 5 * 4 : 0) + SIMT_REF_SLOTS * 4);
     return (n + 15) & ~(size_t) 15;
 }
 
 #if defined(__CUDACC__)
-__device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws) {
+__device__ inline ModSmem carve_warp_slice(uint8_t *base, int cap, WarpScratch *&ws, bool with_wp = true) {
     ws = (WarpScratch *) base;
     ModSmem ms;
     ms.leaves = (SimtLeaf *) (base + sizeof(WarpScratch));
     ms.tab = (SimtLane *) (ms.leaves + SIMT_LANES);
     ms.wp = (int32_t *) (ms.tab + SIMT_LANES);
-    ms.refp = ms.wp + (size_t) cap * 5;
+    ms.refp = ms.wp + (with_wp ? (size_t) cap * 5 : 0);
     ms.rows = cap ? (int16_t *) (ms.refp + (size_t) cap * SIMT_REF_SLOTS) : nullptr;
     ms.info = ws->info;
     ms.cap = cap;
