@@ -528,14 +528,18 @@ def main():
     alg_bytes = comp_bytes + 4 * pixels
     ms_step = total_ms / args.steps
     kavg = {k: sum(x[k] for x in kernel_ms) / len(kernel_ms) for k in kernel_ms[0]}
-    names = {"lf_image": "k_lf_decode<1>", "lf_hfmeta": "k_lf_post+k_lf_decode<2>", "lf_llf": "k_lf_llf", "hf_group": "k_hf_prep+k_hf_group",
-             "back": "k_back_tile", "back_big": "k_back_generic", "modular": "k_modular+k_render"}
+    names = {"lf_image": "k_lf_chan stage 0 (LF image: 3 channels x 5 class kernels)",
+             "lf_hfmeta": "k_lf_post + k_lf_chan stage 1 (HF metadata: 4 channels x 5 class kernels, varblock placement)",
+             "lf_llf": "k_lf_llf", "hf_group": "k_hf_prep+k_hf_group", "back": "k_back_tile", "back_big": "k_back_generic",
+             "modular": "k_modular+k_render"}
+    traffic_key = {"lf_image": "k_lf_chan", "lf_hfmeta": "k_lf_chan", "hf_group": "k_hf_prep+k_hf_group", "back": "k_back_tile"}
     dominant = max(names, key=lambda k: kavg.get(k, 0.0))
     traffic = traffic_total = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        ent = tr.get(names[dominant])
+        ent = tr.get(traffic_key.get(dominant, ""))
         if ent and ent.get("preset", args.preset) == args.preset:
+            # (k_lf_chan: both stages' launches together; the dominant stage is about half of them)
             traffic = ent["dram_bytes_per_frame"] * F
         tot = [v["dram_bytes_per_frame"] for v in tr.values() if isinstance(v, dict) and "dram_bytes_per_frame" in v]
         if tot:

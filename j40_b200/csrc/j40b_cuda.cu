@@ -94,11 +94,11 @@ struct CudaBackend {
         bool lane_mode = false;
         if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
         cudaEventRecord(ev[0], stream);
-        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP); launches += 12; }
+        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP); launches += 15; }
         cudaEventRecord(ev[5], stream);
         kl_lf_post(n, stream, w);
         if (lane_mode) { kl_lf_lane(2, stream, w, n); kl_lf_place(n, stream, w); launches += 2; }
-        else { kl_lf_stage(1, stream, w, n, LF_ROW_CAP); launches += 16; }
+        else { kl_lf_stage(1, stream, w, n, LF_ROW_CAP); launches += 20; }
         cudaEventRecord(ev[6], stream);
         kl_lf_llf(n, stream, w);
         cudaEventRecord(ev[1], stream);

@@ -701,8 +701,10 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
 // Classes: MC_WP  weighted predictor in every leaf, rANS without LZ77, rows in shared memory (the LF image's luma)
 //          MC_GRAD gradient predictor in every leaf, no weighted-predictor property, same coding (its chroma, typically)
 //          MC_WIDE wider than the shared-memory rows, no weighted predictor (the block-info channel of the HF metadata)
-//          MC_REST everything else (generic predictors, prefix codes, LZ77, trees that do not compile)
-enum { MC_NONE = 0, MC_WP = 1, MC_GRAD = 2, MC_WIDE = 3, MC_REST = 4, MC_ANY = 5 };
+//          MC_GEN  any predictors, no weighted predictor, rANS without LZ77, rows in shared memory (chroma with mixed
+//                  predictors, the sharpness and colour-correlation maps)
+//          MC_REST everything else (weighted predictor among others, prefix codes, LZ77, trees that do not compile)
+enum { MC_NONE = 0, MC_WP = 1, MC_GRAD = 2, MC_WIDE = 3, MC_REST = 4, MC_GEN = 5, MC_ANY = 6 };
 
 template <class Sync>
 J40B_HD inline int modular_channel_prep(const CodeCtx &cc, const DTreeNode *tree, bool tree_uses_wp, int32_t *wp_scratch,
@@ -742,6 +744,7 @@ J40B_HD inline int modular_channel_prep(const CodeCtx &cc, const DTreeNode *tree
     if (c.w > ms.cap) return uses_wp ? MC_REST : MC_WIDE;
     if (variant == 2) return MC_WP;
     if (variant == 1 && !uses_wp) return MC_GRAD;
+    if (!uses_wp && !cc.prefix && !cc.lz77) return MC_GEN;
     return MC_REST;
 }
 
@@ -762,8 +765,11 @@ J40B_HD inline void modular_channel_run(int cls, BitReader &br, ErrSlot &es, con
         modular_channel_simt<true, 6, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else if ((K == MC_GRAD || K == MC_ANY) && cls == MC_GRAD) {
         modular_channel_simt<false, 5, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+    } else if ((K == MC_GEN || K == MC_ANY) && cls == MC_GEN) {
+        modular_channel_simt<false, -1, 1, false>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else if ((K == MC_WIDE || K == MC_ANY) && cls == MC_WIDE) {
-        modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        if (!cc.prefix && !cc.lz77) modular_channel_simt<false, -1, 1, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
+        else modular_channel_simt<false, -1, 0, true>(br, es, cc, cs, ms, wp_scratch, refprops, ns, div24, m, cidx, lane, nlanes, sync);
     } else if ((K == MC_REST || K == MC_ANY) && cls == MC_REST) {
         if (ms.info[2]) {
             const int variant = ms.info[2] - 1;

@@ -79,14 +79,16 @@ bool kl_init_lf() {
     return cudaFuncSetAttribute(k_lf_chan<MC_WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
            cudaFuncSetAttribute(k_lf_chan<MC_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
            cudaFuncSetAttribute(k_lf_chan<MC_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
+           cudaFuncSetAttribute(k_lf_chan<MC_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
            cudaFuncSetAttribute(k_lf_chan<MC_REST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
 }
-// all channels of a stage (0: LF image, 1: HF metadata + placement): per channel the four class kernels in a row
+// all channels of a stage (0: LF image, 1: HF metadata + placement): per channel the five class kernels in a row
 void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap) {
     for (int c = 0; c < (stage == 0 ? 3 : 4); ++c) {
         k_lf_chan<MC_WP><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WP, stage, c)), stream>>>(w, stage, c, cap);
         k_lf_chan<MC_GRAD><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GRAD, stage, c)), stream>>>(w, stage, c, cap);
         k_lf_chan<MC_WIDE><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WIDE, stage, c)), stream>>>(w, stage, c, cap);
+        k_lf_chan<MC_GEN><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GEN, stage, c)), stream>>>(w, stage, c, cap);
         k_lf_chan<MC_REST><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_REST, stage, c)), stream>>>(w, stage, c, cap);
     }
 }

@@ -70,6 +70,7 @@ struct HostEmuBackend {
                 for (int i = 0; i < n; ++i) lf_chan_body<MC_WP>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
                 for (int i = 0; i < n; ++i) lf_chan_body<MC_GRAD>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
                 for (int i = 0; i < n; ++i) lf_chan_body<MC_WIDE>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_GEN>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
                 for (int i = 0; i < n; ++i) lf_chan_body<MC_REST>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
             }
         };
