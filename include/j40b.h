@@ -92,6 +92,10 @@ float j40b_batch_event_ms(const j40b_batch *b, const j40b_batch *ref, int which)
  * The parity tests compare these with the reference's own arrays (float intermediates within 1e-5). */
 size_t j40b_batch_debug_dump(j40b_batch *b, int index, int lf_group, int what, void *dst, size_t cap);
 
+/* writes image `index` (after a decode) as a PAM file (P7, RGB_ALPHA) straight from device memory, rows without the stride
+ * padding: the counterpart of dj40.c's stbi_write_png for device-resident output. 0 on success. */
+int j40b_batch_write_pam(j40b_batch *b, int index, const char *path);
+
 /* 1 if a CUDA device is usable by this library, else 0 */
 int j40b_gpu_available(void);
 

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "j40b_batch_wait", "j40b_batch_count", "j40b_batch_error", "j40b_batch_info", "j40b_batch_device_pixels",
     "j40b_batch_read_pixels", "j40b_batch_last_decode_ms", "j40b_batch_kernel_ms", "j40b_batch_stat", "j40b_gpu_available",
     "j40b_batch_mark", "j40b_batch_join", "j40b_batch_mark_ms", "j40b_batch_reset", "j40b_batch_read_all_async",
-    "j40b_batch_add_many", "j40b_batch_event_ms", "j40b_batch_after", "j40b_batch_debug_dump",
+    "j40b_batch_add_many", "j40b_batch_event_ms", "j40b_batch_after", "j40b_batch_debug_dump", "j40b_batch_write_pam",
 ]
 
 
@@ -113,6 +113,8 @@ def lib():
         L.j40b_batch_join.argtypes = [C.c_void_p, C.c_void_p]
         L.j40b_batch_mark_ms.restype = C.c_float
         L.j40b_batch_mark_ms.argtypes = [C.c_void_p]
+        L.j40b_batch_write_pam.restype = C.c_int
+        L.j40b_batch_write_pam.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         L.j40b_batch_debug_dump.restype = C.c_size_t
         L.j40b_batch_debug_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         _LIB = L
@@ -270,6 +272,10 @@ class Batch:
     def debug_dump(self, i, lf_group, what, out):
         """diagnostics: intermediate array `what` (include/j40b.h) of an LF group into the numpy array `out`; bytes written"""
         return int(lib().j40b_batch_debug_dump(self._h, i, lf_group, what, out.ctypes.data, out.nbytes))
+
+    def write_pam(self, i, path):
+        """image i as a PAM (P7, RGB_ALPHA) file, copied from device memory without the stride padding"""
+        return int(lib().j40b_batch_write_pam(self._h, i, os.fsencode(path)))
 
     def last_decode_ms(self):
         return float(lib().j40b_batch_last_decode_ms(self._h))

@@ -102,8 +102,10 @@ struct TileShared {
     uint8_t cell_size64[64];
     uint8_t cover[64];      // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
     uint8_t chunk_vb[64];   // 64-float chunk -> index into vb[]
-    float thr[255];
-    uint8_t lut[SRGB_LUT_BYTES];
+    // sRGB threshold table and start LUT (padded to multiples of 16 bytes: the persistent kernel stages them with bulk copies)
+    alignas(16) float thr[256];
+    alignas(16) uint8_t lut[(SRGB_LUT_BYTES + 15) / 16 * 16];
+    int32_t tables_staged; // the kernel wrapper has filled thr / lut already (once per persistent block)
 };
 
 // number of 1-D transforms of `type` that varblock t contributes to pass 0 (along u) / pass 1 (along v)
@@ -224,8 +226,10 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         ts.kx_hf = J40B_FADD(f.base_corr_x, J40B_FMUL(f.inv_colour_factor, (float) g.xfromy[m64]));
         ts.kb_hf = J40B_FADD(f.base_corr_b, J40B_FMUL(f.inv_colour_factor, (float) g.bfromy[m64]));
     }
-    for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
-    for (int i = tid; i < SRGB_LUT_BYTES / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
+    if (!ts.tables_staged) {
+        for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
+        for (int i = tid; i < SRGB_LUT_BYTES / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
+    }
     for (int i = tid; i < 3 * TILE_CH; i += nth) coef[i] = 0.0f;
     sync();
     J40B_PHASE(0);

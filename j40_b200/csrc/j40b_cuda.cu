@@ -24,6 +24,9 @@ struct CudaBackend {
     int device = 0;
     cudaStream_t stream = nullptr, side = nullptr; // side: highest priority, for the short generic back-end kernel
     cudaEvent_t ev_side[2] = {nullptr, nullptr};
+    cudaStream_t side2 = nullptr;                // normal priority: the sharpness channel of the LF groups (launch_lf)
+    cudaEvent_t ev_side2[2] = {nullptr, nullptr};
+    bool side2_pending = false;
     bool ok = false;
     int num_sms = 148;
     float *big_pool = nullptr;
@@ -47,6 +50,8 @@ struct CudaBackend {
             cudaDeviceGetStreamPriorityRange(&least, &greatest);
             if (!cuda_ok(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, greatest))) { side = nullptr; cudaGetLastError(); }
             for (auto &e : ev_side) if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return false;
+            if (!cuda_ok(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking))) { side2 = nullptr; cudaGetLastError(); }
+            for (auto &e : ev_side2) if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return false;
         }
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
         if (!kl_init_lf() || !kl_init_back() || !kl_init_mod()) return false;
@@ -60,6 +65,8 @@ struct CudaBackend {
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (side) cudaStreamDestroy(side);
+        if (side2) cudaStreamDestroy(side2);
+        for (auto &e : ev_side2) if (e) cudaEventDestroy(e);
         for (auto &e : ev_side) if (e) cudaEventDestroy(e);
         ok = false;
     }
@@ -86,7 +93,8 @@ struct CudaBackend {
     void sync() { cudaStreamSynchronize(stream); }
     int lane_stride() const { return 32 * LANE_WARPS; } // work items per slot of the lane decoders' interleaved buffers
 
-    void launch_lf(const LfWork *w, int n, size_t) {
+    void launch_lf(const LfWork *w, int n, size_t, bool split_ok) {
+        bool split = split_ok;
         // One stream per warp (SIMT-uniform decoder, j40b_modular.h; per channel and decoder class, lf_chan_body) or,
         // with J40B_LF_MODE=lane, one per lane (j40b_modlane.h): 1/20 of the issue slots and no shared memory, but 6-7
         // times the latency per stream (measured: LF image of 64 4K frames 70 ms against 490 ms), which a pipeline can
@@ -94,11 +102,27 @@ struct CudaBackend {
         bool lane_mode = false;
         if (const char *e = getenv("J40B_LF_MODE")) lane_mode = e[0] == 'l';
         cudaEventRecord(ev[0], stream);
-        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP); launches += 15; }
+        // The sharpness channel off the critical path pays for latency (one 4K image: 210 -> 178 ms), not for throughput: with
+        // a dozen batches in flight the extra concurrent kernels cost 8 % (47.7 against 44.0 ms per step). Small launches only.
+        split = split && n < 64;
+        if (const char *e = getenv("J40B_LF_SPLIT")) split = split_ok && atoi(e) != 0; // (1: also for large launches, 0: never)
+        if (lane_mode || !side2) split = false;
+        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP, 0, 3, false); launches += 15; }
         cudaEventRecord(ev[5], stream);
         kl_lf_post(n, stream, w);
         if (lane_mode) { kl_lf_lane(2, stream, w, n); kl_lf_place(n, stream, w); launches += 2; }
-        else { kl_lf_stage(1, stream, w, n, LF_ROW_CAP); launches += 20; }
+        else if (!split) { kl_lf_stage(1, stream, w, n, LF_ROW_CAP, 0, 4, false); launches += 20; }
+        else {
+            // the sharpness channel (a third of the stage, never used by j40) on a side stream, next to the LLF, coefficient
+            // and tile stages; join_side() makes the end of the decode wait for it
+            kl_lf_stage(1, stream, w, n, LF_ROW_CAP, 0, 3, true);
+            cudaEventRecord(ev_side2[0], stream);
+            cudaStreamWaitEvent(side2, ev_side2[0], 0);
+            kl_lf_stage(1, side2, w, n, LF_ROW_CAP, 3, 4, true);
+            cudaEventRecord(ev_side2[1], side2);
+            side2_pending = true;
+            launches += 20;
+        }
         cudaEventRecord(ev[6], stream);
         kl_lf_llf(n, stream, w);
         cudaEventRecord(ev[1], stream);
@@ -167,6 +191,7 @@ struct CudaBackend {
         ++launches;
     }
     void launch_dump(const DumpWork &w, int n) { kl_dump_coeffs(n, stream, w); ++launches; }
+    void join_side() { if (side2_pending) { cudaStreamWaitEvent(stream, ev_side2[1], 0); side2_pending = false; } }
     void mark_modular(int which) { cudaEventRecord(ev[8 + which], stream); mod_marked = true; }
     void launch_palette_delta(const RenderWork *w, int num_c) { kl_palette_delta(stream, w, num_c); ++launches; }
     void launch_render(const RenderWork *w, int width, int height) {
@@ -364,6 +389,22 @@ EXPORT size_t j40b_batch_debug_dump(j40b_batch *b, int i, int lf_group, int what
     cudaSetDevice(b->be.device);
     b->be.sync();
     return b->batch->debug_dump((size_t) i, (size_t) lf_group, what, dst, cap);
+}
+// A consumer of the device-resident output: image i as a PAM file (P7, RGB_ALPHA), rows copied from
+// device memory without the stride padding (cudaMemcpy2D: device pitch -> tight host rows).
+EXPORT int j40b_batch_write_pam(j40b_batch *b, int i, const char *path) {
+    if (!b || !path || !b->decoded || i < 0 || i >= (int) b->batch->results.size() || b->batch->results[(size_t) i].err) return -1;
+    cudaSetDevice(b->be.device);
+    const ImageResult &r = b->batch->results[(size_t) i];
+    const size_t row = (size_t) r.width * 4;
+    std::vector<uint8_t> tight(row * (size_t) r.height);
+    b->be.sync();
+    if (!cuda_ok(cudaMemcpy2D(tight.data(), row, b->batch->device_pixels((size_t) i), (size_t) r.stride, row, (size_t) r.height, cudaMemcpyDeviceToHost))) return -1;
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return -1;
+    fprintf(fp, "P7\nWIDTH %d\nHEIGHT %d\nDEPTH 4\nMAXVAL 255\nTUPLTYPE RGB_ALPHA\nENDHDR\n", r.width, r.height);
+    const bool ok = fwrite(tight.data(), 1, tight.size(), fp) == tight.size();
+    return fclose(fp) == 0 && ok ? 0 : -1;
 }
 EXPORT float j40b_batch_last_decode_ms(const j40b_batch *b) { return b ? b->last_ms : 0.0f; }
 
@@ -666,7 +707,8 @@ static j40_err advance(j40__inner *inner) {
         j40b_batch_info(b, idx, &inner->width, &inner->height, &inner->stride);
         size_t total = (size_t) inner->stride * (size_t) inner->height;
         void *p = nullptr;
-        if (cuda_ok(cudaHostAlloc(&p, total ? total : 1, cudaHostAllocDefault))) inner->pixels_pinned = true;
+        // pinned memory pays for big frames only (cudaHostAlloc itself costs about a millisecond)
+        if (total >= (4u << 20) && cuda_ok(cudaHostAlloc(&p, total, cudaHostAllocDefault))) inner->pixels_pinned = true;
         else { cudaGetLastError(); p = malloc(total ? total : 1); }
         if (!p) err = ERR4("!mem");
         else {

@@ -199,6 +199,28 @@ J40B_HD inline bool lf_stage_header(BitReader &br, ErrSlot &es, const LfWork &w,
     return true;
 }
 
+// inverse transforms of the HF metadata image (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide;
+// none can involve the sharpness channel: its height never equals the block-info channel's 2 rows together with the
+// colour-correlation maps' height) and the varblock placement (j40.h:6585-6720)
+template <class Sync>
+J40B_HD inline void lf_place_tail(const LfWork &w, const ModImage &m, ErrSlot &es, const BitReader &br, const ModSmem &ms,
+                                  int lane, int nlanes, Sync sync) {
+    const DFrame &f = *w.f;
+    DLfGroup &g = *w.g;
+    for (int t = m.nb_transforms - 1; t >= 0; --t) {
+        ModImage one = m;
+        one.nb_transforms = 1;
+        one.tr[0] = m.tr[t];
+        inverse_transforms(one, lane, nlanes);
+        sync();
+    }
+    // the weighted predictor's shared-memory row and the reference-property rows behind it are free now: 8 words per
+    // row of cells serve as the occupancy bitmap of the placement (256 * 8 words; error row 256 * 5, property rows 256 * 2,
+    // sample rows 256 * 1.5 words follow each other in the warp's slice, see carve_warp_slice)
+    if (ms.rows && ms.cap >= 256) place_varblocks_warp(f, g, es, br, (uint32_t *) ms.wp, lane, nlanes, sync);
+    else if (lane == 0) place_varblocks(f, g, es, br);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The two serial stages of an LF group, one *channel* and one decoder class per kernel (modular_channel_prep / _run in
 // j40b_modular.h): stage 0 = the LF image (3 channels, j40.h:6739-6757), stage 1 = the HF metadata image (4 channels)
@@ -208,12 +230,17 @@ J40B_HD inline bool lf_stage_header(BitReader &br, ErrSlot &es, const LfWork &w,
 // counters) and the modular image header through the group's scratch record. Why: a kernel holding every variant
 // needs 168 / 236 registers per thread, the class kernels 64 ... 128, and the register file the long-lived serial
 // warps occupy is what keeps tile and coefficient blocks of other batches off the SMs ("what bounds a step").
+// `split` (multi-section frames): the varblock placement does not wait for the sharpness channel -- 65 536 samples per
+// big LF group that j40 never uses (j40.h:6769-6772) -- but follows the block-info channel; the executor decodes the
+// sharpness channel on a side stream next to the LLF / coefficient / tile stages. Errors keep the reference's order:
+// whatever the sharpness decode raises (running out of data included) precedes a placement error.
 template <int K, class Sync>
 J40B_HD inline void lf_chan_body(const LfWork &w, int stage, int c, WarpScratch &ws, const ModSmem &ms, const int32_t *div24,
-                                 int lane, int nlanes, Sync sync) {
-    if (*w.err) return;
+                                 int lane, int nlanes, Sync sync, bool split = false) {
     const DFrame &f = *w.f;
     DLfGroup &g = *w.g;
+    const bool late = split && stage == 1 && c == 3; // the sharpness channel behind the placement
+    if (late ? !g.placed : *w.err != 0) return;
     const int n8 = g.width8 * g.height8;
     const int nch = stage == 0 ? 3 : 4;
     const int32_t sidx = stage == 0 ? 1 + g.idx : 1 + 2 * f.num_lf_groups + g.idx;
@@ -242,7 +269,7 @@ J40B_HD inline void lf_chan_body(const LfWork &w, int stage, int c, WarpScratch 
             }
         } else {
             const int32_t nvb = (int32_t) br.u(ceil_lg32((uint32_t) n8)) + 1;
-            if (lane == 0) g.nb_varblocks = nvb;
+            if (lane == 0) { g.nb_varblocks = nvb; g.placed = 0; }
             hf_meta_channels(g, nvb, m);
         }
         go = lf_stage_header(br, es, w, stage, m, tree, spec_off, uses_wp, lane == 0);
@@ -272,6 +299,14 @@ J40B_HD inline void lf_chan_body(const LfWork &w, int stage, int c, WarpScratch 
             g.chan_ans = cs.ans_state;
             g.chan_copy[0] = cs.num_to_copy; g.chan_copy[1] = cs.copy_pos; g.chan_copy[2] = cs.num_decoded;
         }
+        if (!(split && stage == 1 && c == 2)) return;
+        // split mode: placement right behind the block-info channel
+        sync();
+        lf_place_tail(w, m, es, br, ms, lane, nlanes, sync);
+        if (lane == 0) {
+            g.placed = 1;
+            if (es.err) *w.err = es.err;
+        }
         return;
     }
     // ---- the stage's epilogue (last channel, or an error)
@@ -287,26 +322,13 @@ J40B_HD inline void lf_chan_body(const LfWork &w, int stage, int c, WarpScratch 
     }
     if (es.err) { if (lane == 0) *w.err = es.err; return; }
     sync();
-    // inverse transforms (an RCT over xfromy/bfromy/blockinfo is possible when their sizes coincide)
-    for (int t = m.nb_transforms - 1; t >= 0; --t) {
-        ModImage one = m;
-        one.nb_transforms = 1;
-        one.tr[0] = m.tr[t];
-        inverse_transforms(one, lane, nlanes);
-        sync();
-    }
-    // the weighted predictor's shared-memory row and the reference-property rows behind it are free now: 8 words per
-    // row of cells serve as the occupancy bitmap of the placement (256 * 8 words; error row 256 * 5, property rows 256 * 2,
-    // sample rows 256 * 1.5 words follow each other in the warp's slice, see carve_warp_slice)
-    if (ms.rows && ms.cap >= 256) place_varblocks_warp(f, g, es, br, (uint32_t *) ms.wp, lane, nlanes, sync);
-    else if (lane == 0) place_varblocks(f, g, es, br);
+    if (!late) lf_place_tail(w, m, es, br, ms, lane, nlanes, sync);
     if (lane == 0) {
-        if (!es.err) {
-            // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
-            // on the per-section state and never copied back, j40.h:7791-7798); running short is still an error
-            if (br.overrun()) es.set_raw(E_SHRT);
-            g.end_bit = br.bits_consumed();
-        }
+        // multi-section frames: the reference drops pad0/excs found at a section's end (they are raised
+        // on the per-section state and never copied back, j40.h:7791-7798); running short is still an error
+        if (late) { if (br.overrun()) *w.err = E_SHRT; }   // (precedes whatever the placement found)
+        else if (!es.err && br.overrun()) es.set_raw(E_SHRT);
+        if (!es.err) g.end_bit = br.bits_consumed();
         if (es.err) *w.err = es.err;
     }
 }

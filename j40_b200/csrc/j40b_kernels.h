@@ -59,7 +59,7 @@ struct WarpAny { __device__ bool operator()(bool p) const { return __any_sync(0x
 bool kl_init_lf();   // raises the dynamic shared-memory limits of the kernels in that translation unit
 bool kl_init_back();
 bool kl_init_mod();
-void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap); // 5 class kernels x channels; launches: 15 / 20
+void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap, int c0, int c1, bool split); // 5 class kernels per channel
 void kl_lf_lane(int stage, cudaStream_t stream, const LfWork *w, int n);
 void kl_lf_place(int n, cudaStream_t stream, const LfWork *w);
 void kl_lf_post(int n, cudaStream_t stream, const LfWork *w);

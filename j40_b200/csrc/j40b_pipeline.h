@@ -539,7 +539,10 @@ public:
         if (!dev) return;
         uint8_t *dwork = dev + upload_bytes;
         if (zero_bytes) be.dev_memset(dwork + zero_off, 0, zero_bytes);
-        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob);
+        // multi-section frames only: the pass groups of a single-section frame start where its LF group ends
+        bool split = true;
+        for (size_t k = 0; k < plans.size(); ++k) if (!plans[k]->err && !plans[k]->df.is_modular && plans[k]->single_section) split = false;
+        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob, split);
         if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
         for (size_t k = 0; k < plans.size(); ++k) { // extra channels behind the coefficients (errors only; planes are scratch)
             const Img &im = img[k];
@@ -566,6 +569,7 @@ public:
             be.launch_render((const RenderWork *) (dev + im.render_off), p.df.width, p.df.height);
         }
         if (any_mod) be.mark_modular(1);
+        be.join_side(); // (the LF groups' sharpness channels, if they ran on a side stream)
     }
 
     // ---- step 4: errors (synchronises)

@@ -125,6 +125,7 @@ struct DLfGroup {
     uint32_t *vb_tok;     // [num_passes][3][h8*w8][2] {first token, count}, written by the pass-group kernel (zeroed before)
     // hand-over between the LF kernels (decode LF image -> post-process -> decode HF metadata -> LLF)
     uint64_t mid_bit;     // bit position after the LF image
+    int32_t placed;       // stage 1: channels 0-2 decoded and the varblocks placed (by the kernel that ends channel 2, `split` mode)
     // hand-over between the per-channel kernels of a stage (lf_chan_body): where the next channel starts
     uint64_t chan_bit;
     uint32_t chan_ans;

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256, J40B_TILE_MINB) k_back_tile(const BackWor
     extern __shared__ __align__(16) float tile_coef[];
     __shared__ TileShared ts;
     ts.phase = phase;
+    ts.tables_staged = 0;
     back_tile_body(items[blockIdx.x], (int) (blockIdx.y & 3), (int) (blockIdx.y >> 2), tile_coef, ts, (int) threadIdx.x, (int) blockDim.x, BlockSync());
 }
 
@@ -44,7 +45,33 @@ __global__ void __launch_bounds__(256, J40B_TILE_MINB) k_back_tile(const BackWor
 __global__ void __launch_bounds__(256, J40B_TILE_MINB) k_back_tile_persistent(const BackWork *items, int ntiles, unsigned long long *phase) {
     extern __shared__ __align__(16) float tile_coef[];
     __shared__ TileShared ts;
+    __shared__ __align__(8) uint64_t bar;
     ts.phase = phase;
+    // the sRGB threshold table and start LUT (the batch's shared tables, 5 KB) once per block: two bulk asynchronous copies
+    // completing on one mbarrier, instead of a cooperative copy loop per tile
+    if (threadIdx.x == 0) {
+        const DFrame &f0 = *items[0].f;
+        const uint32_t bar_s = (uint32_t) __cvta_generic_to_shared(&bar);
+        const uint32_t thr_s = (uint32_t) __cvta_generic_to_shared(ts.thr), lut_s = (uint32_t) __cvta_generic_to_shared(ts.lut);
+        const uint32_t thr_bytes = sizeof(ts.thr), lut_bytes = sizeof(ts.lut);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_s), "r"(thr_bytes + lut_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(thr_s), "l"(f0.srgb_thr), "r"(thr_bytes), "r"(bar_s) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(lut_s), "l"(f0.srgb_lut), "r"(lut_bytes), "r"(bar_s) : "memory");
+        ts.tables_staged = 1;
+    }
+    __syncthreads();
+    {
+        const uint32_t bar_s = (uint32_t) __cvta_generic_to_shared(&bar);
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar_s) : "memory");
+        }
+    }
     for (int t = (int) blockIdx.x; t < ntiles; t += (int) gridDim.x) {
         __syncthreads(); // the previous tile's readers of the shared buffers are done
         const int ti = t & 15;

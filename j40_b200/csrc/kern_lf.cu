@@ -6,19 +6,21 @@ namespace j40b {
 
 // the weighted predictor's error row is part of the slice for the classes that use it, and for the kernel that ends stage
 // 1 (the varblock placement's occupancy bitmap lies over error, property and sample rows)
-__host__ __device__ inline bool lf_chan_needs_wp_row(int K, int stage, int c) { return K == MC_WP || K == MC_REST || (stage == 1 && c == 3); }
+__host__ __device__ inline bool lf_chan_needs_wp_row(int K, int stage, int c, bool split) {
+    return K == MC_WP || K == MC_REST || (stage == 1 && c == (split ? 2 : 3));
+}
 
 // One channel of one serial stage of the LF groups, one decoder class per kernel (lf_chan_body in j40b_exec.h): one warp
 // per LF group; `cap`: width of the shared-memory rows. The work list is ordered largest group first.
 template <int K>
-__global__ void __launch_bounds__(32) k_lf_chan(const LfWork *items, int stage, int c, int cap) {
+__global__ void __launch_bounds__(32) k_lf_chan(const LfWork *items, int stage, int c, int cap, int split) {
     __shared__ int32_t div24[64];
     extern __shared__ __align__(16) uint8_t smem[];
     fill_div24(div24, (int) threadIdx.x, 32);
     __syncwarp();
     WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem, cap, ws, lf_chan_needs_wp_row(K, stage, c));
-    lf_chan_body<K>(items[blockIdx.x], stage, c, *ws, ms, div24, (int) threadIdx.x, 32, WarpSync());
+    ModSmem ms = carve_warp_slice(smem, cap, ws, lf_chan_needs_wp_row(K, stage, c, split != 0));
+    lf_chan_body<K>(items[blockIdx.x], stage, c, *ws, ms, div24, (int) threadIdx.x, 32, WarpSync(), split != 0);
 }
 
 // Lane-per-stream variant (j40b_modlane.h): every thread owns one LF group; 32 * LANE_WARPS work items per block.
@@ -82,14 +84,15 @@ bool kl_init_lf() {
            cudaFuncSetAttribute(k_lf_chan<MC_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
            cudaFuncSetAttribute(k_lf_chan<MC_REST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
 }
-// all channels of a stage (0: LF image, 1: HF metadata + placement): per channel the five class kernels in a row
-void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap) {
-    for (int c = 0; c < (stage == 0 ? 3 : 4); ++c) {
-        k_lf_chan<MC_WP><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WP, stage, c)), stream>>>(w, stage, c, cap);
-        k_lf_chan<MC_GRAD><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GRAD, stage, c)), stream>>>(w, stage, c, cap);
-        k_lf_chan<MC_WIDE><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WIDE, stage, c)), stream>>>(w, stage, c, cap);
-        k_lf_chan<MC_GEN><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GEN, stage, c)), stream>>>(w, stage, c, cap);
-        k_lf_chan<MC_REST><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_REST, stage, c)), stream>>>(w, stage, c, cap);
+// channels [c0, c1) of a stage (0: LF image, 1: HF metadata + placement): per channel the five class kernels in a row
+void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap, int c0, int c1, bool split) {
+    const int sp = split ? 1 : 0;
+    for (int c = c0; c < c1; ++c) {
+        k_lf_chan<MC_WP><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WP, stage, c, split)), stream>>>(w, stage, c, cap, sp);
+        k_lf_chan<MC_GRAD><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GRAD, stage, c, split)), stream>>>(w, stage, c, cap, sp);
+        k_lf_chan<MC_WIDE><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WIDE, stage, c, split)), stream>>>(w, stage, c, cap, sp);
+        k_lf_chan<MC_GEN><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GEN, stage, c, split)), stream>>>(w, stage, c, cap, sp);
+        k_lf_chan<MC_REST><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_REST, stage, c, split)), stream>>>(w, stage, c, cap, sp);
     }
 }
 void kl_lf_lane(int stage, cudaStream_t stream, const LfWork *w, int n) {

@@ -39,7 +39,20 @@ struct HostEmuBackend {
     static int row_cap(int dflt) { const char *e = getenv("HOSTEMU_ROW_CAP"); return e ? atoi(e) : dflt; }
     // HOSTEMU_LANE=1: the lane-per-stream decoders (j40b_modlane.h) instead of the warp-per-stream ones
     static bool lane_mode() { const char *e = getenv("HOSTEMU_LANE"); return e && atoi(e) != 0; }
-    void launch_lf(const LfWork *w, int n, size_t) {
+    // like the device in split mode: the sharpness channel is decoded behind everything else (join_side)
+    const LfWork *pending_w = nullptr;
+    int pending_n = 0;
+    void join_side() {
+        if (!pending_w) return;
+        WarpMem wm(row_cap(256));
+        for (int i = 0; i < pending_n; ++i) lf_chan_body<MC_WP>(pending_w[i], 1, 3, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), true);
+        for (int i = 0; i < pending_n; ++i) lf_chan_body<MC_GRAD>(pending_w[i], 1, 3, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), true);
+        for (int i = 0; i < pending_n; ++i) lf_chan_body<MC_WIDE>(pending_w[i], 1, 3, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), true);
+        for (int i = 0; i < pending_n; ++i) lf_chan_body<MC_GEN>(pending_w[i], 1, 3, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), true);
+        for (int i = 0; i < pending_n; ++i) lf_chan_body<MC_REST>(pending_w[i], 1, 3, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), true);
+        pending_w = nullptr;
+    }
+    void launch_lf(const LfWork *w, int n, size_t, bool split) {
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(256));
         if (lane_mode()) {
@@ -65,18 +78,20 @@ struct HostEmuBackend {
             return;
         }
         // like the device: per stage and channel the four class kernels in a row, every LF group in each
-        auto stage = [&](int st) {
-            for (int c = 0; c < (st == 0 ? 3 : 4); ++c) {
-                for (int i = 0; i < n; ++i) lf_chan_body<MC_WP>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
-                for (int i = 0; i < n; ++i) lf_chan_body<MC_GRAD>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
-                for (int i = 0; i < n; ++i) lf_chan_body<MC_WIDE>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
-                for (int i = 0; i < n; ++i) lf_chan_body<MC_GEN>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
-                for (int i = 0; i < n; ++i) lf_chan_body<MC_REST>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync());
+        if (getenv("HOSTEMU_NO_SPLIT")) split = false;
+        auto stage = [&](int st, int c0, int c1, bool sp) {
+            for (int c = c0; c < c1; ++c) {
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_WP>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), sp);
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_GRAD>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), sp);
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_WIDE>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), sp);
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_GEN>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), sp);
+                for (int i = 0; i < n; ++i) lf_chan_body<MC_REST>(w[i], st, c, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), sp);
             }
         };
-        stage(0);
+        stage(0, 0, 3, false);
         for (int i = 0; i < n; ++i) lf_post_body(w[i], 0, 1, NoSync());
-        stage(1);
+        if (split) { stage(1, 0, 3, true); pending_w = w; pending_n = n; }
+        else stage(1, 0, 4, false);
         for (int i = 0; i < n; ++i) lf_llf_body(w[i], 0, 1, NoSync());
     }
     void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t) {
@@ -98,7 +113,7 @@ struct HostEmuBackend {
     void launch_back(const BackWork *w, int n) {
         std::vector<float> coef(3 * TILE_CH), big(4 * 65536);
         for (int i = 0; i < n; ++i) {
-            for (int t = 0; t < 16; ++t) { TileShared ts; back_tile_body(w[i], t & 3, t >> 2, coef.data(), ts, 0, 1, NoSync()); }
+            for (int t = 0; t < 16; ++t) { TileShared ts; ts.tables_staged = 0; back_tile_body(w[i], t & 3, t >> 2, coef.data(), ts, 0, 1, NoSync()); }
             BackWork bw = w[i];
             bw.big_scratch = big.data();
             back_generic_body(bw, 0, 1, NoSync());

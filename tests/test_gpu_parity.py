@@ -324,3 +324,21 @@ def test_out_of_range_samples_wrap_like_the_reference(oracle, gen, case):
     b, eb, _, sb = J.decode(data)
     assert ea == eb == "" and sa == sb
     assert int((a != b).any(axis=-1).sum()) <= 2
+
+
+def test_pam_writer_consumes_device_output(oracle, gen, tmp_path):
+    """j40b_batch_write_pam: device-resident pixels to a PAM file without the stride padding"""
+    data = streams.make(gen, "vardct", 264, 136, 90, dict(mix=1, tree=1))
+    b = J.Batch(0)
+    b.add(data)
+    b.upload()
+    b.decode()
+    assert b.wait() == 0
+    path = tmp_path / "a.pam"
+    assert b.write_pam(0, str(path)) == 0
+    raw = path.read_bytes()
+    head, body = raw.split(b"ENDHDR\n", 1)
+    assert head == b"P7\nWIDTH 264\nHEIGHT 136\nDEPTH 4\nMAXVAL 255\nTUPLTYPE RGB_ALPHA\n"
+    a, _, _, _ = oracle.decode(data)
+    assert body == a.tobytes()
+    b.close()

@@ -225,3 +225,20 @@ def test_local_tree_with_lz77_needs_a_window(oracle, emu):
     a, ea, _, _ = oracle.decode(data)
     b, eb, _ = emu.decode(data)
     assert ea == eb != "" and a is None and b is None
+
+
+@pytest.mark.parametrize("case", streams.VARDCT_CASES[1::4], ids=[c[0] for c in streams.VARDCT_CASES[1::4]])
+def test_without_the_sharpness_split(oracle, emu, gen, case, monkeypatch):
+    """multi-section frames decode the sharpness channel of the LF groups behind everything else (the emulator runs it
+    last, like the side stream of the device); HOSTEMU_NO_SPLIT keeps it on the critical path (what single-section
+    frames always do). Both orders must give the reference's result -- and the reference's error on corrupt input."""
+    monkeypatch.setenv("HOSTEMU_NO_SPLIT", "1")
+    _, w, h, seed, opts = case
+    data = streams.make(gen, "vardct", w, h, seed, opts)
+    _cmp(oracle, emu, data)
+    for name, bad in streams.corruptions(data, 1, 12):
+        a, ea, _, _ = oracle.decode(bad)
+        b, eb, _ = emu.decode(bad)
+        assert ea == eb, (name, ea, eb)
+        if ea == "":
+            assert np.array_equal(a, b), name
