@@ -323,10 +323,11 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             // tokens of a varblock were written in decoding order: Y, X, B
             int c = 1;
             if (j >= (int) t.cnt[1]) { j -= t.cnt[1]; c = 0; if (j >= (int) t.cnt[0]) { j -= t.cnt[0]; c = 2; } }
-            const DToken tk = w.tokens[t.first[c] + (uint32_t) j];
-            const int32_t pos = f.order[pass][t.order_idx][c][tk.pos]; // the token carries the scan index
+            const DToken *tk = w.tokens + t.first[c] + (uint32_t) j;
+            if (tk->is_ext()) continue; // second or third word of a wide value
+            const int32_t pos = f.order[pass][t.order_idx][c][tk->pos()]; // the token carries the scan index
             const int p = t.chunk_off + tile_swz(pos, t.mlog);
-            float q = (float) tk.val;
+            float q = (float) token_value(tk);
             if (npass > 1) {
                 // several passes: their values add up first (j40.h:6989; integers, exact in any order); dequantised below
                 tile_add(c == 0 ? &coefx[p] : c == 1 ? &coefy[p] : &coefb[p], q);

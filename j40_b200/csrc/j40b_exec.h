@@ -724,9 +724,10 @@ J40B_HD inline void dump_coeffs_body(const DumpWork &w, int voff, int tid, int n
             const uint32_t *slot = g.vb_tok + (((size_t) pass * 3 + c) * n8 + voff) * 2;
             const int32_t *order = f.order[pass][d.order_idx][c];
             for (uint32_t k = tid; k < slot[1]; k += nth) {
-                const DToken t = w.tokens[slot[0] + k];
-                const int32_t pos = order[t.pos];
-                coef[c][pos] = J40B_FADD(coef[c][pos], (float) t.val);
+                const DToken *t = w.tokens + slot[0] + k;
+                if (t->is_ext()) continue;
+                const int32_t pos = order[t->pos()];
+                coef[c][pos] = J40B_FADD(coef[c][pos], (float) token_value(t));
             }
         }
         sync();

@@ -178,11 +178,14 @@ struct HfLane {
         const int32_t v = symbol(ctx);
         if (es.err) { done = true; return; }
         if (v) {
-            if (tok >= tok_end) { es.set_raw(E_TOKV); done = true; return; }
-            DToken t;
-            t.pos = (uint32_t) i;
-            t.val = unpack_signed(v);
-            tokens[tok++] = t;
+            const int32_t val = unpack_signed(v);
+            const bool wide = token_needs_wide(val);
+            if (tok + (wide ? 3u : 1u) > tok_end) { es.set_raw(E_TOKV); done = true; return; }
+            tokens[tok++] = DToken::make((uint32_t) i, wide ? TOKEN_WIDE : val);
+            if (wide) {
+                tokens[tok++] = DToken::make(0, val & 0xffff);
+                tokens[tok++] = DToken::make(0, (int32_t) ((uint32_t) val >> 16));
+            }
         }
         prev = v != 0;
         nz -= prev;

@@ -158,7 +158,8 @@ public:
                     int grow = (int) (g / (size_t) d.gcolumns), gcol = (int) (g % (size_t) d.gcolumns);
                     gb.gw = std::min(d.width, (gcol + 1) * 256) - gcol * 256;
                     gb.gh = std::min(d.height, (grow + 1) * 256) - grow * 256;
-                    size_t full = (size_t) 3 * 64 * ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8);
+                    // words of the token list: one per non-zero coefficient, three for a value outside 16 bits
+                    size_t full = (size_t) 3 * 3 * 64 * ceil_div(gb.gw, 8) * ceil_div(gb.gh, 8);
                     size_t cap = full_token_cap ? full : std::min(full, (size_t) p.pg_sec[pg].size * 3 + 256);
                     if (!full_token_cap && token_squeeze) cap = std::min<size_t>(cap, 64); // tests: force the overflow + retry path
                     gb.tok_first = tok_total; gb.tok_cap = cap;

@@ -138,7 +138,26 @@ struct DLfGroup {
     ModTransform tr1[MOD_MAX_TRANSFORMS], tr2[MOD_MAX_TRANSFORMS];
 };
 
-struct DToken { uint32_t pos; int32_t val; }; // pos = index in the scan order (the back-end applies the order table)
+// One non-zero HF coefficient as the entropy kernel leaves it for the back end: 4 bytes, the index in the scan order
+// (< 65536 for every transform; the back end applies the order table) and the value. A value outside -32767..32767
+// (corrupt or crafted streams only) takes three words: {pos, -32768}, then {0, low half}, {0, high half}; position 0 is
+// a varblock's first LLF coefficient and never coded in an HF section, so the two extension words identify themselves
+// to a reader that visits the list one word per thread.
+struct DToken {
+    uint32_t w;
+    J40B_HD J40B_INLINE uint32_t pos() const { return w & 0xffffu; }
+    J40B_HD J40B_INLINE int32_t val() const { return (int32_t) w >> 16; }
+    J40B_HD J40B_INLINE bool is_ext() const { return (w & 0xffffu) == 0; }
+    J40B_HD static J40B_INLINE DToken make(uint32_t pos, int32_t val16) { DToken t; t.w = pos | (uint32_t) val16 << 16; return t; }
+};
+constexpr int32_t TOKEN_WIDE = -32768;
+J40B_HD J40B_INLINE bool token_needs_wide(int32_t v) { return (uint32_t) (v + 32767) > 65534u; }
+// value of the token at t[0]; t[1], t[2] are read only behind the wide marker
+J40B_HD J40B_INLINE int32_t token_value(const DToken *t) {
+    const int32_t v = t[0].val();
+    if (v != TOKEN_WIDE) return v;
+    return (int32_t) ((t[1].w >> 16) | (t[2].w & 0xffff0000u));
+}
 
 struct HfVb;
 // one record per (pass, group); the records of pass p follow those of pass p - 1 (num_groups apart)
@@ -817,9 +836,10 @@ J40B_HD inline void varblock_to_pixels(const DFrame &f, const uint8_t *arena, co
             // positions within one varblock-channel and pass are distinct (a scan order is a permutation); the
             // passes add up (j40.h:6989): integer-valued floats, exact in any order
             for (uint32_t k = tid; k < cnt; k += nth) {
-                DToken t = tokens[first + k];
-                const int32_t pos = order[t.pos];
-                coef[c][pos] = J40B_FADD(coef[c][pos], (float) t.val);
+                const DToken *t = tokens + first + k;
+                if (t->is_ext()) continue;
+                const int32_t pos = order[t->pos()];
+                coef[c][pos] = J40B_FADD(coef[c][pos], (float) token_value(t));
             }
         }
         sync();

@@ -55,6 +55,9 @@ VARDCT_CASES = [
     ("lf_local_tree_hf_meta_prefix", 520, 392, 42, dict(mix=1, tree=1, lf_local_tree=2, ans=0)),
     ("lf_local_tree_both_two_lf_groups", 2100, 300, 43, dict(mix=1, tree=2, lf_local_tree=7, hfmul=6)),
     ("lf_local_tree_single_group", 200, 100, 44, dict(mix=1, tree=1, lf_local_tree=3, lz77=1)),
+    # coefficient values outside 16 bits (three-word form of the token list), cancelling over the passes
+    ("wide_tokens_two_passes", 520, 392, 45, dict(mix=1, tree=1, passes=2, coef_spike=40000)),
+    ("wide_tokens_three_passes_all_transforms", 300, 264, 46, dict(mix=2, tree=1, passes=3, coef_spike=5000000)),
 ]
 
 # samples far outside [0, 1]: a RAW dequantisation matrix whose written denominator is `raw_dq_lie` times the one the
@@ -63,6 +66,9 @@ WRAP_CASES = [
     ("int16_wrap_x8", 136, 72, 5, dict(mix=0, tree=1, raw_dq=1, raw_dq_lie=8, hfmul=4)),
     ("int16_wrap_x512", 136, 72, 5, dict(mix=0, tree=1, raw_dq=1, raw_dq_lie=512, hfmul=4)),
     ("int16_wrap_x16384_mixed", 264, 136, 6, dict(mix=1, tree=1, raw_dq=0x11, raw_dq_lie=16384, hfmul=4)),
+    # ... and single-pass coefficient values outside 16 bits (+-70000, +-32767, +-32768) in a few varblocks
+    ("wide_tokens_single_pass", 264, 136, 7, dict(mix=1, tree=1, coef_spike=70000)),
+    ("wide_tokens_single_pass_dct64", 256, 256, 8, dict(force=18, tree=1, hfmul=12, coef_spike=1 << 21)),
 ]
 
 MODULAR_CASES = [

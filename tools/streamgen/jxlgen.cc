@@ -56,7 +56,7 @@ __attribute__((visibility("default"))) int jxlgen_vardct(const char *params, con
         GETI(custom_orders, "orders"); GETI(num_hf_presets, "presets"); GETI(explicit_frame_header, "explicit_fh");
         GETI(container, "container"); GETI(container_jxlp, "jxlp"); GETI(permuted_toc, "permuted"); GETI(lz77_coeffs, "lz77");
         GETI(quant_deadzone, "deadzone"); GETI(force_dctsel, "force"); GETI(alpha, "alpha"); GETI(raw_dq, "raw_dq");
-        GETI(passes, "passes"); GETI(raw_dq_lie, "raw_dq_lie"); GETI(lf_local_tree, "lf_local_tree"); GETI(big_take, "big_take"); GETI(big_thr, "big_thr");
+        GETI(passes, "passes"); GETI(coef_spike, "coef_spike"); GETI(raw_dq_lie, "raw_dq_lie"); GETI(lf_local_tree, "lf_local_tree"); GETI(big_take, "big_take"); GETI(big_thr, "big_thr");
         ImageRGB8 im;
         if (rgb) { im.w = p.width; im.h = p.height; im.px.assign(rgb, rgb + (size_t) p.width * (size_t) p.height * 3); }
         else im = synth_photo(p.width, p.height, p.seed);

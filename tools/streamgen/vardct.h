@@ -58,6 +58,9 @@ struct VarDCTParams {
                                // own (a copy of the global one, stored with the sub-bitstream, j40.h:3827-3835); bit 2: odd LF groups only
     float raw_dq_lie = 1.0f;   // RAW matrices: the denominator written is this many times the one used for quantising, so that the
                                // decoder's coefficients come out that much larger (out-of-range samples; tests of the int16 wrap, j40.h:7234)
+    int coef_spike = 0;        // != 0: quantised values outside 16 bits (the decoder's wide token form). One pass: a few varblocks get
+                               // +-spike and the 16-bit boundary values at their last coefficients; several passes: every 7th
+                               // position carries +-spike in pass 0 and its opposite in pass 1 (the sum stays small)
     int passes = 1;            // > 1: the quantised coefficients are split over this many passes (the decoder adds them up);
                                // pass p has its own code spec and, with custom_orders, its own coefficient orders
     float big_take = 0.75f;    // transform_mix 1: probability of taking a larger transform where the content allows it
@@ -690,6 +693,11 @@ private:
                 }
             }
         }
+        if (P.coef_spike && P.passes == 1 && (vb.x8 * 5 + vb.y8 * 3) % 23 == 0) {
+            const int32_t sp[6] = {P.coef_spike, -P.coef_spike, 32767, -32767, 32768, -32768};
+            for (int c = 0; c < 3; ++c) for (int k = 0; k < 2; ++k)
+                vb.q[c][(size_t) (size - 1 - k * 3 - c)] = sp[(vb.x8 + vb.y8 + c * 2 + k) % 6];
+        }
     }
 
     // --------------------------------------------------------------------------------------
@@ -714,6 +722,10 @@ private:
     int32_t pass_share(int32_t v, int i, int size, int pass) const {
         const int n = P.passes;
         if (n == 1) return v;
+        if (P.coef_spike && i % 7 == 3) {
+            const int32_t sp = i % 14 == 3 ? P.coef_spike : -P.coef_spike;
+            return pass == 0 ? v + sp : pass == 1 ? -sp : 0;
+        }
         if (i < size / 8) { // low frequencies: passes 0 and 1 share the value
             if (pass == 0) return v / 2;
             if (pass == 1) return v - v / 2;
