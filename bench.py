@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=0, help="weak scaling: distinct streams per rank, cycled to fill the batch")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
+    ap.add_argument("--debug-skip", type=int, default=0, help="measurement aid, NOT a bench value: leave stages out of the pipelined "
+                    "region (bit 0 tile kernel, bit 1 coefficient kernel, bit 2 LF-group kernels) to see what each costs the others")
     ap.add_argument("--streams", type=int, default=12, help="batch objects (CUDA streams) the timed steps are pipelined over")
     ap.add_argument("--e2e-sets", type=int, default=2, help="groups of `streams` batch objects the end-to-end loop alternates between")
     ap.add_argument("--e2e-mode", default="rolling", choices=["waves", "rolling"], help="waves: a group of objects is resubmitted when all of it has "
@@ -349,6 +351,9 @@ def main():
     # timed region: K steps pipelined over the M batch objects (one CUDA stream each), so that the latency-bound
     # LF-group kernels of one step overlap the HF / back kernels of its neighbours. All K steps run inside the
     # region; device time is taken with CUDA events on stream 0 after joining every stream.
+    if args.debug_skip:
+        os.environ["J40B_DEBUG_SKIP"] = str(args.debug_skip)
+        args.skip_e2e = args.skip_latency = True
     for _ in range(args.warmup):
         for bm in batches:
             bm.decode()
@@ -374,6 +379,7 @@ def main():
     for bm in batches[:min(M, args.steps * C_)]:      # stage times of the last decode of each object, as stretched by co-running
         for n, v in bm.kernel_ms().items():
             stage_sum[n] = stage_sum.get(n, 0.0) + v
+    os.environ.pop("J40B_DEBUG_SKIP", None)
     if os.environ.get("J40B_TIMELINE"):
         for k, bm in enumerate(batches):
             print("timeline batch %d: " % k + " ".join("%s=%.1f" % (n, bm.event_ms(b, i)) for n, i in
@@ -586,6 +592,7 @@ def main():
                    "parity_gate": "every distinct frame of every batch object compared with the reference before timing, and again as it arrives in host memory in the end-to-end loop",
                    "parallelism": f"batch-sharded x{world}, no collective"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "latency": latency, "gpu_launches": int(launches),
+        **({"INVALID_debug_skip": args.debug_skip} if args.debug_skip else {}),
         "clocks": sampler.result(), "device_bytes": int(dev_bytes),
     }
     print(json.dumps(line))

@@ -86,6 +86,8 @@ struct TileVb {
     uint16_t cnt[3];     // number of tokens of channel c
 };
 
+struct alignas(16) TilePx4 { uint32_t v[4]; };
+
 struct TileShared {
     unsigned long long *phase; // diagnostic builds: global per-phase cycle counters
     int32_t nvb, nchunks;
@@ -98,6 +100,13 @@ struct TileShared {
     // same code: pstart[pass][type][v] = tasks of that type in varblocks before v, [64] = their total.
     // type = 2 * (log2 N - 3) + ALONG_MINOR (see idct_swz)
     uint16_t pstart[2][8][65];
+    // ... and the inverse map: the types' task lists of a pass laid end to end in units of 8 tasks (a varblock contributes
+    // a multiple of 24), tmap[pass][tbase[pass][type] + (k >> 3)] = index into vb[] of task k of that type
+    uint8_t tmap[2][192];
+    uint16_t tbase[2][8];
+    int32_t tmap_used[2];
+    // flattened token list of pass 0: tokmap[m] = index into vb[] of the varblock that holds token 64 m
+    uint8_t tokmap[576];
     float kx_hf, kb_hf;     // chroma-from-luma factors of this tile (one 64x64 cell of the XFromY / BFromY maps)
     uint8_t cell_size64[64];
     uint8_t cover[64];      // tile cell -> index into vb[], 0xff = not handled here (generic path / outside)
@@ -136,6 +145,19 @@ J40B_HD inline void tile_type_scan(TileShared &ts, int nvb, int tid, int nth) {
                 carry += __shfl_sync(0xffffffffu, x, 31);
             }
             if (lane == 0) ts.pstart[pass][type][64] = (uint16_t) carry;
+            if (carry == 0) continue;
+            int tb = 0;
+            if (lane == 0) {
+                tb = atomicAdd(&ts.tmap_used[pass], carry >> 3);
+                ts.tbase[pass][type] = (uint16_t) tb;
+            }
+            tb = __shfl_sync(0xffffffffu, tb, 0);
+            __syncwarp();
+            for (int v = lane; v < nvb; v += 32) {
+                const int cnt = tile_task_count(ts.vb[v], pass, type) >> 3;
+                uint8_t *m = ts.tmap[pass] + tb + (ts.pstart[pass][type][v] >> 3);
+                for (int e = 0; e < cnt; ++e) m[e] = (uint8_t) v;
+            }
         }
         return;
     }
@@ -148,17 +170,32 @@ J40B_HD inline void tile_type_scan(TileShared &ts, int nvb, int tid, int nth) {
             if (v < nvb) sum += tile_task_count(ts.vb[v], pass, type);
         }
         ts.pstart[pass][type][64] = (uint16_t) sum;
+        if (sum == 0) continue;
+#if defined(__CUDA_ARCH__)
+        const int tb = atomicAdd(&ts.tmap_used[pass], sum >> 3);
+#else
+        const int tb = ts.tmap_used[pass];
+        ts.tmap_used[pass] += sum >> 3;
+#endif
+        ts.tbase[pass][type] = (uint16_t) tb;
+        for (int v = 0; v < nvb; ++v) {
+            const int cnt = tile_task_count(ts.vb[v], pass, type) >> 3;
+            uint8_t *m = ts.tmap[pass] + tb + (ts.pstart[pass][type][v] >> 3);
+            for (int e = 0; e < cnt; ++e) m[e] = (uint8_t) v;
+        }
     }
 }
 
 // all 1-D transforms of one type in one pass: task k -> (varblock, channel, transform number)
 template <int LOGN, bool MINOR>
 J40B_HD J40B_INLINE void tile_pass_type(float *coef, const TileShared &ts, int pass, int nvb, int tid, int nth) {
-    const uint16_t *start = ts.pstart[pass][2 * (LOGN - 3) + (MINOR ? 1 : 0)];
+    const int type = 2 * (LOGN - 3) + (MINOR ? 1 : 0);
+    const uint16_t *start = ts.pstart[pass][type];
     const int total = start[64];
+    if (total == 0) return;
+    const uint8_t *map = ts.tmap[pass] + ts.tbase[pass][type];
     for (int k = tid; k < total; k += nth) {
-        int lo = 0, hi = nvb - 1; // last varblock whose first task is <= k (varblocks of other types have none)
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int) start[mid] <= k) lo = mid; else hi = mid - 1; }
+        const int lo = map[k >> 3];
         const TileVb &t = ts.vb[lo];
         const int j = k - (int) start[lo];
         const int lcnt = pass == 0 ? t.log_rows : t.log_cols;
@@ -225,9 +262,10 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const int m64 = ((grp.gy8 >> 3) + ty) * g.width64 + (grp.gx8 >> 3) + tx;
         ts.kx_hf = J40B_FADD(f.base_corr_x, J40B_FMUL(f.inv_colour_factor, (float) g.xfromy[m64]));
         ts.kb_hf = J40B_FADD(f.base_corr_b, J40B_FMUL(f.inv_colour_factor, (float) g.bfromy[m64]));
+        ts.tmap_used[0] = ts.tmap_used[1] = 0;
     }
     if (!ts.tables_staged) {
-        for (int i = tid; i < 255; i += nth) ts.thr[i] = f.srgb_thr[i];
+        for (int i = tid; i < 256; i += nth) ts.thr[i] = f.srgb_thr[i];
         for (int i = tid; i < SRGB_LUT_BYTES / 4; i += nth) ((uint32_t *) ts.lut)[i] = ((const uint32_t *) f.srgb_lut)[i];
     }
     for (int i = tid; i < 3 * TILE_CH; i += nth) coef[i] = 0.0f;
@@ -268,6 +306,10 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
             t.m[2] = J40B_FMUL(t.m[1], f.b_qm_mult);
             for (int k = 0; k < 3; ++k) { t.first[k] = ts.cell_first[c][k]; t.cnt[k] = ts.cell_cnt[c][k]; }
             ts.tstart[rank] = (uint16_t) tstart;
+            {
+                const int tend = tstart + t.cnt[0] + t.cnt[1] + t.cnt[2];
+                for (int m = (tstart + 63) >> 6; (m << 6) < tend; ++m) ts.tokmap[m] = (uint8_t) rank;
+            }
             for (int k = 0; k < ts.cell_size64[c]; ++k) ts.chunk_vb[off64 + k] = (uint8_t) rank;
             for (int i = 0; i < (1 << (d.log_rows - 3)); ++i) for (int j = 0; j < (1 << (d.log_columns - 3)); ++j) {
                 ts.cover[((c >> 3) + i) * 8 + (c & 7) + j] = (uint8_t) rank;
@@ -315,8 +357,15 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const float qbn = f.quant_bias_num;
         const float kx_hf = ts.kx_hf, kb_hf = ts.kb_hf;
         const int total = ts.tstart[nvb];
+        const int nblk = (total + 63) >> 6;
         for (int k = tid; k < total; k += nth) {
+            // last varblock whose first token is <= k; pass 0 has a map of every 64th token to narrow the search with
             int lo = 0, hi = nvb - 1;
+            if (pass == 0) {
+                const int m = k >> 6;
+                lo = ts.tokmap[m];
+                if (m + 1 < nblk) hi = ts.tokmap[m + 1];
+            }
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int) ts.tstart[mid] <= k) lo = mid; else hi = mid - 1; }
             const TileVb &t = ts.vb[lo];
             int j = k - (int) ts.tstart[lo];
@@ -415,29 +464,39 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
     const float wrap_hi = f.srgb_wrap_hi;
     uint8_t *rgba = w.rgba;
     const size_t rgba_stride = (size_t) w.rgba_stride;
-    for (int pix = tid; pix < 4096; pix += nth) {
-        const int py = pix >> 6, px = pix & 63;
+    // four horizontally adjacent pixels per thread (they share a cell, hence a varblock): one 16-byte store
+    for (int q4 = tid; q4 < 1024; q4 += nth) {
+        const int py = q4 >> 4, px = (q4 & 15) * 4;
         const int X = gx0 + px, Y = gy0 + py;
         if (X >= fw || Y >= fh) continue;
         const uint8_t vi = ts.cover[(py >> 3) * 8 + (px >> 3)];
         if (vi == 0xff) continue;
         const TileVb &t = ts.vb[vi];
         const int ly = py - t.cy * 8, lx = px - t.cx * 8;
-        const int R = 1 << t.log_rows, C = 1 << t.log_cols;
         // special transforms and wide blocks end as [y][x]; square / tall DCT blocks as [x][y]
-        const int idx = t.chunk_off + tile_swz((t.special || t.log_cols > t.log_rows) ? ly * C + lx : lx * R + ly, t.mlog);
-        float sx = coefx[idx], sy = coefy[idx], sb = coefb[idx];
-        float p0 = J40B_FSUB(J40B_FADD(sy, sx), cb0), p1 = J40B_FSUB(J40B_FSUB(sy, sx), cb1), p2 = J40B_FSUB(sb, cb2);
-        float l0 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p0, p0), p0), ob0), itscale);
-        float l1 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p1, p1), p1), ob1), itscale);
-        float l2 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p2, p2), p2), ob2), itscale);
-        uint32_t out = 0xff000000u;
+        const bool rows = t.special || t.log_cols > t.log_rows;
+        const int i0 = rows ? (ly << t.log_cols) + lx : (lx << t.log_rows) + ly, di = rows ? 1 : 1 << t.log_rows;
+        const int chunk_off = t.chunk_off, mlog = t.mlog;
+        TilePx4 o;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v = J40B_FADD(J40B_FADD(J40B_FMUL(l0, om[c * 3 + 0]), J40B_FMUL(l1, om[c * 3 + 1])), J40B_FMUL(l2, om[c * 3 + 2]));
-            out |= (uint32_t) (srgb_needs_wrap(v, wrap_hi) ? srgb_u8_wrapped(v, 8) : srgb_u8_lut(ts.thr, ts.lut, v)) << (8 * c);
+        for (int e = 0; e < 4; ++e) {
+            const int idx = chunk_off + tile_swz(i0 + e * di, mlog);
+            float sx = coefx[idx], sy = coefy[idx], sb = coefb[idx];
+            float p0 = J40B_FSUB(J40B_FADD(sy, sx), cb0), p1 = J40B_FSUB(J40B_FSUB(sy, sx), cb1), p2 = J40B_FSUB(sb, cb2);
+            float l0 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p0, p0), p0), ob0), itscale);
+            float l1 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p1, p1), p1), ob1), itscale);
+            float l2 = J40B_FMUL(J40B_FADD(J40B_FMUL(J40B_FMUL(p2, p2), p2), ob2), itscale);
+            uint32_t out = 0xff000000u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = J40B_FADD(J40B_FADD(J40B_FMUL(l0, om[c * 3 + 0]), J40B_FMUL(l1, om[c * 3 + 1])), J40B_FMUL(l2, om[c * 3 + 2]));
+                out |= (uint32_t) (srgb_needs_wrap(v, wrap_hi) ? srgb_u8_wrapped(v, 8) : srgb_u8_lut(ts.thr, ts.lut, v)) << (8 * c);
+            }
+            o.v[e] = out;
         }
-        *(uint32_t *) (rgba + (size_t) Y * rgba_stride + (size_t) X * 4) = out;
+        uint8_t *dst = rgba + (size_t) Y * rgba_stride + (size_t) X * 4;
+        if (X + 3 < fw) *(TilePx4 *) dst = o; // 16-byte aligned: X is a multiple of 4, the stride one of 32
+        else for (int e = 0; X + e < fw; ++e) ((uint32_t *) dst)[e] = o.v[e];
     }
     J40B_PHASE(6);
 }

@@ -93,8 +93,13 @@ struct CudaBackend {
     void sync() { cudaStreamSynchronize(stream); }
     int lane_stride() const { return 32 * LANE_WARPS; } // work items per slot of the lane decoders' interleaved buffers
 
+    // J40B_DEBUG_SKIP (measurement aid, bench.py --debug-skip; results are wrong with it): bit 0 leaves out the tile kernel,
+    // bit 1 the coefficient kernel, bit 2 the LF-group stage kernels -- what each stage costs the others in a pipeline
+    static int debug_skip() { const char *e = getenv("J40B_DEBUG_SKIP"); return e ? atoi(e) : 0; }
+
     void launch_lf(const LfWork *w, int n, size_t, bool split_ok) {
         bool split = split_ok;
+        if (debug_skip() & 4) { for (int i : {0, 5, 6, 1}) cudaEventRecord(ev[i], stream); return; }
         // One stream per warp (SIMT-uniform decoder, j40b_modular.h; per channel and decoder class, lf_chan_body) or,
         // with J40B_LF_MODE=lane, one per lane (j40b_modlane.h): 1/20 of the issue slots and no shared memory, but 6-7
         // times the latency per stream (measured: LF image of 64 4K frames 70 ms against 490 ms), which a pipeline can
@@ -140,7 +145,7 @@ struct CudaBackend {
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
         const int per_block = HF_WARPS * lanes;
-        kl_hf_group((n + per_block - 1) / per_block, (size_t) spec_cap, stream, w, n, lanes, spec_cap);
+        if (!(debug_skip() & 2)) kl_hf_group((n + per_block - 1) / per_block, (size_t) spec_cap, stream, w, n, lanes, spec_cap);
         cudaEventRecord(ev[2], stream);
         ++launches;
     }
@@ -165,7 +170,7 @@ struct CudaBackend {
         if (tile_prio && big_pool && side) {
             kl_back_tile(n, side, w);
             cudaEventRecord(ev_side[1], side);
-        } else {
+        } else if (!(debug_skip() & 1)) {
             kl_back_tile(n, stream, w);
         }
         cudaEventRecord(ev[3], stream);

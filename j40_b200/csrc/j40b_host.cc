@@ -1531,6 +1531,7 @@ const GlobalTables &GlobalTables::get() {
         static const int8_t ORDER_LOG[13][2] = {{3, 3}, {3, 3}, {4, 4}, {5, 5}, {3, 4}, {3, 5}, {4, 5}, {6, 6}, {5, 6}, {7, 7}, {6, 7}, {8, 8}, {7, 8}};
         for (int i = 0; i < 13; ++i) t->order[i] = compute_natural_order(ORDER_LOG[i][0], ORDER_LOG[i][1]);
         compute_srgb_thresholds(8, t->srgb_thr);
+        t->srgb_thr[255] = NAN;
         { // smallest float whose encoded value (255 * sRGB(v) + 0.5, the expression of j40.h:7233-7234) reaches 32768
             uint32_t lo = 1, hi = 0x7f7fffffu;
             while (lo < hi) {
@@ -1547,8 +1548,8 @@ const GlobalTables &GlobalTables::get() {
             int n = 0;
             while (n < 255 && t->srgb_thr[n] <= (float) b / (float) SRGB_LUT_N) ++n;
             t->srgb_lut[b] = (uint8_t) n;
-            // srgb_u8_lut() takes at most two steps inside a bucket
-            if (b > 0 && n - t->srgb_lut[b - 1] > 2) { fprintf(stderr, "j40_b200: sRGB start table too coarse\n"); abort(); }
+            // srgb_u8_lut() takes one step inside a bucket
+            if (b > 0 && n - t->srgb_lut[b - 1] > 1) { fprintf(stderr, "j40_b200: sRGB start table too coarse\n"); abort(); }
         }
         g = t;
     });

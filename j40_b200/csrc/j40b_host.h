@@ -90,7 +90,7 @@ struct FramePlan {
 struct GlobalTables {
     std::vector<float> dq[17];        // [n][3]
     std::vector<int32_t> order[13];
-    float srgb_thr[255];
+    float srgb_thr[256]; // [255] = NaN: ends the search of srgb_u8_lut()
     float srgb_wrap_hi;     // smallest sample whose encoded value reaches 32768 (the reference's int16 cast wraps from there)
     uint8_t srgb_lut[4100]; // SRGB_LUT_BYTES
     static const GlobalTables &get();

@@ -81,7 +81,7 @@ public:
         size_t gt_dq[17], gt_order[13], gt_thr;
         for (int i = 0; i < 17; ++i) gt_dq[i] = up_alloc(gt.dq[i].size() * 4);
         for (int i = 0; i < 13; ++i) gt_order[i] = up_alloc(gt.order[i].size() * 4);
-        gt_thr = up_alloc(255 * 4);
+        gt_thr = up_alloc(256 * 4);
         size_t gt_lut = up_alloc(SRGB_LUT_BYTES);
         size_t work = 0;                    // device-only area cursor (follows the upload blob)
         auto wk_alloc = [&](size_t bytes) { size_t o = align_up(work, 256); work = o + bytes; return o; };
@@ -320,7 +320,7 @@ public:
         // ---- fill the staging blob with device addresses
         for (int i = 0; i < 17; ++i) memcpy(staging + gt_dq[i], gt.dq[i].data(), gt.dq[i].size() * 4);
         for (int i = 0; i < 13; ++i) memcpy(staging + gt_order[i], gt.order[i].data(), gt.order[i].size() * 4);
-        memcpy(staging + gt_thr, gt.srgb_thr, 255 * 4);
+        memcpy(staging + gt_thr, gt.srgb_thr, 256 * 4);
         memcpy(staging + gt_lut, gt.srgb_lut, SRGB_LUT_BYTES);
         LfWork *lfw = (LfWork *) (staging + lfw_off);
         HfWork *hfw = (HfWork *) (staging + hfw_off);

@@ -81,7 +81,7 @@ struct DFrame {
     // device pointers, filled in by the executor (shared library tables or per-image custom ones)
     const float *dq[17];             // float[n][3] per parameter set
     const int32_t *order[MAX_PASSES][13][3]; // int32_t[size] per pass, order and channel
-    const float *srgb_thr;           // float[255]: smallest v whose 8-bit output is >= k+1
+    const float *srgb_thr;           // float[256]: smallest v whose 8-bit output is >= k+1; [255] = NaN
     const uint8_t *srgb_lut;         // uint8[SRGB_LUT_N + 1]: number of thresholds <= b / SRGB_LUT_N
     float srgb_wrap_hi;              // samples >= this wrap around in the reference's int16 cast (srgb_u8_wrapped)
     int32_t global_tree_uses_wp, have_global_tree;
@@ -773,17 +773,16 @@ J40B_HD J40B_INLINE int srgb_u8_from_linear(const float *thr, float v) {
 }
 
 // Same result through a start table of SRGB_LUT_N + 1 entries: lut[b] = number of thresholds <= b / SRGB_LUT_N
-// (b = floor(SRGB_LUT_N v) clamped to [0, SRGB_LUT_N]). The thresholds are at least 1 / (255 * 12.92) apart, wider
-// than a bucket, so at most one more lies inside bucket b (the host checks "at most two" when it builds the
-// table); two branch-free steps finish the search. Used by the tile kernel.
+// (b = floor(SRGB_LUT_N v) with v clamped to [0, 1]; the product is exact, SRGB_LUT_N being a power of two). The
+// thresholds are at least 1 / (255 * 12.92) apart, wider than a bucket, so at most one more lies inside bucket b (the
+// host checks that when it builds the table) and one branch-free step finishes the search. thr[255] is NaN, which ends
+// the search at 255; v <= 0 and NaN (clamped to 0; the reference's cast gives 0 after clamping) fall into bucket 0
+// below thr[0] > 0. Used by the tile kernel.
 enum { SRGB_LUT_N = 4096, SRGB_LUT_BYTES = 4100 };
 J40B_HD J40B_INLINE int srgb_u8_lut(const float *thr, const uint8_t *lut, float v) {
-    if (!(v > 0.0f)) return 0; // thr[0] > 0; NaN also lands here (the reference's cast gives 0 after clamping)
-    int b = v >= 1.0f ? SRGB_LUT_N : (int) J40B_FMUL(v, (float) SRGB_LUT_N);
-    int code = lut[b];
-    code += (code < 255 && thr[code < 255 ? code : 254] <= v) ? 1 : 0;
-    code += (code < 255 && thr[code < 255 ? code : 254] <= v) ? 1 : 0;
-    return code;
+    const float vc = fminf(fmaxf(v, 0.0f), 1.0f);
+    const int code = lut[(int) J40B_FMUL(vc, (float) SRGB_LUT_N)];
+    return code + (thr[code] <= v ? 1 : 0);
 }
 
 // Samples outside the range the threshold table covers. The reference converts the sRGB-encoded value with an unchecked
