@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--total-frames", type=int, default=256, help="strong scaling: size of the fixed batch (distinct frames)")
     ap.add_argument("--frames-per-gpu", type=int, default=0, help="weak scaling: frames per GPU and step (0 = the workload's default)")
     ap.add_argument("--distinct", type=int, default=0, help="weak scaling: distinct streams per rank, cycled to fill the batch")
+    ap.add_argument("--obj-frames", type=int, default=0, help="frames per batch object (0 = the workload's default); experiments")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
     ap.add_argument("--debug-skip", type=int, default=0, help="measurement aid, NOT a bench value: leave stages out of the pipelined "
@@ -254,6 +255,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     kind, w, h, F_default, distinct_default, obj_frames = WORKLOADS[args.workload]
+    if args.obj_frames > 0:
+        obj_frames = args.obj_frames
     args.frames_per_gpu = args.frames_per_gpu or F_default
     args.distinct = args.distinct or distinct_default
     if args.warmup < 3 and args.impl == "ours":
@@ -359,6 +362,10 @@ def main():
             bm.decode()
         for bm in batches:
             assert bm.wait() == 0
+    if os.environ.get("J40B_LF_SMHIST"):   # diagnostics: clear the per-SM residency counters of the serial LF kernels
+        os.environ["J40B_LF_SMHIST_DUMP"] = "1"
+        batches[0].wait()
+        os.environ.pop("J40B_LF_SMHIST_DUMP")
     sampler = ClockSampler(local_rank)
     sampler.start()
     if dist:
@@ -379,6 +386,10 @@ def main():
     for bm in batches[:min(M, args.steps * C_)]:      # stage times of the last decode of each object, as stretched by co-running
         for n, v in bm.kernel_ms().items():
             stage_sum[n] = stage_sum.get(n, 0.0) + v
+    if os.environ.get("J40B_LF_SMHIST"):   # ... and print them for the timed region
+        os.environ["J40B_LF_SMHIST_DUMP"] = "1"
+        batches[0].wait()
+        os.environ.pop("J40B_LF_SMHIST_DUMP")
     os.environ.pop("J40B_DEBUG_SKIP", None)
     if os.environ.get("J40B_TIMELINE"):
         for k, bm in enumerate(batches):

@@ -64,7 +64,8 @@ float j40b_batch_last_decode_ms(const j40b_batch *b);
 float j40b_batch_kernel_ms(const j40b_batch *b, int which);
 
 /* statistics: 0 device bytes allocated, 1 bytes uploaded (H2D), 2 kernels launched by the last decode,
- * 3 compressed bytes, 4 pixels */
+ * 3 compressed bytes, 4 pixels, 5 lanes per LF group in the last decode's serial LF kernels (32, 16 or 8; 1: one
+ * LF group per lane) */
 int64_t j40b_batch_stat(const j40b_batch *b, int what);
 
 /* Timing several batches in flight at once (each batch owns a CUDA stream; decodes of different batches

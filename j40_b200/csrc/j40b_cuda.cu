@@ -6,6 +6,7 @@
 #include "../../include/j40.h"
 #include "../../include/j40b.h"
 #include <cuda_runtime.h>
+#include <atomic>
 #include <errno.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,6 +33,8 @@ struct CudaBackend {
     float *big_pool = nullptr;
     int big_blocks = 0;
     int64_t launches = 0;
+    int last_lf_lanes = 0;
+    int turn = 0; // which of the process's batch objects this is: rotates where its kernels' blocks start (kern_lf.cu)
     cudaEvent_t ev[10] = {nullptr};
     bool mod_marked = false;
     float kernel_ms[9] = {0};
@@ -44,6 +47,7 @@ struct CudaBackend {
         cudaDeviceProp prop;
         if (!cuda_ok(cudaGetDeviceProperties(&prop, dev))) return false;
         num_sms = prop.multiProcessorCount;
+        { static std::atomic<int> next_turn{0}; turn = next_turn++; }
         if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
         {
             int least = 0, greatest = 0;
@@ -54,7 +58,7 @@ struct CudaBackend {
             for (auto &e : ev_side2) if (!cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return false;
         }
         for (auto &e : ev) if (!cuda_ok(cudaEventCreate(&e))) return false;
-        if (!kl_init_lf() || !kl_init_back() || !kl_init_mod()) return false;
+        if (!kl_init_lf() || !kl_init_hf() || !kl_init_back() || !kl_init_mod()) return false;
         ok = true;
         return true;
     }
@@ -97,7 +101,7 @@ struct CudaBackend {
     // bit 1 the coefficient kernel, bit 2 the LF-group stage kernels -- what each stage costs the others in a pipeline
     static int debug_skip() { const char *e = getenv("J40B_DEBUG_SKIP"); return e ? atoi(e) : 0; }
 
-    void launch_lf(const LfWork *w, int n, size_t, bool split_ok) {
+    void launch_lf(const LfWork *w, int n, size_t, bool split_ok, int tree_lanes) {
         bool split = split_ok;
         if (debug_skip() & 4) { for (int i : {0, 5, 6, 1}) cudaEventRecord(ev[i], stream); return; }
         // One stream per warp (SIMT-uniform decoder, j40b_modular.h; per channel and decoder class, lf_chan_body) or,
@@ -112,18 +116,25 @@ struct CudaBackend {
         split = split && n < 64;
         if (const char *e = getenv("J40B_LF_SPLIT")) split = split_ok && atoi(e) != 0; // (1: also for large launches, 0: never)
         if (lane_mode || !side2) split = false;
-        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP, 0, 3, false); launches += 15; }
+        // Lanes per LF group (kern_lf.cu): 32 for small launches, where latency is what counts -- a warp that carries several
+        // streams is as slow as its slowest; with hundreds of LF groups per launch (a pipeline of batches is bound by issue
+        // slots) as few as the compiled trees allow. J40B_LF_LANES=32|16|8 overrides (the trees must still fit).
+        int lanes = 32;
+        if (n >= 64) lanes = tree_lanes <= 8 ? 8 : tree_lanes <= 16 ? 16 : 32;
+        if (const char *e = getenv("J40B_LF_LANES")) { const int v = atoi(e); if ((v == 8 || v == 16 || v == 32) && tree_lanes <= v) lanes = v; }
+        last_lf_lanes = lane_mode ? 1 : lanes;
+        if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP, 0, 3, false, lanes, num_sms, turn); launches += 15; }
         cudaEventRecord(ev[5], stream);
         kl_lf_post(n, stream, w);
         if (lane_mode) { kl_lf_lane(2, stream, w, n); kl_lf_place(n, stream, w); launches += 2; }
-        else if (!split) { kl_lf_stage(1, stream, w, n, LF_ROW_CAP, 0, 4, false); launches += 20; }
+        else if (!split) { kl_lf_stage(1, stream, w, n, LF_ROW_CAP, 0, 4, false, lanes, num_sms, turn); launches += 20; }
         else {
             // the sharpness channel (a third of the stage, never used by j40) on a side stream, next to the LLF, coefficient
             // and tile stages; join_side() makes the end of the decode wait for it
-            kl_lf_stage(1, stream, w, n, LF_ROW_CAP, 0, 3, true);
+            kl_lf_stage(1, stream, w, n, LF_ROW_CAP, 0, 3, true, lanes, num_sms, turn);
             cudaEventRecord(ev_side2[0], stream);
             cudaStreamWaitEvent(side2, ev_side2[0], 0);
-            kl_lf_stage(1, side2, w, n, LF_ROW_CAP, 3, 4, true);
+            kl_lf_stage(1, side2, w, n, LF_ROW_CAP, 3, 4, true, lanes, num_sms, turn);
             cudaEventRecord(ev_side2[1], side2);
             side2_pending = true;
             launches += 20;
@@ -145,7 +156,7 @@ struct CudaBackend {
         lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
         if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
         const int per_block = HF_WARPS * lanes;
-        if (!(debug_skip() & 2)) kl_hf_group((n + per_block - 1) / per_block, (size_t) spec_cap, stream, w, n, lanes, spec_cap);
+        if (!(debug_skip() & 2)) kl_hf_group((n + per_block - 1) / per_block, (size_t) spec_cap, stream, w, n, lanes, spec_cap, num_sms, turn);
         cudaEventRecord(ev[2], stream);
         ++launches;
     }
@@ -336,6 +347,7 @@ EXPORT int j40b_batch_wait(j40b_batch *b) {
     cudaError_t ce = cudaGetLastError();
     gather_times(b);
     if (getenv("J40B_PHASE_DUMP")) kl_back_phase_dump();
+    if (getenv("J40B_LF_SMHIST_DUMP")) kl_lf_smhist_dump();
     // internal conditions: a token arena that turned out too small (redo with worst-case capacity), LF-group
     // sub-bitstreams with trees of their own (the host reads them where the device found them; at most one round per
     // stage of an LF group)
@@ -465,6 +477,7 @@ EXPORT int64_t j40b_batch_stat(const j40b_batch *b, int what) {
     case 2: return b->last_launches;
     case 3: { int64_t s = 0; for (auto &p : b->batch->plans) s += (int64_t) p->cs_size; return s; }
     case 4: { int64_t s = 0; for (auto &r : b->batch->results) if (!r.err) s += (int64_t) r.width * r.height; return s; }
+    case 5: return b->batch->be.last_lf_lanes;
     default: return 0;
     }
 }

@@ -304,13 +304,17 @@ struct ModSmem {
     SimtLeaf *leaves; // [SIMT_LANES]
     int32_t *info;   // [8] scratch flags shared by the lanes
     int32_t cap;     // widest channel the SIMT path can take
+    uint64_t *tabs;  // room for copies of the leaves' alias tables (device; null: read them through L1)
+    int32_t tabs_entries;
+    int32_t lanes;   // lanes that decode this stream together (32, or 16 / 8 when a warp is shared by 2 / 4 streams): the
+                     // compiled tree may have that many inner nodes and leaves
 };
 
 // Compiles the pruned tree into per-lane decision forms. Returns false if it does not fit (more than 32 inner
 // nodes or leaves, more than SIMT_REF_SLOTS distinct reference properties, a reference property without its
 // channel): the caller then walks the tree instead. refprops[s] = property number of slot s.
 J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, const CodeCtx &cc, SimtLane *tab, SimtLeaf *leaves,
-                                      int32_t *refprops, int32_t *nslots) {
+                                      int32_t *refprops, int32_t *nslots, int max_lanes = SIMT_LANES) {
     int inner_of[192], ni = 0, nl = 0, ns = 0;
     if (n <= 0 || n > 192) return false;
     for (int i = 0; i < SIMT_LANES; ++i) {
@@ -320,8 +324,8 @@ J40B_HD inline bool simt_compile_tree(const DTreeNode *t, int n, int nref, const
     }
     for (int i = 0; i < n; ++i) {
         inner_of[i] = -1;
-        if (t[i].a >= 0) { if (++nl > SIMT_LANES) return false; continue; }
-        if (ni >= SIMT_LANES) return false;
+        if (t[i].a >= 0) { if (++nl > max_lanes) return false; continue; }
+        if (ni >= max_lanes) return false;
         inner_of[i] = ni;
         SimtLane &L = tab[ni++];
         const int prop = -1 - t[i].a;
@@ -396,13 +400,19 @@ J40B_HD J40B_INLINE bool simt_decision(const SimtLane &L, int32_t x, int32_t xs,
 }
 
 // index (into ModSmem::leaves) of the leaf the current sample falls into
-template <bool INTERIOR>
+template <bool INTERIOR, bool FULL>
 J40B_HD J40B_INLINE int32_t simt_tree_leaf(const SimtLane *tab, const SimtLane &mine, int32_t x, int32_t xs, int32_t y, int32_t pn, int32_t pw,
                                            int32_t pnw, int32_t pne, int32_t pnn, int32_t pww, int32_t pnww, int32_t maxerr,
-                                           const int32_t *refp, int32_t cap) {
+                                           const int32_t *refp, int32_t cap, uint32_t gmask, int32_t gshift) {
 #ifdef __CUDA_ARCH__
-    const uint32_t dec = __ballot_sync(0xffffffffu, simt_decision<INTERIOR>(mine, x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap));
-    const uint32_t hit = __ballot_sync(0xffffffffu, mine.leaf_node >= 0 && (dec & mine.care) == mine.want);
+    // A warp shared by several streams (!FULL): the lanes of a group only ever need each other, and they are always
+    // together -- every branch of this decoder is uniform within a group -- so they vote and shuffle among whoever is
+    // converged with them right now (__activemask(): a plain VOTE / SHFL; naming the group's mask instead makes the
+    // compiler guard every collective with a MATCH.ANY convergence check, 5 instructions each). The groups execute as one
+    // instruction stream while their control flow agrees, and one after the other where it does not.
+    const uint32_t am = FULL ? 0xffffffffu : __activemask();
+    const uint32_t dec = (__ballot_sync(am, simt_decision<INTERIOR>(mine, x, xs, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, refp, cap)) & gmask) >> gshift;
+    const uint32_t hit = (__ballot_sync(am, mine.leaf_node >= 0 && (dec & mine.care) == mine.want) & gmask) >> gshift;
     return __ffs((int) hit) - 1;
 #else
     uint32_t dec = 0;
@@ -429,6 +439,7 @@ struct WpSimt {
 struct SimtCtx {
     const SimtLane *tab; const SimtLeaf *leaves; const int32_t *refp; const int32_t *div24;
     int32_t cap, width, y, seg0, dist_mult, my_i;
+    uint32_t gmask; int32_t gshift; // the lanes that decode this stream: their bits in the warp, the first one's number
     // device, per lane: the alias table of "my" leaf's cluster (any valid table for lanes without a leaf), read one
     // sample ahead of the tree decision; masks selecting this lane's weighted sub-predictor without branches
     const uint64_t *my_table;
@@ -464,7 +475,7 @@ J40B_HD J40B_INLINE int32_t mod_predict(int32_t predictor, int32_t pw, int32_t p
 // One sample. PRED >= 0: every leaf of the compiled tree uses that predictor (no dispatch); MODE: see
 // code_cluster; INTERIOR: y >= 2 and 2 <= x < width - 2, so no neighbour falls off the image.
 // Returns false on error (uniform across the lanes).
-template <bool USE_WP, int PRED, int MODE, bool INTERIOR>
+template <bool USE_WP, int PRED, int MODE, bool INTERIOR, bool FULL>
 J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader &br, ErrSlot &es, const CodeCtx &cc, CodeState &cs, int32_t x) {
     const int32_t y = S.y, width = S.width;
     const int32_t n_ee = INTERIOR ? S.nrow[x + 2] : (y > 0 && x + 2 < width ? S.nrow[x + 2] : S.n_e);
@@ -500,7 +511,8 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
             int32_t errsum = wp.e_n[0] + wp.e_w[0] + wp.e_nw[0] + wp.e_ww[0] + wp.e_ne[0] + (INTERIOR || x + 1 < width ? 0 : wp.e_w[0]);
             int32_t shift = imax(floor_lg32((uint32_t) errsum + 1) - 5, 0);
             int32_t wi = (int32_t) (4 + (((int64_t) wpp.w[i] * S.div24[errsum >> shift]) >> shift));
-            for (int k = 0; k < 4; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k);
+            const uint32_t am = FULL ? 0xffffffffu : __activemask();
+            for (int k = 0; k < 4; ++k) w[k] = __shfl_sync(am, wi, S.gshift + k);
         }
 #else
         for (int i = 0; i < 4; ++i) {
@@ -528,12 +540,13 @@ J40B_HD J40B_INLINE bool simt_sample(SimtCtx &S, const SimtLane &mine, BitReader
         if (iabs(maxerr) < iabs(wp.te_ne)) maxerr = wp.te_ne;
     }
 
-    const int32_t li = simt_tree_leaf<INTERIOR>(S.tab, mine, x, x - S.seg0, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap);
+    const int32_t li = simt_tree_leaf<INTERIOR, FULL>(S.tab, mine, x, x - S.seg0, y, pn, pw, pnw, pne, pnn, pww, pnww, maxerr, S.refp, S.cap, S.gmask, S.gshift);
     const SimtLeaf leaf = S.leaves[li];
     int32_t val;
 #ifdef __CUDA_ARCH__
     if (MODE == 1) {
-        const uint32_t elo = __shfl_sync(0xffffffffu, (uint32_t) e_mine, li), ehi = __shfl_sync(0xffffffffu, (uint32_t) (e_mine >> 32), li);
+        const uint32_t am = FULL ? 0xffffffffu : __activemask();
+        const uint32_t elo = __shfl_sync(am, (uint32_t) e_mine, S.gshift + li), ehi = __shfl_sync(am, (uint32_t) (e_mine >> 32), S.gshift + li);
         val = ans_symbol_entry(br, cs.ans_state, cc.log_bucket, (uint64_t) ehi << 32 | elo);
         val = hybrid_int(br, es, val, leaf.cl.cfg);
         if (es.err) val = 0;
@@ -601,9 +614,26 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
     SimtCtx S;
     S.tab = ms.tab; S.leaves = ms.leaves; S.refp = ms.refp; S.div24 = div24;
     S.cap = cap; S.width = width; S.dist_mult = m.dist_mult;
+    S.gmask = sync.mask(); S.gshift = sync.shift();
     S.my_i = lane < 4 ? lane : 4; // this lane's weighted-predictor index (device)
     S.m0 = -(int32_t) (S.my_i == 0); S.m1 = -(int32_t) (S.my_i == 1); S.m2 = -(int32_t) (S.my_i == 2); S.m4 = -(int32_t) (S.my_i == 4);
     S.my_table = (const uint64_t *) (cc.arena + ms.leaves[mine.leaf_node >= 0 ? (lane & (SIMT_LANES - 1)) : 0].cl.table_off);
+#ifdef __CUDA_ARCH__
+    if (MODE == 1 && ms.tabs) {
+        // The alias tables of this channel's leaves (leaf j's in slot j, as far as they fit) into the stream's slice of shared
+        // memory: one entry is fetched per sample on the critical path, and next to a dozen other streams and the tile
+        // kernels of other batches an SM has too little L1 left to keep the tables of all of them (measured: hit rate 98 %
+        // with one stream per SM, 46-55 % with four)
+        const int tlen = 1 << (12 - cc.log_bucket);
+        for (int j = 0; j < ms.lanes && ms.tab[j].leaf_node >= 0 && (j + 1) * tlen <= ms.tabs_entries; ++j) {
+            const uint64_t *src = (const uint64_t *) (cc.arena + ms.leaves[j].cl.table_off);
+            for (int e = lane; e < tlen; e += nlanes) ms.tabs[j * tlen + e] = src[e];
+        }
+        sync();
+        const int mj = mine.leaf_node >= 0 ? (lane & (SIMT_LANES - 1)) : 0;
+        if ((mj + 1) * tlen <= ms.tabs_entries) S.my_table = ms.tabs + mj * tlen;
+    }
+#endif
     S.wpp = m.wp;
     WpSimt &wp = S.wp;
     // the first call below always reads a symbol (or continues an LZ77 copy that an earlier channel began):
@@ -677,10 +707,10 @@ J40B_HD inline void modular_channel_simt(BitReader &br, ErrSlot &es, const CodeC
             int32_t x = seg0;
             if (y >= 2 && width >= 5) {
                 const int32_t e0 = seg1 < 2 ? seg1 : 2, e1 = seg1 < width - 2 ? seg1 : width - 2;
-                for (; x < e0; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
-                for (; x < e1; ++x) if (!simt_sample<USE_WP, PRED, MODE, true>(S, mine, br, es, cc, cs, x)) return;
+                for (; x < e0; ++x) if (!simt_sample<USE_WP, PRED, MODE, false, Sync::kFull>(S, mine, br, es, cc, cs, x)) return;
+                for (; x < e1; ++x) if (!simt_sample<USE_WP, PRED, MODE, true, Sync::kFull>(S, mine, br, es, cc, cs, x)) return;
             }
-            for (; x < seg1; ++x) if (!simt_sample<USE_WP, PRED, MODE, false>(S, mine, br, es, cc, cs, x)) return;
+            for (; x < seg1; ++x) if (!simt_sample<USE_WP, PRED, MODE, false, Sync::kFull>(S, mine, br, es, cc, cs, x)) return;
         }
     }
     sync();
@@ -723,7 +753,7 @@ J40B_HD inline int modular_channel_prep(const CodeCtx &cc, const DTreeNode *tree
             if (c.w == r.w && c.h == r.h && c.hshift == r.hshift && c.vshift == r.vshift) ++nref;
         }
         int32_t nslots = 0;
-        bool simt = ms.rows && n > 0 && (c.w <= ms.cap || !uses_wp || wp_scratch) && simt_compile_tree(ptree, n, nref, cc, ms.tab, ms.leaves, ms.info + 4, &nslots);
+        bool simt = ms.rows && n > 0 && (c.w <= ms.cap || !uses_wp || wp_scratch) && simt_compile_tree(ptree, n, nref, cc, ms.tab, ms.leaves, ms.info + 4, &nslots, ms.lanes);
         // fast variants: rANS without LZ77 and one predictor (gradient or weighted) shared by all leaves
         int variant = 0;
         if (simt && !cc.prefix && !cc.lz77) {

@@ -91,6 +91,7 @@ public:
         auto zk_alloc = [&](size_t bytes) { size_t o = align_up(zero, 256); zero = o + bytes; return o; };
         size_t n_lf = 0, n_hf = 0, n_grp = 0, n_mod = 0;
         max_global_blob = max_coeff_blob = max_ec_blob = 0;
+        lf_tree_lanes = 1;
         for (size_t k = 0; k < n; ++k) {
             FramePlan &p = *plans[k];
             Img &im = img[k];
@@ -371,6 +372,23 @@ public:
                     LfWork &w = lfw[ilf++];
                     w.f = dframe; w.arena = darena; w.cs = dcs;
                     w.g = (DLfGroup *) (dev + im.lfg_off) + i;
+                    // lanes the compiled trees of this LF group's channels need at most (the pruning and the count that
+                    // modular_channel_prep / simt_compile_tree do on the device)
+                    for (int st = 0; st < 2; ++st) {
+                        const bool local = !p.lfg_local.empty() && p.lfg_local[2 * i + (size_t) st].present;
+                        const uint32_t toff = local ? p.lfg_local[2 * i + (size_t) st].tree_off : d.global_tree_off;
+                        if (!local && !d.have_global_tree) continue;
+                        const DTreeNode *tree = (const DTreeNode *) (p.arena.bytes.data() + toff);
+                        const int32_t sidx = st == 0 ? 1 + (int32_t) i : 1 + 2 * d.num_lf_groups + (int32_t) i;
+                        for (int c = 0; c < (st == 0 ? 3 : 4); ++c) {
+                            DTreeNode pruned[PTREE_CAP];
+                            bool uses_wp = false;
+                            const int nn = prune_tree(tree, c, sidx, pruned, PTREE_CAP, &uses_wp);
+                            int inner = 0;
+                            for (int k = 0; k < nn; ++k) inner += pruned[k].a < 0;
+                            lf_tree_lanes = std::max(lf_tree_lanes, nn == 0 ? 32 : std::max(inner, nn - inner));
+                        }
+                    }
                     w.err = derr + i;
                     w.llf_scratch = (float *) (dwork + b.llf_scratch);
                     w.lane_scratch = (ModLaneScratch *) (dwork + b.lane);
@@ -543,7 +561,7 @@ public:
         // multi-section frames only: the pass groups of a single-section frame start where its LF group ends
         bool split = true;
         for (size_t k = 0; k < plans.size(); ++k) if (!plans[k]->err && !plans[k]->df.is_modular && plans[k]->single_section) split = false;
-        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob, split);
+        if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob, split, lf_tree_lanes);
         if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
         for (size_t k = 0; k < plans.size(); ++k) { // extra channels behind the coefficients (errors only; planes are scratch)
             const Img &im = img[k];
@@ -740,6 +758,7 @@ private:
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, ppw_off = 0, num_lf = 0, num_hf = 0, num_grp = 0;
     bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry
     size_t max_global_blob = 0, max_coeff_blob = 0, max_ec_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
+    int lf_tree_lanes = 1; // most inner nodes / leaves of any LF-group channel's pruned tree in the batch
 };
 
 } // namespace j40b

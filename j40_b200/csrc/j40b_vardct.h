@@ -51,7 +51,12 @@ J40B_HD J40B_INLINE DctSelectInfo dct_select_info(int dctsel) {
     return r;
 }
 
-struct NoSync { J40B_HD void operator()() const {} };
+struct NoSync {
+    static constexpr bool kFull = true;
+    J40B_HD void operator()() const {}
+    J40B_HD uint32_t mask() const { return 0xffffffffu; }
+    J40B_HD int shift() const { return 0; }
+};
 
 // ---------------------------------------------------------------------------------------------
 // frame-level constants the kernels need (one per image, in device memory)

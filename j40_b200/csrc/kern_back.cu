@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(128) k_dump_coeffs(DumpWork w) {
 void kl_dump_coeffs(int n, cudaStream_t stream, const DumpWork &w) { if (n > 0) k_dump_coeffs<<<n, 128, 0, stream>>>(w); }
 
 bool kl_init_back() {
-    return cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4) == cudaSuccess &&
+    return kl_carveout(k_back_tile, "J40B_CARVEOUT_BACK") && kl_carveout(k_back_tile_persistent, "J40B_CARVEOUT_BACK") && kl_carveout(k_back_generic, "J40B_CARVEOUT_BACK") && kl_carveout(k_dump_coeffs, "J40B_CARVEOUT_BACK") &&
+           cudaFuncSetAttribute(k_back_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4) == cudaSuccess &&
            cudaFuncSetAttribute(k_back_tile_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE_CH * 4) == cudaSuccess;
 }
 void kl_back_tile(int n, cudaStream_t stream, const BackWork *w) {

@@ -16,12 +16,17 @@ __global__ void __launch_bounds__(128) k_hf_prep(const HfPrepWork *items, int n)
 // or pass (at the boundaries) and specs that do not fit read their tables from global memory instead.
 // `lanes` (<= 32) sections per warp: with small batches fewer lanes per warp give more warps (latency hiding);
 // the host picks it from the number of sections (CudaBackend::launch_hf).
-__global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items, int n, int lanes, int spec_cap) {
+// `rot`: as in k_lf_chan (kern_lf.cu) -- block b works as block (b - rot) mod gridDim.x, so that the few dozen blocks of
+// the batches in flight do not all start on the same SMs.
+__global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items, int n, int lanes, int spec_cap, int rot) {
     extern __shared__ __align__(128) uint8_t spec_copy[];
     __shared__ uint16_t ctx_lut[128];
     __shared__ __align__(8) uint64_t bar;
     const int per_block = HF_WARPS * lanes;
-    const int first = (int) blockIdx.x * per_block;
+    int blk = (int) blockIdx.x - rot;
+    if (blk < 0) blk += (int) gridDim.x;
+    const int first = blk * per_block;
+    if (first >= n) return;
     const HfWork &w0 = items[first];
     const int pass0 = w0.grp->pass;
     const uint32_t spec_off = w0.f->coeff_spec_off[pass0];
@@ -58,9 +63,12 @@ __global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items,
     else hf_lanes_run<0>(w, active, copy, w0.arena, pass0, ctx_lut, WarpAny(), WarpSync());
 }
 
+bool kl_init_hf() { return kl_carveout(k_hf_prep, "J40B_CARVEOUT_HF") && kl_carveout(k_hf_group, "J40B_CARVEOUT_HF"); }
 void kl_hf_prep(int n, cudaStream_t stream, const HfPrepWork *w) { k_hf_prep<<<(n + 3) / 4, 128, 0, stream>>>(w, n); }
-void kl_hf_group(int blocks, size_t smem, cudaStream_t stream, const HfWork *w, int n, int lanes, int spec_cap) {
-    k_hf_group<<<blocks, 32 * HF_WARPS, smem, stream>>>(w, n, lanes, spec_cap);
+void kl_hf_group(int blocks, size_t smem, cudaStream_t stream, const HfWork *w, int n, int lanes, int spec_cap, int spread, int turn) {
+    const int grid = blocks >= 16 && blocks < spread ? spread : blocks;
+    const int rot = blocks >= 16 ? kl_rotation(turn, grid) : 0;
+    k_hf_group<<<grid, 32 * HF_WARPS, smem, stream>>>(w, n, lanes, spec_cap, rot);
 }
 
 } // namespace j40b

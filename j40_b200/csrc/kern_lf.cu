@@ -1,6 +1,8 @@
 // j40-b200: LF-group kernels (serial modular decoders of the LF image and the HF metadata, parallel post stages)
 #include "j40b_kernels.h"
 #include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
 
 namespace j40b {
 
@@ -11,16 +13,80 @@ __host__ __device__ inline bool lf_chan_needs_wp_row(int K, int stage, int c, bo
 }
 
 // One channel of one serial stage of the LF groups, one decoder class per kernel (lf_chan_body in j40b_exec.h): one warp
-// per LF group; `cap`: width of the shared-memory rows. The work list is ordered largest group first.
-template <int K>
-__global__ void __launch_bounds__(32) k_lf_chan(const LfWork *items, int stage, int c, int cap, int split) {
+// per 32 / G LF groups, G lanes each; `cap`: width of the shared-memory rows. The work list is ordered largest group first.
+//
+// G < 32: the per-sample instruction stream is the same for every stream of a class, and in a pipeline of batches the
+// serial decoders are bound by issue slots (the integer pipe), not by latency: measured, the LF stages of 12 batches in
+// flight cost 19.4 of a 44.4 ms step. A warp that carries 2 or 4 streams in lock step spends one instruction on 2 or 4
+// samples. Each group of G lanes keeps the complete decoder state of its stream in its own registers and its own slice of
+// shared memory, and talks only to itself (votes, shuffles and barriers under the group's mask), so the groups need not
+// agree on anything: where their control flow differs (a refill, a long symbol, an edge sample, an error) the hardware
+// runs them one after the other and joins them again. The compiled tree must fit G lanes (host: lf_group_lanes()).
+//
+// `rot`: the grid is at least one block per SM, and block b works as block (b - rot) mod gridDim.x of the work list (those
+// beyond the list leave at once). The hardware hands the blocks of a grid to the SMs in a fixed order, and the work list
+// starts with the big LF groups: without the rotation the long-lived warps of every batch in flight land on the same SMs
+// (with G = 8 a 64-frame batch has 32 of them: a dozen batches stacked 12 deep on 32 SMs, the other 116 idle -- measured as
+// "four streams per warp cost a quarter of the instructions and the pipeline runs no faster"). Each batch object rotates
+// by a different amount (CudaBackend::launch_lf).
+// diagnostics (J40B_LF_SMHIST=1, kl_lf_smhist_dump): warp residency of these kernels per SM, in cycles, and the most warps an
+// SM held at once
+__device__ unsigned long long g_lf_sm_busy[256];
+__device__ unsigned int g_lf_sm_now[256], g_lf_sm_max[256];
+struct LfSmHist {
+    unsigned int smid = 0; long long t0 = 0; bool on;
+    __device__ LfSmHist(bool on_) : on(on_) {
+        if (!on || (threadIdx.x & 31)) return;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicMax(&g_lf_sm_max[smid & 255], atomicAdd(&g_lf_sm_now[smid & 255], 1u) + 1u);
+        t0 = clock64();
+    }
+    __device__ ~LfSmHist() {
+        if (!on || (threadIdx.x & 31)) return;
+        atomicAdd(&g_lf_sm_busy[smid & 255], (unsigned long long) (clock64() - t0));
+        atomicSub(&g_lf_sm_now[smid & 255], 1u);
+    }
+};
+void kl_lf_smhist_dump() {
+    unsigned long long busy[256]; unsigned int mx[256];
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(busy, g_lf_sm_busy, sizeof(busy)) != cudaSuccess || cudaMemcpyFromSymbol(mx, g_lf_sm_max, sizeof(mx)) != cudaSuccess) return;
+    unsigned long long tot = 0;
+    for (int i = 0; i < 256; ++i) tot += busy[i];
+    fprintf(stderr, "lf smhist (share of warp-cycles in 1/1000, max warps at once):");
+    for (int i = 0; i < 160; ++i) fprintf(stderr, " %d:%.1f/%u", i, tot ? 1000.0 * (double) busy[i] / (double) tot : 0.0, mx[i]);
+    fprintf(stderr, "\n");
+    memset(busy, 0, sizeof(busy)); memset(mx, 0, sizeof(mx));
+    cudaMemcpyToSymbol(g_lf_sm_busy, busy, sizeof(busy)); cudaMemcpyToSymbol(g_lf_sm_max, mx, sizeof(mx));
+}
+
+template <int K, int G>
+__global__ void __launch_bounds__(32) k_lf_chan(const LfWork *items, int n, int stage, int c, int cap, int split, int rot) {
+    int blk = (int) blockIdx.x - rot;
+    if (blk < 0) blk += (int) gridDim.x;
+    if (blk * (32 / G) >= n) return;
+    LfSmHist hist((split & 2) != 0);
     __shared__ int32_t div24[64];
     extern __shared__ __align__(16) uint8_t smem[];
     fill_div24(div24, (int) threadIdx.x, 32);
     __syncwarp();
+    const bool with_wp = lf_chan_needs_wp_row(K, stage, c, (split & 1) != 0);
+    if (G == 32) {
+        WarpScratch *ws;
+        ModSmem ms = carve_warp_slice(smem, cap, ws, with_wp, LF_TAB_BYTES);
+        lf_chan_body<K>(items[blk], stage, c, *ws, ms, div24, (int) threadIdx.x, 32, WarpSync(), (split & 1) != 0);
+        return;
+    }
+    const int grp = (int) threadIdx.x / G, lane = (int) threadIdx.x % G;
+    const int i = blk * (32 / G) + grp;
+    if (i >= n) return;
     WarpScratch *ws;
-    ModSmem ms = carve_warp_slice(smem, cap, ws, lf_chan_needs_wp_row(K, stage, c, split != 0));
-    lf_chan_body<K>(items[blockIdx.x], stage, c, *ws, ms, div24, (int) threadIdx.x, 32, WarpSync(), split != 0);
+    ModSmem ms = carve_warp_slice(smem + (size_t) grp * warp_slice_bytes(cap, with_wp, LF_TAB_BYTES), cap, ws, with_wp, LF_TAB_BYTES);
+    ms.lanes = G;
+    GroupSync sync;
+    sync.s = grp * G;
+    sync.m = (G == 32 ? 0xffffffffu : (1u << G) - 1u) << sync.s;
+    lf_chan_body<K>(items[i], stage, c, *ws, ms, div24, lane, G, sync, (split & 1) != 0);
 }
 
 // Lane-per-stream variant (j40b_modlane.h): every thread owns one LF group; 32 * LANE_WARPS work items per block.
@@ -76,24 +142,45 @@ __global__ void __launch_bounds__(128) k_lf_llf(const LfWork *items) {
 }
 
 
-bool kl_init_lf() {
-    const int lf_smem = (int) warp_slice_bytes(LF_ROW_CAP);
-    return cudaFuncSetAttribute(k_lf_chan<MC_WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
-           cudaFuncSetAttribute(k_lf_chan<MC_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
-           cudaFuncSetAttribute(k_lf_chan<MC_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
-           cudaFuncSetAttribute(k_lf_chan<MC_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess &&
-           cudaFuncSetAttribute(k_lf_chan<MC_REST>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem) == cudaSuccess;
+template <int K, int G>
+static bool lf_chan_attr() {
+    return kl_carveout(k_lf_chan<K, G>, "J40B_CARVEOUT_LF") &&
+           cudaFuncSetAttribute(k_lf_chan<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) warp_slice_bytes(LF_ROW_CAP, true, LF_TAB_BYTES) * (32 / G)) == cudaSuccess;
 }
-// channels [c0, c1) of a stage (0: LF image, 1: HF metadata + placement): per channel the five class kernels in a row
-void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap, int c0, int c1, bool split) {
-    const int sp = split ? 1 : 0;
+template <int G>
+static bool lf_chan_attrs() {
+    return lf_chan_attr<MC_WP, G>() && lf_chan_attr<MC_GRAD, G>() && lf_chan_attr<MC_WIDE, G>() && lf_chan_attr<MC_GEN, G>() && lf_chan_attr<MC_REST, G>();
+}
+bool kl_init_lf() {
+    return lf_chan_attrs<32>() && lf_chan_attrs<16>() && lf_chan_attrs<8>() && kl_carveout(k_lf_post, "J40B_CARVEOUT_LF") && kl_carveout(k_lf_llf, "J40B_CARVEOUT_LF") &&
+           kl_carveout(k_lf_place, "J40B_CARVEOUT_LF") && kl_carveout(k_lf_lane<1>, "J40B_CARVEOUT_LF") && kl_carveout(k_lf_lane<2>, "J40B_CARVEOUT_LF");
+}
+
+template <int K, int G>
+static void lf_chan_launch(cudaStream_t stream, const LfWork *w, int n, int stage, int c, int cap, bool split, int spread, int turn) {
+    const int per = 32 / G, blocks = (n + per - 1) / per;
+    static const bool smhist = getenv("J40B_LF_SMHIST") != nullptr;
+    // small launches (a single image: latency) are left alone; the others cover every SM and start at a place of their own
+    const int grid = blocks >= 16 && blocks < spread ? spread : blocks;
+    const int rot = blocks >= 16 ? kl_rotation(turn, grid) : 0;
+    k_lf_chan<K, G><<<grid, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(K, stage, c, split), LF_TAB_BYTES) * per, stream>>>(w, n, stage, c, cap, (split ? 1 : 0) | (smhist ? 2 : 0), rot);
+}
+template <int G>
+static void lf_stage_launch(int stage, cudaStream_t stream, const LfWork *w, int n, int cap, int c0, int c1, bool split, int spread, int turn) {
     for (int c = c0; c < c1; ++c) {
-        k_lf_chan<MC_WP><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WP, stage, c, split)), stream>>>(w, stage, c, cap, sp);
-        k_lf_chan<MC_GRAD><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GRAD, stage, c, split)), stream>>>(w, stage, c, cap, sp);
-        k_lf_chan<MC_WIDE><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_WIDE, stage, c, split)), stream>>>(w, stage, c, cap, sp);
-        k_lf_chan<MC_GEN><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_GEN, stage, c, split)), stream>>>(w, stage, c, cap, sp);
-        k_lf_chan<MC_REST><<<n, 32, warp_slice_bytes(cap, lf_chan_needs_wp_row(MC_REST, stage, c, split)), stream>>>(w, stage, c, cap, sp);
+        lf_chan_launch<MC_WP, G>(stream, w, n, stage, c, cap, split, spread, turn);
+        lf_chan_launch<MC_GRAD, G>(stream, w, n, stage, c, cap, split, spread, turn);
+        lf_chan_launch<MC_WIDE, G>(stream, w, n, stage, c, cap, split, spread, turn);
+        lf_chan_launch<MC_GEN, G>(stream, w, n, stage, c, cap, split, spread, turn);
+        lf_chan_launch<MC_REST, G>(stream, w, n, stage, c, cap, split, spread, turn);
     }
+}
+// channels [c0, c1) of a stage (0: LF image, 1: HF metadata + placement): per channel the five class kernels in a row;
+// `lanes` (32, 16 or 8) lanes per LF group; `spread`: SMs of the device, `turn`: which batch object this is (see k_lf_chan)
+void kl_lf_stage(int stage, cudaStream_t stream, const LfWork *w, int n, int cap, int c0, int c1, bool split, int lanes, int spread, int turn) {
+    if (lanes == 8) lf_stage_launch<8>(stage, stream, w, n, cap, c0, c1, split, spread, turn);
+    else if (lanes == 16) lf_stage_launch<16>(stage, stream, w, n, cap, c0, c1, split, spread, turn);
+    else lf_stage_launch<32>(stage, stream, w, n, cap, c0, c1, split, spread, turn);
 }
 void kl_lf_lane(int stage, cudaStream_t stream, const LfWork *w, int n) {
     const int per_block = 32 * LANE_WARPS, blocks = (n + per_block - 1) / per_block;

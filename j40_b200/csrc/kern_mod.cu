@@ -54,7 +54,8 @@ void kl_palette_delta(cudaStream_t stream, const RenderWork *w, int num_c) { k_p
 
 bool kl_init_mod() {
     const int mod_smem = (int) (SPEC_COPY_BYTES + warp_slice_bytes(MOD_ROW_CAP));
-    return cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem) == cudaSuccess;
+    return kl_carveout(k_modular, "J40B_CARVEOUT_MOD") && kl_carveout(k_mod_lane, "J40B_CARVEOUT_MOD") && kl_carveout(k_render, "J40B_CARVEOUT_MOD") && kl_carveout(k_palette_delta, "J40B_CARVEOUT_MOD") &&
+           cudaFuncSetAttribute(k_modular, cudaFuncAttributeMaxDynamicSharedMemorySize, mod_smem) == cudaSuccess;
 }
 void kl_modular(int n, cudaStream_t stream, ModWork *w, int cap, int spec_cap) {
     k_modular<<<n, 32, (size_t) spec_cap + warp_slice_bytes(cap), stream>>>(w, cap, spec_cap);

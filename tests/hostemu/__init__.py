@@ -49,6 +49,10 @@ def decode(data: bytes):
     return out, err_str(err), stride.value
 
 
+def last_tree_lanes() -> int:
+    return int(lib().hostemu_last_tree_lanes())
+
+
 def dump(data: bytes, lf_group: int, what: int, out):
     """intermediate array `what` (include/j40b.h, j40b_batch_debug_dump) of an LF group into numpy array `out`"""
     return int(lib().hostemu_dump(data, len(data), lf_group, what, out.ctypes.data, out.nbytes))

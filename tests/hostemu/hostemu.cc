@@ -10,6 +10,8 @@
 
 using namespace j40b;
 
+static int g_last_tree_lanes = 1;
+
 struct HostEmuBackend {
     void *dev_alloc(size_t n) { return calloc(n ? n : 1, 1); }
     void dev_free(void *p) { free(p); }
@@ -31,7 +33,7 @@ struct HostEmuBackend {
         int32_t div24[64];
         ModSmem ms;
         explicit WarpMem(int cap) : wp((size_t) cap * (5 + SIMT_REF_SLOTS) + 1), rows((size_t) cap * 3 + 1) {
-            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = wp.data() + (size_t) cap * 5; ms.tab = tab; ms.leaves = leaves; ms.info = ws.info; ms.cap = cap;
+            ms.wp = wp.data(); ms.rows = cap ? rows.data() : nullptr; ms.refp = wp.data() + (size_t) cap * 5; ms.tab = tab; ms.leaves = leaves; ms.info = ws.info; ms.cap = cap; ms.tabs = nullptr; ms.tabs_entries = 0; ms.lanes = getenv("HOSTEMU_SIMT_LANES") ? atoi(getenv("HOSTEMU_SIMT_LANES")) : SIMT_LANES;
             fill_div24(div24, 0, 1);
         }
     };
@@ -52,7 +54,8 @@ struct HostEmuBackend {
         for (int i = 0; i < pending_n; ++i) lf_chan_body<MC_REST>(pending_w[i], 1, 3, wm.ws, wm.ms, wm.div24, 0, 1, NoSync(), true);
         pending_w = nullptr;
     }
-    void launch_lf(const LfWork *w, int n, size_t, bool split) {
+    void launch_lf(const LfWork *w, int n, size_t, bool split, int tree_lanes) {
+        g_last_tree_lanes = tree_lanes; // (what the device would size its lane groups by)
         std::vector<uint8_t> copy(40 * 1024);
         WarpMem wm(row_cap(256));
         if (lane_mode()) {
@@ -180,6 +183,8 @@ __attribute__((visibility("default"))) uint32_t hostemu_decode(const uint8_t *da
 }
 
 __attribute__((visibility("default"))) void hostemu_free(void *p) { free(p); }
+// most inner nodes / leaves of any LF-group channel's pruned MA tree in the last decode (1: no LF groups)
+__attribute__((visibility("default"))) int hostemu_last_tree_lanes() { return g_last_tree_lanes; }
 
 // decodes one image and returns intermediate array `what` of LF group `lfg` (Batch::debug_dump); bytes written or 0
 __attribute__((visibility("default"))) size_t hostemu_dump(const uint8_t *data, size_t size, int lfg, int what, void *dst, size_t cap) {

@@ -281,6 +281,32 @@ def test_lane_per_stream_decoders(oracle, gen, case, monkeypatch):
     _cmp(oracle, streams.make(gen, kind, w, h, seed, opts))
 
 
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_lf_groups_sharing_a_warp(oracle, gen, lanes, monkeypatch):
+    """2 or 4 LF groups per warp in the serial LF kernels (kern_lf.cu, G = 16 / 8 lanes per group), which the executor picks
+    by itself for launches of 64 and more LF groups, forced on a small batch: frames of different sizes, coding tools and
+    decoder classes side by side, so that the groups of a warp disagree on geometry and control flow; a corrupt stream
+    among them (its group leaves early)"""
+    monkeypatch.setenv("J40B_LF_LANES", str(lanes))
+    opts = [dict(mix=1, tree=1), dict(mix=1, tree=1, ans=0), dict(mix=2, tree=1), dict(mix=1, tree=1, lz77=1),
+            dict(mix=1, tree=1, alpha=1), dict(mix=0, tree=1, hfmul=4), dict(mix=1, tree=1, block_ctx=1, orders=0x1f)]
+    datas = [streams.make(gen, "vardct", 136 + 72 * (i % 5), 72 + 56 * (i % 4), 300 + i, opts[i % len(opts)]) for i in range(21)]
+    datas.append(streams.make(gen, "vardct", 2100, 300, 6, dict(mix=1, tree=1, hfmul=6)))  # two LF groups
+    datas.insert(2, datas[3][: len(datas[3]) * 2 // 3])  # truncated inside the LF group's section or a pass group's
+    b = J.Batch(0)
+    b.add_many(datas)
+    b.upload()
+    b.decode()
+    b.wait()
+    assert b.stat(5) == lanes, "the trees of these streams were expected to fit the lane groups"
+    for i, d in enumerate(datas):
+        a, ea, _, _ = oracle.decode(d)
+        assert b.error(i) == ea, (i, b.error(i), ea)
+        if ea == "":
+            assert np.array_equal(b.read_pixels(i), a), i
+    b.close()
+
+
 def test_lane_mode_large_batch_matches(oracle, gen, monkeypatch):
     """80 small VarDCT frames + a modular frame of 72 groups in one batch through the lane kernels (full warps, lanes of
     different geometry side by side)"""

@@ -242,3 +242,20 @@ def test_without_the_sharpness_split(oracle, emu, gen, case, monkeypatch):
         assert ea == eb, (name, ea, eb)
         if ea == "":
             assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("case", streams.VARDCT_CASES[2::5], ids=[c[0] for c in streams.VARDCT_CASES[2::5]])
+def test_trees_that_do_not_fit_the_lane_group(oracle, emu, gen, case, monkeypatch):
+    """The device gives an LF group 32, 16 or 8 lanes (kern_lf.cu) and the compiled MA tree may have as many inner nodes and
+    leaves; the host sizes the groups from the pruned trees (Batch::lf_tree_lanes, reported here by the emulator). A tree
+    that does not fit is walked node by node instead (class MC_REST): HOSTEMU_SIMT_LANES=4 sends every tree of these streams
+    that way."""
+    _, w, h, seed, opts = case
+    data = streams.make(gen, "vardct", w, h, seed, opts)
+    _cmp(oracle, emu, data)
+    need = emu.last_tree_lanes()
+    assert 1 <= need <= 32
+    if opts.get("tree") == 1 and not opts.get("lf_local_tree"):
+        assert need == 5
+    monkeypatch.setenv("HOSTEMU_SIMT_LANES", "4")
+    _cmp(oracle, emu, data)

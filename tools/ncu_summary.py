@@ -21,7 +21,24 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
-        "smsp__thread_inst_executed_per_inst_executed.ratio"]
+        "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_drain_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_misc_per_issue_active.ratio",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "sm__cycles_active.avg"]
 
 
 def main():
