@@ -911,9 +911,11 @@ J40B_HD inline void modular_header(BitReader &br, ErrSlot &es, bool have_global_
         if (!local_tree) { es.set(br, E_TODO); return; }
         *local_tree = 1;
     }
-    m.dist_mult = 0;
-    for (int i = m.nb_meta_channels; i < m.num_channels; ++i) m.dist_mult = imax(m.dist_mult, m.ch[i].w);
-    m.dist_mult = imin(m.dist_mult, 1 << 21);
+    // (in a local and stored once: `m` may be shared memory that every lane of a warp writes the same values to, and a
+    // running maximum kept there is a read-modify-write between lanes -- compute-sanitizer racecheck, round 2)
+    int32_t dist_mult = 0;
+    for (int i = m.nb_meta_channels; i < m.num_channels; ++i) dist_mult = imax(dist_mult, m.ch[i].w);
+    m.dist_mult = imin(dist_mult, 1 << 21);
 }
 
 // one pixel of an inverse RCT (j40.h:4341-4399); v[0..2] in, v'[perm[i]] out

@@ -5,13 +5,14 @@ import sys, random
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tools import streamgen
 rnd=random.Random(int(sys.argv[1])); n=0
+os.makedirs(sys.argv[3], exist_ok=True)
 while n < int(sys.argv[2]):
     kind=rnd.choice(["vardct","modular"])
     w=rnd.choice([8,64,100,200,257,300]); h=rnd.choice([8,64,120,136,264])
     if kind=="vardct":
         kw=dict(mix=rnd.choice([0,1,2]),tree=rnd.choice([0,1,2]),ans=rnd.choice([0,1]),alpha=rnd.choice([0,0,1]),raw_dq=rnd.choice([0,0,0x11]),
                 container=rnd.choice([0,1]),lz77=rnd.choice([0,0,1]),orders=rnd.choice([0,0x1f]),block_ctx=0,seed=rnd.randrange(1000),
-                passes=rnd.choice([1,1,2,3]),lf_local_tree=rnd.choice([0,0,1,2,3,7]))
+                passes=rnd.choice([1,1,2,3]),lf_local_tree=rnd.choice([0,0,1,2,3,7]),coef_spike=rnd.choice([0,0,0,40000,1<<21]))
         if w <= 256 and h <= 256: kw["passes"]=1
         if kw["container"]: kw["jxlp"]=rnd.choice([0,1])
         try: data=streamgen.vardct(w,h,**kw)[0]
