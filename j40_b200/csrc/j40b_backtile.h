@@ -446,14 +446,18 @@ J40B_HD inline void back_tile_body(const BackWork &w, int tx, int ty, float *coe
         const TileVb &t = ts.vb[sp / 3];
         if (t.special) inverse_special(t.dctsel, coef + (sp % 3) * TILE_CH + t.chunk_off);
     }
-    tile_pass(coef, ts, 0, nvb, tid, nth);
-    sync();
-    J40B_PHASE(4);
     // ---- 5. pass B: 1-D inverse DCTs along the vertical frequency v ([v][x] -> [y][x]: column x, along v;
-    // [x][v] -> [x][y]: row x, along v)
-    tile_pass(coef, ts, 1, nvb, tid, nth);
-    sync();
-    J40B_PHASE(5);
+    // [x][v] -> [x][y]: row x, along v). One copy of the eight typed transform loops serves both passes (not unrolled:
+    // the kernel's code is what its warps wait for most once the instruction count is down -- ncu: `no_instruction`
+    // 3.2 stall cycles per issue with a 290 KB kernel, and every tile walks all of its phases)
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int pass = 0; pass < 2; ++pass) {
+        tile_pass(coef, ts, pass, nvb, tid, nth);
+        sync();
+        J40B_PHASE(4 + pass);
+    }
     // ---- 6. XYB -> sRGB -> RGBA8 (j40.h:7208-7237, 7941-7952), one thread per pixel, row-major
     const int gx0 = g.left + (grp.gx8 + tx * 8) * 8, gy0 = g.top + (grp.gy8 + ty * 8) * 8;
     const int fw = f.width, fh = f.height;
