@@ -144,18 +144,23 @@ struct CudaBackend {
         cudaEventRecord(ev[1], stream);
         launches += 2;
     }
-    void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t spec_bytes) {
+    // lanes (sections) per block of the coefficient kernel for a launch of n sections: HF_WARPS warps of `lanes` each --
+    // full warps as soon as that still leaves two warps per SM (a warp of 32 lanes costs the same issue slots per iteration
+    // as one of 8) and fewer lanes per warp for small launches (a single 4K image has 135 sections), where latency is
+    // what counts
+    int hf_block_lanes(int n) const {
+        int lanes = (n + num_sms * 2 - 1) / (num_sms * 2);
+        lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
+        if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
+        return HF_WARPS * lanes;
+    }
+    // `n`: sections including the padding of the work list to whole blocks of `per_block` lanes (Batch::upload)
+    void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t spec_bytes, int per_block) {
         kl_hf_prep(ngroups, stream, pw);
         ++launches;
         int spec_cap = spec_bytes <= SPEC_COPY_BYTES ? (int) ((spec_bytes + 15) & ~(size_t) 15) : 0;
         if (const char *e = getenv("J40B_HF_STAGE")) if (!atoi(e)) spec_cap = 0; // experiment: tables through L1, no shared memory
-        // sections per warp (one per lane): full warps as soon as that still leaves two warps per SM -- a warp of 32 lanes
-        // costs the same issue slots per iteration as one of 8 -- and fewer lanes per warp for small launches (a single
-        // 4K image has 135 sections), where latency is what counts
-        int lanes = (n + num_sms * 2 - 1) / (num_sms * 2);
-        lanes = lanes < 4 ? 4 : lanes > 32 ? 32 : lanes;
-        if (const char *e = getenv("J40B_HF_LANES")) { int v = atoi(e); if (v >= 1 && v <= 32) lanes = v; }
-        const int per_block = HF_WARPS * lanes;
+        const int lanes = per_block / HF_WARPS;
         if (!(debug_skip() & 2)) kl_hf_group((n + per_block - 1) / per_block, (size_t) spec_cap, stream, w, n, lanes, spec_cap, num_sms, turn);
         cudaEventRecord(ev[2], stream);
         ++launches;

@@ -276,6 +276,20 @@ public:
             lf_wring_off = wk_alloc(4 * slots * 2 * LF_RING_W * 5 * LS);
         }
         lfw_off = up_alloc(sizeof(LfWork) * std::max<size_t>(n_lf, 1));
+        // The coefficient kernel's work list is padded so that no block of `hf_per_block` lanes holds sections of two
+        // images or passes: the lanes of a block then all decode with the block's staged copy of the code spec (a lane
+        // of another image reads its tables through L1 and holds up its whole warp; with 135 sections per 4K frame and
+        // 128 lanes per block nearly every block had such lanes). Padding items have grp == nullptr.
+        hf_per_block = n_hf ? std::max(1, be.hf_block_lanes((int) n_hf)) : 1;
+        {
+            size_t padded = 0;
+            for (size_t k = 0; k < n; ++k) {
+                const Img &im = img[k];
+                if (plans[k]->err || plans[k]->df.is_modular || !im.ng) continue;
+                padded += (im.npg / im.ng) * align_up(im.ng, (size_t) hf_per_block);
+            }
+            n_hf = padded;
+        }
         hfw_off = up_alloc(sizeof(HfWork) * std::max<size_t>(n_hf, 1));
         bkw_off = up_alloc(sizeof(BackWork) * std::max<size_t>(n_grp, 1));
         ppw_off = up_alloc(sizeof(HfPrepWork) * std::max<size_t>(n_grp, 1));
@@ -333,7 +347,7 @@ public:
             FramePlan &p = *plans[k];
             Img &im = img[k];
             if (p.err) continue;
-            const size_t ihf_image = ihf;
+            std::vector<HfWork> hf_img; // this image's sections; sorted and padded into hfw below
             results[k].rgba_off = upload_bytes + im.rgba_off;
             DFrame d = p.df;
             // tables: per-image custom ones live in the arena, library defaults in the shared block
@@ -419,7 +433,8 @@ public:
                     g.tok_used = 0;
                     g.vbs = (HfVb *) (dwork + gb.vbs);
                     g.nvb = 0;
-                    HfWork &w = hfw[ihf++];
+                    hf_img.emplace_back();
+                    HfWork &w = hf_img.back();
                     w.f = dframe; w.arena = darena; w.cs = dcs;
                     w.g = (DLfGroup *) (dev + im.lfg_off) + g.lfg;
                     w.grp = (DGroup *) (dev + im.grp_off) + pg;
@@ -439,10 +454,14 @@ public:
                 // pass groups of one image, longest section first: the lanes of a warp (one group each) then
                 // carry similar amounts of work, and the long ones start first
                 // (pass by pass: the lanes of a block share one staged code spec)
-                std::stable_sort(hfw + ihf_image, hfw + ihf, [&](const HfWork &a, const HfWork &b2) {
+                std::stable_sort(hf_img.begin(), hf_img.end(), [&](const HfWork &a, const HfWork &b2) {
                     const DGroup &ga = gr[a.grp - (DGroup *) (dev + im.grp_off)], &gb2 = gr[b2.grp - (DGroup *) (dev + im.grp_off)];
                     return ga.pass != gb2.pass ? ga.pass < gb2.pass : ga.sec_size > gb2.sec_size;
                 });
+                for (size_t s0 = 0; s0 < hf_img.size(); s0 += im.ng) { // one pass's sections, then padding up to a whole block
+                    for (size_t i = 0; i < im.ng; ++i) hfw[ihf++] = hf_img[s0 + i];
+                    for (size_t i = im.ng; i < align_up(im.ng, (size_t) hf_per_block); ++i) memset(&hfw[ihf++], 0, sizeof(HfWork));
+                }
                 if (im.nec) {
                     ModWork *mw = (ModWork *) (staging + im.mod_off);
                     const int nch = p.gmod.num_channels - p.num_gm_channels;
@@ -562,7 +581,7 @@ public:
         bool split = true;
         for (size_t k = 0; k < plans.size(); ++k) if (!plans[k]->err && !plans[k]->df.is_modular && plans[k]->single_section) split = false;
         if (num_lf) be.launch_lf((const LfWork *) (dev + lfw_off), (int) num_lf, max_global_blob, split, lf_tree_lanes);
-        if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob);
+        if (num_hf) be.launch_hf((const HfPrepWork *) (dev + ppw_off), (int) num_grp, (const HfWork *) (dev + hfw_off), (int) num_hf, max_coeff_blob, hf_per_block);
         for (size_t k = 0; k < plans.size(); ++k) { // extra channels behind the coefficients (errors only; planes are scratch)
             const Img &im = img[k];
             if (plans[k]->err || !im.nec) continue;
@@ -758,6 +777,7 @@ private:
     size_t lfw_off = 0, hfw_off = 0, bkw_off = 0, ppw_off = 0, num_lf = 0, num_hf = 0, num_grp = 0;
     bool token_squeeze = getenv("J40B_TEST_TOKEN_SQUEEZE") != nullptr; // see prepare(): exercises the token-arena retry
     size_t max_global_blob = 0, max_coeff_blob = 0, max_ec_blob = 0; // largest code-spec blobs of the batch (shared-memory staging sizes)
+    int hf_per_block = 1;  // lanes per block of the coefficient kernel (the work list is padded to it per image and pass)
     int lf_tree_lanes = 1; // most inner nodes / leaves of any LF-group channel's pruned tree in the batch
 };
 

@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(32 * HF_WARPS) k_hf_group(const HfWork *items,
     }
     const int warp = (int) threadIdx.x >> 5, lane = (int) threadIdx.x & 31;
     const int i = first + warp * lanes + lane;
-    const bool active = lane < lanes && i < n && !*items[i < n ? i : first].lf_err;
-    const HfWork *w = &items[i < n ? i : first];
+    const bool real = lane < lanes && i < n && items[i < n ? i : first].grp != nullptr; // (padding items have no group)
+    const HfWork *w = &items[real ? i : first];
+    const bool active = real && !*w->lf_err;
     // the fast path (rANS, no LZ77) is taken when every section of the warp qualifies
     const bool plain = __all_sync(0xffffffffu, !active || hf_is_plain_ans(*w));
     const uint8_t *copy = staged ? spec_copy : nullptr;

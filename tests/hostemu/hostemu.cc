@@ -97,12 +97,14 @@ struct HostEmuBackend {
         else stage(1, 0, 4, false);
         for (int i = 0; i < n; ++i) lf_llf_body(w[i], 0, 1, NoSync());
     }
-    void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t) {
+    // (the device pads the work list to whole blocks per image and pass; a small block here so that the padding shows up)
+    int hf_block_lanes(int) const { return getenv("HOSTEMU_HF_BLOCK") ? atoi(getenv("HOSTEMU_HF_BLOCK")) : 8; }
+    void launch_hf(const HfPrepWork *pw, int ngroups, const HfWork *w, int n, size_t, int) {
         for (int i = 0; i < ngroups; ++i) hf_prep_body(pw[i], 0, 1, NoSync());
         std::vector<uint8_t> copy(40 * 1024);
         auto any = [](bool p) { return p; };
         for (int i = 0; i < n; ++i) {
-            if (*w[i].lf_err) continue;
+            if (!w[i].grp || *w[i].lf_err) continue;
             // like the device kernel: every other "warp" gets a staged copy of the code spec tables
             const int pass = w[i].grp->pass;
             bool staged = (i & 1) && stage_spec_blob(w[i].arena, w[i].f->coeff_spec_off[pass], copy.data(), (uint32_t) copy.size(), 0, 1);

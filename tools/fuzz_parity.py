@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Random sweep over the test-stream writer's options: every stream goes through the reference (oracle) and through the CPU
 emulation of the kernel bodies (tests/hostemu); any difference in error code, stride or pixels is printed.
-usage: python tools/fuzz_parity.py <seed> <seconds>      (round 1: ~40 000 streams, no difference)"""
+usage: python tools/fuzz_parity.py <seed> <seconds>      (round 1: ~40 000 streams, no difference; round 2, with passes / local trees / wide
+coefficient values / delta palettes among the options: see DESIGN.md §6)"""
 import sys, random, time
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -28,6 +29,11 @@ while time.time()-t0 < float(sys.argv[2]):
         if kw["container"]: kw["jxlp"] = rnd.choice([0,1])
         if not (kw["smooth"] and kw["x_qm"] == 3 and kw["b_qm"] == 2): kw["explicit_fh"] = 1
         else: kw["explicit_fh"] = rnd.choice([0,1])
+        # round-2 features: passes, MA trees local to LF-group sections, coefficient values outside 16 bits, the transform mix
+        if ngroups > 1 and rnd.random() < 0.4: kw["passes"] = rnd.choice([2, 3, 5])
+        if rnd.random() < 0.3: kw["lf_local_tree"] = rnd.choice([1, 2, 3, 7])
+        if rnd.random() < 0.25: kw["coef_spike"] = rnd.choice([32767, 32768, 40000, 1 << 21])
+        if kw["mix"] == 1 and rnd.random() < 0.3: kw["big_take"] = rnd.choice([0.1, 0.35, 0.8]); kw["big_thr"] = rnd.choice([0.01, 0.03, 0.2])
         kw["seed"] = rnd.randrange(100000)
         try: d,_ = streamgen.vardct(w,h,**kw)
         except Exception as e: genfail+=1; continue
@@ -36,6 +42,7 @@ while time.time()-t0 < float(sys.argv[2]):
                   local_tree=rnd.choice([0,0,1,2]), group_shift=rnd.choice([7,8,9,10]), rct=rnd.choice([-1]+list(range(0,42,5))), smooth=rnd.choice([0,1]),
                   clusters=rnd.choice([1,2,8,32]), container=rnd.choice([0,1]))
         if kw["palette"] and kw["tree"] == 2: kw["tree"] = 1
+        if kw["palette"] and rnd.random() < 0.5: kw["pal_deltas"] = rnd.choice([3, 20, 50]); kw["pal_pred"] = rnd.choice([0, 1, 4, 5, 6, 13])
         kw["seed"] = rnd.randrange(100000)
         try: d,_ = streamgen.modular(w,h,**kw)
         except Exception as e: genfail+=1; continue
