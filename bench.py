@@ -523,6 +523,7 @@ def main():
     if rank == 0 and not args.skip_latency:
         latency = latency_section(J, ref, np, args)
 
+    lf_lanes = int(b.stat(5))   # lanes per LF group the serial LF kernels of the last decode used (32, 16 or 8)
     for bm in batches[1:]:
         bm.close()
     b.close()
@@ -552,7 +553,7 @@ def main():
     traffic_key = {"lf_image": "k_lf_chan", "lf_hfmeta": "k_lf_chan", "hf_group": "k_hf_prep+k_hf_group", "back": "k_back_tile"}
     dominant = max(names, key=lambda k: kavg.get(k, 0.0))
     traffic = traffic_total = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch and frame from the committed ncu launch list (profiles/)
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         ent = tr.get(traffic_key.get(dominant, ""))
         if ent and ent.get("preset", args.preset) == args.preset:
@@ -589,7 +590,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if kind == "vardct" else "i16", "data": "synthetic",
         "config": {"workload": workload_name(args), "preset": args.preset if kind == "vardct" else None,
-                   "frames_per_gpu": F, "batch_objects_per_step": C_,
+                   "frames_per_gpu": F, "batch_objects_per_step": C_, "lf_lanes_per_lf_group": lf_lanes if kind == "vardct" else None,
                    "groups_per_gpu": F * ((w + 255) // 256) * ((h + 255) // 256),
                    "compressed_bytes_per_gpu": comp_bytes, "bits_per_pixel": 8.0 * comp_bytes / pixels,
                    "hf_symbols_per_pixel": sum(s["hf_symbols"] for s in stats) / npx,
