@@ -259,3 +259,12 @@ def test_trees_that_do_not_fit_the_lane_group(oracle, emu, gen, case, monkeypatc
         assert need == 5
     monkeypatch.setenv("HOSTEMU_SIMT_LANES", "4")
     _cmp(oracle, emu, data)
+
+
+@pytest.mark.parametrize("block", [1, 32, 128])
+def test_coefficient_work_list_padding(oracle, emu, gen, block, monkeypatch):
+    """the coefficient kernel's work list is padded to whole blocks per image and pass (Batch::hf_per_block; padding items
+    have no group): 6 groups x 3 passes and a single group, with blocks of 1 (no padding), 32 and 128 lanes"""
+    monkeypatch.setenv("HOSTEMU_HF_BLOCK", str(block))
+    _cmp(oracle, emu, streams.make(gen, "vardct", 520, 392, 91, dict(mix=1, tree=1, passes=3, orders=0x1f)))
+    _cmp(oracle, emu, streams.make(gen, "vardct", 200, 136, 92, dict(mix=1, tree=1)))
