@@ -116,11 +116,12 @@ struct CudaBackend {
         split = split && n < 64;
         if (const char *e = getenv("J40B_LF_SPLIT")) split = split_ok && atoi(e) != 0; // (1: also for large launches, 0: never)
         if (lane_mode || !side2) split = false;
-        // Lanes per LF group (kern_lf.cu): 32 for small launches, where latency is what counts -- a warp that carries several
-        // streams is as slow as its slowest; with hundreds of LF groups per launch (a pipeline of batches is bound by issue
-        // slots) as few as the compiled trees allow. J40B_LF_LANES=32|16|8 overrides (the trees must still fit).
+        // Lanes per LF group (kern_lf.cu): 32 -- one LF group per warp -- unless J40B_LF_LANES=16|8 asks for 2 or 4 LF groups
+        // per warp (the compiled trees must fit that many lanes). Measured with a dozen 64-frame batches in flight: 4 groups
+        // per warp need a quarter of the warp instructions and gain 2 % of the pipelined step (43.4 against 44.3 ms), because
+        // the step is not bound by issue slots; alone the stages take 24 % longer (a shared warp is as slow as its slowest
+        // stream, and carries the union of their branches). Not the default for that.
         int lanes = 32;
-        if (n >= 64) lanes = tree_lanes <= 8 ? 8 : tree_lanes <= 16 ? 16 : 32;
         if (const char *e = getenv("J40B_LF_LANES")) { const int v = atoi(e); if ((v == 8 || v == 16 || v == 32) && tree_lanes <= v) lanes = v; }
         last_lf_lanes = lane_mode ? 1 : lanes;
         if (lane_mode) { kl_lf_lane(1, stream, w, n); ++launches; } else { kl_lf_stage(0, stream, w, n, LF_ROW_CAP, 0, 3, false, lanes, num_sms, turn); launches += 15; }

@@ -283,8 +283,8 @@ def test_lane_per_stream_decoders(oracle, gen, case, monkeypatch):
 
 @pytest.mark.parametrize("lanes", [8, 16])
 def test_lf_groups_sharing_a_warp(oracle, gen, lanes, monkeypatch):
-    """2 or 4 LF groups per warp in the serial LF kernels (kern_lf.cu, G = 16 / 8 lanes per group), which the executor picks
-    by itself for launches of 64 and more LF groups, forced on a small batch: frames of different sizes, coding tools and
+    """2 or 4 LF groups per warp in the serial LF kernels (kern_lf.cu, G = 16 / 8 lanes per group; J40B_LF_LANES), on a small
+    batch: frames of different sizes, coding tools and
     decoder classes side by side, so that the groups of a warp disagree on geometry and control flow; a corrupt stream
     among them (its group leaves early)"""
     monkeypatch.setenv("J40B_LF_LANES", str(lanes))
