@@ -21,7 +21,8 @@ __host__ __device__ inline bool lf_chan_needs_wp_row(int K, int stage, int c, bo
 // samples. Each group of G lanes keeps the complete decoder state of its stream in its own registers and its own slice of
 // shared memory, and talks only to itself (votes, shuffles and barriers under the group's mask), so the groups need not
 // agree on anything: where their control flow differs (a refill, a long symbol, an edge sample, an error) the hardware
-// runs them one after the other and joins them again. The compiled tree must fit G lanes (host: lf_group_lanes()).
+// runs them one after the other and joins them again. The compiled tree must fit G lanes (host: Batch::lf_tree_lanes;
+// CudaBackend::launch_lf takes G < 32 only on request, J40B_LF_LANES: 2 % for a pipeline of batches, 24 % more latency).
 //
 // `rot`: the grid is at least one block per SM, and block b works as block (b - rot) mod gridDim.x of the work list (those
 // beyond the list leave at once). The hardware hands the blocks of a grid to the SMs in a fixed order, and the work list

@@ -274,8 +274,8 @@ _LANE_CASES = [("vardct",) + c for c in streams.VARDCT_CASES[::2]] + [("modular"
 
 @pytest.mark.parametrize("case", _LANE_CASES, ids=[c[1] for c in _LANE_CASES])
 def test_lane_per_stream_decoders(oracle, gen, case, monkeypatch):
-    """the lane-per-stream serial decoders (k_lf_lane, k_lf_place, k_mod_lane; j40b_modlane.h), which the executor
-    picks by itself only for launches of 64 and more streams, forced on small images"""
+    """the lane-per-stream serial decoders (k_lf_lane, k_lf_place, k_mod_lane; j40b_modlane.h; opt-in: J40B_LF_MODE=lane)
+    on small images"""
     monkeypatch.setenv("J40B_LF_MODE", "lane")
     kind, _, w, h, seed, opts = case
     _cmp(oracle, streams.make(gen, kind, w, h, seed, opts))
