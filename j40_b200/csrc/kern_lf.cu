@@ -15,21 +15,21 @@ __host__ __device__ inline bool lf_chan_needs_wp_row(int K, int stage, int c, bo
 // One channel of one serial stage of the LF groups, one decoder class per kernel (lf_chan_body in j40b_exec.h): one warp
 // per 32 / G LF groups, G lanes each; `cap`: width of the shared-memory rows. The work list is ordered largest group first.
 //
-// G < 32: the per-sample instruction stream is the same for every stream of a class, and in a pipeline of batches the
-// serial decoders are bound by issue slots (the integer pipe), not by latency: measured, the LF stages of 12 batches in
-// flight cost 19.4 of a 44.4 ms step. A warp that carries 2 or 4 streams in lock step spends one instruction on 2 or 4
-// samples. Each group of G lanes keeps the complete decoder state of its stream in its own registers and its own slice of
-// shared memory, and talks only to itself (votes, shuffles and barriers under the group's mask), so the groups need not
-// agree on anything: where their control flow differs (a refill, a long symbol, an edge sample, an error) the hardware
-// runs them one after the other and joins them again. The compiled tree must fit G lanes (host: Batch::lf_tree_lanes;
-// CudaBackend::launch_lf takes G < 32 only on request, J40B_LF_LANES: 2 % for a pipeline of batches, 24 % more latency).
+// G < 32: the per-sample instruction stream is the same for every stream of a class, so a warp that carries 2 or 4 streams
+// in lock step spends one instruction on 2 or 4 samples (measured over 1024 LF groups: 8.0 G -> 2.15 G warp instructions,
+// 29.85 of 32 lanes active, same time per sample). Each group of G lanes keeps the complete decoder state of its stream in
+// its own registers and its own slice of shared memory, and talks only to itself (votes and shuffles among whoever is
+// converged, barriers under the group's mask), so the groups need not agree on anything: where their control flow differs
+// (a refill, a long symbol, an edge sample, an error) the hardware runs them one after the other and joins them again. The
+// compiled tree must fit G lanes (host: Batch::lf_tree_lanes). CudaBackend::launch_lf takes G < 32 only on request
+// (J40B_LF_LANES): a pipeline of batches turned out not to be bound by issue slots and gains 2 %, a batch alone takes 24 %
+// longer ("Lane groups").
 //
 // `rot`: the grid is at least one block per SM, and block b works as block (b - rot) mod gridDim.x of the work list (those
-// beyond the list leave at once). The hardware hands the blocks of a grid to the SMs in a fixed order, and the work list
-// starts with the big LF groups: without the rotation the long-lived warps of every batch in flight land on the same SMs
-// (with G = 8 a 64-frame batch has 32 of them: a dozen batches stacked 12 deep on 32 SMs, the other 116 idle -- measured as
-// "four streams per warp cost a quarter of the instructions and the pipeline runs no faster"). Each batch object rotates
-// by a different amount (CudaBackend::launch_lf).
+// beyond the list leave at once), each batch object rotating by a different amount (CudaBackend::turn), so that the
+// long-lived warps of the batches in flight -- the work list starts with the big LF groups -- do not depend on the order in
+// which the hardware hands blocks to SMs. Measured (J40B_LF_SMHIST): residency is even over the SMs to +- 15 %; the
+// rotation itself moved the LF stages of a pipeline from 19.4 to 18.8 ms per step.
 // diagnostics (J40B_LF_SMHIST=1, kl_lf_smhist_dump): warp residency of these kernels per SM, in cycles, and the most warps an
 // SM held at once
 __device__ unsigned long long g_lf_sm_busy[256];
